@@ -1,0 +1,258 @@
+// Host-side preparation (TMA tensor maps, tile selection) and launch of the GEMM kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gemm_sm100.cuh"
+
+namespace ardae {
+
+// ------------------------------------------------------------------ error plumbing
+inline std::string& last_error_string() {
+  static thread_local std::string s;
+  return s;
+}
+inline int fail(int code, const std::string& msg) {
+  last_error_string() = msg;
+  return code;
+}
+#define ARDAE_CUDA_OK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ::ardae::fail(static_cast<int>(_e), std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------ driver entry point
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map, 128-byte swizzle.  inner = contiguous dimension (elements).
+inline int encode_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+                          uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer,
+                          CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return fail(-10, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return fail(-11, "TMA base pointer not 16-byte aligned");
+  if ((pitch_elems * 4) % 16 != 0) return fail(-12, "TMA row pitch not a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {pitch_elems * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu pitch=%llu box=%ux%u",
+             static_cast<int>(r), (unsigned long long)inner, (unsigned long long)outer,
+             (unsigned long long)pitch_elems, box_inner, box_outer);
+    return fail(-13, buf);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ NT GEMM
+struct GemmNTDesc {
+  const float* A = nullptr; int lda = 0;   // [M, K]
+  const float* B = nullptr; int ldb = 0;   // [N, K]
+  float* out = nullptr; int ldo = 0;       // [M, N]
+  float* out2 = nullptr; int ldo2 = 0;
+  const float* aux1 = nullptr; int ld1 = 0;
+  const float* aux2 = nullptr; int ld2 = 0;
+  int M = 0, N = 0, K = 0;
+  int mode = EPI_LINEAR;
+  float alpha = 1.0f;
+  const float* bias = nullptr;
+  const float* group_bias = nullptr; int group = 1, ldg = 0;
+  const float* row_scale = nullptr; const float* col_vec = nullptr;
+  float* colsum = nullptr;
+  float* colsum_w = nullptr; const float* row_w = nullptr;
+  int round_out = 1;
+  int force_block_n = 0;
+};
+
+struct PreparedNT {
+  GemmNTParams params;
+  const void* fn = nullptr;
+  dim3 grid;
+  int smem = 0;
+};
+
+template <int BLOCK_N>
+inline const void* nt_kernel_for_mode(int mode) {
+  switch (mode) {
+    case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR>);
+    case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU>);
+    case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS>);
+    case EPI_MUL_SIG: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_SIG>);
+    case EPI_MUL_STEP: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_STEP>);
+    case EPI_TANGENT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_TANGENT>);
+    case EPI_ADJOINT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_ADJOINT>);
+    default: return nullptr;
+  }
+}
+
+inline int pick_block_n(int N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  const int pad256 = ((N + 255) / 256) * 256;
+  const int pad128 = ((N + 127) / 128) * 128;
+  return pad128 < pad256 ? 128 : 256;
+}
+
+inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(-2, "gemm_nt: empty problem");
+  if (d.mode < 0 || d.mode >= EPI_NUM_MODES) return fail(-2, "gemm_nt: bad mode");
+  const bool has_aux1 = d.mode >= EPI_MUL_SIG, has_aux2 = d.mode >= EPI_TANGENT;
+  const bool has_out2 = d.mode == EPI_TANGENT;
+  if (!d.A || !d.B || !d.out || (has_aux1 && !d.aux1) || (has_aux2 && !d.aux2) ||
+      (has_out2 && !d.out2))
+    return fail(-2, "gemm_nt: missing operand pointer");
+  const int bn = d.force_block_n ? d.force_block_n : pick_block_n(d.N);
+  PreparedNT pr;
+  std::memset(&pr.params, 0, sizeof(pr.params));
+  GemmNTParams& p = pr.params;
+  int rc;
+  if ((rc = encode_tmap_2d(&p.tmA, d.A, d.K, d.M, d.lda, kBlockK, kBlockM))) return rc;
+  if ((rc = encode_tmap_2d(&p.tmB, d.B, d.K, d.N, d.ldb, kBlockK, bn))) return rc;
+  if ((rc = encode_tmap_2d(&p.tmOut, d.out, d.N, d.M, d.ldo, 32, kBlockM))) return rc;
+  if (has_out2 && (rc = encode_tmap_2d(&p.tmOut2, d.out2, d.N, d.M, d.ldo2, 32, kBlockM))) return rc;
+  if (has_aux1 && (rc = encode_tmap_2d(&p.tmAux1, d.aux1, d.N, d.M, d.ld1, 32, kBlockM))) return rc;
+  if (has_aux2 && (rc = encode_tmap_2d(&p.tmAux2, d.aux2, d.N, d.M, d.ld2, 32, kBlockM))) return rc;
+  p.M = d.M; p.N = d.N; p.K = d.K; p.alpha = d.alpha;
+  p.bias = d.bias; p.group_bias = d.group_bias; p.group = d.group > 0 ? d.group : 1; p.ldg = d.ldg;
+  p.row_scale = d.row_scale; p.col_vec = d.col_vec;
+  p.colsum = d.colsum; p.colsum_w = d.colsum_w; p.row_w = d.row_w;
+  p.round_out = d.round_out;
+  if (p.row_scale && !p.col_vec) return fail(-2, "gemm_nt: row_scale without col_vec");
+  if (p.colsum_w && !p.row_w) return fail(-2, "gemm_nt: colsum_w without row_w");
+  switch (bn) {
+    case 32: pr.fn = nt_kernel_for_mode<32>(d.mode); pr.smem = GemmNTConfig<32>::kSmemBytes; break;
+    case 64: pr.fn = nt_kernel_for_mode<64>(d.mode); pr.smem = GemmNTConfig<64>::kSmemBytes; break;
+    case 128: pr.fn = nt_kernel_for_mode<128>(d.mode); pr.smem = GemmNTConfig<128>::kSmemBytes; break;
+    case 256: pr.fn = nt_kernel_for_mode<256>(d.mode); pr.smem = GemmNTConfig<256>::kSmemBytes; break;
+    default: return fail(-2, "gemm_nt: bad BLOCK_N");
+  }
+  pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, 1);
+  ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
+  *out = pr;
+  return 0;
+}
+
+inline int launch_prepared_nt(const PreparedNT& pr, cudaStream_t stream) {
+  void* args[1] = {const_cast<GemmNTParams*>(&pr.params)};
+  ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(kGemmThreads), args, pr.smem, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ TN GEMM (weight gradient)
+struct GemmTNDesc {
+  const float* X0 = nullptr; int ldx0 = 0;  // [K, M]
+  const float* Y0 = nullptr; int ldy0 = 0;  // [K, N]
+  const float* X1 = nullptr; int ldx1 = 0;  // optional second pair
+  const float* Y1 = nullptr; int ldy1 = 0;
+  int M = 0, N = 0, K = 0;
+  float* out = nullptr; int ldo = 0;  // [M, N] destination
+  float scale = 1.0f, beta = 0.0f;    // out = beta*out + scale*(X0^T Y0 + X1^T Y1)
+  float* workspace = nullptr;         // split-K partials
+  size_t workspace_bytes = 0;
+  int target_ctas = 296;
+};
+
+struct PreparedTN {
+  GemmTNParams params;
+  const void* fn = nullptr;
+  dim3 grid;
+  int smem = 0;
+  // reduce
+  int nsplit = 0, Mpad = 0, Npad = 0;
+  float* out = nullptr; int M = 0, N = 0, ldo = 0;
+  float scale = 1.0f, beta = 0.0f;
+};
+
+inline size_t tn_workspace_bytes(int M, int N, int K, int target_ctas = 296) {
+  const int bn = pick_block_n(N);
+  const int mt = (M + kBlockM - 1) / kBlockM, nt = (N + bn - 1) / bn;
+  const int total_kb = (K + kBlockK - 1) / kBlockK;
+  int nsplit = target_ctas / (mt * nt);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > total_kb) nsplit = total_kb;
+  return static_cast<size_t>(nsplit) * mt * kBlockM * nt * bn * sizeof(float);
+}
+
+inline int prepare_gemm_tn(const GemmTNDesc& d, PreparedTN* out) {
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(-2, "gemm_tn: empty problem");
+  if (!d.X0 || !d.Y0 || !d.out || !d.workspace) return fail(-2, "gemm_tn: missing pointer");
+  const int bn = pick_block_n(d.N);
+  const int mt = (d.M + kBlockM - 1) / kBlockM, nt = (d.N + bn - 1) / bn;
+  const int total_kb = (d.K + kBlockK - 1) / kBlockK;
+  int nsplit = d.target_ctas / (mt * nt);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > total_kb) nsplit = total_kb;
+  const int kb_per_split = (total_kb + nsplit - 1) / nsplit;
+  nsplit = (total_kb + kb_per_split - 1) / kb_per_split;
+  const size_t need = static_cast<size_t>(nsplit) * mt * kBlockM * nt * bn * sizeof(float);
+  if (need > d.workspace_bytes) return fail(-3, "gemm_tn: workspace too small");
+  PreparedTN pr;
+  std::memset(&pr.params, 0, sizeof(pr.params));
+  GemmTNParams& p = pr.params;
+  int rc;
+  if ((rc = encode_tmap_2d(&p.tmX0, d.X0, d.M, d.K, d.ldx0, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = encode_tmap_2d(&p.tmY0, d.Y0, d.N, d.K, d.ldy0, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  p.npairs = 1;
+  if (d.X1 != nullptr) {
+    if (!d.Y1) return fail(-2, "gemm_tn: X1 without Y1");
+    if ((rc = encode_tmap_2d(&p.tmX1, d.X1, d.M, d.K, d.ldx1, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = encode_tmap_2d(&p.tmY1, d.Y1, d.N, d.K, d.ldy1, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    p.npairs = 2;
+  }
+  p.M = d.M; p.N = d.N; p.K = d.K; p.kb_per_split = kb_per_split; p.partial = d.workspace;
+  switch (bn) {
+    case 32: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<32>); pr.smem = GemmTNConfig<32>::kSmemBytes; break;
+    case 64: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<64>); pr.smem = GemmTNConfig<64>::kSmemBytes; break;
+    case 128: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<128>); pr.smem = GemmTNConfig<128>::kSmemBytes; break;
+    case 256: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<256>); pr.smem = GemmTNConfig<256>::kSmemBytes; break;
+    default: return fail(-2, "gemm_tn: bad BLOCK_N");
+  }
+  pr.grid = dim3(nsplit, mt, nt);
+  pr.nsplit = nsplit; pr.Mpad = mt * kBlockM; pr.Npad = nt * bn;
+  pr.out = d.out; pr.M = d.M; pr.N = d.N; pr.ldo = d.ldo; pr.scale = d.scale; pr.beta = d.beta;
+  ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
+  *out = pr;
+  return 0;
+}
+
+inline int launch_prepared_tn(const PreparedTN& pr, cudaStream_t stream) {
+  void* args[1] = {const_cast<GemmTNParams*>(&pr.params)};
+  ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(kGemmThreads), args, pr.smem, stream));
+  const int total = pr.M * pr.N;
+  splitk_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
+      pr.params.partial, pr.nsplit, pr.Mpad, pr.Npad, pr.out, pr.M, pr.N, pr.ldo, pr.scale, pr.beta);
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ardae
