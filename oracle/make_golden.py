@@ -1,0 +1,116 @@
+"""Generate tests/golden/*.npz by executing the REFERENCE modules (fp64, CPU, injected noise).
+
+Run in the build container only (needs /root/reference):  python oracle/make_golden.py
+The fixtures pin oracle/ardae_oracle.py (tests/test_oracle_golden.py) and, through it, the CUDA path.
+Sizes are tiny so the files stay small; the architecture (layer structure, concat pattern,
+activation, heads, optimizers) is the one ivae_ardae.py builds for configs 1 and 2.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+CASES = {
+    # 25gaussians-shaped (run_vae_25gaussians.sh): relu ToyIPVAE, CDAE L=3
+    'toy_small': dict(kind='toy',
+                      model=dict(input_dim=2, noise_dim=3, h_dim=16, num_hidden_layers=2, nonlinearity='relu', z_dim=2),
+                      cdae=dict(input_dim=2, context_dim=2, h_dim=16, num_hidden_layers=3, nonlinearity='softplus'),
+                      B=6, hp=dict(std_scale=10000., delta=0.1, nz_cdae=8, nstd=1, nz_model=1, beta=1.0,
+                                   m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
+    # dbMNIST-shaped (run_vae_dbmnist.sh:37): softplus MNISTIPVAE, CDAE L=5
+    'mnist_small': dict(kind='mnist',
+                        model=dict(input_dim=20, noise_dim=5, h_dim=12, num_hidden_layers=2, nonlinearity='softplus', z_dim=4),
+                        cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=5, nonlinearity='softplus'),
+                        B=5, hp=dict(std_scale=10000., delta=0.1, nz_cdae=6, nstd=2, nz_model=1, beta=0.7,
+                                     m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
+    # same, every matrix scaled x3 -> softplus / sigmoid in their saturated regions
+    'mnist_small_x3': dict(kind='mnist',
+                           model=dict(input_dim=20, noise_dim=5, h_dim=12, num_hidden_layers=2, nonlinearity='softplus', z_dim=4),
+                           cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=5, nonlinearity='softplus'),
+                           B=5, hp=dict(std_scale=100., delta=0.1, nz_cdae=6, nstd=1, nz_model=2, beta=1.0,
+                                        m_lr=1e-3, m_beta1=0.9, d_lr=1e-3, d_momentum=0.9), wscale=3.0),
+}
+
+
+def t2n(d):
+    return {k: (v.detach().numpy().copy() if v is not None else None) for k, v in d.items()}
+
+
+def make_case(name, c):
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % (2 ** 31))
+    dt = torch.float64
+    model, cdae = rh.build_reference(c['kind'], c['model'], c['cdae'], dtype=dt, seed=1234)
+    if c['wscale'] != 1.0:
+        with torch.no_grad():
+            for m in (model, cdae):
+                for k, p in m.named_parameters():
+                    if p.dim() == 2:
+                        p.mul_(c['wscale'])
+    hp = c['hp']
+    mopt, copt = rh.build_optimizers(model, cdae, hp)
+    B, D, n, d = c['B'], c['model']['input_dim'], c['model']['noise_dim'], c['model']['z_dim']
+    nz, nstd, nzm = hp['nz_cdae'], hp['nstd'], hp['nz_model']
+    arrays = {}
+    for k, v in model.state_dict().items():
+        arrays['m0/' + k] = v.numpy().copy()
+    for k, v in cdae.state_dict().items():
+        arrays['c0/' + k] = v.numpy().copy()
+    for step in range(2):
+        if c['kind'] == 'mnist':
+            xc = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
+            xm = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
+        else:
+            xc = torch.randn(B, D, dtype=dt, generator=g) * 2
+            xm = torch.randn(B, D, dtype=dt, generator=g) * 2
+        noise = dict(enc_cdae=torch.randn(B * nz, n, dtype=dt, generator=g),
+                     xi=torch.randn(B, nz * nstd, 1, dtype=dt, generator=g),
+                     eps_cdae=torch.randn(B, nz * nstd, d, dtype=dt, generator=g),
+                     enc_model=torch.randn(B * nzm, n, dtype=dt, generator=g))
+        out = rh.ref_train_step(model, cdae, mopt, copt, xc, xm, noise, hp, do_step=True)
+        p = 's%d/' % step
+        arrays[p + 'x_cdae'], arrays[p + 'x_model'] = xc.numpy(), xm.numpy()
+        for k, v in noise.items():
+            arrays[p + 'noise/' + k] = v.numpy()
+        for k in ('zbar', 'z_cdae', 'std', 'cdae_loss', 'cdae_score', 'model_loss', 'recon', 'prior', 'z_model', 'entropy_grad'):
+            arrays[p + k] = out[k].detach().numpy().copy()
+        for k, v in t2n(out['cdae_grads']).items():
+            if v is not None:
+                arrays[p + 'cdae_grads/' + k] = v
+        for k, v in t2n(out['model_grads']).items():
+            arrays[p + 'model_grads/' + k] = v
+        for k, v in model.state_dict().items():
+            arrays[p + 'm_after/' + k] = v.numpy().copy()
+        for k, v in cdae.state_dict().items():
+            arrays[p + 'c_after/' + k] = v.numpy().copy()
+    assert out['cdae_grads']['neglogprob.fc.bias'] is None
+    # IWS (evaluate_iws) on the stepped weights
+    b, S = 3, 16
+    if c['kind'] == 'mnist':
+        xe = torch.bernoulli(torch.full((b, D), 0.3, dtype=dt), generator=g)
+    else:
+        xe = torch.randn(b, D, dtype=dt, generator=g) * 2
+    enc_noise = torch.randn(b, S, n, dtype=dt, generator=g)
+    eta = torch.randn(b, S, d, dtype=dt, generator=g)
+    arrays['iws/x'], arrays['iws/enc_noise'], arrays['iws/eta'] = xe.numpy(), enc_noise.numpy(), eta.numpy()
+    arrays['iws/logprob'] = rh.ref_iws(model, xe, enc_noise, eta).numpy()
+    meta = dict(kind=c['kind'], model=c['model'], cdae=c['cdae'], B=B, hp=hp, wscale=c['wscale'], iws=dict(b=b, S=S))
+    arrays['meta'] = np.array(json.dumps(meta))
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print('%s: %d arrays, %.1f KB, cdae_loss=%.6g model_loss=%.6g iws=%.6g' % (
+        name, len(arrays), os.path.getsize(path) / 1024., float(arrays['s1/cdae_loss']),
+        float(arrays['s1/model_loss']), float(arrays['iws/logprob'])))
+
+
+if __name__ == '__main__':
+    for name, c in CASES.items():
+        make_case(name, c)
