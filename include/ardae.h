@@ -1,0 +1,95 @@
+/* libardae -- C ABI of the B200-native AR-DAE hot path.
+ *
+ * The reference (lim0606/pytorch-ardae-vae) has no FFI: its path sits behind Python nn.Module /
+ * Optimizer objects.  This library is what a reference-side binding loads in place of
+ * the PyTorch library calls those objects make; each entry point names the reference interface it
+ * replaces (file:line, relative to the reference root).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *  - plain C: device pointers + sizes, no torch types.  All tensors fp32, row-major, contiguous
+ *    unless a pitch is given.  The library never allocates or frees caller tensors; plans carve
+ *    their scratch out of a caller-provided workspace (query the size first).
+ *  - every call is stream-ordered and asynchronous on the cudaStream_t passed (as void*).
+ *  - return value: 0 = ok, negative = invalid argument / unsupported shape, positive = CUDA error
+ *    code; ardae_last_error() returns the message of the last failure on the calling thread.
+ *  - handles are not thread-safe; calls sharing a handle must be serialized by the caller.
+ *  - sm_100a only.  There is no CPU fallback: without a B200 every compute entry point fails.
+ */
+#ifndef ARDAE_H_
+#define ARDAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARDAE_VERSION 100
+#if defined(__GNUC__)
+#define ARDAE_API __attribute__((visibility("default")))
+#else
+#define ARDAE_API
+#endif
+
+ARDAE_API int ardae_version(void);
+ARDAE_API const char* ardae_last_error(void);
+/* 0 if device `dev` is an sm_100 part and the TMA descriptor entry point resolves. */
+ARDAE_API int ardae_check_device(int dev);
+
+/* ------------------------------------------------------------------------------------------
+ * Conditional AR-DAE, `net.MLPGradCARDAE` (models/graddae/mlp.py:341-483; constructed at
+ * ivae_ardae.py:595-606 with enc_ctx = enc_input = True, softplus).
+ * Parameter tensors are passed as 6L+2 device pointers in state_dict order:
+ *   ctx_encode.layers.{0..L-2}.{weight,bias}, ctx_encode.fc.{weight,bias},
+ *   inp_encode.(same), neglogprob.layers.{0..L-1}.{weight,bias}, neglogprob.fc.{weight,bias}
+ * with nn.Linear [out,in] layout.  `grads` has the same order; gradients are ACCUMULATED into it
+ * (autograd semantics); the entry of neglogprob.fc.bias is never written (the reference leaves
+ * its .grad = None).  The pointers must stay valid and fixed for the life of the handle; their
+ * CONTENTS may change between calls (weights are re-read every call).
+ */
+typedef struct ardae_cdae_s* ardae_cdae_t;
+
+typedef struct {
+  int input_dim;         /* d  */
+  int context_dim;       /* c  */
+  int h_dim;             /* H, multiple of 4 */
+  int num_hidden_layers; /* L >= 2 */
+  int batch;             /* B  distinct context rows */
+  int samples;           /* S  rows per context row; N = B*S, row index b*S+k */
+  int train;             /* 1: loss + gradients (forward + backward); 0: glogprob only */
+} ardae_cdae_config;
+
+ARDAE_API int ardae_cdae_workspace_bytes(const ardae_cdae_config* cfg, size_t* bytes);
+ARDAE_API int ardae_cdae_create(const ardae_cdae_config* cfg, float* const* params, float* const* grads,
+                      int num_tensors, void* workspace, size_t workspace_bytes, ardae_cdae_t* out);
+ARDAE_API void ardae_cdae_destroy(ardae_cdae_t h);
+/* number of kernel launches one train / score call issues */
+ARDAE_API int ardae_cdae_num_launches(ardae_cdae_t h);
+
+/* Replaces ConditionalARDAE.forward + cdae_loss.backward() (graddae/mlp.py:400-444,
+ * ivae_ardae.py:768-771).  x [N,d] = input flattened, ctx [B,c], sigma [N] (= std, signed),
+ * eps [N,d]: the Gaussian noise of add_gaussian_noise (graddae/mlp.py:21-23) -- supplied by the
+ * caller (gen_eps = 0) or drawn in-kernel with Philox from `seed` and written back (gen_eps = 1).
+ * inv_count = 1/(N_total*d): the mse_loss mean (pass the GLOBAL row count under data parallelism
+ * so that summing gradients over ranks reproduces the reference mean).
+ * loss_out: device scalar (overwritten).  score_out: optional [N,d], receives g = grad log p. */
+ARDAE_API int ardae_cdae_train(ardae_cdae_t h, const float* x, const float* ctx, const float* sigma,
+                     float* eps, int gen_eps, uint64_t seed, float inv_count, float* loss_out,
+                     float* score_out, void* stream);
+
+/* Replaces ConditionalARDAE.glogprob (graddae/mlp.py:446-483; ivae_ardae.py:829).
+ * Needs a handle created with train = 0.  score_out [N,d]. */
+ARDAE_API int ardae_cdae_score(ardae_cdae_t h, const float* x, const float* ctx, const float* sigma,
+                     float* score_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Utilities */
+/* out[i] ~ N(0,1), Philox4x32-10 + Box-Muller (replaces torch.randn at ivae_ardae.py:761 and
+ * Encoder.sample_noise, ivae/toy.py:61-65, which draws on the CPU and copies). */
+ARDAE_API int ardae_randn(float* out, size_t n, uint64_t seed, uint32_t stream_id, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARDAE_H_ */

@@ -1,0 +1,76 @@
+"""ctypes binding of libardae.so (C ABI declared in include/ardae.h).
+
+There is deliberately no fallback: if the CUDA library is missing or the device is not a B200
+every compute call raises.  PyTorch is used only for device memory, streams and autograd plumbing.
+"""
+import ctypes
+import os
+
+import torch
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libardae.so')
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+
+class CdaeConfig(ctypes.Structure):
+    _fields_ = [('input_dim', ctypes.c_int), ('context_dim', ctypes.c_int), ('h_dim', ctypes.c_int),
+                ('num_hidden_layers', ctypes.c_int), ('batch', ctypes.c_int), ('samples', ctypes.c_int),
+                ('train', ctypes.c_int)]
+
+
+def _declare(lib):
+    vp, i, sz, u64, u32, f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint64,
+                              ctypes.c_uint32, ctypes.c_float)
+    lib.ardae_version.restype = i
+    lib.ardae_last_error.restype = ctypes.c_char_p
+    lib.ardae_check_device.argtypes = [i]
+    lib.ardae_cdae_workspace_bytes.argtypes = [ctypes.POINTER(CdaeConfig), ctypes.POINTER(sz)]
+    lib.ardae_cdae_create.argtypes = [ctypes.POINTER(CdaeConfig), ctypes.POINTER(vp), ctypes.POINTER(vp), i, vp, sz,
+                                      ctypes.POINTER(vp)]
+    lib.ardae_cdae_destroy.argtypes = [vp]
+    lib.ardae_cdae_destroy.restype = None
+    lib.ardae_cdae_num_launches.argtypes = [vp]
+    lib.ardae_cdae_train.argtypes = [vp, vp, vp, vp, vp, i, u64, f, vp, vp, vp]
+    lib.ardae_cdae_score.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ardae_randn.argtypes = [vp, sz, u64, u32, vp]
+    for name in dir(lib):
+        pass
+    return lib
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(_LIB_PATH):
+            raise RuntimeError('libardae.so not built (%s). Run `python -c "import __graft_entry__ as g; g.build()"` '
+                               'or `make -C pytorch-ardae-vae_b200/csrc`. There is no CPU fallback.' % _LIB_PATH)
+        _LIB = _declare(ctypes.CDLL(_LIB_PATH))
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('libardae error %d: %s' % (rc, lib().ardae_last_error().decode()))
+
+
+def require_cuda(t, name):
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32):
+        raise RuntimeError('%s must be a float32 CUDA tensor (the AR-DAE path has no CPU fallback)' % name)
+    return t.contiguous()
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr

@@ -1,0 +1,342 @@
+// Plan for the mlp-grad conditional AR-DAE (reference: models/graddae/mlp.py:341-483).
+//   train : loss = mean((sigma*g + eps)^2), g = -dE/dx~, plus every parameter gradient of that
+//           double-backprop loss, computed with the primal / score / tangent / adjoint sweeps of
+//           SURVEY.md 8a-3 as a chain of tcgen05 GEMMs with fused epilogues.
+//   score : glogprob only (sweeps 1-2).
+// Precision: the PRIMAL forward runs "3xTF32" (operands split into tf32 hi/lo pairs, fp32-accurate
+// products).  With std_scale = 1e4 the inputs reach |x| ~ 1e4..1e5, pre-activations ~1e4, and the
+// loss gradient lives on the units within O(10) of their softplus kink: a plain tf32 forward
+// (relative 5e-4 -> absolute +-10) makes those sigmoids garbage (measured: 47 % gradient error on
+// the reference-generated fixture).  The score / tangent / adjoint / weight-gradient sweeps are
+// linear in their operands and run plain tf32 (measured gradient error ~1e-3).
+// Parameter tensors arrive as per-tensor device pointers in state_dict order:
+//   ctx_encode (W,b) x L ; inp_encode (W,b) x L ; neglogprob (W,b) x (L+1).
+#pragma once
+#include <cstring>
+#include <memory>
+
+#include "kernels.cuh"
+#include "plan.cuh"
+
+namespace ardae {
+
+struct CdaeConfig {
+  int d = 0, c = 0, H = 0, L = 0;  // input_dim, context_dim, h_dim, num_hidden_layers
+  int B = 0, S = 0;                // data rows, samples per data row (N = B*S)
+  int train = 1;                   // 0: score-only plan
+};
+
+struct CdaeBindings {  // per-call user pointers (plain device memory, no TMA)
+  const float* x = nullptr;      // [N, d]
+  const float* ctx = nullptr;    // [B, c]
+  const float* sigma = nullptr;  // [N]
+  float* eps = nullptr;          // [N, d]  (input, or output when gen_eps)
+  int gen_eps = 0;
+  uint64_t seed = 0;
+  float inv_count = 0.0f;        // 1 / (N_global * d)
+  float* loss_out = nullptr;     // device scalar
+  float* score_out = nullptr;    // [N, d] or null
+};
+
+// Collects DeriveItems and emits the single weight-derivation launch.
+struct DeriveList {
+  std::vector<DeriveItem> host;
+  int blocks = 0;
+  // W[rows(out), cols(in)] at src (pitch src_ld).  want3: forward 3xTF32 operand; wantT: transpose.
+  W3 add(Workspace& ws, const float* src, int rows, int cols, int src_ld, bool want3, bool wantT) {
+    W3 w;
+    w.in = cols; w.out = rows; w.kp = round_up(cols, 32);
+    DeriveItem it;
+    std::memset(&it, 0, sizeof(it));
+    it.src = src; it.rows = rows; it.cols = cols; it.src_ld = src_ld;
+    if (want3) {
+      w.b3 = Mat(ws.floats(static_cast<size_t>(rows) * 3 * w.kp), rows, 3 * w.kp, 3 * w.kp);
+      it.dst3 = w.b3.p; it.kp = w.kp; it.ld3 = 3 * w.kp;
+    }
+    if (wantT) {
+      w.T = ws.mat(cols, rows);
+      it.dstT = w.T.p; it.ldT = w.T.ld;
+    }
+    it.first_block = blocks;
+    it.tiles_x = (cols + 31) / 32;
+    blocks += it.tiles_x * ((rows + 31) / 32);
+    host.push_back(it);
+    return w;
+  }
+  int emit(Workspace& ws, Plan& plan) {
+    float* table = ws.floats((host.size() * sizeof(DeriveItem) + 3) / 4 + 1);
+    if (ws.dry) {
+      plan.add(nullptr);
+      return 0;
+    }
+    DeriveItem* dev = reinterpret_cast<DeriveItem*>(table);
+    ARDAE_CUDA_OK(cudaMemcpy(dev, host.data(), host.size() * sizeof(DeriveItem), cudaMemcpyHostToDevice));
+    const int nitems = static_cast<int>(host.size());
+    const int nb = blocks;
+    plan.add([dev, nitems, nb](cudaStream_t s) {
+      derive_weights_kernel<<<nb, 256, 0, s>>>(dev, nitems);
+      return static_cast<int>(cudaGetLastError());
+    });
+    return 0;
+  }
+};
+
+struct CdaePlan {
+  CdaeConfig cfg;
+  Plan plan;
+  Workspace ws;
+  CdaeBindings bind;  // ops read this at launch time
+  DeriveList derive;
+  size_t tn_need = 0;  // split-K partial workspace, measured by the dry build
+
+  int ntensors() const { return 6 * cfg.L + 2; }
+
+  // returns 0 or error; when ws.dry only measures
+  int build(float* const* params, float* const* grads) {
+    const int d = cfg.d, c = cfg.c, H = cfg.H, L = cfg.L, B = cfg.B, S = cfg.S;
+    const int N = B * S;
+    if (d <= 0 || c <= 0 || H <= 0 || L < 2 || B <= 0 || S <= 0)
+      return fail(-2, "cdae: bad config (need d,c,H,B,S > 0 and num_hidden_layers >= 2)");
+    if (H % 4 != 0) return fail(-2, "cdae: h_dim must be a multiple of 4");
+    plan.dry = ws.dry;
+    const bool dry = ws.dry;
+    const bool train = cfg.train != 0;
+    auto P = [&](int i) -> float* { return dry ? nullptr : params[i]; };
+    auto G = [&](int i) -> float* { return (dry || !train) ? nullptr : grads[i]; };
+    auto iC = [&](int l) { return 2 * l; };          // ctx_encode weight l (bias +1)
+    auto iA = [&](int l) { return 2 * L + 2 * l; };  // inp_encode
+    auto iW = [&](int l) { return 4 * L + 2 * l; };  // neglogprob (l == L: fc)
+
+    // ---- derived weights
+    derive = DeriveList();
+    std::vector<W3> Cw(L), Aw(L), Ww(L);
+    for (int l = 0; l < L; ++l) Cw[l] = derive.add(ws, P(iC(l)), H, l == 0 ? c : H, l == 0 ? c : H, true, train);
+    for (int l = 0; l < L; ++l) Aw[l] = derive.add(ws, P(iA(l)), H, l == 0 ? d : H, l == 0 ? d : H, true, true);
+    for (int l = 1; l < L; ++l) Ww[l] = derive.add(ws, P(iW(l)), H, H, H, true, true);
+    const int ld1 = 2 * H + 1;
+    W3 W1u = derive.add(ws, P(iW(0)), H, H, ld1, true, true);
+    W3 W1c = derive.add(ws, P(iW(0)) ? P(iW(0)) + H : nullptr, H, H, ld1, true, train);
+    Ww[0] = W1u;
+    int rc = derive.emit(ws, plan);
+    if (rc) return rc;
+    float* wsig = ws.floats(H);  // exact fp32 copy of W_1[:, 2H]
+    const float* wo = P(iW(L));
+
+    // ---- activations
+    Pair xt = make_pair(ws, N, d), ctxp = make_pair(ws, B, c);
+    Mat gmat = ws.mat(N, d), rowbias = ws.mat(B, H);
+    float* sig = ws.floats(N);
+    std::vector<Pair> Cc(L), U(L), V(L);
+    std::vector<Mat> DA(L), DP(L);
+    for (int l = 0; l < L; ++l) Cc[l] = make_pair(ws, B, H);
+    for (int l = 0; l < L; ++l) U[l] = make_pair(ws, N, H);
+    for (int l = 0; l < L; ++l) V[l] = make_pair(ws, N, H);
+    for (int l = 0; l < L; ++l) DA[l] = ws.mat(N, H);
+    for (int l = 0; l < L; ++l) DP[l] = ws.mat(N, H);
+    std::vector<Mat> UD(L), VD(L), TA(L), TP(L), DC(L);
+    Mat rmat, gsum;
+    float* tn_ws = nullptr;
+    size_t tn_ws_bytes = 0;
+    if (train) {
+      rmat = ws.mat(N, d);
+      gsum = ws.mat(B, H);
+      for (int l = 0; l < L; ++l) UD[l] = ws.mat(N, H);
+      for (int l = 0; l < L; ++l) VD[l] = ws.mat(N, H);
+      for (int l = 0; l < L; ++l) TA[l] = ws.mat(N, H);
+      for (int l = 0; l < L; ++l) TP[l] = ws.mat(N, H);
+      for (int l = 0; l < L; ++l) DC[l] = ws.mat(B, H);
+      if (dry) {
+        const int shapes[4][3] = {{H, H, N}, {H, d, N}, {H, H, B}, {H, c, B}};
+        tn_need = 0;
+        for (auto& sh : shapes) {
+          const size_t b = tn_workspace_bytes(sh[0], sh[1], sh[2]);
+          if (b > tn_need) tn_need = b;
+        }
+      }
+      tn_ws_bytes = tn_need;
+      tn_ws = ws.floats(tn_ws_bytes / 4);
+    }
+    CdaeBindings* bd = &bind;
+
+    // ---- prologue: sigma copy, x~ = x + sigma*eps (tf32 pair), context pair, exact w_sigma
+    {
+      const float* w1 = P(iW(0));
+      plan.add([=](cudaStream_t s) {
+        ARDAE_CUDA_OK(cudaMemcpyAsync(sig, bd->sigma, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+        if (bd->loss_out) ARDAE_CUDA_OK(cudaMemsetAsync(bd->loss_out, 0, sizeof(float), s));
+        cdae_perturb_kernel<<<grid_for(static_cast<size_t>(N) * d), 256, 0, s>>>(
+            bd->x, sig, bd->eps, xt.buf.p, N, d, xt.buf.ld, xt.kp, bd->gen_eps, bd->seed);
+        split2d_kernel<<<grid_for(static_cast<size_t>(B) * c), 256, 0, s>>>(
+            bd->ctx, c, ctxp.buf.p, ctxp.buf.ld, B, c, ctxp.kp, 1.0f, 0.0f);
+        copy2d_kernel<<<1, 256, 0, s>>>(w1 + 2 * H, ld1, wsig, 1, H, 1, 1, 1.0f, 0.0f, 0);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    // ---- context branch on the B distinct rows (reference runs it on all N: graddae/mlp.py:415,426)
+    for (int l = 0; l < L; ++l) {
+      GemmNTDesc g = nt3_desc(l == 0 ? ctxp : Cc[l - 1], Cw[l], Cc[l], EPI_SOFTPLUS);
+      g.bias = P(iC(l) + 1);
+      plan.nt(g);
+    }
+    {
+      GemmNTDesc g = nt3_desc_plain(Cc[L - 1], W1c, rowbias, EPI_LINEAR);
+      g.bias = P(iW(0) + 1);
+      plan.nt(g);
+    }
+    // ---- sweep 1: primal forward (3xTF32)
+    for (int l = 0; l < L; ++l) {
+      GemmNTDesc g = nt3_desc(l == 0 ? xt : U[l - 1], Aw[l], U[l], EPI_SOFTPLUS);
+      g.bias = P(iA(l) + 1);
+      plan.nt(g);
+    }
+    {
+      GemmNTDesc g = nt3_desc(U[L - 1], W1u, V[0], EPI_SOFTPLUS);
+      g.group_bias = rowbias.p; g.group = S; g.ldg = rowbias.ld;
+      g.row_scale = sig; g.col_vec = wsig;
+      plan.nt(g);
+    }
+    for (int l = 1; l < L; ++l) {
+      GemmNTDesc g = nt3_desc(V[l - 1], Ww[l], V[l], EPI_SOFTPLUS);
+      g.bias = P(iW(l) + 1);
+      plan.nt(g);
+    }
+    // ---- sweep 2: score backward (tf32)
+    {
+      const Mat vl = V[L - 1].hi(), dpl = DP[L - 1];
+      plan.add([=](cudaStream_t s) {
+        cdae_init_delta_kernel<<<grid_for(static_cast<size_t>(N) * H), 256, 0, s>>>(vl.p, vl.ld, wo, dpl.p, dpl.ld, N, H);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(DP[l], Ww[l].T, DP[l - 1], EPI_MUL_SIG);
+      set_aux1(g, V[l - 1].hi());
+      plan.nt(g);
+    }
+    {
+      GemmNTDesc g = nt_desc(DP[0], W1u.T, DA[L - 1], EPI_MUL_SIG);
+      set_aux1(g, U[L - 1].hi());
+      plan.nt(g);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(DA[l], Aw[l].T, DA[l - 1], EPI_MUL_SIG);
+      set_aux1(g, U[l - 1].hi());
+      plan.nt(g);
+    }
+    {
+      GemmNTDesc g = nt_desc(DA[0], Aw[0].T, gmat, EPI_LINEAR);
+      g.round_out = 0;
+      plan.nt(g);
+    }
+    if (!train) {
+      plan.add([=](cudaStream_t s) {
+        unpad_kernel<<<grid_for(static_cast<size_t>(N) * d), 256, 0, s>>>(gmat.p, gmat.ld, bd->score_out, N, d, 1.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return plan.error;
+    }
+    // ---- loss + residual direction r
+    plan.add([=](cudaStream_t s) {
+      cdae_loss_kernel<<<grid_for(static_cast<size_t>(N) * gmat.ld), 256, 0, s>>>(
+          gmat.p, gmat.ld, sig, bd->eps, rmat.p, N, d, bd->inv_count, bd->loss_out, bd->score_out);
+      return static_cast<int>(cudaGetLastError());
+    });
+    // ---- sweep 3: tangent forward (also emits t = delta * tangent_pre * (1 - sig))
+    for (int l = 0; l < L; ++l) {
+      GemmNTDesc g = nt_desc(l == 0 ? rmat : UD[l - 1], Aw[l].hi(), UD[l], EPI_TANGENT);
+      set_aux1(g, U[l].hi()); set_aux2(g, DA[l]); set_out2(g, TA[l]);
+      plan.nt(g);
+    }
+    for (int l = 0; l < L; ++l) {
+      GemmNTDesc g = nt_desc(l == 0 ? UD[L - 1] : VD[l - 1], Ww[l].hi(), VD[l], EPI_TANGENT);
+      set_aux1(g, V[l].hi()); set_aux2(g, DP[l]); set_out2(g, TP[l]);
+      if (l == L - 1) {
+        g.colsum = G(iW(L)); g.colsum_scale = -1.0f;  // d w_o = -sum_n vdot_L
+        g.colsum2 = G(iW(L - 1) + 1);                 // d beta_L = sum_n adj p_L (= t_L)
+      }
+      plan.nt(g);
+    }
+    // ---- sweep 4: adjoint backward (in place over the t buffers)
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(TP[l], Ww[l].T, TP[l - 1], EPI_ADJOINT);
+      set_aux1(g, V[l - 1].hi()); set_aux2(g, TP[l - 1]);
+      g.colsum = G(iW(l - 1) + 1);
+      if (l - 1 == 0) {  // d w_1sigma = sum_n sigma_n * adj p_1
+        g.colsum_w = G(iW(0)) ? G(iW(0)) + 2 * H : nullptr;
+        g.colsum_w_stride = ld1;
+        g.row_w = sig;
+      }
+      plan.nt(g);
+    }
+    {
+      GemmNTDesc g = nt_desc(TP[0], W1u.T, TA[L - 1], EPI_ADJOINT);
+      set_aux1(g, U[L - 1].hi()); set_aux2(g, TA[L - 1]);
+      g.colsum = G(iA(L - 1) + 1);
+      plan.nt(g);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(TA[l], Aw[l].T, TA[l - 1], EPI_ADJOINT);
+      set_aux1(g, U[l - 1].hi()); set_aux2(g, TA[l - 1]);
+      g.colsum = G(iA(l - 1) + 1);
+      plan.nt(g);
+    }
+    // ---- weight gradients: dW = adj^T . act + delta^T . tangent   (accumulated into .grad)
+    auto tn2 = [&](const Mat& X0, const Mat& Y0, const Mat* X1, const Mat* Y1, float* dst, int ldo) {
+      GemmTNDesc t;
+      t.X0 = X0.p; t.ldx0 = X0.ld; t.Y0 = Y0.p; t.ldy0 = Y0.ld;
+      if (X1) { t.X1 = X1->p; t.ldx1 = X1->ld; t.Y1 = Y1->p; t.ldy1 = Y1->ld; }
+      t.M = X0.cols; t.N = Y0.cols; t.K = X0.rows; t.out = dst; t.ldo = ldo;
+      t.scale = 1.0f; t.beta = 1.0f; t.workspace = tn_ws; t.workspace_bytes = tn_ws_bytes;
+      plan.tn(t);
+    };
+    const Mat xt_hi = xt.hi();
+    for (int l = L - 1; l >= 1; --l) {
+      const Mat y = V[l - 1].hi();
+      tn2(TP[l], y, &DP[l], &VD[l - 1], G(iW(l)), H);
+    }
+    {
+      const Mat y = U[L - 1].hi();
+      tn2(TP[0], y, &DP[0], &UD[L - 1], G(iW(0)), ld1);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      const Mat y = U[l - 1].hi();
+      tn2(TA[l], y, &DA[l], &UD[l - 1], G(iA(l)), H);
+    }
+    tn2(TA[0], xt_hi, &DA[0], &rmat, G(iA(0)), d);
+    // ---- context branch backward (B rows)
+    {
+      const Mat ap1 = TP[0];
+      plan.add([=](cudaStream_t s) {
+        group_sum_kernel<<<B, 256, 0, s>>>(ap1.p, ap1.ld, gsum.p, gsum.ld, B, S, H, 1);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    {
+      const Mat y = Cc[L - 1].hi();
+      tn2(gsum, y, nullptr, nullptr, G(iW(0)) ? G(iW(0)) + H : nullptr, ld1);
+    }
+    {
+      GemmNTDesc g = nt_desc(gsum, W1c.T, DC[L - 1], EPI_MUL_SIG);
+      set_aux1(g, Cc[L - 1].hi());
+      g.colsum = G(iC(L - 1) + 1);
+      plan.nt(g);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(DC[l], Cw[l].T, DC[l - 1], EPI_MUL_SIG);
+      set_aux1(g, Cc[l - 1].hi());
+      g.colsum = G(iC(l - 1) + 1);
+      plan.nt(g);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      const Mat y = Cc[l - 1].hi();
+      tn2(DC[l], y, nullptr, nullptr, G(iC(l)), H);
+    }
+    {
+      const Mat y = ctxp.hi();
+      tn2(DC[0], y, nullptr, nullptr, G(iC(0)), c);
+    }
+    return plan.error;
+  }
+};
+
+}  // namespace ardae

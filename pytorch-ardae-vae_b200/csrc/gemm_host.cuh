@@ -87,9 +87,12 @@ struct GemmNTDesc {
   const float* bias = nullptr;
   const float* group_bias = nullptr; int group = 1, ldg = 0;
   const float* row_scale = nullptr; const float* col_vec = nullptr;
-  float* colsum = nullptr;
-  float* colsum_w = nullptr; const float* row_w = nullptr;
+  float* colsum = nullptr; float colsum_scale = 1.0f;
+  float* colsum_w = nullptr; const float* row_w = nullptr; int colsum_w_stride = 1;
+  float* colsum2 = nullptr;
   int round_out = 1;
+  int split_out = 0;   // modes LINEAR/RELU/SOFTPLUS: out = tf32 hi part, out2 = tf32 lo part
+  int a_k_wrap = 0;
   int force_block_n = 0;
 };
 
@@ -101,15 +104,23 @@ struct PreparedNT {
 };
 
 template <int BLOCK_N>
-inline const void* nt_kernel_for_mode(int mode) {
+inline const void* nt_kernel_for_mode(int mode, int split) {
+  if (split) {
+    switch (mode) {
+      case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, true>);
+      case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, true>);
+      case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, true>);
+      default: return nullptr;
+    }
+  }
   switch (mode) {
-    case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR>);
-    case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU>);
-    case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS>);
-    case EPI_MUL_SIG: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_SIG>);
-    case EPI_MUL_STEP: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_STEP>);
-    case EPI_TANGENT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_TANGENT>);
-    case EPI_ADJOINT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_ADJOINT>);
+    case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, false>);
+    case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, false>);
+    case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, false>);
+    case EPI_MUL_SIG: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_SIG, false>);
+    case EPI_MUL_STEP: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_STEP, false>);
+    case EPI_TANGENT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_TANGENT, false>);
+    case EPI_ADJOINT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_ADJOINT, false>);
     default: return nullptr;
   }
 }
@@ -127,7 +138,8 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(-2, "gemm_nt: empty problem");
   if (d.mode < 0 || d.mode >= EPI_NUM_MODES) return fail(-2, "gemm_nt: bad mode");
   const bool has_aux1 = d.mode >= EPI_MUL_SIG, has_aux2 = d.mode >= EPI_TANGENT;
-  const bool has_out2 = d.mode == EPI_TANGENT;
+  const bool has_out2 = d.mode == EPI_TANGENT || d.split_out;
+  if (d.split_out && d.mode > EPI_SOFTPLUS) return fail(-2, "gemm_nt: split_out needs a plain activation mode");
   if (!d.A || !d.B || !d.out || (has_aux1 && !d.aux1) || (has_aux2 && !d.aux2) ||
       (has_out2 && !d.out2))
     return fail(-2, "gemm_nt: missing operand pointer");
@@ -136,7 +148,9 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   std::memset(&pr.params, 0, sizeof(pr.params));
   GemmNTParams& p = pr.params;
   int rc;
-  if ((rc = encode_tmap_2d(&p.tmA, d.A, d.K, d.M, d.lda, kBlockK, kBlockM))) return rc;
+  const uint64_t a_inner = d.a_k_wrap > 0 ? d.a_k_wrap : d.K;
+  if (d.a_k_wrap > 0 && d.a_k_wrap % kBlockK != 0) return fail(-2, "gemm_nt: a_k_wrap must be a multiple of 32");
+  if ((rc = encode_tmap_2d(&p.tmA, d.A, a_inner, d.M, d.lda, kBlockK, kBlockM))) return rc;
   if ((rc = encode_tmap_2d(&p.tmB, d.B, d.K, d.N, d.ldb, kBlockK, bn))) return rc;
   if ((rc = encode_tmap_2d(&p.tmOut, d.out, d.N, d.M, d.ldo, 32, kBlockM))) return rc;
   if (has_out2 && (rc = encode_tmap_2d(&p.tmOut2, d.out2, d.N, d.M, d.ldo2, 32, kBlockM))) return rc;
@@ -146,14 +160,15 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   p.bias = d.bias; p.group_bias = d.group_bias; p.group = d.group > 0 ? d.group : 1; p.ldg = d.ldg;
   p.row_scale = d.row_scale; p.col_vec = d.col_vec;
   p.colsum = d.colsum; p.colsum_w = d.colsum_w; p.row_w = d.row_w;
-  p.round_out = d.round_out;
+  p.colsum2 = d.colsum2; p.colsum_scale = d.colsum_scale; p.colsum_w_stride = d.colsum_w_stride;
+  p.round_out = d.round_out; p.a_k_wrap = d.a_k_wrap;
   if (p.row_scale && !p.col_vec) return fail(-2, "gemm_nt: row_scale without col_vec");
   if (p.colsum_w && !p.row_w) return fail(-2, "gemm_nt: colsum_w without row_w");
   switch (bn) {
-    case 32: pr.fn = nt_kernel_for_mode<32>(d.mode); pr.smem = GemmNTConfig<32>::kSmemBytes; break;
-    case 64: pr.fn = nt_kernel_for_mode<64>(d.mode); pr.smem = GemmNTConfig<64>::kSmemBytes; break;
-    case 128: pr.fn = nt_kernel_for_mode<128>(d.mode); pr.smem = GemmNTConfig<128>::kSmemBytes; break;
-    case 256: pr.fn = nt_kernel_for_mode<256>(d.mode); pr.smem = GemmNTConfig<256>::kSmemBytes; break;
+    case 32: pr.fn = nt_kernel_for_mode<32>(d.mode, d.split_out); pr.smem = GemmNTConfig<32>::kSmemBytes; break;
+    case 64: pr.fn = nt_kernel_for_mode<64>(d.mode, d.split_out); pr.smem = GemmNTConfig<64>::kSmemBytes; break;
+    case 128: pr.fn = nt_kernel_for_mode<128>(d.mode, d.split_out); pr.smem = GemmNTConfig<128>::kSmemBytes; break;
+    case 256: pr.fn = nt_kernel_for_mode<256>(d.mode, d.split_out); pr.smem = GemmNTConfig<256>::kSmemBytes; break;
     default: return fail(-2, "gemm_nt: bad BLOCK_N");
   }
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, 1);

@@ -48,10 +48,14 @@ struct alignas(64) GemmNTParams {
   int group, ldg;
   const float* row_scale;   // [M] or null   pre += row_scale[m] * col_vec[n]
   const float* col_vec;     // [N]
-  float* colsum;            // [N] or null   colsum[n]  += sum_m out[m,n]
-  float* colsum_w;          // [N] or null   colsum_w[n] += sum_m out[m,n] * row_w[m]
+  float* colsum;            // [N] or null   colsum[n]  += colsum_scale * sum_m out[m,n]
+  float* colsum_w;          // or null       colsum_w[n*colsum_w_stride] += sum_m out[m,n]*row_w[m]
   const float* row_w;       // [M]
+  float* colsum2;           // [N] or null   colsum2[n] += sum_m out2[m,n]   (EPI_TANGENT only)
+  float colsum_scale;
+  int colsum_w_stride;
   int round_out;            // round stored outputs to tf32 (rna)
+  int a_k_wrap;             // if > 0 the A operand's k coordinate wraps: col = (kb*32) % a_k_wrap
 };
 
 struct alignas(64) GemmTNParams {
@@ -106,14 +110,19 @@ struct GemmNTConfig {
   static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
-template <int BLOCK_N, int MODE>
+// SPLIT (modes LINEAR / RELU / SOFTPLUS only): the fp32 result is stored as a tf32 pair
+//   out = hi = rna(res), out2 = lo = rna(res - hi)
+// so that a following "3xTF32" GEMM (A' = [hi | lo | hi] via a_k_wrap, B' = [W_hi | W_hi | W_lo])
+// reproduces an fp32-accurate product on the tf32 tensor pipe.
+template <int BLOCK_N, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
   using Cfg = GemmNTConfig<BLOCK_N>;
   constexpr int NSTAGE = Cfg::kNumStages;
   constexpr bool kHasAux1 = MODE >= EPI_MUL_SIG;
   constexpr bool kHasAux2 = MODE >= EPI_TANGENT;
-  constexpr bool kHasOut2 = MODE == EPI_TANGENT;
+  constexpr bool kHasOut2 = (MODE == EPI_TANGENT) || SPLIT;
+  static_assert(!SPLIT || MODE <= EPI_SOFTPLUS, "SPLIT only for plain activations");
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
@@ -168,7 +177,9 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
         ptx::mbar_expect_tx(&full_bar[s], Cfg::kStage);
         uint8_t* sa = smem + s * Cfg::kStage;
-        ptx::tma_load_2d(sa, &p.tmA, &full_bar[s], kb * kBlockK, m0);
+        int ka = kb * kBlockK;
+        if (p.a_k_wrap > 0) ka %= p.a_k_wrap;
+        ptx::tma_load_2d(sa, &p.tmA, &full_bar[s], ka, m0);
         ptx::tma_load_2d(sa + Cfg::kStageA, &p.tmB, &full_bar[s], kb * kBlockK, n0);
       }
     }
@@ -281,7 +292,11 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
               res = pre * s + aux2v[j];
             }
           }
-          if (p.round_out) {
+          if (SPLIT) {
+            const float hi = ptx::round_tf32(res);
+            res2 = ptx::round_tf32(res - hi);
+            res = hi;
+          } else if (p.round_out) {
             res = ptx::round_tf32(res);
             res2 = ptx::round_tf32(res2);
           }
@@ -306,11 +321,28 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) w[i] = v[i] * rw;
         const float t = warp_transpose_reduce32(w, lane);
-        if (nc + lane < p.N) atomicAdd(p.colsum_w + nc + lane, t);
+        if (nc + lane < p.N)
+          atomicAdd(p.colsum_w + static_cast<size_t>(nc + lane) * p.colsum_w_stride, t);
       }
       if (p.colsum != nullptr) {
         const float t = warp_transpose_reduce32(v, lane);
-        if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, t);
+        if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, p.colsum_scale * t);
+      }
+      if (MODE == EPI_TANGENT && p.colsum2 != nullptr) {
+        // re-read this thread's own out2 row from the staging tile (still intact until the
+        // next chunk's barrier) instead of keeping 32 more registers live
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t4 =
+              *reinterpret_cast<const float4*>(out2_buf + row_off + ((q ^ swz) << 4));
+          const bool ok = row_ok;
+          v[q * 4 + 0] = (ok && nc + q * 4 + 0 < p.N) ? t4.x : 0.0f;
+          v[q * 4 + 1] = (ok && nc + q * 4 + 1 < p.N) ? t4.y : 0.0f;
+          v[q * 4 + 2] = (ok && nc + q * 4 + 2 < p.N) ? t4.z : 0.0f;
+          v[q * 4 + 3] = (ok && nc + q * 4 + 3 < p.N) ? t4.w : 0.0f;
+        }
+        const float t = warp_transpose_reduce32(v, lane);
+        if (nc + lane < p.N) atomicAdd(p.colsum2 + nc + lane, t);
       }
     }
     if (leader) ptx::tma_store_wait_all<0>();

@@ -1,0 +1,262 @@
+// Small HBM-bound kernels around the GEMM chain: weight derivation (tf32-rounded copies and
+// transposes), noise / perturbation prologues, loss epilogues, reductions, optimizers.
+// All are grid-stride, coalesced over the contiguous dimension, vectorised where rows allow it.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ptx_sm100.cuh"
+
+namespace ardae {
+
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum; result valid in thread 0.  blockDim.x <= 1024.
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < (blockDim.x + 31) / 32) ? red[lane] : 0.0f;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
+struct Philox {
+  static __device__ __forceinline__ uint4 round4(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    return make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+  }
+  static __device__ __forceinline__ uint4 gen(uint64_t seed, uint64_t ctr, uint32_t stream) {
+    uint4 c = make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), stream, 0u);
+    uint2 k = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      c = round4(c, k);
+      k.x += 0x9E3779B9u;
+      k.y += 0xBB67AE85u;
+    }
+    return c;
+  }
+};
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+  const float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+// out[i] = N(0,1), i < n   (4 normals per Philox call)
+__global__ void randn_kernel(float* __restrict__ out, size_t n, uint64_t seed, uint32_t stream) {
+  const size_t nq = (n + 3) / 4;
+  for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
+       q += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 r = Philox::gen(seed, q, stream);
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    const float v[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < n) out[q * 4 + j] = v[j];
+  }
+}
+
+// ---------------------------------------------------------------- weight derivation
+// For every parameter matrix W[rows, cols] (nn.Linear layout) produce, tf32-rounded:
+//   dst [rows, ld]   straight copy (ld = padded pitch, pad columns zero)
+//   dstT[cols, ldT]  transpose     (the B operand of the backward-data GEMMs)
+//   dst3[rows, ld3] "3xTF32" B operand [W_hi | W_hi | W_lo], each segment kp columns wide
+//                   (kp = cols rounded up to the 32-column k-block; pad columns stay zero)
+struct DeriveItem {
+  const float* src;
+  float* dst;
+  float* dstT;
+  float* dst3;
+  int rows, cols, src_ld, ld, ldT, kp, ld3;
+  int first_block;  // prefix sum over 32x32 tiles
+  int tiles_x;      // ceil(ld/32)
+};
+__global__ void derive_weights_kernel(const DeriveItem* __restrict__ items, int nitems) {
+  __shared__ float tile[32][33];
+  int it = 0;
+  while (it + 1 < nitems && static_cast<int>(blockIdx.x) >= items[it + 1].first_block) ++it;
+  const DeriveItem d = items[it];
+  const int t = blockIdx.x - d.first_block;
+  const int tx = t % d.tiles_x, ty = t / d.tiles_x;
+  const int c0 = tx * 32, r0 = ty * 32;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int r = r0 + ly + j, c = c0 + lx;
+    float v = 0.0f;
+    if (r < d.rows && c < d.cols) {
+      const float w = d.src[static_cast<size_t>(r) * d.src_ld + c];
+      v = ptx::round_tf32(w);
+      if (d.dst3 != nullptr) {
+        float* o = d.dst3 + static_cast<size_t>(r) * d.ld3 + c;
+        o[0] = v;
+        o[d.kp] = v;
+        o[2 * d.kp] = ptx::round_tf32(w - v);
+      }
+    }
+    tile[ly + j][lx] = v;
+    if (d.dst != nullptr && r < d.rows && c < d.ld) d.dst[static_cast<size_t>(r) * d.ld + c] = v;
+  }
+  __syncthreads();
+  if (d.dstT != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int c = c0 + ly + j, r = r0 + lx;  // transposed: row index c of dstT, col r
+      if (c < d.cols && r < d.ldT) d.dstT[static_cast<size_t>(c) * d.ldT + r] = (r < d.rows) ? tile[lx][ly + j] : 0.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- generic 2-D copy / affine
+// dst[r, c] = round?( a * src[r, c] + b ),  c < cols;  zero for cols <= c < dst_cols
+__global__ void copy2d_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst,
+                              int dst_ld, int rows, int cols, int dst_cols, float a, float b,
+                              int round) {
+  const size_t total = static_cast<size_t>(rows) * dst_cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / dst_cols), c = static_cast<int>(i - static_cast<size_t>(r) * dst_cols);
+    float v = 0.0f;
+    if (c < cols) {
+      v = a * src[static_cast<size_t>(r) * src_ld + c] + b;
+      if (round) v = ptx::round_tf32(v);
+    }
+    dst[static_cast<size_t>(r) * dst_ld + c] = v;
+  }
+}
+
+// dst[r, c] = hi, dst[r, kp + c] = lo of (a * src[r, c] + b), c < cols  (tf32 pair, see gemm SPLIT)
+__global__ void split2d_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst,
+                               int dst_ld, int rows, int cols, int kp, float a, float b) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<size_t>(r) * cols);
+    const float v = a * src[static_cast<size_t>(r) * src_ld + c] + b;
+    const float hi = ptx::round_tf32(v);
+    dst[static_cast<size_t>(r) * dst_ld + c] = hi;
+    dst[static_cast<size_t>(r) * dst_ld + kp + c] = ptx::round_tf32(v - hi);
+  }
+}
+
+// out[b, c] = sum_{k<S} in[(b*S+k), c]
+__global__ void group_sum_kernel(const float* __restrict__ in, int in_ld, float* __restrict__ out,
+                                 int out_ld, int B, int S, int cols, int round) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float acc = 0.0f;
+    const float* p = in + static_cast<size_t>(b) * S * in_ld + c;
+    for (int k = 0; k < S; ++k) acc += p[static_cast<size_t>(k) * in_ld];
+    out[static_cast<size_t>(b) * out_ld + c] = round ? ptx::round_tf32(acc) : acc;
+  }
+}
+
+// ---------------------------------------------------------------- CDAE prologue / epilogues
+// x~[n, j] = x[n, j] + sigma[n] * eps[n, j]  (models/graddae/mlp.py:21-23), stored as the tf32
+// pair xt[n, j] = hi, xt[n, kp + j] = lo.  If gen_eps, eps is first drawn here (Philox) and
+// stored; eps == nullptr means "no noise" (glogprob).
+__global__ void cdae_perturb_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
+                                    float* __restrict__ eps, float* __restrict__ xt, int N, int d,
+                                    int ldx, int kp, int gen_eps, uint64_t seed) {
+  const size_t total = static_cast<size_t>(N) * d;
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(e / d), j = static_cast<int>(e - static_cast<size_t>(n) * d);
+    float v = x[e];
+    if (eps != nullptr) {
+      float ev;
+      if (gen_eps) {
+        const uint4 r = Philox::gen(seed, e >> 2, 7u);
+        const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+        const float q[4] = {a.x, a.y, b.x, b.y};
+        ev = q[e & 3];
+        eps[e] = ev;
+      } else {
+        ev = eps[e];
+      }
+      v += sigma[n] * ev;
+    }
+    const float hi = ptx::round_tf32(v);
+    xt[static_cast<size_t>(n) * ldx + j] = hi;
+    xt[static_cast<size_t>(n) * ldx + kp + j] = ptx::round_tf32(v - hi);
+  }
+}
+
+// dpL[n, j] = -w_o[j] * sig(vL[n, j]),  sig from the stored softplus output
+__global__ void cdae_init_delta_kernel(const float* __restrict__ vL, int ld,
+                                       const float* __restrict__ wo, float* __restrict__ dp,
+                                       int ld_dp, int N, int H) {
+  const size_t total = static_cast<size_t>(N) * H;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / H), j = static_cast<int>(i - static_cast<size_t>(n) * H);
+    const float u = vL[static_cast<size_t>(n) * ld + j];
+    const float e = __expf(-u);
+    const float s = (u < 0.01f) ? u * (1.0f - u * (0.5f - u * (1.0f / 6.0f))) : 1.0f - e;
+    dp[static_cast<size_t>(n) * ld_dp + j] = ptx::round_tf32(-wo[j] * s);
+  }
+}
+
+// resid = sigma*g + eps ; loss += inv_count * sum resid^2 ; r = 2*inv_count*sigma*resid
+// (models/graddae/mlp.py:395-398,441 and SURVEY 8a-3).  g, r: [N, ld]; eps: [N, d].
+__global__ void cdae_loss_kernel(const float* __restrict__ g, int ld, const float* __restrict__ sigma,
+                                 const float* __restrict__ eps, float* __restrict__ r, int N, int d,
+                                 float inv_count, float* __restrict__ loss_out,
+                                 float* __restrict__ score_out) {
+  float acc = 0.0f;
+  const size_t total = static_cast<size_t>(N) * ld;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / ld), j = static_cast<int>(i - static_cast<size_t>(n) * ld);
+    float rv = 0.0f;
+    if (j < d) {
+      const float s = sigma[n];
+      const float gv = g[i];
+      const float res = s * gv + eps[static_cast<size_t>(n) * d + j];
+      acc += res * res;
+      rv = ptx::round_tf32(2.0f * inv_count * s * res);
+      if (score_out) score_out[static_cast<size_t>(n) * d + j] = gv;
+    }
+    if (r) r[i] = rv;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(loss_out, acc * inv_count);
+}
+
+// dst[n*d + j] = src[n*ld + j]
+__global__ void unpad_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int N,
+                             int d, float scale) {
+  const size_t total = static_cast<size_t>(N) * d;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / d), j = static_cast<int>(i - static_cast<size_t>(n) * d);
+    dst[i] = scale * src[static_cast<size_t>(n) * ld + j];
+  }
+}
+
+inline int grid_for(size_t total, int block = 256, int max_blocks = 148 * 8) {
+  size_t b = (total + block - 1) / block;
+  if (b < 1) b = 1;
+  if (b > static_cast<size_t>(max_blocks)) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+}  // namespace ardae

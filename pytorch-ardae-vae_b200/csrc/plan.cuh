@@ -1,0 +1,134 @@
+// Plan infrastructure: row-major matrix views, a bump allocator over the caller's workspace,
+// and a recorded list of stream-ordered launches (GEMMs with pre-encoded TMA maps + small kernels).
+#pragma once
+#include <functional>
+#include <vector>
+
+#include "gemm_host.cuh"
+
+namespace ardae {
+
+struct Mat {
+  float* p = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+  Mat() {}
+  Mat(float* p_, int r, int c, int l) : p(p_), rows(r), cols(c), ld(l) {}
+  Mat cols_from(int c0, int n) const { return Mat(p ? p + c0 : nullptr, rows, n, ld); }
+  Mat rows_from(int r0, int n) const {
+    return Mat(p ? p + static_cast<size_t>(r0) * ld : nullptr, n, cols, ld);
+  }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Bump allocator.  In dry mode (base == nullptr) it only measures.
+struct Workspace {
+  uint8_t* base = nullptr;
+  size_t size = 0, off = 0;
+  bool dry = true;
+  float* floats(size_t n) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    float* p = dry ? reinterpret_cast<float*>(static_cast<uintptr_t>(256) + off)
+                   : reinterpret_cast<float*>(base + off);
+    off += n * sizeof(float);
+    return p;
+  }
+  // [rows, cols] with a pitch that satisfies TMA (multiple of 4 floats)
+  Mat mat(int rows, int cols) {
+    const int ld = round_up(cols, 4);
+    return Mat(floats(static_cast<size_t>(rows) * ld), rows, cols, ld);
+  }
+  bool fits() const { return dry || off <= size; }
+};
+
+struct Plan {
+  bool dry = true;
+  int error = 0;
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  int num_gemm_nt = 0, num_gemm_tn = 0, num_small = 0;
+
+  void fail_with(int rc) {
+    if (error == 0) error = rc;
+  }
+  void add(std::function<int(cudaStream_t)> f) {
+    ++num_small;
+    if (!dry) ops.push_back(std::move(f));
+  }
+  void nt(const GemmNTDesc& d) {
+    ++num_gemm_nt;
+    if (dry) return;
+    PreparedNT pr;
+    int rc = prepare_gemm_nt(d, &pr);
+    if (rc) return fail_with(rc);
+    ops.push_back([pr](cudaStream_t s) { return launch_prepared_nt(pr, s); });
+  }
+  void tn(const GemmTNDesc& d) {
+    ++num_gemm_tn;
+    if (dry) return;
+    PreparedTN pr;
+    int rc = prepare_gemm_tn(d, &pr);
+    if (rc) return fail_with(rc);
+    ops.push_back([pr](cudaStream_t s) { return launch_prepared_tn(pr, s); });
+  }
+  int run(cudaStream_t s) const {
+    for (const auto& f : ops) {
+      int rc = f(s);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  int launches() const { return num_gemm_nt + 2 * num_gemm_tn + num_small; }
+};
+
+// An activation stored as a tf32 pair: buf[rows, 2*kp] with hi in columns [0,w) and
+// lo = rna(x - hi) in columns [kp, kp+w); kp = w rounded up to the 32-column k-block, pad
+// columns are zero (the workspace is zeroed at plan creation and pads are never written).
+struct Pair {
+  Mat buf;
+  int w = 0, kp = 0;
+  Mat hi() const { return buf.cols_from(0, w); }
+  Mat lo() const { return buf.cols_from(kp, w); }
+  Mat a3() const { return Mat(buf.p, buf.rows, 3 * kp, buf.ld); }  // [hi | lo | hi] via a_k_wrap
+};
+inline Pair make_pair(Workspace& ws, int rows, int w) {
+  Pair p;
+  p.w = w;
+  p.kp = round_up(w, 32);
+  p.buf = Mat(ws.floats(static_cast<size_t>(rows) * 2 * p.kp), rows, 2 * p.kp, 2 * p.kp);
+  return p;
+}
+// A weight in the layouts the kernels consume.
+struct W3 {
+  Mat b3;  // [out, 3*kp]  = [W_hi | W_hi | W_lo]  (3xTF32 B operand of the forward GEMMs)
+  Mat T;   // [in, out]    tf32-rounded transpose   (B operand of the backward-data GEMMs)
+  int in = 0, out = 0, kp = 0;
+  Mat hi() const { return b3.cols_from(0, in); }  // [out, in] tf32-rounded (tangent sweep)
+};
+
+// Out[M,N] = epi(A . W^T + bias)   A:[M,K]  W:[N,K]
+inline GemmNTDesc nt_desc(const Mat& A, const Mat& W, const Mat& out, int mode) {
+  GemmNTDesc d;
+  d.A = A.p; d.lda = A.ld; d.B = W.p; d.ldb = W.ld; d.out = out.p; d.ldo = out.ld;
+  d.M = A.rows; d.K = A.cols; d.N = W.rows; d.mode = mode;
+  return d;
+}
+inline void set_aux1(GemmNTDesc& d, const Mat& m) { d.aux1 = m.p; d.ld1 = m.ld; }
+inline void set_aux2(GemmNTDesc& d, const Mat& m) { d.aux2 = m.p; d.ld2 = m.ld; }
+inline void set_out2(GemmNTDesc& d, const Mat& m) { d.out2 = m.p; d.ldo2 = m.ld; }
+// fp32-accurate forward layer on the tf32 pipe: out(pair) = act(A(pair) . W^T + ...)
+inline GemmNTDesc nt3_desc(const Pair& A, const W3& W, const Pair& out, int mode) {
+  GemmNTDesc d = nt_desc(A.a3(), W.b3, out.hi(), mode);
+  d.a_k_wrap = 2 * A.kp;
+  d.split_out = 1;
+  set_out2(d, out.lo());
+  return d;
+}
+// same, plain fp32 output (no split)
+inline GemmNTDesc nt3_desc_plain(const Pair& A, const W3& W, const Mat& out, int mode) {
+  GemmNTDesc d = nt_desc(A.a3(), W.b3, out, mode);
+  d.a_k_wrap = 2 * A.kp;
+  d.round_out = 0;
+  return d;
+}
+
+}  // namespace ardae
