@@ -84,6 +84,68 @@ ARDAE_API int ardae_cdae_score(ardae_cdae_t h, const float* x, const float* ctx,
                      float* score_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Implicit-posterior VAE with the noise-concat MLP encoder: `net.ToyIPVAE` (models/ivae/toy.py:
+ * 30-109,154-194,694-858) and `net.MNISTIPVAE` (models/ivae/mnist.py:38-301), enc_type 'concat'.
+ * Parameter tensors in state_dict order (weights [out,in]):
+ *   encode.inp_encode (n_inp linears), encode.fc.layers (n_fc), encode.fc.fc,
+ *   decode.main (n_dec linears), then decode.reparam.{mean_fn,logvar_fn} (toy) | logit_fn (mnist).
+ * kind 0 = toy: Gaussian decoder, noise re-concatenated at every fc layer (layers.py:707-724);
+ * kind 1 = mnist: x <- 2x-1, noise concatenated once, Bernoulli decoder.
+ */
+typedef struct ardae_model_s* ardae_model_t;
+
+typedef struct {
+  int kind;
+  int input_dim, noise_dim, h_dim, z_dim;
+  int n_inp, n_fc, n_dec; /* linears in inp_encode; hidden layers of encode.fc; linears in decode.main */
+  int act;                /* 0 relu, 1 softplus */
+  int batch, nz;          /* B data rows, nz noise samples per row: R = B*nz rows, row index b*nz+k */
+  int mode;               /* 0: encode only; 1: forward + backward */
+} ardae_model_config;
+
+ARDAE_API int ardae_model_workspace_bytes(const ardae_model_config* cfg, size_t* bytes);
+ARDAE_API int ardae_model_create(const ardae_model_config* cfg, float* const* params, float* const* grads,
+                                 int num_tensors, void* workspace, size_t workspace_bytes, ardae_model_t* out);
+ARDAE_API void ardae_model_destroy(ardae_model_t h);
+ARDAE_API int ardae_model_num_launches(ardae_model_t h, int which); /* 0 fwd, 1 bwd */
+
+/* Replaces Encoder.forward / ImplicitPosteriorVAE.forward_hidden (toy.py:90-109,811-822):
+ * z_out [R, z_dim] = f(x [B, D], noise [R, n]); noise == NULL means zeros (encode(std=0)). */
+ARDAE_API int ardae_model_encode(ardae_model_t h, const float* x, const float* noise, float* z_out, void* stream);
+
+/* Replaces ImplicitPosteriorVAE.forward (toy.py:824-858 / mnist.py:267-301, lmbd = 0): encoder,
+ * decoder, per-row recon + beta*prior.  sums[3] (device) <- mean loss, recon, prior over
+ * 1/inv_rows rows (pass the GLOBAL row count under data parallelism).  heads_out (optional):
+ * head-major [nH][R][D] = logits (mnist) or mu, logvar (toy).  Keeps the tape for backward. */
+ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* noise, float beta, float inv_rows,
+                                  float* z_out, float* sums, float* heads_out, void* stream);
+
+/* Replaces model_loss.backward() and (S*(z - zbar)).backward(grad) (ivae_ardae.py:804,834) in one
+ * pass: accumulates d(loss_scale*loss)/dtheta plus the pull-back of gz_scale*gz (an upstream
+ * gradient on z, [R, z_dim], may be NULL) into `grads`.  loss_scale == 0 skips the decoder. */
+ARDAE_API int ardae_model_backward(ardae_model_t h, float loss_scale, const float* gz, float gz_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Step glue and optimizers */
+/* sigma schedule, ivae_ardae.py:753-767: x_out [B*nz*nstd, d] = S*(z - zbar) (expanded over nstd),
+ * std_out[b] = delta * mean_d std_k(S*(z-zbar)) (unbiased over nz), sigma_out = std_b * xi
+ * (xi [B*nz*nstd] supplied, or NULL = Philox draw from seed).  z [B,nz,d], zbar [B,d]. */
+ARDAE_API int ardae_sigma_schedule(const float* z, const float* zbar, int B, int nz, int d, int nstd, float S,
+                                   float delta, const float* xi, uint64_t seed, float* x_out, float* sigma_out,
+                                   float* std_out, void* stream);
+/* out [R,d] = S*(z [R,d] - zbar [R/nz, d])  (ivae_ardae.py:827) */
+ARDAE_API int ardae_scaled_diff(const float* z, const float* zbar, int R, int nz, int d, float S, float* out,
+                                void* stream);
+/* utils.Adam.step (utils/optim.py:49-108, PyTorch-1.2 epsilon placement) over a flat arena of n
+ * floats (n % 4 == 0, 16-byte aligned); `step` is the 1-based step count; grads are pre-multiplied
+ * by gscale (e.g. 1/world_size). */
+ARDAE_API int ardae_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                              float beta1, float beta2, float eps, int step, float gscale, void* stream);
+/* torch.optim.RMSprop.step (centered = False) as constructed at ivae_ardae.py:626. */
+ARDAE_API int ardae_rmsprop_step(float* p, const float* g, float* square_avg, float* momentum_buf, size_t n,
+                                 float lr, float alpha, float eps, float momentum, float gscale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Utilities */
 /* out[i] ~ N(0,1), Philox4x32-10 + Box-Muller (replaces torch.randn at ivae_ardae.py:761 and
  * Encoder.sample_noise, ivae/toy.py:61-65, which draws on the CPU and copies). */

@@ -20,6 +20,11 @@ class CdaeConfig(ctypes.Structure):
                 ('train', ctypes.c_int)]
 
 
+class ModelConfig(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int) for k in ('kind', 'input_dim', 'noise_dim', 'h_dim', 'z_dim', 'n_inp', 'n_fc',
+                                            'n_dec', 'act', 'batch', 'nz', 'mode')]
+
+
 def _declare(lib):
     vp, i, sz, u64, u32, f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint64,
                               ctypes.c_uint32, ctypes.c_float)
@@ -35,8 +40,19 @@ def _declare(lib):
     lib.ardae_cdae_train.argtypes = [vp, vp, vp, vp, vp, i, u64, f, vp, vp, vp]
     lib.ardae_cdae_score.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ardae_randn.argtypes = [vp, sz, u64, u32, vp]
-    for name in dir(lib):
-        pass
+    lib.ardae_model_workspace_bytes.argtypes = [ctypes.POINTER(ModelConfig), ctypes.POINTER(sz)]
+    lib.ardae_model_create.argtypes = [ctypes.POINTER(ModelConfig), ctypes.POINTER(vp), ctypes.POINTER(vp), i, vp,
+                                       sz, ctypes.POINTER(vp)]
+    lib.ardae_model_destroy.argtypes = [vp]
+    lib.ardae_model_destroy.restype = None
+    lib.ardae_model_num_launches.argtypes = [vp, i]
+    lib.ardae_model_encode.argtypes = [vp, vp, vp, vp, vp]
+    lib.ardae_model_forward.argtypes = [vp, vp, vp, f, f, vp, vp, vp, vp]
+    lib.ardae_model_backward.argtypes = [vp, f, vp, f, vp]
+    lib.ardae_sigma_schedule.argtypes = [vp, vp, i, i, i, i, f, f, vp, u64, vp, vp, vp, vp]
+    lib.ardae_scaled_diff.argtypes = [vp, vp, i, i, i, f, vp, vp]
+    lib.ardae_adam_step.argtypes = [vp, vp, vp, vp, sz, f, f, f, f, i, f, vp]
+    lib.ardae_rmsprop_step.argtypes = [vp, vp, vp, vp, sz, f, f, f, f, f, vp]
     return lib
 
 

@@ -19,6 +19,9 @@ class ParamArena(object):
             self.offsets.append(off)
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.total = off
+        import weakref
+        for p in self.params:
+            p._ardae_owner = weakref.ref(module)
         self.flat = None
         self.grad_flat = None
         self.stage_flat = None

@@ -51,7 +51,7 @@ class ConditionalARDAE(nn.Module):
                               num_hidden_layers=num_hidden_layers - 1, use_nonlinearity_output=True)
         self.neglogprob = MLP(2 * h_dim + 1, h_dim, 1, nonlinearity=nonlinearity,
                               num_hidden_layers=num_hidden_layers, use_nonlinearity_output=False)
-        self._arena = None
+        self._arena = ParamArena(self)
         self._plans = {}
         self.inv_count_override = None  # data parallel: 1 / (global N * d)
         self.last_score = None
@@ -63,8 +63,6 @@ class ConditionalARDAE(nn.Module):
 
     # ------------------------------------------------------------------ plumbing
     def _ensure(self):
-        if self._arena is None:
-            self._arena = ParamArena(self)
         if not self._arena.device_ok():
             self._arena.ensure()
             for _, (h, _ws) in self._plans.items():

@@ -1,0 +1,300 @@
+"""`ToyIPVAE` / `MNISTIPVAE` -- drop-ins for the reference's implicit-posterior VAEs with the
+noise-concat MLP encoder (models/ivae/toy.py, models/ivae/mnist.py; enc_type='concat', the only
+encoder type ivae_ardae.py's configs 1-3 build).
+
+Same constructor kwargs, attribute / state_dict names, method signatures and return tuples
+(SURVEY.md 8b); the arithmetic is the libardae CUDA plan (csrc/model.cuh).  Autograd contract: the
+`z` and `loss` returned by `forward` are attached to the graph (ivae_ardae.py calls `.backward` on
+both, :804 and :834); `encode` / `forward_hidden` return plain tensors (every call site in the
+reference step detaches them).
+"""
+import ctypes
+import math
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .arena import ParamArena
+from .layers import MLP, ContextConcatMLP
+
+
+def normal_energy_func(x, mu=0., logvar=0.):
+    """utils/energy.py:69-77 (kept for API parity: model.energy_func)."""
+    x = x.view(x.size(0), -1)
+    return torch.sum(0.5 * (logvar + (x - mu) ** 2 / math.exp(logvar) + math.log(2. * math.pi)), dim=1)
+
+
+class Identity(nn.Module):
+    def forward(self, input):
+        return input
+
+
+class NormalDistributionLinear(nn.Module):
+    """models/reparam.py:62-71 (parameter container + sampler)."""
+
+    def __init__(self, input_size, output_size, nonlinearity=None):
+        super().__init__()
+        if nonlinearity is not None:
+            raise NotImplementedError('logvar clipping is not used by ToyIPVAE')
+        self.input_size, self.output_size, self.nonlinearity = input_size, output_size, nonlinearity
+        self.mean_fn = nn.Linear(input_size, output_size)
+        self.logvar_fn = nn.Linear(input_size, output_size)
+
+    def sample_gaussian(self, mu, logvar):
+        return mu + torch.exp(0.5 * logvar) * torch.randn_like(logvar)
+
+
+class BernoulliDistributionLinear(nn.Module):
+    """models/reparam.py:163-174 (parameter container + relaxed-Bernoulli sampler :106-120)."""
+
+    def __init__(self, input_size, output_size, hard=False):
+        super().__init__()
+        self.input_size, self.output_size, self.hard = input_size, output_size, hard
+        self.logit_fn = nn.Linear(input_size, output_size)
+
+    def sample_logistic_sigmoid(self, logits, temperature=1.0, hard=False):
+        noise = torch.rand_like(logits)
+        y = logits + torch.log(torch.div(noise, 1. - noise) + 1e-20)
+        return torch.sigmoid(y / temperature)
+
+
+def _weight_init(m):  # models/ivae/mnist.py:20-25
+    if isinstance(m, (nn.Conv2d, nn.Linear)):
+        nn.init.xavier_uniform_(m.weight)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias)
+
+
+class ConcatEncoder(nn.Module):
+    """models/ivae/toy.py:154-194 (kind='toy') / models/ivae/mnist.py:123-165 (kind='mnist')."""
+
+    def __init__(self, kind, input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, std=1.,
+                 init='gaussian'):
+        super().__init__()
+        self.kind = kind
+        self.input_dim, self.noise_dim, self.h_dim, self.z_dim = input_dim, noise_dim, h_dim, z_dim
+        self.nonlinearity, self.num_hidden_layers, self.std, self.init = nonlinearity, num_hidden_layers, std, init
+        self.enc_noise = False
+        if kind == 'toy':
+            self.inp_encode = MLP(input_dim, h_dim, h_dim, nonlinearity, num_hidden_layers - 1, True)
+            self.nos_encode = Identity()
+            self.fc = ContextConcatMLP(h_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, False)
+        else:
+            self.inp_encode = MLP(input_dim, h_dim, h_dim, nonlinearity, num_hidden_layers, True)
+            self.nos_encode = Identity()
+            self.fc = MLP(h_dim + noise_dim, h_dim, z_dim, nonlinearity, 1, False)
+        if init == 'gaussian':
+            self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.normal_(self.fc.fc.weight)
+
+    def sample_noise(self, batch_size, std=None, device=None):
+        """ivae/toy.py:61-65 draws on the CPU generator and copies; here the draw is on-device."""
+        std = std if std is not None else self.std
+        device = device if device is not None else next(self.parameters()).device
+        if std == 0:
+            return torch.zeros(batch_size, self.noise_dim, device=device)
+        return std * torch.randn(batch_size, self.noise_dim, device=device)
+
+    def forward(self, x, noise=None, std=None, nz=1):
+        owner = self._owner()
+        batch_size = x.size(0)
+        if noise is None:
+            zero = std is not None and std == 0
+            noise = None if zero else self.sample_noise(batch_size * nz, std=std, device=x.device)
+        else:
+            assert noise.size(0) == batch_size * nz
+            assert noise.size(1) == self.noise_dim
+        return owner._encode(x, noise, nz)
+
+    def _forward_inp(self, x):
+        raise NotImplementedError('the B200 path evaluates inp_encode inside the fused encode plan; '
+                                  'use model.encode / model.logprob')
+
+
+class Decoder(nn.Module):
+    def __init__(self, kind, input_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, init='gaussian'):
+        super().__init__()
+        self.kind = kind
+        self.input_dim, self.h_dim, self.z_dim = input_dim, h_dim, z_dim
+        self.nonlinearity, self.num_hidden_layers, self.init = nonlinearity, num_hidden_layers, init
+        if kind == 'toy':  # models/ivae/toy.py:711-720
+            self.main = MLP(z_dim, h_dim, h_dim, nonlinearity, num_hidden_layers - 1, True)
+            self.reparam = NormalDistributionLinear(h_dim, input_dim)
+            if init == 'gaussian':
+                nn.init.normal_(self.reparam.mean_fn.weight)
+        else:  # models/ivae/mnist.py:180-181
+            self.main = MLP(z_dim, h_dim, h_dim, nonlinearity, num_hidden_layers, True)
+            self.reparam = BernoulliDistributionLinear(h_dim, input_dim)
+
+    def forward(self, z):
+        raise NotImplementedError('the decoder runs inside model.forward / model.logprob on the B200 path')
+
+
+class _ForwardFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, key, z, sums, *params):
+        ctx.model, ctx.key = model, key
+        ctx.set_materialize_grads(False)
+        return z, sums[0].clone()
+
+    @staticmethod
+    def backward(ctx, gz, gloss):
+        m = ctx.model
+        h = m._plans[ctx.key][0]
+        ar = m._arena
+        L = _lib.lib()
+        if gloss is not None:
+            ar.stage_flat.zero_()
+            _lib.check(L.ardae_model_backward(h, ctypes.c_float(1.0), None, ctypes.c_float(0.0), _lib.stream_ptr()))
+            ar.accumulate_staged(gloss)
+        if gz is not None:
+            ar.stage_flat.zero_()
+            g = _lib.require_cuda(gz, 'grad_z')
+            _lib.check(L.ardae_model_backward(h, ctypes.c_float(0.0), _lib.ptr(g), ctypes.c_float(1.0),
+                                              _lib.stream_ptr()))
+            # only encoder tensors receive this pull-back; decoder slots of the stage arena stay zero
+            ar.accumulate_staged(1.0)
+        return (None, None, None, None) + (None,) * len(ar.params)
+
+
+class ImplicitPosteriorVAE(nn.Module):
+    KIND = None
+
+    def __init__(self, energy_func=normal_energy_func, input_dim=2, noise_dim=2, h_dim=64, z_dim=2,
+                 nonlinearity='tanh', num_hidden_layers=1, init='gaussian', enc_type='concat'):
+        super().__init__()
+        if enc_type != 'concat':
+            raise NotImplementedError("the B200 path implements enc_type='concat' (what ivae_ardae.py builds)")
+        if nonlinearity not in ('relu', 'softplus'):
+            raise NotImplementedError("nonlinearity must be 'relu' or 'softplus'")
+        if energy_func is not normal_energy_func:
+            raise NotImplementedError('only the N(0,I) prior energy is fused')
+        self.energy_func = energy_func
+        self.input_dim, self.noise_dim, self.h_dim, self.z_dim = input_dim, noise_dim, h_dim, z_dim
+        self.latent_dim = z_dim
+        self.nonlinearity, self.num_hidden_layers, self.init, self.enc_type = nonlinearity, num_hidden_layers, init, enc_type
+        kind = self.KIND
+        if kind == 'toy':
+            self.encode = ConcatEncoder(kind, input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, init=init)
+            self.decode = Decoder(kind, input_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, init=init)
+            self._n_inp, self._n_fc, self._n_dec = num_hidden_layers, num_hidden_layers, num_hidden_layers
+        else:
+            self.encode = ConcatEncoder(kind, input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers + 1, init=init)
+            self.decode = Decoder(kind, input_dim, h_dim, z_dim, nonlinearity, num_hidden_layers)
+            self.decode.apply(_weight_init)  # mnist.py:233-238
+            if init == 'gaussian':
+                self.encode.reset_parameters()
+            self._n_inp, self._n_fc, self._n_dec = num_hidden_layers + 2, 1, num_hidden_layers + 1
+        object.__setattr__(self.encode, '_owner', weakref.ref(self))
+        self._arena = ParamArena(self)
+        self._plans = {}
+        self.inv_rows_override = None  # data parallel: 1 / global row count
+
+    # ------------------------------------------------------------------ plumbing
+    def _ensure(self):
+        if not self._arena.device_ok():
+            self._arena.ensure()
+            self._drop_plans()
+        return self._arena
+
+    def _drop_plans(self):
+        for _, (h, _ws) in self._plans.items():
+            _lib.lib().ardae_model_destroy(h)
+        self._plans = {}
+
+    def __del__(self):
+        try:
+            self._drop_plans()
+        except Exception:
+            pass
+
+    def _plan(self, B, nz, mode, slot=0):
+        key = (B, nz, mode, slot)
+        if key not in self._plans:
+            L = _lib.lib()
+            ar = self._ensure()
+            cfg = _lib.ModelConfig(0 if self.KIND == 'toy' else 1, self.input_dim, self.noise_dim, self.h_dim,
+                                   self.z_dim, self._n_inp, self._n_fc, self._n_dec,
+                                   1 if self.nonlinearity == 'softplus' else 0, B, nz, mode)
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(L.ardae_model_workspace_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
+            ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=ar.flat.device)
+            off = (-ws.data_ptr()) % 256
+            params = _lib.ptr_array(ar.views(ar.flat))
+            grads = _lib.ptr_array(ar.views(ar.stage_flat))
+            h = ctypes.c_void_p(0)
+            _lib.check(L.ardae_model_create(ctypes.byref(cfg), params, grads, len(ar.params),
+                                            ctypes.c_void_p(ws.data_ptr() + off), nbytes.value, ctypes.byref(h)))
+            self._plans[key] = (h, ws)
+        return key
+
+    def _encode(self, x, noise, nz):
+        B = x.size(0)
+        xf = _lib.require_cuda(x.detach(), 'input').view(B, self.input_dim)
+        nf = None if noise is None else _lib.require_cuda(noise.detach(), 'noise')
+        key = self._plan(B, nz, 0)
+        z = torch.empty(B * nz, self.z_dim, dtype=torch.float32, device=xf.device)
+        _lib.check(_lib.lib().ardae_model_encode(self._plans[key][0], _lib.ptr(xf), _lib.ptr(nf), _lib.ptr(z),
+                                                 _lib.stream_ptr()))
+        return z.view(B, nz, self.z_dim)
+
+    # ------------------------------------------------------------------ reference API
+    def forward_hidden(self, input, std=None, nz=1):
+        """toy.py:811-822 / mnist.py:254-265."""
+        batch_size = input.size(0)
+        input = input.view(batch_size, self.input_dim)
+        eps = self.encode.sample_noise(batch_size * nz, std=std, device=input.device)
+        return self.encode(input, noise=eps, std=std, nz=nz)
+
+    def forward(self, input, beta=1.0, eta=0.0, lmbd=0.0, std=None, nz=1, noise=None):
+        """toy.py:824-858 / mnist.py:267-301.  `noise` (optional [B*nz, n]) injects the encoder noise."""
+        if lmbd > 0:
+            raise NotImplementedError  # same as the reference (toy.py:845-846)
+        batch_size = input.size(0)
+        x = _lib.require_cuda(input.detach(), 'input').view(batch_size, self.input_dim)
+        if noise is None:
+            noise = self.encode.sample_noise(batch_size * nz, std=std, device=x.device)
+        nf = _lib.require_cuda(noise.detach(), 'noise')
+        ar = self._ensure()
+        key = self._plan(batch_size, nz, 1)
+        R = batch_size * nz
+        z = torch.empty(R, self.z_dim, dtype=torch.float32, device=x.device)
+        sums = torch.empty(3, dtype=torch.float32, device=x.device)
+        nH = 2 if self.KIND == 'toy' else 1
+        heads = torch.empty(nH, R, self.input_dim, dtype=torch.float32, device=x.device)
+        inv_rows = self.inv_rows_override if self.inv_rows_override is not None else 1.0 / R
+        _lib.check(_lib.lib().ardae_model_forward(self._plans[key][0], _lib.ptr(x), _lib.ptr(nf),
+                                                  ctypes.c_float(beta), ctypes.c_float(inv_rows), _lib.ptr(z),
+                                                  _lib.ptr(sums), _lib.ptr(heads), _lib.stream_ptr()))
+        z3, loss = _ForwardFn.apply(self, key, z.view(batch_size, nz, self.z_dim), sums, *ar.params)
+        if self.KIND == 'toy':
+            mu, logvar = heads[0], heads[1]
+            xhat = self.decode.reparam.sample_gaussian(mu, logvar)
+            mean = mu
+        else:
+            logit = heads[0]
+            xhat = self.decode.reparam.sample_logistic_sigmoid(logit)
+            mean = torch.sigmoid(logit)
+        return xhat, mean, z3, loss, sums[1].detach(), sums[2].detach()
+
+    def logprob(self, input, sample_size=128, z=None, std=None):
+        raise NotImplementedError('IWS evaluator: see ardae.iws (next SURVEY 8 row)')
+
+
+class ToyIPVAE(ImplicitPosteriorVAE):
+    """net.ToyIPVAE (models/__init__.py; models/ivae/toy.py:739-1024)."""
+    KIND = 'toy'
+
+
+class MNISTIPVAE(ImplicitPosteriorVAE):
+    """net.MNISTIPVAE (models/ivae/mnist.py:201-518)."""
+    KIND = 'mnist'
+
+    def __init__(self, energy_func=normal_energy_func, input_dim=784, noise_dim=100, h_dim=300, z_dim=32,
+                 nonlinearity='softplus', num_hidden_layers=1, init='gaussian', enc_type='concat'):
+        super().__init__(energy_func, input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, init,
+                         enc_type)

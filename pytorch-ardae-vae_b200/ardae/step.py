@@ -1,0 +1,131 @@
+"""Fused AR-DAE training step: the body of train() (ivae_ardae.py:707-846, cdae_ctx_type='lt0') as
+one stream-ordered sequence of libardae calls -- no autograd graph, no host sync, no `.item()`.
+
+Differences from the reference's execution (not from its results):
+  * `model.encode(x, std=0)` is evaluated once per minibatch instead of twice (:735/:748, :813/:826
+    are pairwise identical);
+  * the ELBO backward (:804) and the entropy-gradient injection (:834) are one backward pass with the
+    summed upstream gradient on z;
+  * noise is drawn on the device (Philox) unless injected through `noise=` (parity runs);
+  * under data parallelism each rank holds a batch shard, losses/gradients are normalised by the
+    GLOBAL row counts and the two flat gradient buffers are summed with one NCCL allreduce each.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class TrainStep(object):
+    def __init__(self, model, cdae, model_opt, cdae_opt, std_scale=10000., delta=0.1, nz_cdae=256, nstd=1,
+                 nz_model=1, num_cdae_updates=1, process_group=None, seed=1234):
+        self.model, self.cdae, self.mopt, self.copt = model, cdae, model_opt, cdae_opt
+        self.S, self.delta = float(std_scale), float(delta)
+        self.nz, self.nstd, self.nzm, self.ncu = int(nz_cdae), int(nstd), int(nz_model), int(num_cdae_updates)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+        self.seed = int(seed) * 1000003 + self.rank * 7919
+        self.counter = 0
+        self.launches = 0
+        self.last_std = None
+
+    def _next_seed(self):
+        self.counter += 1
+        return ctypes.c_uint64((self.seed + self.counter * 0x9E3779B97F4A7C15) & ((1 << 64) - 1))
+
+    def _randn(self, rows, cols, dev):
+        out = torch.empty(rows, cols, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().ardae_randn(_lib.ptr(out), ctypes.c_size_t(out.numel()), self._next_seed(), 3,
+                                          _lib.stream_ptr()))
+        return out
+
+    def _allreduce(self, flat):
+        if self.world > 1:
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def cdae_update(self, x, noise=None):
+        L = _lib.lib()
+        m, c = self.model, self.cdae
+        B = x.size(0)
+        d, n = m.z_dim, m.noise_dim
+        dev = x.device
+        xs = _lib.require_cuda(x, 'x').view(B, -1)
+        zbar = m._encode(xs, None, 1)                                                    # :735,:748
+        enc = noise['enc_cdae'] if noise is not None else self._randn(B * self.nz, n, dev)
+        z = m._encode(xs, enc, self.nz)                                                  # :749
+        N = B * self.nz * self.nstd
+        xc = torch.empty(N, d, dtype=torch.float32, device=dev)
+        sigma = torch.empty(N, dtype=torch.float32, device=dev)
+        std = torch.empty(B, dtype=torch.float32, device=dev)
+        xi = _lib.require_cuda(noise['xi'], 'xi').reshape(-1) if noise is not None else None
+        _lib.check(L.ardae_sigma_schedule(_lib.ptr(z), _lib.ptr(zbar), B, self.nz, d, self.nstd,
+                                          ctypes.c_float(self.S), ctypes.c_float(self.delta), _lib.ptr(xi),
+                                          self._next_seed(), _lib.ptr(xc), _lib.ptr(sigma), _lib.ptr(std),
+                                          _lib.stream_ptr()))                           # :753-767
+        ar = c._ensure()
+        h = c._plan(B, self.nz * self.nstd, True)
+        ar.stage_flat.zero_()
+        if noise is not None:
+            eps = _lib.require_cuda(noise['eps_cdae'], 'eps').reshape(N, d).clone()
+            gen = 0
+        else:
+            eps = torch.empty(N, d, dtype=torch.float32, device=dev)
+            gen = 1
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        inv = 1.0 / float(N * self.world * d)
+        _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(zbar), _lib.ptr(sigma), _lib.ptr(eps), gen,
+                                      self._next_seed(), ctypes.c_float(inv), _lib.ptr(loss), None,
+                                      _lib.stream_ptr()))                               # :768-771
+        self._allreduce(ar.stage_flat)
+        self.copt.step_flat(ar.stage_flat, skip=(len(ar.params) - 1,))                   # :779
+        self.last_std = std
+        return loss
+
+    def model_update(self, x, beta, noise=None):
+        L = _lib.lib()
+        m, c = self.model, self.cdae
+        B = x.size(0)
+        d, n = m.z_dim, m.noise_dim
+        dev = x.device
+        xs = _lib.require_cuda(x, 'x').view(B, -1)
+        R = B * self.nzm
+        enc = noise['enc_model'] if noise is not None else self._randn(R, n, dev)
+        ar = m._ensure()
+        key = m._plan(B, self.nzm, 1)
+        hm = m._plans[key][0]
+        z = torch.empty(R, d, dtype=torch.float32, device=dev)
+        sums = torch.empty(3, dtype=torch.float32, device=dev)
+        inv_rows = 1.0 / float(R * self.world)
+        _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),
+                                         ctypes.c_float(inv_rows), _lib.ptr(z), _lib.ptr(sums), None,
+                                         _lib.stream_ptr()))                            # :801
+        zbar = m._encode(xs, None, 1)                                                    # :813,:826
+        xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
+        _lib.check(L.ardae_scaled_diff(_lib.ptr(z), _lib.ptr(zbar), R, self.nzm, d, ctypes.c_float(self.S),
+                                       _lib.ptr(xsd), _lib.stream_ptr()))               # :827
+        c._ensure()
+        hs = c._plan(B, self.nzm, False)
+        zero_sigma = torch.zeros(R, dtype=torch.float32, device=dev)
+        g = torch.empty(R, d, dtype=torch.float32, device=dev)
+        _lib.check(L.ardae_cdae_score(hs, _lib.ptr(xsd), _lib.ptr(zbar), _lib.ptr(zero_sigma), _lib.ptr(g),
+                                      _lib.stream_ptr()))                               # :829
+        ar.stage_flat.zero_()
+        gz_scale = self.S * beta * inv_rows                                              # :834
+        _lib.check(L.ardae_model_backward(hm, ctypes.c_float(1.0), _lib.ptr(g), ctypes.c_float(gz_scale),
+                                          _lib.stream_ptr()))                           # :804 + :834
+        self._allreduce(ar.stage_flat)
+        self.mopt.step_flat(ar.stage_flat)                                               # :846
+        return sums, g, z
+
+    def __call__(self, x_cdae, x_model, beta=1.0, noise=None):
+        """One iteration.  x_cdae: the minibatch (or list of num_cdae_updates minibatches) for the CDAE
+        update(s); x_model: the minibatch of the model update.  Returns device tensors (no sync)."""
+        xs = x_cdae if isinstance(x_cdae, (list, tuple)) else [x_cdae] * self.ncu
+        closs = None
+        for i in range(self.ncu):
+            closs = self.cdae_update(xs[i], noise)
+        sums, g, z = self.model_update(x_model, beta, noise)
+        return dict(cdae_loss=closs, model_loss=sums[0:1], recon=sums[1:2], prior=sums[2:3], std=self.last_std,
+                    entropy_grad=g, z_model=z)

@@ -1,12 +1,17 @@
 // extern "C" surface of libardae.so (declared in include/ardae.h).
 #include "../../include/ardae.h"
 
-#include "cdae.cuh"
+#include <cmath>
+
+#include "model.cuh"
 
 using namespace ardae;
 
 struct ardae_cdae_s {
   CdaePlan p;
+};
+struct ardae_model_s {
+  ModelPlan p;
 };
 
 extern "C" {
@@ -87,6 +92,133 @@ ARDAE_API int ardae_cdae_score(ardae_cdae_t h, const float* x, const float* ctx,
   b = CdaeBindings();
   b.x = x; b.ctx = ctx; b.sigma = sigma; b.score_out = score_out;
   return h->p.plan.run(static_cast<cudaStream_t>(stream));
+}
+
+static void to_mcfg(const ardae_model_config* c, ModelConfig* o) {
+  o->kind = c->kind; o->D = c->input_dim; o->n = c->noise_dim; o->h = c->h_dim; o->zd = c->z_dim;
+  o->n_inp = c->n_inp; o->n_fc = c->n_fc; o->n_dec = c->n_dec; o->act = c->act; o->B = c->batch;
+  o->nz = c->nz; o->mode = c->mode;
+}
+
+ARDAE_API int ardae_model_workspace_bytes(const ardae_model_config* cfg, size_t* bytes) {
+  if (!cfg || !bytes) return fail(-1, "null argument");
+  ModelPlan p;
+  to_mcfg(cfg, &p.cfg);
+  p.ws.dry = true;
+  int rc = p.build(nullptr, nullptr);
+  if (rc) return rc;
+  *bytes = p.ws.off + 256;
+  return 0;
+}
+
+ARDAE_API int ardae_model_create(const ardae_model_config* cfg, float* const* params, float* const* grads,
+                                 int num_tensors, void* workspace, size_t workspace_bytes, ardae_model_t* out) {
+  if (!cfg || !params || !workspace || !out) return fail(-1, "null argument");
+  if (cfg->mode && !grads) return fail(-1, "forward+backward plan needs grads");
+  std::unique_ptr<ardae_model_s> h(new ardae_model_s());
+  to_mcfg(cfg, &h->p.cfg);
+  if (num_tensors != h->p.ntensors()) return fail(-2, "model: unexpected number of parameter tensors");
+  h->p.ws.dry = true;
+  int rc = h->p.build(nullptr, nullptr);
+  if (rc) return rc;
+  if (h->p.ws.off + 256 > workspace_bytes) return fail(-3, "model: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(-11, "workspace must be 256-byte aligned");
+  h->p.fwd = Plan(); h->p.bwd_dec = Plan(); h->p.bwd_enc = Plan();
+  h->p.ws = Workspace();
+  h->p.ws.dry = false;
+  h->p.ws.base = static_cast<uint8_t*>(workspace);
+  h->p.ws.size = workspace_bytes;
+  ARDAE_CUDA_OK(cudaMemset(workspace, 0, workspace_bytes));
+  rc = h->p.build(params, grads);
+  if (rc) return rc;
+  *out = h.release();
+  return 0;
+}
+
+ARDAE_API void ardae_model_destroy(ardae_model_t h) { delete h; }
+ARDAE_API int ardae_model_num_launches(ardae_model_t h, int which) {
+  if (!h) return 0;
+  return which == 0 ? h->p.fwd.launches() + 4 : h->p.bwd_dec.launches() + h->p.bwd_enc.launches();
+}
+
+ARDAE_API int ardae_model_encode(ardae_model_t h, const float* x, const float* noise, float* z_out, void* stream) {
+  if (!h || !x || !z_out) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 0) return fail(-2, "handle was created with mode = 1 (use ardae_model_forward)");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.x = x; b.noise = noise; b.z_out = z_out;
+  return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* noise, float beta, float inv_rows,
+                                  float* z_out, float* sums, float* heads_out, void* stream) {
+  if (!h || !x || !z_out || !sums) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 1) return fail(-2, "handle was created with mode = 0");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.x = x; b.noise = noise; b.z_out = z_out; b.sums = sums; b.heads_out = heads_out; b.beta = beta;
+  b.inv_rows = inv_rows;
+  return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_backward(ardae_model_t h, float loss_scale, const float* gz, float gz_scale, void* stream) {
+  if (!h) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 1) return fail(-2, "handle was created with mode = 0");
+  ModelBindings& b = h->p.bind;
+  b.loss_scale = loss_scale; b.gz = gz; b.gz_scale = gz_scale;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (loss_scale != 0.0f) {
+    int rc = h->p.bwd_dec.run(s);
+    if (rc) return rc;
+  }
+  return h->p.bwd_enc.run(s);
+}
+
+ARDAE_API int ardae_sigma_schedule(const float* z, const float* zbar, int B, int nz, int d, int nstd, float S,
+                                   float delta, const float* xi, uint64_t seed, float* x_out, float* sigma_out,
+                                   float* std_out, void* stream) {
+  if (!z || !zbar || !x_out || !sigma_out) return fail(-1, "null argument");
+  if (B <= 0 || nz < 2 || d <= 0 || nstd <= 0) return fail(-2, "sigma_schedule: need B>0, nz>=2, d>0, nstd>0");
+  sigma_schedule_kernel<<<B, 128, sizeof(float) * 4, static_cast<cudaStream_t>(stream)>>>(
+      z, zbar, nz, d, nstd, S, delta, xi, seed, x_out, sigma_out, std_out);
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+ARDAE_API int ardae_scaled_diff(const float* z, const float* zbar, int R, int nz, int d, float S, float* out,
+                                void* stream) {
+  if (!z || !zbar || !out) return fail(-1, "null argument");
+  scaled_diff_kernel<<<grid_for(static_cast<size_t>(R) * d), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, zbar, R, nz, d, S, out);
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+ARDAE_API int ardae_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                              float beta1, float beta2, float eps, int step, float gscale, void* stream) {
+  if (!p || !g || !exp_avg || !exp_avg_sq) return fail(-1, "null argument");
+  if (n % 4 != 0 || ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                      reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15))
+    return fail(-11, "optimizer arenas must be 16-byte aligned with n % 4 == 0");
+  const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), step);
+  adam_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, exp_avg, exp_avg_sq, n, static_cast<float>(lr / bc1), static_cast<float>(1.0 / std::sqrt(bc2)), beta1,
+      beta2, eps, gscale);
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+ARDAE_API int ardae_rmsprop_step(float* p, const float* g, float* square_avg, float* momentum_buf, size_t n,
+                                 float lr, float alpha, float eps, float momentum, float gscale, void* stream) {
+  if (!p || !g || !square_avg || !momentum_buf) return fail(-1, "null argument");
+  if (n % 4 != 0 || ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                      reinterpret_cast<uintptr_t>(square_avg) | reinterpret_cast<uintptr_t>(momentum_buf)) & 15))
+    return fail(-11, "optimizer arenas must be 16-byte aligned with n % 4 == 0");
+  rmsprop_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, square_avg, momentum_buf, n, lr, alpha, eps, momentum, gscale);
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 ARDAE_API int ardae_randn(float* out, size_t n, uint64_t seed, uint32_t stream_id, void* stream) {

@@ -120,7 +120,8 @@ __global__ void derive_weights_kernel(const DeriveItem* __restrict__ items, int 
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       const int c = c0 + ly + j, r = r0 + lx;  // transposed: row index c of dstT, col r
-      if (c < d.cols && r < d.ldT) d.dstT[static_cast<size_t>(c) * d.ldT + r] = (r < d.rows) ? tile[lx][ly + j] : 0.0f;
+      // an item owns round_up(rows, 4) columns of its dstT rows (several items may share one buffer)
+      if (c < d.cols && r < ((d.rows + 3) & ~3)) d.dstT[static_cast<size_t>(c) * d.ldT + r] = (r < d.rows) ? tile[lx][ly + j] : 0.0f;
     }
   }
 }
@@ -249,6 +250,244 @@ __global__ void unpad_kernel(const float* __restrict__ src, int ld, float* __res
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(i / d), j = static_cast<int>(i - static_cast<size_t>(n) * d);
     dst[i] = scale * src[static_cast<size_t>(n) * ld + j];
+  }
+}
+
+// zbuf[r, j] = hi[r, j] + lo[r, j]; optionally also to a contiguous user buffer
+__global__ void pair_sum_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int ld,
+                                float* __restrict__ zbuf, int ldz, float* __restrict__ out, int R, int w) {
+  const size_t total = static_cast<size_t>(R) * w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / w), j = static_cast<int>(i - static_cast<size_t>(r) * w);
+    const float v = hi[static_cast<size_t>(r) * ld + j] + lo[static_cast<size_t>(r) * ld + j];
+    zbuf[static_cast<size_t>(r) * ldz + j] = v;
+    if (out != nullptr) out[i] = v;
+  }
+}
+
+// colsum[c] += scale * sum_r X[r, c]   (one block per 32 columns x a slab of rows)
+__global__ void colsum_kernel(const float* __restrict__ X, int ld, int rows, int cols,
+                              float* __restrict__ out, float scale) {
+  __shared__ float red[8][33];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lx;
+  float acc = 0.0f;
+  if (c < cols)
+    for (int r = blockIdx.y * 8 + ly; r < rows; r += gridDim.y * 8) acc += X[static_cast<size_t>(r) * ld + c];
+  red[ly][lx] = acc;
+  __syncthreads();
+  if (ly == 0) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) acc += red[j][lx];
+    if (c < cols) atomicAdd(out + c, scale * acc);
+  }
+}
+
+// ---------------------------------------------------------------- ELBO terms (model update)
+// Bernoulli decoder (models/ivae/mnist.py:240-249, utils/vae.py:21-30, utils/energy.py:69-77):
+//   recon_r = sum_px softplus(l) - x*l ; prior_r = 0.5*sum_d (z^2 + log 2pi)
+//   sums[0] += (recon_r + beta*prior_r)/R_total ; sums[1] += recon_r/R_total ; sums[2] += prior_r/R_total
+//   dlogit[r, px] = gscale * (sigmoid(l) - x)      (gscale = 1/R_total; written tf32-rounded)
+// One block per row r; x row index = r / nz.
+__global__ void bern_elbo_kernel(const float* __restrict__ logit, int ldl, const float* __restrict__ x,
+                                 int D, const float* __restrict__ z, int ldz, int zd, int nz, float beta,
+                                 float inv_rows, float* __restrict__ sums, float* __restrict__ dlogit,
+                                 int ldd) {
+  const int r = blockIdx.x;
+  const float* l = logit + static_cast<size_t>(r) * ldl;
+  const float* xr = x + static_cast<size_t>(r / nz) * D;
+  float rec = 0.0f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float lv = l[j], xv = xr[j];
+    const float e = __expf(-fabsf(lv));
+    const float sp = fmaxf(lv, 0.0f) + ((e < 1e-4f) ? (e - 0.5f * e * e) : __logf(1.0f + e));
+    rec += sp - xv * lv;
+    if (dlogit != nullptr) {
+      const float sg = (lv >= 0.0f) ? 1.0f / (1.0f + e) : e / (1.0f + e);
+      dlogit[static_cast<size_t>(r) * ldd + j] = ptx::round_tf32(inv_rows * (sg - xv));
+    }
+  }
+  float pri = 0.0f;
+  for (int j = threadIdx.x; j < zd; j += blockDim.x) {
+    const float zv = z[static_cast<size_t>(r) * ldz + j];
+    pri += 0.5f * (zv * zv + kLog2Pi);
+  }
+  rec = block_sum(rec);
+  pri = block_sum(pri);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 0, (rec + beta * pri) * inv_rows);
+    atomicAdd(sums + 1, rec * inv_rows);
+    atomicAdd(sums + 2, pri * inv_rows);
+  }
+}
+// Gaussian decoder (models/ivae/toy.py:794-803, utils/vae.py:36-52):
+//   recon_r = 0.5*sum_D [lv + (x-mu)^2/exp(lv) + log 2pi]
+//   heads [R, 2D] = [mu | logvar] ; dheads = gscale * [ -(x-mu)/e^lv | 0.5*(1 - (x-mu)^2/e^lv) ]
+__global__ void gauss_elbo_kernel(const float* __restrict__ heads, int ldh, int Dp,
+                                  const float* __restrict__ x,
+                                  int D, const float* __restrict__ z, int ldz, int zd, int nz, float beta,
+                                  float inv_rows, float* __restrict__ sums, float* __restrict__ dheads,
+                                  int ldd) {
+  const int r = blockIdx.x;
+  const float* hrow = heads + static_cast<size_t>(r) * ldh;
+  const float* xr = x + static_cast<size_t>(r / nz) * D;
+  float rec = 0.0f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float mu = hrow[j], lv = hrow[Dp + j], df = xr[j] - mu;
+    const float iv = __expf(-lv);
+    rec += 0.5f * (lv + df * df * iv + kLog2Pi);
+    if (dheads != nullptr) {
+      dheads[static_cast<size_t>(r) * ldd + j] = ptx::round_tf32(-inv_rows * df * iv);
+      dheads[static_cast<size_t>(r) * ldd + Dp + j] = ptx::round_tf32(inv_rows * 0.5f * (1.0f - df * df * iv));
+    }
+  }
+  float pri = 0.0f;
+  for (int j = threadIdx.x; j < zd; j += blockDim.x) {
+    const float zv = z[static_cast<size_t>(r) * ldz + j];
+    pri += 0.5f * (zv * zv + kLog2Pi);
+  }
+  rec = block_sum(rec);
+  pri = block_sum(pri);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 0, (rec + beta * pri) * inv_rows);
+    atomicAdd(sums + 1, rec * inv_rows);
+    atomicAdd(sums + 2, pri * inv_rows);
+  }
+}
+// dz_total[r, j] = loss_scale * (dz_dec[r, j] + beta*inv_rows*z[r, j]) + gz_scale*gz[r, j]  (tf32)
+__global__ void dz_total_kernel(const float* __restrict__ dz_dec, int ld_dec, const float* __restrict__ z,
+                                int ldz, const float* __restrict__ gz, float gz_scale, float loss_scale,
+                                float beta_inv_rows,
+                                float* __restrict__ out, int ld_out, int R, int zd) {
+  const size_t total = static_cast<size_t>(R) * zd;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / zd), j = static_cast<int>(i - static_cast<size_t>(r) * zd);
+    float v = 0.0f;
+    if (loss_scale != 0.0f)
+      v = loss_scale * (dz_dec[static_cast<size_t>(r) * ld_dec + j] + beta_inv_rows * z[static_cast<size_t>(r) * ldz + j]);
+    if (gz != nullptr) v += gz_scale * gz[i];
+    out[static_cast<size_t>(r) * ld_out + j] = ptx::round_tf32(v);
+  }
+}
+
+// ---------------------------------------------------------------- sigma schedule (ivae_ardae.py:753-767)
+// One block per data row b.  lsm = S*(z - zbar); s_b = delta * mean_d std_k(lsm) (unbiased over nz);
+// outputs: x_out[(b*nz + k)*nstd + t, :] = lsm[b,k,:] ; sigma_out[same] = s_b * xi[same] ;
+// std_out[b] = s_b.  xi == nullptr -> drawn with Philox.
+__global__ void sigma_schedule_kernel(const float* __restrict__ z, const float* __restrict__ zbar,
+                                      int nz, int d, int nstd, float S, float delta,
+                                      const float* __restrict__ xi, uint64_t seed,
+                                      float* __restrict__ x_out, float* __restrict__ sigma_out,
+                                      float* __restrict__ std_out) {
+  extern __shared__ float sm[];  // [blockDim.x]
+  const int b = blockIdx.x;
+  const float* zb = z + static_cast<size_t>(b) * nz * d;
+  const float* zm = zbar + static_cast<size_t>(b) * d;
+  // per-dimension unbiased std over the nz samples; thread t handles dims t, t+blockDim, ...
+  float acc = 0.0f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float m0 = zm[j];
+    float mean = 0.0f;
+    for (int k = 0; k < nz; ++k) mean += S * (zb[static_cast<size_t>(k) * d + j] - m0);
+    mean /= nz;
+    float var = 0.0f;
+    for (int k = 0; k < nz; ++k) {
+      const float v = S * (zb[static_cast<size_t>(k) * d + j] - m0) - mean;
+      var += v * v;
+    }
+    acc += sqrtf(var / (nz - 1));
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) sm[0] = delta * acc / d;
+  __syncthreads();
+  const float sb = sm[0];
+  if (threadIdx.x == 0 && std_out) std_out[b] = sb;
+  const int rows = nz * nstd;
+  for (int i = threadIdx.x; i < rows * d; i += blockDim.x) {
+    const int row = i / d, j = i - row * d;
+    const int k = row / nstd;
+    x_out[(static_cast<size_t>(b) * rows + row) * d + j] = S * (zb[static_cast<size_t>(k) * d + j] - zm[j]);
+  }
+  for (int row = threadIdx.x; row < rows; row += blockDim.x) {
+    const size_t e = static_cast<size_t>(b) * rows + row;
+    float xv;
+    if (xi != nullptr) {
+      xv = xi[e];
+    } else {
+      const uint4 r = Philox::gen(seed, e >> 2, 11u);
+      const float2 p = box_muller(r.x, r.y), q = box_muller(r.z, r.w);
+      const float v4[4] = {p.x, p.y, q.x, q.y};
+      xv = v4[e & 3];
+    }
+    sigma_out[e] = sb * xv;
+  }
+}
+// x_out[r, :] = S * (z[r, :] - zbar[r / nz, :])
+__global__ void scaled_diff_kernel(const float* __restrict__ z, const float* __restrict__ zbar, int R,
+                                   int nz, int d, float S, float* __restrict__ out) {
+  const size_t total = static_cast<size_t>(R) * d;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / d), j = static_cast<int>(i - static_cast<size_t>(r) * d);
+    out[i] = S * (z[i] - zbar[static_cast<size_t>(r / nz) * d + j]);
+  }
+}
+
+// ---------------------------------------------------------------- optimizers (one flat pass)
+// Reference Adam (utils/optim.py:59-106, PyTorch-1.2 epsilon placement):
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / ((sqrt(v)+eps)/sqrt(bc2))
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr_bc1, float inv_sqrt_bc2,
+                            float b1, float b2, float eps, float gscale) {
+  const size_t n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = gscale * ga[j];
+      ma[j] = b1 * ma[j] + (1.0f - b1) * gr;
+      va[j] = b2 * va[j] + (1.0f - b2) * gr * gr;
+      const float denom = (sqrtf(va[j]) + eps) * inv_sqrt_bc2;
+      pa[j] -= lr_bc1 * ma[j] / denom;
+    }
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+}
+// torch.optim.RMSprop (centered=False): sq = a*sq + (1-a)*g*g ; avg = sqrt(sq)+eps ;
+//   momentum > 0: buf = mu*buf + g/avg ; p -= lr*buf      else p -= lr*g/avg
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g,
+                               float* __restrict__ sq, float* __restrict__ buf, size_t n, float lr,
+                               float alpha, float eps, float mu, float gscale) {
+  const size_t n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* s4 = reinterpret_cast<float4*>(sq);
+  float4* b4 = reinterpret_cast<float4*>(buf);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], ss = s4[i], bb = b4[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* sa = &ss.x; float* ba = &bb.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = gscale * ga[j];
+      sa[j] = alpha * sa[j] + (1.0f - alpha) * gr * gr;
+      const float avg = sqrtf(sa[j]) + eps;
+      if (mu > 0.0f) {
+        ba[j] = mu * ba[j] + gr / avg;
+        pa[j] -= lr * ba[j];
+      } else {
+        pa[j] -= lr * gr / avg;
+      }
+    }
+    p4[i] = pp; s4[i] = ss; b4[i] = bb;
   }
 }
 

@@ -1,0 +1,177 @@
+"""GPU parity of the whole AR-DAE training step (CDAE update + model update + both optimizers):
+fused TrainStep and the drop-in module API vs the reference-generated fixtures (2 consecutive steps).
+
+Tolerances (tf32 backward sweeps, 3xTF32 forward):
+  losses (cdae, vae, recon, prior)      rel <= 2e-3
+  z, zbar                               rel <= 1e-5      (fp32-accurate forward)
+  sigma scale std_b                     rel <= 1e-4
+  CDAE score / entropy gradient         rel-L2 <= 1e-2
+  every parameter gradient tensor       rel-L2 <= 2e-2
+  parameter UPDATE (after - before)     rel-L2 <= 5e-2 (RMSprop) / 0.15 (Adam): at t = 1 Adam's update is
+                                        lr*g/(|g|+eps) ~ lr*sign(g), so the few elements whose |g| is below
+                                        the 1e-3 gradient error flip sign; the optimizer arithmetic itself is
+                                        pinned to 1e-6 in test_optimizers_match_oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, load_case, rel_err, sub
+
+pytestmark = pytest.mark.gpu
+
+
+def build(meta, z):
+    import ardae
+    m, c, hp = meta['model'], meta['cdae'], meta['hp']
+    cls = ardae.ToyIPVAE if meta['kind'] == 'toy' else ardae.MNISTIPVAE
+    model = cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
+                num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',
+                z_dim=m['z_dim'])
+    cdae = ardae.MLPGradCARDAE(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
+                               num_hidden_layers=c['num_hidden_layers'], nonlinearity='softplus')
+    f = lambda d: {k: torch.from_numpy(np.asarray(v)).float() for k, v in d.items()}
+    model.load_state_dict(f(sub(z, 'm0/')))
+    cdae.load_state_dict(f(sub(z, 'c0/')))
+    model, cdae = model.cuda(), cdae.cuda()
+    mopt = ardae.Adam(model.parameters(), lr=hp['m_lr'], betas=(hp['m_beta1'], 0.999))
+    copt = ardae.RMSprop(cdae.parameters(), lr=hp['d_lr'], momentum=hp['d_momentum'])
+    return model, cdae, mopt, copt
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).float().cuda()
+
+
+def params_np(mod):
+    return {k: v.detach().cpu().numpy().astype(np.float64) for k, v in mod.state_dict().items()}
+
+
+def update_err(before, after, ref_before, ref_after):
+    got = np.concatenate([(after[k] - before[k]).ravel() for k in sorted(before)])
+    ref = np.concatenate([(ref_after[k] - ref_before[k]).ravel() for k in sorted(before)])
+    return rel_err(got, ref)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_fused_step_matches_reference_fixture(name):
+    import ardae
+    z, meta = load_case(name)
+    hp = meta['hp']
+    model, cdae, mopt, copt = build(meta, z)
+    step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=hp['std_scale'], delta=hp['delta'],
+                           nz_cdae=hp['nz_cdae'], nstd=hp['nstd'], nz_model=hp['nz_model'])
+    ref_m_prev, ref_c_prev = sub(z, 'm0/'), sub(z, 'c0/')
+    for s in range(2):
+        p = 's%d/' % s
+        noise = {k: t(v) for k, v in sub(z, p + 'noise/').items()}
+        m_before, c_before = params_np(model), params_np(cdae)
+        out = step(t(z[p + 'x_cdae']), t(z[p + 'x_model']), beta=hp['beta'], noise=noise)
+        torch.cuda.synchronize()
+        # x3 case, step 1: the fixture itself is ill-conditioned there (see test_oracle_golden)
+        loose = name.endswith('_x3') and s == 1
+        ltol = 2e-2 if loose else 2e-3
+        for k in ('cdae_loss', 'model_loss', 'recon', 'prior'):
+            e = abs(out[k].item() - float(z[p + k])) / abs(float(z[p + k]))
+            assert e <= ltol, (s, k, e)
+        assert rel_err(out['std'].cpu().numpy(), z[p + 'std'].ravel()) <= (1e-2 if loose else 1e-4)
+        assert rel_err(out['z_model'].cpu().numpy().ravel(), z[p + 'z_model'].ravel()) <= (1e-3 if loose else 1e-5)
+        eg = rel_err(out['entropy_grad'].cpu().numpy().ravel(), z[p + 'entropy_grad'].ravel())
+        assert eg <= (5e-2 if loose else 1e-2), (s, 'entropy_grad', eg)
+        m_after, c_after = params_np(model), params_np(cdae)
+        ref_m_after, ref_c_after = sub(z, p + 'm_after/'), sub(z, p + 'c_after/')
+        ue_c = update_err(c_before, c_after, ref_c_prev, ref_c_after)
+        ue_m = update_err(m_before, m_after, ref_m_prev, ref_m_after)
+        print('%s step %d: cdae_loss %.6g (ref %.6g) model_loss %.6g (ref %.6g) entropy_grad rel %.2e '
+              'update rel: cdae %.2e model %.2e' % (name, s, out['cdae_loss'].item(), float(z[p + 'cdae_loss']),
+                                                    out['model_loss'].item(), float(z[p + 'model_loss']), eg, ue_c, ue_m))
+        assert ue_c <= (0.3 if loose else 5e-2) and ue_m <= (0.3 if loose else 0.15)
+        # the gradients the optimizers consumed are still in the stage arenas
+        gtol = 0.2 if loose else 2e-2
+        for mod, pref in ((cdae, 'cdae_grads/'), (model, 'model_grads/')):
+            ar, ref = mod._arena, sub(z, p + pref)
+            for k, nme in enumerate(ar.names):
+                if nme in ref:
+                    e = rel_err(ar.view(ar.stage_flat, k).cpu().numpy(), ref[nme])
+                    assert e <= gtol, (s, nme, e)
+        assert np.array_equal(c_after['neglogprob.fc.bias'], c_before['neglogprob.fc.bias'])  # never updated
+        ref_m_prev, ref_c_prev = ref_m_after, ref_c_after
+
+
+@pytest.mark.parametrize('name', ['toy_small', 'mnist_small'])
+def test_dropin_loop_matches_fused(name):
+    """The reference's own step body (ivae_ardae.py:713-846) written against the drop-in module API
+    (autograd .backward() calls, optimizer objects) must give what the fused driver gives."""
+    import ardae
+    z, meta = load_case(name)
+    hp = meta['hp']
+    S_, delta, nz, nstd, nzm, beta = hp['std_scale'], hp['delta'], hp['nz_cdae'], hp['nstd'], hp['nz_model'], hp['beta']
+    noise = {k: t(v) for k, v in sub(z, 's0/noise/').items()}
+    xc, xm = t(z['s0/x_cdae']), t(z['s0/x_model'])
+    # ---- fused
+    model, cdae, mopt, copt = build(meta, z)
+    out = ardae.TrainStep(model, cdae, mopt, copt, std_scale=S_, delta=delta, nz_cdae=nz, nstd=nstd,
+                          nz_model=nzm)(xc, xm, beta=beta, noise=noise)
+    pm_f, pc_f = params_np(model), params_np(cdae)
+    # ---- drop-in loop, written like the reference
+    model, cdae, mopt, copt = build(meta, z)
+    B = xc.size(0)
+    cdae_optimizer, model_optimizer = copt, mopt
+    cdae_optimizer.zero_grad()
+    context = model.encode(xc, std=0).detach()
+    latent_mean = model.encode(xc, std=0).detach()
+    latent = model.encode(xc, noise=noise['enc_cdae'], nz=nz).detach()
+    latent_sub_mean = S_ * (latent - latent_mean)
+    std_qz = torch.std(latent_sub_mean, dim=1, keepdim=True)
+    std = delta * torch.mean(std_qz, dim=2, keepdim=True)
+    stdmat = std * noise['xi']
+    lsm = latent_sub_mean.unsqueeze(2).expand(B, nz, nstd, latent.size(-1)).reshape(B, nz * nstd, -1)
+    _, cdae_loss = cdae(lsm, context, std=stdmat, scale=S_, eps=noise['eps_cdae'])
+    cdae_loss.backward()
+    cdae_optimizer.step()
+    model_optimizer.zero_grad()
+    _, _, latent, model_loss, recon_loss, prior_loss = model(xm, beta=beta, eta=0., lmbd=0., nz=nzm,
+                                                             noise=noise['enc_model'])
+    model_loss.backward(retain_graph=True)
+    context = model.encode(xm, std=0).detach()
+    latent_mean = model.encode(xm, std=0).detach()
+    latent_sub_mean = S_ * (latent - latent_mean).detach()
+    stdmat0 = torch.zeros(xm.size(0), nzm, 1, device='cuda')
+    grad = cdae.glogprob(latent_sub_mean, context, std=stdmat0, scale=S_).detach()
+    (S_ * (latent - latent_mean)).backward(beta * grad.detach() / float(xm.size(0) * nzm))
+    model_optimizer.step()
+    torch.cuda.synchronize()
+    assert abs(cdae_loss.item() - out['cdae_loss'].item()) <= 1e-5 * abs(cdae_loss.item())
+    assert abs(model_loss.item() - out['model_loss'].item()) <= 1e-5 * abs(model_loss.item())
+    pm_d, pc_d = params_np(model), params_np(cdae)
+    for k in pm_f:
+        assert rel_err(pm_d[k], pm_f[k]) <= 1e-5, k
+    for k in pc_f:
+        assert rel_err(pc_d[k], pc_f[k]) <= 1e-5, k
+    assert cdae.neglogprob.fc.bias.grad is None
+
+
+@pytest.mark.parametrize('kind', ['adam', 'rmsprop'])
+def test_optimizers_match_oracle(kind):
+    """Flat optimizer kernels vs the oracle's restatement of utils/optim.py:49-108 and torch RMSprop
+    (themselves pinned to the reference by test_oracle_golden), 3 steps, exact gradients."""
+    import ctypes
+    import ardae_oracle as orc
+    from ardae import _lib
+    rng = np.random.RandomState(0)
+    n = 4096 + 64
+    P = {'w': rng.randn(n)}
+    st = {}
+    p = t(P['w']); s1 = torch.zeros_like(p); s2 = torch.zeros_like(p)
+    for step in range(1, 4):
+        g = rng.randn(n) * 10.0 ** rng.uniform(-9, 1, size=n)
+        if kind == 'adam':
+            orc.adam_step(P, {'w': g}, st, lr=1e-3, beta1=0.5)
+            _lib.check(_lib.lib().ardae_adam_step(_lib.ptr(p), _lib.ptr(t(g)), _lib.ptr(s1), _lib.ptr(s2), n, 1e-3, 0.5,
+                                                  0.999, 1e-8, step, 1.0, _lib.stream_ptr()))
+        else:
+            orc.rmsprop_step(P, {'w': g}, st, lr=1e-3, momentum=0.5)
+            _lib.check(_lib.lib().ardae_rmsprop_step(_lib.ptr(p), _lib.ptr(t(g)), _lib.ptr(s1), _lib.ptr(s2), n, 1e-3,
+                                                     0.99, 1e-8, 0.5, 1.0, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert np.max(np.abs(p.cpu().numpy() - P['w'])) <= 2e-6
