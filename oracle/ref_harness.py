@@ -17,6 +17,8 @@ _REF_MODULES = None
 
 def find_reference():
     here = os.path.dirname(os.path.abspath(__file__))
+    if os.environ.get('ARDAE_NO_REF'):
+        return None
     for cand in (os.environ.get('ARDAE_REF'), os.path.join(here, '..', 'baseline', '_ref'), '/root/reference'):
         if cand and os.path.isfile(os.path.join(cand, 'models', 'graddae', 'mlp.py')):
             return os.path.abspath(cand)

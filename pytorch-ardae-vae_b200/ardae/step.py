@@ -30,6 +30,39 @@ class TrainStep(object):
         self.counter = 0
         self.launches = 0
         self.last_std = None
+        self.profile = None  # set to a list to collect (name, start_event, end_event) per segment
+
+    class _Seg(object):
+        def __init__(self, owner, name):
+            self.o, self.name = owner, name
+
+        def __enter__(self):
+            if self.o.profile is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.o.profile is not None:
+                self.e1.record()
+                self.o.profile.append((self.name, self.e0, self.e1))
+
+    def _seg(self, name):
+        return TrainStep._Seg(self, name)
+
+    def count_launches(self, B):
+        """Kernel launches of one iteration (for bench.py's gpu_launches)."""
+        L = _lib.lib()
+        m, c = self.model, self.cdae
+        n = 0
+        n += 2 * L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0)][0], 0)        # zbar (x2 minibatches)
+        n += L.ardae_model_num_launches(m._plans[m._plan(B, self.nz, 0)][0], 0)      # z samples
+        n += L.ardae_cdae_num_launches(c._plan(B, self.nz * self.nstd, True))
+        n += L.ardae_cdae_num_launches(c._plan(B, self.nzm, False))
+        k = m._plan(B, self.nzm, 1)
+        n += L.ardae_model_num_launches(m._plans[k][0], 0) + L.ardae_model_num_launches(m._plans[k][0], 1)
+        n += 2 + 1 + 1 + 2 + 2  # randn x2, sigma schedule, scaled diff, optimizers, stage memsets
+        return n
 
     def _next_seed(self):
         self.counter += 1
@@ -52,9 +85,10 @@ class TrainStep(object):
         d, n = m.z_dim, m.noise_dim
         dev = x.device
         xs = _lib.require_cuda(x, 'x').view(B, -1)
-        zbar = m._encode(xs, None, 1)                                                    # :735,:748
-        enc = noise['enc_cdae'] if noise is not None else self._randn(B * self.nz, n, dev)
-        z = m._encode(xs, enc, self.nz)                                                  # :749
+        with self._seg('encode'):
+            zbar = m._encode(xs, None, 1)                                                # :735,:748
+            enc = noise['enc_cdae'] if noise is not None else self._randn(B * self.nz, n, dev)
+            z = m._encode(xs, enc, self.nz)                                              # :749
         N = B * self.nz * self.nstd
         xc = torch.empty(N, d, dtype=torch.float32, device=dev)
         sigma = torch.empty(N, dtype=torch.float32, device=dev)
@@ -75,11 +109,14 @@ class TrainStep(object):
             gen = 1
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         inv = 1.0 / float(N * self.world * d)
-        _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(zbar), _lib.ptr(sigma), _lib.ptr(eps), gen,
-                                      self._next_seed(), ctypes.c_float(inv), _lib.ptr(loss), None,
-                                      _lib.stream_ptr()))                               # :768-771
-        self._allreduce(ar.stage_flat)
-        self.copt.step_flat(ar.stage_flat, skip=(len(ar.params) - 1,))                   # :779
+        with self._seg('cdae_train'):
+            _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(zbar), _lib.ptr(sigma), _lib.ptr(eps), gen,
+                                          self._next_seed(), ctypes.c_float(inv), _lib.ptr(loss), None,
+                                          _lib.stream_ptr()))                           # :768-771
+        with self._seg('cdae_allreduce'):
+            self._allreduce(ar.stage_flat)
+        with self._seg('cdae_opt'):
+            self.copt.step_flat(ar.stage_flat, skip=(len(ar.params) - 1,))               # :779
         self.last_std = std
         return loss
 
@@ -98,9 +135,10 @@ class TrainStep(object):
         z = torch.empty(R, d, dtype=torch.float32, device=dev)
         sums = torch.empty(3, dtype=torch.float32, device=dev)
         inv_rows = 1.0 / float(R * self.world)
-        _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),
-                                         ctypes.c_float(inv_rows), _lib.ptr(z), _lib.ptr(sums), None,
-                                         _lib.stream_ptr()))                            # :801
+        with self._seg('model_fwd'):
+            _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),
+                                             ctypes.c_float(inv_rows), _lib.ptr(z), _lib.ptr(sums), None,
+                                             _lib.stream_ptr()))                        # :801
         zbar = m._encode(xs, None, 1)                                                    # :813,:826
         xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
         _lib.check(L.ardae_scaled_diff(_lib.ptr(z), _lib.ptr(zbar), R, self.nzm, d, ctypes.c_float(self.S),
@@ -113,10 +151,13 @@ class TrainStep(object):
                                       _lib.stream_ptr()))                               # :829
         ar.stage_flat.zero_()
         gz_scale = self.S * beta * inv_rows                                              # :834
-        _lib.check(L.ardae_model_backward(hm, ctypes.c_float(1.0), _lib.ptr(g), ctypes.c_float(gz_scale),
-                                          _lib.stream_ptr()))                           # :804 + :834
-        self._allreduce(ar.stage_flat)
-        self.mopt.step_flat(ar.stage_flat)                                               # :846
+        with self._seg('model_bwd'):
+            _lib.check(L.ardae_model_backward(hm, ctypes.c_float(1.0), _lib.ptr(g), ctypes.c_float(gz_scale),
+                                              _lib.stream_ptr()))                       # :804 + :834
+        with self._seg('model_allreduce'):
+            self._allreduce(ar.stage_flat)
+        with self._seg('model_opt'):
+            self.mopt.step_flat(ar.stage_flat)                                           # :846
         return sums, g, z
 
     def __call__(self, x_cdae, x_model, beta=1.0, noise=None):
