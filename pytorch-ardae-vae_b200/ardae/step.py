@@ -17,6 +17,17 @@ import torch
 from . import _lib
 
 
+def dp_scales(B_local, nz, nstd, d, nz_model, world):
+    """Normalisation constants of one rank under batch-sharded data parallelism: every rank
+    scales its loss / gradient contributions by the GLOBAL counts, so that a plain SUM allreduce of the
+    flat gradient buffers reproduces the reference's means over the whole batch
+    (mse_loss mean over N*d, graddae/mlp.py:397; loss.mean() over B, ivae/mnist.py:249; 1/(B*nz_model) at
+    ivae_ardae.py:834)."""
+    n_local = B_local * nz * nstd
+    return dict(cdae_inv_count=1.0 / float(n_local * world * d),
+                model_inv_rows=1.0 / float(B_local * nz_model * world))
+
+
 class TrainStep(object):
     def __init__(self, model, cdae, model_opt, cdae_opt, std_scale=10000., delta=0.1, nz_cdae=256, nstd=1,
                  nz_model=1, num_cdae_updates=1, process_group=None, seed=1234):
@@ -108,7 +119,7 @@ class TrainStep(object):
             eps = torch.empty(N, d, dtype=torch.float32, device=dev)
             gen = 1
         loss = torch.empty(1, dtype=torch.float32, device=dev)
-        inv = 1.0 / float(N * self.world * d)
+        inv = dp_scales(B, self.nz, self.nstd, d, self.nzm, self.world)['cdae_inv_count']
         with self._seg('cdae_train'):
             _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(zbar), _lib.ptr(sigma), _lib.ptr(eps), gen,
                                           self._next_seed(), ctypes.c_float(inv), _lib.ptr(loss), None,
@@ -134,7 +145,7 @@ class TrainStep(object):
         hm = m._plans[key][0]
         z = torch.empty(R, d, dtype=torch.float32, device=dev)
         sums = torch.empty(3, dtype=torch.float32, device=dev)
-        inv_rows = 1.0 / float(R * self.world)
+        inv_rows = dp_scales(B, self.nz, self.nstd, d, self.nzm, self.world)['model_inv_rows']
         with self._seg('model_fwd'):
             _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),
                                              ctypes.c_float(inv_rows), _lib.ptr(z), _lib.ptr(sums), None,

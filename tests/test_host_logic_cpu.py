@@ -1,0 +1,107 @@
+"""CPU-only checks of the host-side mirror of the reference interface: constructor
+signatures, state_dict keys / shapes identical to the reference's (taken from the reference-generated
+fixtures), init semantics, error behaviour, and that nothing silently falls back to CPU compute."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load_case, sub
+
+
+def build(meta):
+    import ardae
+    m, c = meta['model'], meta['cdae']
+    cls = ardae.ToyIPVAE if meta['kind'] == 'toy' else ardae.MNISTIPVAE
+    model = cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
+                num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',
+                z_dim=m['z_dim'])
+    cdae = ardae.MLPGradCARDAE(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
+                               num_hidden_layers=c['num_hidden_layers'], nonlinearity=c['nonlinearity'],
+                               noise_type='gaussian', enc_ctx=True, enc_input=True)
+    return model, cdae
+
+
+@pytest.mark.parametrize('name', ['toy_small', 'mnist_small'])
+def test_state_dict_layout_matches_reference(name):
+    z, meta = load_case(name)
+    model, cdae = build(meta)
+    for mod, pref in ((model, 'm0/'), (cdae, 'c0/')):
+        ref = sub(z, pref)
+        sd = mod.state_dict()
+        assert list(sd.keys()) == [k[len(pref):] for k in z.files if k.startswith(pref)]  # same order too
+        for k, v in sd.items():
+            assert tuple(v.shape) == tuple(ref[k].shape), k
+        # a reference checkpoint loads without key or shape errors
+        mod.load_state_dict({k: torch.from_numpy(np.asarray(v)).float() for k, v in ref.items()})
+
+
+def test_full_size_parameter_counts():
+    """config-2 model 1 062 816 params, CDAE 938 241; config-1 271 386 / 528 129."""
+    import ardae
+    m2 = ardae.MNISTIPVAE(input_dim=784, noise_dim=100, h_dim=300, num_hidden_layers=2, nonlinearity='softplus',
+                          enc_type='concat', z_dim=32)
+    c2 = ardae.MLPGradCARDAE(input_dim=32, context_dim=32, std=1., h_dim=256, num_hidden_layers=5, nonlinearity='softplus')
+    m1 = ardae.ToyIPVAE(input_dim=2, noise_dim=10, h_dim=256, num_hidden_layers=2, nonlinearity='relu',
+                        enc_type='concat', z_dim=2)
+    c1 = ardae.MLPGradCARDAE(input_dim=2, context_dim=2, std=1., h_dim=256, num_hidden_layers=3, nonlinearity='softplus')
+    n = lambda mod: sum(p.numel() for p in mod.parameters())
+    assert (n(m2), n(c2), n(m1), n(c1)) == (1062816, 938241, 271386, 528129)
+
+
+def test_init_semantics():
+    """toy.py:189-190,719-720 / mnist.py:20-25,158-159: normal_ on encode.fc.fc.weight (and toy mean_fn),
+    xavier + zero bias on the whole MNIST decoder."""
+    import ardae
+    torch.manual_seed(0)
+    m = ardae.MNISTIPVAE(input_dim=784, noise_dim=100, h_dim=300, num_hidden_layers=2, nonlinearity='softplus', z_dim=32)
+    assert abs(m.encode.fc.fc.weight.std().item() - 1.0) < 0.05
+    assert all(float(l.bias.detach().abs().max()) == 0.0 for l in m.decode.main.linears())
+    assert float(m.decode.reparam.logit_fn.bias.detach().abs().max()) == 0.0
+    t = ardae.ToyIPVAE(input_dim=2, noise_dim=10, h_dim=256, num_hidden_layers=2, nonlinearity='relu', z_dim=2)
+    assert abs(t.decode.reparam.mean_fn.weight.std().item() - 1.0) < 0.15
+
+
+def test_unsupported_configurations_raise():
+    import ardae
+    with pytest.raises(NotImplementedError):
+        ardae.MLPGradCARDAE(input_dim=2, context_dim=2, std=1., h_dim=16, num_hidden_layers=3, nonlinearity='tanh')
+    with pytest.raises(NotImplementedError):
+        ardae.ToyIPVAE(input_dim=2, noise_dim=2, h_dim=16, num_hidden_layers=2, nonlinearity='relu', enc_type='scale', z_dim=2)
+    t = ardae.ToyIPVAE(input_dim=2, noise_dim=2, h_dim=16, num_hidden_layers=2, nonlinearity='relu', z_dim=2)
+    with pytest.raises(NotImplementedError):  # same as the reference for lmbd > 0 (toy.py:845-846)
+        t.forward(torch.zeros(2, 2), lmbd=1.0)
+
+
+def test_cpu_tensors_fail_loudly():
+    """No CPU fallback: the product path refuses to compute without the CUDA library / device."""
+    import ardae
+    z, meta = load_case('toy_small')
+    model, cdae = build(meta)
+    with pytest.raises(RuntimeError):
+        cdae(torch.zeros(2, 3, 2), torch.zeros(2, 1, 2), std=torch.zeros(2, 3, 1))
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(2, 2))
+    with pytest.raises(RuntimeError):
+        model.encode(torch.zeros(2, 2), std=0)
+
+
+def test_product_package_never_imports_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'pytorch-ardae-vae_b200')
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert 'ardae_oracle' not in src and 'ref_harness' not in src, f
+
+
+def test_optimizer_api():
+    import ardae
+    z, meta = load_case('toy_small')
+    model, cdae = build(meta)
+    mo = ardae.Adam(model.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    co = ardae.RMSprop(cdae.parameters(), lr=1e-4, momentum=0.5)
+    assert mo.param_groups[0]['lr'] == 1e-4 and co.param_groups[0]['momentum'] == 0.5
+    assert 'state' in mo.state_dict() and 'param_groups' in co.state_dict()
+    with pytest.raises(NotImplementedError):
+        ardae.Adam(model.parameters(), amsgrad=True)
