@@ -100,7 +100,7 @@ typedef struct {
   int n_inp, n_fc, n_dec; /* linears in inp_encode; hidden layers of encode.fc; linears in decode.main */
   int act;                /* 0 relu, 1 softplus */
   int batch, nz;          /* B data rows, nz noise samples per row: R = B*nz rows, row index b*nz+k */
-  int mode;               /* 0: encode only; 1: forward + backward */
+  int mode;               /* 0: encode only; 1: forward + backward; 2: IWS log-likelihood */
 } ardae_model_config;
 
 ARDAE_API int ardae_model_workspace_bytes(const ardae_model_config* cfg, size_t* bytes);
@@ -124,6 +124,16 @@ ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* 
  * pass: accumulates d(loss_scale*loss)/dtheta plus the pull-back of gz_scale*gz (an upstream
  * gradient on z, [R, z_dim], may be NULL) into `grads`.  loss_scale == 0 skips the decoder. */
 ARDAE_API int ardae_model_backward(ardae_model_t h, float loss_scale, const float* gz, float gz_scale, void* stream);
+
+/* Replaces ImplicitPosteriorVAE.logprob = logprob_w_cov_gaussian_posterior (toy.py:878-939 /
+ * mnist.py:378-437; called by evaluate_iws, ivae_ardae.py:644-673), batched over the images instead
+ * of a Python loop.  Handle created with mode = 2, batch = images per call, nz = sample_size
+ * (>= 2*z_dim, z_dim <= 64).  noise [B*S, n]: encoder noise; eta [B*S, z_dim]: the standard normal
+ * behind MultivariateNormal.rsample (NULL = Philox from seed).  out [B] <- log(mean_k exp(w_k - max)
+ * + 1e-10) + max per image; *total (device, optional) += sum_i out[i]; *status (device, optional)
+ * <- 1+i if image i's sample covariance is not positive definite. */
+ARDAE_API int ardae_model_iws(ardae_model_t h, const float* x, const float* noise, const float* eta, uint64_t seed,
+                              float* out, float* total, int* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Step glue and optimizers */

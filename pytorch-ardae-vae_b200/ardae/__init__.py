@@ -3,3 +3,24 @@ from .cdae import ConditionalARDAE, MLPGradCARDAE  # noqa: F401
 from .ivae import MNISTIPVAE, ToyIPVAE, normal_energy_func  # noqa: F401
 from .optim import Adam, RMSprop  # noqa: F401
 from .step import TrainStep  # noqa: F401
+
+
+def evaluate_iws(data, model, iws_samples, batch_size=32, process_group=None):
+    """evaluate_iws (ivae_ardae.py:644-673): mean over the images of model.logprob(x, sample_size=iws_samples).
+    `data`: an iterable of (x, _) batches like the reference's loader, or one tensor [n, D].  Images are
+    processed `batch_size` at a time (the reference scripts use eval batch 1 and a Python loop per image);
+    under data parallelism each rank passes its own shard and the partial sums are allreduced."""
+    import torch
+    total, count = None, 0
+    if torch.is_tensor(data):
+        data = [(data[i:i + batch_size], None) for i in range(0, data.size(0), batch_size)]
+    for x, _ in data:
+        x = x.cuda() if not x.is_cuda else x
+        per = model.logprob(x, sample_size=iws_samples, return_per_image=True)
+        s = per.sum()
+        total = s if total is None else total + s
+        count += x.size(0)
+    t = torch.stack([total, torch.tensor(float(count), device=total.device)])
+    if process_group is not None:
+        torch.distributed.all_reduce(t, group=process_group)
+    return t[0] / t[1]

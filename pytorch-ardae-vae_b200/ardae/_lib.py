@@ -49,6 +49,7 @@ def _declare(lib):
     lib.ardae_model_encode.argtypes = [vp, vp, vp, vp, vp]
     lib.ardae_model_forward.argtypes = [vp, vp, vp, f, f, vp, vp, vp, vp]
     lib.ardae_model_backward.argtypes = [vp, f, vp, f, vp]
+    lib.ardae_model_iws.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp]
     lib.ardae_sigma_schedule.argtypes = [vp, vp, i, i, i, i, f, f, vp, u64, vp, vp, vp, vp]
     lib.ardae_scaled_diff.argtypes = [vp, vp, i, i, i, f, vp, vp]
     lib.ardae_adam_step.argtypes = [vp, vp, vp, vp, sz, f, f, f, f, i, f, vp]

@@ -281,8 +281,30 @@ class ImplicitPosteriorVAE(nn.Module):
             mean = torch.sigmoid(logit)
         return xhat, mean, z3, loss, sums[1].detach(), sums[2].detach()
 
-    def logprob(self, input, sample_size=128, z=None, std=None):
-        raise NotImplementedError('IWS evaluator: see ardae.iws (next SURVEY 8 row)')
+    def logprob(self, input, sample_size=128, z=None, std=None, noise=None, eta=None, return_per_image=False):
+        """toy.py:875-939 / mnist.py:318-319,378-437 (`logprob_w_cov_gaussian_posterior`): importance-weighted
+        log-likelihood with the moment-matched full-covariance Gaussian proposal, batched over the images.
+        `noise` [b, S, n] / `eta` [b, S, z] inject the encoder noise and the MVN.rsample normal draw."""
+        batch_size = input.size(0)
+        assert sample_size >= 2 * self.z_dim  # mnist.py:382
+        x = _lib.require_cuda(input.detach(), 'input').view(batch_size, self.input_dim)
+        S = int(sample_size)
+        if noise is None:
+            noise = self.encode.sample_noise(batch_size * S, std=std, device=x.device)
+        nf = _lib.require_cuda(noise.detach(), 'noise').reshape(batch_size * S, self.noise_dim)
+        ef = None if eta is None else _lib.require_cuda(eta.detach(), 'eta').reshape(batch_size * S, self.z_dim)
+        self._ensure()
+        key = self._plan(batch_size, S, 2)
+        out = torch.empty(batch_size, dtype=torch.float32, device=x.device)
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if ef is None else 0
+        _lib.check(_lib.lib().ardae_model_iws(self._plans[key][0], _lib.ptr(x), _lib.ptr(nf), _lib.ptr(ef),
+                                              ctypes.c_uint64(seed), _lib.ptr(out), None, _lib.ptr(status),
+                                              _lib.stream_ptr()))
+        self.last_iws_status = status
+        if return_per_image:
+            return out
+        return out.mean()
 
 
 class ToyIPVAE(ImplicitPosteriorVAE):

@@ -114,7 +114,7 @@ ARDAE_API int ardae_model_workspace_bytes(const ardae_model_config* cfg, size_t*
 ARDAE_API int ardae_model_create(const ardae_model_config* cfg, float* const* params, float* const* grads,
                                  int num_tensors, void* workspace, size_t workspace_bytes, ardae_model_t* out) {
   if (!cfg || !params || !workspace || !out) return fail(-1, "null argument");
-  if (cfg->mode && !grads) return fail(-1, "forward+backward plan needs grads");
+  if (cfg->mode == 1 && !grads) return fail(-1, "forward+backward plan needs grads");
   std::unique_ptr<ardae_model_s> h(new ardae_model_s());
   to_mcfg(cfg, &h->p.cfg);
   if (num_tensors != h->p.ntensors()) return fail(-2, "model: unexpected number of parameter tensors");
@@ -158,6 +158,16 @@ ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* 
   b = ModelBindings();
   b.x = x; b.noise = noise; b.z_out = z_out; b.sums = sums; b.heads_out = heads_out; b.beta = beta;
   b.inv_rows = inv_rows;
+  return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_iws(ardae_model_t h, const float* x, const float* noise, const float* eta, uint64_t seed,
+                              float* out, float* total, int* status, void* stream) {
+  if (!h || !x || !noise || !out) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 2) return fail(-2, "handle was not created with mode = 2 (IWS)");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.x = x; b.noise = noise; b.eta = eta; b.seed = seed; b.iws_out = out; b.iws_total = total; b.status = status;
   return h->p.fwd.run(static_cast<cudaStream_t>(stream));
 }
 

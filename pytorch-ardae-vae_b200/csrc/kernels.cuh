@@ -435,6 +435,161 @@ __global__ void scaled_diff_kernel(const float* __restrict__ z, const float* __r
   }
 }
 
+// ---------------------------------------------------------------- IWS evaluator (ivae/mnist.py:378-437)
+// One block per image i.  z[i] = [S, d] encoder samples.  Computes the moment-matched Gaussian proposal
+// (mean, unbiased covariance: utils/stat.py:127-158), its Cholesky factor L (what MultivariateNormal
+// builds), newz_k = mu + L eta_k (rsample), and lw0_k = log N(newz_k; 0, I) - log N(newz_k; mu, Sigma).
+// newz is written as the tf32 pair the decoder's first 3xTF32 GEMM consumes.  d <= 64.
+// eta == nullptr -> Philox draw.  Dynamic smem: (d*d + 2*d + 64*d) floats.
+__global__ void iws_moments_kernel(const float* __restrict__ z, int ldz, int S, int d,
+                                   const float* __restrict__ eta, uint64_t seed,
+                                   float* __restrict__ newz_pair, int ldp, int kp,
+                                   float* __restrict__ lw0, int* __restrict__ status) {
+  extern __shared__ float sm[];
+  float* cov = sm;               // [d*d]
+  float* mu = cov + d * d;       // [d]
+  float* red = mu + d;           // [d] scratch
+  float* tile = red + d;         // [64*d] sample tile
+  const int img = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const float* zi = z + static_cast<size_t>(img) * S * ldz;
+  // ---- mean
+  for (int j = tid; j < d; j += nt) {
+    float a = 0.0f;
+    for (int k = 0; k < S; ++k) a += zi[static_cast<size_t>(k) * ldz + j];
+    mu[j] = a / S;
+  }
+  for (int e = tid; e < d * d; e += nt) cov[e] = 0.0f;
+  __syncthreads();
+  // ---- covariance (lower + upper, thread e owns entry (e / d, e % d)), samples staged through smem
+  const int per = (d * d + nt - 1) / nt;
+  for (int k0 = 0; k0 < S; k0 += 64) {
+    const int kn = min(64, S - k0);
+    for (int t = tid; t < kn * d; t += nt) {
+      const int kk = t / d, j = t - kk * d;
+      tile[t] = zi[static_cast<size_t>(k0 + kk) * ldz + j] - mu[j];
+    }
+    __syncthreads();
+    for (int q = 0; q < per; ++q) {
+      const int e = tid + q * nt;
+      if (e < d * d) {
+        const int a = e / d, b = e - a * d;
+        float acc = 0.0f;
+        for (int kk = 0; kk < kn; ++kk) acc += tile[kk * d + a] * tile[kk * d + b];
+        cov[e] += acc;
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < d * d; e += nt) cov[e] *= 1.0f / (S - 1);
+  __syncthreads();
+  // ---- Cholesky (in place, lower), warp 0; column j at a time
+  if (tid < 32) {
+    for (int j = 0; j < d; ++j) {
+      float diag = cov[j * d + j];
+      for (int k = 0; k < j; ++k) diag -= cov[j * d + k] * cov[j * d + k];
+      if (!(diag > 0.0f)) {
+        if (tid == 0 && status) atomicExch(status, 1 + img);
+        diag = 1e-30f;
+      }
+      const float ljj = sqrtf(diag);
+      __syncwarp();
+      for (int i = j + 1 + tid; i < d; i += 32) {
+        float v = cov[i * d + j];
+        for (int k = 0; k < j; ++k) v -= cov[i * d + k] * cov[j * d + k];
+        cov[i * d + j] = v / ljj;
+      }
+      if (tid == 0) cov[j * d + j] = ljj;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  float logdet = 0.0f;
+  for (int j = 0; j < d; ++j) logdet += __logf(cov[j * d + j]);
+  // ---- samples: newz = mu + L eta ; lw0 = logprior - logq
+  for (int k = tid; k < S; k += nt) {
+    const size_t row = static_cast<size_t>(img) * S + k;
+    float ev[64];
+    float e2 = 0.0f;
+    for (int j = 0; j < d; ++j) {
+      float v;
+      if (eta != nullptr) {
+        v = eta[row * d + j];
+      } else {
+        const size_t e = row * d + j;
+        const uint4 r = Philox::gen(seed, e >> 2, 13u);
+        const float2 p0 = box_muller(r.x, r.y), p1 = box_muller(r.z, r.w);
+        const float q4[4] = {p0.x, p0.y, p1.x, p1.y};
+        v = q4[e & 3];
+      }
+      ev[j] = v;
+      e2 += v * v;
+    }
+    float z2 = 0.0f;
+    for (int i = 0; i < d; ++i) {
+      float v = mu[i];
+      for (int j = 0; j <= i; ++j) v += cov[i * d + j] * ev[j];
+      z2 += v * v;
+      const float hi = ptx::round_tf32(v);
+      newz_pair[row * ldp + i] = hi;
+      newz_pair[row * ldp + kp + i] = ptx::round_tf32(v - hi);
+    }
+    // logprior = -0.5*(z2 + d*log2pi) ; logq = -0.5*e2 - logdet - 0.5*d*log2pi
+    lw0[row] = -0.5f * z2 + 0.5f * e2 + logdet;
+  }
+}
+// w_r = lw0_r + loglik_r ; loglik from the decoder heads.  One block per row.
+//   kind 1 (Bernoulli): -sum_px softplus(l) - x*l        kind 0 (Gaussian): -0.5*sum [(x-mu)^2/e^lv + lv + log2pi]
+__global__ void iws_loglik_kernel(const float* __restrict__ heads, int ldh, int Dp, const float* __restrict__ x,
+                                  int D, int S, int kind, const float* __restrict__ lw0, float* __restrict__ w) {
+  const int r = blockIdx.x;
+  const float* h = heads + static_cast<size_t>(r) * ldh;
+  const float* xr = x + static_cast<size_t>(r / S) * D;
+  float acc = 0.0f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    if (kind == 1) {
+      const float lv = h[j];
+      const float e = __expf(-fabsf(lv));
+      const float sp = fmaxf(lv, 0.0f) + ((e < 1e-4f) ? (e - 0.5f * e * e) : __logf(1.0f + e));
+      acc -= sp - xr[j] * lv;
+    } else {
+      const float m = h[j], lv = h[Dp + j], df = xr[j] - m;
+      acc -= 0.5f * (df * df * __expf(-lv) + lv + kLog2Pi);
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) w[r] = acc + lw0[r];
+}
+// out[i] = log(mean_k exp(w[i,k] - max) + 1e-10) + max   (ivae/mnist.py:431-434: NOT a plain logsumexp)
+__global__ void iws_logmeanexp_kernel(const float* __restrict__ w, int S, float* __restrict__ out,
+                                      float* __restrict__ total) {
+  __shared__ float sh_max;
+  const int i = blockIdx.x;
+  const float* wi = w + static_cast<size_t>(i) * S;
+  float m = -INFINITY;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) m = fmaxf(m, wi[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float redm[32];
+  if ((threadIdx.x & 31) == 0) redm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x + 31) / 32 ? redm[threadIdx.x] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) sh_max = m;
+  }
+  __syncthreads();
+  m = sh_max;
+  float s = 0.0f;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) s += __expf(wi[k] - m);
+  s = block_sum(s);
+  if (threadIdx.x == 0) {
+    const float v = logf(s / S + 1e-10f) + m;
+    out[i] = v;
+    if (total) atomicAdd(total, v);
+  }
+}
+
 // ---------------------------------------------------------------- optimizers (one flat pass)
 // Reference Adam (utils/optim.py:59-106, PyTorch-1.2 epsilon placement):
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / ((sqrt(v)+eps)/sqrt(bc2))

@@ -20,7 +20,7 @@ struct ModelConfig {
   int n_inp = 0, n_fc = 0, n_dec = 0;  // number of linears in inp_encode, hidden fc layers, decode.main
   int act = 1;    // 0 relu, 1 softplus
   int B = 0, nz = 1;
-  int mode = 0;   // 0 encode only, 1 forward + backward
+  int mode = 0;   // 0 encode only, 1 forward + backward, 2 IWS log-likelihood (forward only)
 };
 
 struct ModelBindings {
@@ -35,6 +35,12 @@ struct ModelBindings {
   float loss_scale = 0.0f;
   const float* gz = nullptr;     // [R, zd] upstream gradient on z, or null
   float gz_scale = 1.0f;
+  // IWS (mode 2)
+  const float* eta = nullptr;    // [R, zd] standard normal behind MVN.rsample, or null (Philox)
+  uint64_t seed = 0;
+  float* iws_out = nullptr;      // [B] per-image log p_hat(x)
+  float* iws_total = nullptr;    // device scalar, += sum over images
+  int* status = nullptr;         // set to 1+image if a covariance is not positive definite
 };
 
 struct ModelPlan {
@@ -54,7 +60,8 @@ struct ModelPlan {
     if (D <= 0 || n <= 0 || h <= 0 || zd <= 0 || B <= 0 || nz <= 0 || c.n_inp < 1 || c.n_fc < 1 || c.n_dec < 1)
       return fail(-2, "model: bad config");
     if (c.kind != 0 && c.kind != 1) return fail(-2, "model: kind must be 0 (toy) or 1 (mnist)");
-    const bool dry = ws.dry, train = c.mode != 0;
+    const bool dry = ws.dry, train = c.mode == 1, dec = c.mode != 0;
+    if (c.mode == 2 && (zd > 64 || nz < 2 * zd)) return fail(-2, "iws: need z_dim <= 64 and sample_size >= 2*z_dim (ivae/mnist.py:382)");
     fwd.dry = bwd_dec.dry = bwd_enc.dry = dry;
     const int ACT = c.act ? EPI_SOFTPLUS : EPI_RELU;
     const int DACT = c.act ? EPI_MUL_SIG : EPI_MUL_STEP;
@@ -88,21 +95,21 @@ struct ModelPlan {
     }
     for (int l = 0; l < c.n_dec; ++l) {
       const int in = l == 0 ? zd : h;
-      Dw[l] = derive.add(ws, P(iD(l)), h, in, in, true, train);
+      if (dec) Dw[l] = derive.add(ws, P(iD(l)), h, in, in, true, train);
     }
     // heads: combined [nH*D, h] forward operand and [h, nH*D] transpose
     W3 Hw;
     Hw.in = h; Hw.out = nH * D; Hw.kp = round_up(h, 32);
-    if (train) {
+    if (dec) {
       Hw.b3 = Mat(ws.floats(static_cast<size_t>(nH) * D * 3 * Hw.kp), nH * D, 3 * Hw.kp, 3 * Hw.kp);
-      Hw.T = ws.mat(h, nH * Dp);
+      if (train) Hw.T = ws.mat(h, nH * Dp);
       for (int k = 0; k < nH; ++k) {
         DeriveItem it;
         std::memset(&it, 0, sizeof(it));
         it.src = P(iH(k)); it.rows = D; it.cols = h; it.src_ld = h;
         it.dst3 = dry ? nullptr : Hw.b3.p + static_cast<size_t>(k) * D * Hw.b3.ld;
         it.kp = Hw.kp; it.ld3 = Hw.b3.ld;
-        it.dstT = dry ? nullptr : Hw.T.p + k * Dp; it.ldT = Hw.T.ld;
+        it.dstT = (dry || !train) ? nullptr : Hw.T.p + k * Dp; it.ldT = Hw.T.ld;
         it.first_block = derive.blocks;
         it.tiles_x = (h + 31) / 32;
         derive.blocks += it.tiles_x * ((D + 31) / 32);
@@ -127,9 +134,16 @@ struct ModelPlan {
     Mat gsum0;
     float* tn_ws = nullptr;
     size_t tn_bytes = 0;
-    if (train) {
+    float *lw0 = nullptr, *wbuf = nullptr;
+    if (dec) {
       for (int l = 0; l < c.n_dec; ++l) Dh[l] = make_pair(ws, R, h);
       heads = ws.mat(R, nH * Dp);
+    }
+    if (c.mode == 2) {
+      lw0 = ws.floats(R);
+      wbuf = ws.floats(R);
+    }
+    if (train) {
       dheads = ws.mat(R, nH * Dp);
       dzdec = ws.mat(R, zd);
       dzt = ws.mat(R, zd);
@@ -218,7 +232,16 @@ struct ModelPlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
-    if (!train) return fwd.error;
+    if (!dec) return fwd.error;
+    if (c.mode == 2) {
+      // moment-matched Gaussian proposal per image; overwrites the z pair with newz = mu + L eta
+      const size_t smem = sizeof(float) * (static_cast<size_t>(zd) * zd + 2 * zd + 64 * zd);
+      fwd.add([=](cudaStream_t s) {
+        iws_moments_kernel<<<B, 256, smem, s>>>(zbuf.p, zbuf.ld, nz, zd, bd->eta, bd->seed, zp.buf.p, zp.buf.ld,
+                                                zp.kp, lw0, bd->status);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
     // decoder
     for (int l = 0; l < c.n_dec; ++l) {
       GemmNTDesc g = nt3_desc(l == 0 ? zp : Dh[l - 1], Dw[l], Dh[l], ACT);
@@ -232,6 +255,14 @@ struct ModelPlan {
       GemmNTDesc g = nt3_desc_plain(Dh[c.n_dec - 1], hk, heads.cols_from(k * Dp, D), EPI_LINEAR);
       g.bias = P(iH(k) + 1);
       fwd.nt(g);
+    }
+    if (c.mode == 2) {
+      fwd.add([=](cudaStream_t s) {
+        iws_loglik_kernel<<<R, 128, 0, s>>>(heads.p, heads.ld, Dp, bd->x, D, nz, toy ? 0 : 1, lw0, wbuf);
+        iws_logmeanexp_kernel<<<B, 256, 0, s>>>(wbuf, nz, bd->iws_out, bd->iws_total);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return fwd.error;
     }
     fwd.add([=](cudaStream_t s) {
       if (toy)
