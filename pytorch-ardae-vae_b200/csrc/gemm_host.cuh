@@ -94,13 +94,51 @@ struct GemmNTDesc {
   int split_out = 0;   // modes LINEAR/RELU/SOFTPLUS: out = tf32 hi part, out2 = tf32 lo part
   int a_k_wrap = 0;
   int force_block_n = 0;
+  int persist = 0;     // 0 auto, 1 force the persistent kernel, -1 force the tile-per-CTA kernel
+  int debug_flags = 0;
 };
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool SPLIT>
+inline const void* nt_persist_kernel_for_mode(int mode, int* smem) {
+#define ARDAE_PK(M)                                                                   \
+  case M:                                                                             \
+    *smem = GemmNTPersistConfig<M, SPLIT>::kSmemBytes;                                \
+    return reinterpret_cast<const void*>(&gemm_nt_persist_kernel<M, SPLIT>);
+  switch (mode) {
+    ARDAE_PK(EPI_LINEAR)
+    ARDAE_PK(EPI_RELU)
+    ARDAE_PK(EPI_SOFTPLUS)
+    default: break;
+  }
+  if (!SPLIT) {
+    switch (mode) {
+      case EPI_MUL_SIG: *smem = GemmNTPersistConfig<EPI_MUL_SIG, false>::kSmemBytes; return reinterpret_cast<const void*>(&gemm_nt_persist_kernel<EPI_MUL_SIG, false>);
+      case EPI_MUL_STEP: *smem = GemmNTPersistConfig<EPI_MUL_STEP, false>::kSmemBytes; return reinterpret_cast<const void*>(&gemm_nt_persist_kernel<EPI_MUL_STEP, false>);
+      case EPI_TANGENT: *smem = GemmNTPersistConfig<EPI_TANGENT, false>::kSmemBytes; return reinterpret_cast<const void*>(&gemm_nt_persist_kernel<EPI_TANGENT, false>);
+      case EPI_ADJOINT: *smem = GemmNTPersistConfig<EPI_ADJOINT, false>::kSmemBytes; return reinterpret_cast<const void*>(&gemm_nt_persist_kernel<EPI_ADJOINT, false>);
+      default: break;
+    }
+  }
+#undef ARDAE_PK
+  return nullptr;
+}
 
 struct PreparedNT {
   GemmNTParams params;
   const void* fn = nullptr;
   dim3 grid;
   int smem = 0;
+  int threads = kGemmThreads;
 };
 
 template <int BLOCK_N>
@@ -161,7 +199,9 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   p.row_scale = d.row_scale; p.col_vec = d.col_vec;
   p.colsum = d.colsum; p.colsum_w = d.colsum_w; p.row_w = d.row_w;
   p.colsum2 = d.colsum2; p.colsum_scale = d.colsum_scale; p.colsum_w_stride = d.colsum_w_stride;
-  p.round_out = d.round_out; p.a_k_wrap = d.a_k_wrap;
+  p.round_out = d.round_out; p.a_k_wrap = d.a_k_wrap; p.debug_flags = d.debug_flags;
+  p.vec_ok = (((reinterpret_cast<uintptr_t>(d.bias) | reinterpret_cast<uintptr_t>(d.group_bias) |
+                reinterpret_cast<uintptr_t>(d.col_vec)) & 15) == 0 && d.ldg % 4 == 0) ? 1 : 0;
   if (p.row_scale && !p.col_vec) return fail(-2, "gemm_nt: row_scale without col_vec");
   if (p.colsum_w && !p.row_w) return fail(-2, "gemm_nt: colsum_w without row_w");
   switch (bn) {
@@ -172,6 +212,19 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
     default: return fail(-2, "gemm_nt: bad BLOCK_N");
   }
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, 1);
+  const int tiles_m = (d.M + kBlockM - 1) / kBlockM;
+  // measured on B200 (tests/native/gemm_selftest): with the lean epilogue the tile-per-CTA kernel at
+  // 2 CTAs/SM is on par with the persistent one, so the persistent kernel is opt-in
+  const bool want_persist = d.persist > 0;
+  if (want_persist) {
+    if (bn != 256 || d.N > 256) return fail(-2, "gemm_nt: persistent kernel needs N <= 256");
+    int smem = 0;
+    const void* fn = d.split_out ? nt_persist_kernel_for_mode<true>(d.mode, &smem)
+                                 : nt_persist_kernel_for_mode<false>(d.mode, &smem);
+    if (fn == nullptr) return fail(-2, "gemm_nt: no persistent kernel for this mode");
+    pr.fn = fn; pr.smem = smem; pr.threads = 256;
+    pr.grid = dim3(tiles_m < num_sms() ? tiles_m : num_sms(), 1, 1);
+  }
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;
   return 0;
@@ -179,7 +232,7 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
 
 inline int launch_prepared_nt(const PreparedNT& pr, cudaStream_t stream) {
   void* args[1] = {const_cast<GemmNTParams*>(&pr.params)};
-  ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(kGemmThreads), args, pr.smem, stream));
+  ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(pr.threads), args, pr.smem, stream));
   return 0;
 }
 

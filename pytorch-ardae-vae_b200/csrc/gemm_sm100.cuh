@@ -56,6 +56,8 @@ struct alignas(64) GemmNTParams {
   int colsum_w_stride;
   int round_out;            // round stored outputs to tf32 (rna)
   int a_k_wrap;             // if > 0 the A operand's k coordinate wraps: col = (kb*32) % a_k_wrap
+  int debug_flags;          // profiling experiments only: 1 = skip TMA stores, 2 = skip epilogue math
+  int vec_ok;               // bias / group_bias / col_vec are 16-byte aligned: float4 broadcast loads
 };
 
 struct alignas(64) GemmTNParams {
@@ -97,6 +99,145 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
+
+// add[j] += scale * src[j], j < 32 (all lanes read the same addresses: broadcast loads)
+__device__ __forceinline__ void add_cols32(const float* __restrict__ src, float scale, bool vec,
+                                           int remaining, float (&add)[32]) {
+  if (vec) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
+      add[q * 4 + 0] = fmaf(scale, t.x, add[q * 4 + 0]);
+      add[q * 4 + 1] = fmaf(scale, t.y, add[q * 4 + 1]);
+      add[q * 4 + 2] = fmaf(scale, t.z, add[q * 4 + 2]);
+      add[q * 4 + 3] = fmaf(scale, t.w, add[q * 4 + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < remaining) add[j] = fmaf(scale, __ldg(src + j), add[j]);
+  }
+}
+
+// One 32-column chunk of the fused epilogue for the thread that owns one accumulator row.
+//   accu: the 32 fp32 accumulator columns; a1/a2: this row of the aux staging tiles (swizzled 16-byte
+//   chunks); o1/o2: this row of the out staging tiles.  v[] returns the (unmasked) `out` values.
+// Kept lean on purpose: the epilogue is instruction-issue bound (round-1 ncu: 1500 warp-instructions
+// per chunk with per-element predicated bias loads; now ~1 FFMA + the activation per element).
+template <int MODE, bool SPLIT, bool ROUND>
+__device__ __forceinline__ void epilogue_chunk_body(const GemmNTParams& p, const uint32_t (&accu)[32],
+                                                    const float (&add)[32], const uint8_t* a1,
+                                                    const uint8_t* a2, uint8_t* o1, uint8_t* o2, int swz,
+                                                    float (&v)[32]) {
+  constexpr bool kHasAux1 = MODE >= EPI_MUL_SIG;
+  constexpr bool kHasAux2 = MODE >= EPI_TANGENT;
+  constexpr bool kHasOut2 = (MODE == EPI_TANGENT) || SPLIT;
+  const float alpha = p.alpha;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint32_t soff = static_cast<uint32_t>((q ^ swz) << 4);
+    float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f), x2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kHasAux1) x1 = *reinterpret_cast<const float4*>(a1 + soff);
+    if (kHasAux2) x2 = *reinterpret_cast<const float4*>(a2 + soff);
+    const float aux1v[4] = {x1.x, x1.y, x1.z, x1.w};
+    const float aux2v[4] = {x2.x, x2.y, x2.z, x2.w};
+    float o[4], ob[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float pre = fmaf(alpha, __uint_as_float(accu[q * 4 + j]), add[q * 4 + j]);
+      float res, res2 = 0.0f;
+      if (MODE == EPI_LINEAR) {
+        res = pre;
+      } else if (MODE == EPI_RELU) {
+        res = fmaxf(pre, 0.0f);
+      } else if (MODE == EPI_SOFTPLUS) {
+        res = softplus_f(pre);
+      } else if (MODE == EPI_MUL_STEP) {
+        res = aux1v[j] > 0.0f ? pre : 0.0f;
+      } else {
+        float sg, oms;
+        sig_from_softplus(aux1v[j], sg, oms);
+        if (MODE == EPI_MUL_SIG) {
+          res = pre * sg;
+        } else if (MODE == EPI_TANGENT) {
+          res = pre * sg;
+          res2 = aux2v[j] * pre * oms;
+        } else {  // EPI_ADJOINT
+          res = fmaf(pre, sg, aux2v[j]);
+        }
+      }
+      if (SPLIT) {
+        const float hi = ptx::round_tf32(res);
+        res2 = ptx::round_tf32(res - hi);
+        res = hi;
+      } else if (ROUND) {
+        res = ptx::round_tf32(res);
+        if (kHasOut2) res2 = ptx::round_tf32(res2);
+      }
+      o[j] = res;
+      ob[j] = res2;
+      v[q * 4 + j] = res;
+    }
+    *reinterpret_cast<float4*>(o1 + soff) = make_float4(o[0], o[1], o[2], o[3]);
+    if (kHasOut2) *reinterpret_cast<float4*>(o2 + soff) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+  }
+}
+
+template <int MODE, bool SPLIT>
+__device__ __forceinline__ void epilogue_chunk(const GemmNTParams& p, const uint32_t (&accu)[32],
+                                               const uint8_t* a1, const uint8_t* a2, uint8_t* o1,
+                                               uint8_t* o2, int swz, int nc, float rs, const float* gb_row,
+                                               float (&v)[32]) {
+  float add[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) add[j] = 0.0f;
+  const bool vec = p.vec_ok && (nc + 32 <= p.N);
+  const int remaining = p.N - nc;
+  if (p.bias != nullptr) add_cols32(p.bias + nc, 1.0f, vec, remaining, add);
+  if (gb_row != nullptr) add_cols32(gb_row + nc, 1.0f, vec, remaining, add);
+  if (p.row_scale != nullptr) add_cols32(p.col_vec + nc, rs, vec, remaining, add);
+  if (SPLIT || p.round_out)
+    epilogue_chunk_body<MODE, SPLIT, true>(p, accu, add, a1, a2, o1, o2, swz, v);
+  else
+    epilogue_chunk_body<MODE, SPLIT, false>(p, accu, add, a1, a2, o1, o2, swz, v);
+}
+
+// Column sums of one chunk (see GemmNTParams::colsum*).  o2 = this row of the out2 staging tile.
+template <int MODE>
+__device__ __forceinline__ void epilogue_colsums(const GemmNTParams& p, float (&v)[32], const uint8_t* o2,
+                                                 int swz, int nc, bool row_ok, float rw, int lane) {
+  if (p.colsum == nullptr && p.colsum_w == nullptr && (MODE != EPI_TANGENT || p.colsum2 == nullptr)) return;
+  const bool full = nc + 32 <= p.N;
+  if (!row_ok || !full) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (row_ok && nc + i < p.N) ? v[i] : 0.0f;
+  }
+  if (p.colsum_w != nullptr) {
+    float w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = v[i] * rw;
+    const float t = warp_transpose_reduce32(w, lane);
+    if (nc + lane < p.N) atomicAdd(p.colsum_w + static_cast<size_t>(nc + lane) * p.colsum_w_stride, t);
+  }
+  if (p.colsum != nullptr) {
+    const float t = warp_transpose_reduce32(v, lane);
+    if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, p.colsum_scale * t);
+  }
+  if (MODE == EPI_TANGENT && p.colsum2 != nullptr) {
+    // re-read this thread's own out2 row from the staging tile instead of keeping 32 more registers live
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t4 = *reinterpret_cast<const float4*>(o2 + ((q ^ swz) << 4));
+      v[q * 4 + 0] = (row_ok && nc + q * 4 + 0 < p.N) ? t4.x : 0.0f;
+      v[q * 4 + 1] = (row_ok && nc + q * 4 + 1 < p.N) ? t4.y : 0.0f;
+      v[q * 4 + 2] = (row_ok && nc + q * 4 + 2 < p.N) ? t4.z : 0.0f;
+      v[q * 4 + 3] = (row_ok && nc + q * 4 + 3 < p.N) ? t4.w : 0.0f;
+    }
+    const float t = warp_transpose_reduce32(v, lane);
+    if (nc + lane < p.N) atomicAdd(p.colsum2 + nc + lane, t);
+  }
+}
+
 template <int BLOCK_N>
 struct GemmNTConfig {
   static constexpr int kStageA = kBlockM * kBlockK * 4;
@@ -131,8 +272,8 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
   uint64_t* empty_bar = full_bar + NSTAGE;
   uint64_t* tmem_full_bar = empty_bar + NSTAGE;
-  uint64_t* aux_bar = tmem_full_bar + 1;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2);
+  uint64_t* aux_bar = tmem_full_bar + 1;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,8 +296,7 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
         ptx::mbar_init(&empty_bar[s], 1);
       }
       ptx::mbar_init(tmem_full_bar, 1);
-      ptx::mbar_init(&aux_bar[0], 1);
-      ptx::mbar_init(&aux_bar[1], 1);
+      for (int a = 0; a < 4; ++a) ptx::mbar_init(&aux_bar[a], 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -212,19 +352,28 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
     const bool row_ok = m < p.M;
     const bool leader = (warp == 2 && lane == 0);
     constexpr int NCHUNK = BLOCK_N / 32;
-    uint8_t* aux1_buf[2] = {smem + 0 * kTileBytes, smem + 1 * kTileBytes};
-    uint8_t* aux2_buf[2] = {smem + 2 * kTileBytes, smem + 3 * kTileBytes};
-    uint8_t* out_buf = smem + 4 * kTileBytes;
-    uint8_t* out2_buf = smem + 5 * kTileBytes;
-    constexpr uint32_t kAuxBytes = kTileBytes * ((kHasAux1 ? 1 : 0) + (kHasAux2 ? 1 : 0));
+    // The six 16 KB staging tiles alias the (drained) main-loop stages:
+    //   aux ring: NAUX slots of (aux1 [+ aux2]); out ring: NOUT tiles (+ NOUT for out2)
+    constexpr int kAuxSlot = (kHasAux1 ? kTileBytes : 0) + (kHasAux2 ? kTileBytes : 0);
+    constexpr int NAUX = !kHasAux1 ? 0 : (kHasAux2 ? 2 : 4);
+    constexpr int NOUT = (MODE == EPI_TANGENT) ? 1 : (kHasAux1 ? 2 : (kHasOut2 ? 3 : 6));
+    static_assert(NAUX * kAuxSlot + NOUT * kTileBytes * (kHasOut2 ? 2 : 1) <= kNumEpiStagingTiles * kTileBytes, "staging");
+    uint8_t* aux_base = smem;
+    uint8_t* out_base = smem + NAUX * kAuxSlot;
+    uint8_t* out2_base = out_base + NOUT * kTileBytes;
+    int nchunks = (p.N - n0 + 31) / 32;
+    if (nchunks > NCHUNK) nchunks = NCHUNK;
 
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
 
     if (kHasAux1 && leader) {
-      ptx::mbar_expect_tx(&aux_bar[0], kAuxBytes);
-      ptx::tma_load_2d(aux1_buf[0], &p.tmAux1, &aux_bar[0], n0, m0);
-      if (kHasAux2) ptx::tma_load_2d(aux2_buf[0], &p.tmAux2, &aux_bar[0], n0, m0);
+      for (int c = 0; c < NAUX && c < nchunks; ++c) {
+        ptx::mbar_expect_tx(&aux_bar[c], kAuxSlot);
+        ptx::tma_load_2d(aux_base + c * kAuxSlot, &p.tmAux1, &aux_bar[c], n0 + c * 32, m0);
+        if (kHasAux2)
+          ptx::tma_load_2d(aux_base + c * kAuxSlot + kTileBytes, &p.tmAux2, &aux_bar[c], n0 + c * 32, m0);
+      }
     }
     const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[m] : 0.0f;
     const float rw = (p.colsum_w != nullptr && row_ok) ? p.row_w[m] : 0.0f;
@@ -235,115 +384,44 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
 
 #pragma unroll 1
-    for (int c = 0; c < NCHUNK; ++c) {
+    for (int c = 0; c < nchunks; ++c) {
       const int nc = n0 + c * 32;
-      if (nc >= p.N) break;  // uniform across the CTA
-      if (leader) ptx::tma_store_wait_read<0>();
-      ptx::named_bar_sync(1, 128);
-      if (kHasAux1 && leader && (c + 1 < NCHUNK) && (nc + 32 < p.N)) {
-        const int b = (c + 1) & 1;
-        ptx::mbar_expect_tx(&aux_bar[b], kAuxBytes);
-        ptx::tma_load_2d(aux1_buf[b], &p.tmAux1, &aux_bar[b], nc + 32, m0);
-        if (kHasAux2) ptx::tma_load_2d(aux2_buf[b], &p.tmAux2, &aux_bar[b], nc + 32, m0);
-      }
       uint32_t accu[32];
       ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, accu);
-      if (kHasAux1) ptx::mbar_wait(&aux_bar[c & 1], (c >> 1) & 1);
+      const int a = NAUX > 0 ? c % (NAUX > 0 ? NAUX : 1) : 0;
+      if (kHasAux1) ptx::mbar_wait(&aux_bar[a], (c / (NAUX > 0 ? NAUX : 1)) & 1);
       ptx::tmem_ld_wait();
-
-      float v[32];  // becomes `out` in place
-      const uint8_t* a1 = aux1_buf[c & 1] + row_off;
-      const uint8_t* a2 = aux2_buf[c & 1] + row_off;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint32_t soff = static_cast<uint32_t>((q ^ swz) << 4);
-        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f), x2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kHasAux1) x1 = *reinterpret_cast<const float4*>(a1 + soff);
-        if (kHasAux2) x2 = *reinterpret_cast<const float4*>(a2 + soff);
-        const float aux1v[4] = {x1.x, x1.y, x1.z, x1.w};
-        const float aux2v[4] = {x2.x, x2.y, x2.z, x2.w};
-        float o[4], o2[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = nc + q * 4 + j;
-          const int colc = col < p.N ? col : p.N - 1;
-          float pre = p.alpha * __uint_as_float(accu[q * 4 + j]);
-          if (p.bias != nullptr) pre += __ldg(p.bias + colc);
-          if (gb_row != nullptr) pre += __ldg(gb_row + colc);
-          if (p.row_scale != nullptr) pre += rs * __ldg(p.col_vec + colc);
-          float res, res2 = 0.0f;
-          if (MODE == EPI_LINEAR) {
-            res = pre;
-          } else if (MODE == EPI_RELU) {
-            res = fmaxf(pre, 0.0f);
-          } else if (MODE == EPI_SOFTPLUS) {
-            res = softplus_f(pre);
-          } else if (MODE == EPI_MUL_STEP) {
-            res = aux1v[j] > 0.0f ? pre : 0.0f;
-          } else {
-            float s, oms;
-            sig_from_softplus(aux1v[j], s, oms);
-            if (MODE == EPI_MUL_SIG) {
-              res = pre * s;
-            } else if (MODE == EPI_TANGENT) {
-              res = pre * s;
-              res2 = aux2v[j] * pre * oms;
-            } else {  // EPI_ADJOINT
-              res = pre * s + aux2v[j];
-            }
-          }
-          if (SPLIT) {
-            const float hi = ptx::round_tf32(res);
-            res2 = ptx::round_tf32(res - hi);
-            res = hi;
-          } else if (p.round_out) {
-            res = ptx::round_tf32(res);
-            res2 = ptx::round_tf32(res2);
-          }
-          o[j] = res;
-          o2[j] = res2;
-          v[q * 4 + j] = (row_ok && col < p.N) ? res : 0.0f;
-        }
-        *reinterpret_cast<float4*>(out_buf + row_off + soff) = make_float4(o[0], o[1], o[2], o[3]);
-        if (kHasOut2)
-          *reinterpret_cast<float4*>(out2_buf + row_off + soff) =
-              make_float4(o2[0], o2[1], o2[2], o2[3]);
+      const uint8_t* slot = aux_base + a * kAuxSlot;
+      uint8_t* ob = out_base + (c % NOUT) * kTileBytes;
+      uint8_t* ob2 = out2_base + (c % NOUT) * kTileBytes;
+      if (NOUT == 1) {
+        // single staging tile: the previous store must have drained it before anyone writes
+        if (leader) ptx::tma_store_wait_read<0>();
+        ptx::named_bar_sync(1, 128);
       }
+      float v[32];  // `out` values of this thread's row (masked), for the column sums
+      if (!(p.debug_flags & 2))
+        epilogue_chunk<MODE, SPLIT>(p, accu, slot + row_off, slot + kTileBytes + row_off, ob + row_off,
+                                    ob2 + row_off, swz, nc, rs, gb_row, v);
       ptx::fence_proxy_async_smem();
+      // ring of NOUT >= 2 tiles: the tile chunk c+1 will write was last read by store(c+1-NOUT);
+      // the leader waits for it BEFORE the barrier, so passing the barrier publishes "free"
+      if (NOUT >= 2 && leader) ptx::tma_store_wait_read<(NOUT >= 2 ? NOUT - 2 : 0)>();
       ptx::named_bar_sync(2, 128);
       if (leader) {
-        ptx::tma_store_2d(&p.tmOut, out_buf, nc, m0);
-        if (kHasOut2) ptx::tma_store_2d(&p.tmOut2, out2_buf, nc, m0);
-        ptx::tma_store_commit();
-      }
-      if (p.colsum_w != nullptr) {
-        float w[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) w[i] = v[i] * rw;
-        const float t = warp_transpose_reduce32(w, lane);
-        if (nc + lane < p.N)
-          atomicAdd(p.colsum_w + static_cast<size_t>(nc + lane) * p.colsum_w_stride, t);
-      }
-      if (p.colsum != nullptr) {
-        const float t = warp_transpose_reduce32(v, lane);
-        if (nc + lane < p.N) atomicAdd(p.colsum + nc + lane, p.colsum_scale * t);
-      }
-      if (MODE == EPI_TANGENT && p.colsum2 != nullptr) {
-        // re-read this thread's own out2 row from the staging tile (still intact until the
-        // next chunk's barrier) instead of keeping 32 more registers live
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 t4 =
-              *reinterpret_cast<const float4*>(out2_buf + row_off + ((q ^ swz) << 4));
-          const bool ok = row_ok;
-          v[q * 4 + 0] = (ok && nc + q * 4 + 0 < p.N) ? t4.x : 0.0f;
-          v[q * 4 + 1] = (ok && nc + q * 4 + 1 < p.N) ? t4.y : 0.0f;
-          v[q * 4 + 2] = (ok && nc + q * 4 + 2 < p.N) ? t4.z : 0.0f;
-          v[q * 4 + 3] = (ok && nc + q * 4 + 3 < p.N) ? t4.w : 0.0f;
+        if (!(p.debug_flags & 1)) {
+          ptx::tma_store_2d(&p.tmOut, ob, nc, m0);
+          if (kHasOut2) ptx::tma_store_2d(&p.tmOut2, ob2, nc, m0);
         }
-        const float t = warp_transpose_reduce32(v, lane);
-        if (nc + lane < p.N) atomicAdd(p.colsum2 + nc + lane, t);
+        ptx::tma_store_commit();
+        if (kHasAux1 && c + NAUX < nchunks) {  // every thread is past its reads of slot a
+          ptx::mbar_expect_tx(&aux_bar[a], kAuxSlot);
+          ptx::tma_load_2d(aux_base + a * kAuxSlot, &p.tmAux1, &aux_bar[a], nc + NAUX * 32, m0);
+          if (kHasAux2)
+            ptx::tma_load_2d(aux_base + a * kAuxSlot + kTileBytes, &p.tmAux2, &aux_bar[a], nc + NAUX * 32, m0);
+        }
       }
+      epilogue_colsums<MODE>(p, v, ob2 + row_off, swz, nc, row_ok, rw, lane);
     }
     if (leader) ptx::tma_store_wait_all<0>();
   }
@@ -353,6 +431,232 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Persistent variant for the hot shape (N <= 256, many row tiles): one CTA per SM loops over row
+// tiles; the accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
+// overlaps the TMA/MMA main loop of tile i+1; aux tiles arrive through their own TMA ring fed by a
+// dedicated producer warp; out tiles are double-buffered and leave through TMA stores.
+// Warps: 0 = A/B TMA producer, 1 = MMA issuer + TMEM owner, 2 = aux TMA producer, 3 = idle,
+//        4..7 = epilogue (TMEM lane quarter = warp & 3).
+template <int MODE, bool SPLIT>
+struct GemmNTPersistConfig {
+  static constexpr bool kHasAux1 = MODE >= EPI_MUL_SIG;
+  static constexpr bool kHasAux2 = MODE >= EPI_TANGENT;
+  static constexpr bool kHasOut2 = (MODE == EPI_TANGENT) || SPLIT;
+  static constexpr int kBlockN = 256;
+  static constexpr int kStageA = kBlockM * kBlockK * 4;
+  static constexpr int kStageB = kBlockN * kBlockK * 4;
+  static constexpr int kStage = kStageA + kStageB;                       // 48 KB
+  static constexpr int kNumStages = 2;
+  static constexpr int kAuxSlotBytes = (kHasAux1 ? kTileBytes : 0) + (kHasAux2 ? kTileBytes : 0);
+  static constexpr int kNumAux = !kHasAux1 ? 0 : (kHasAux2 ? 2 : 4);
+  // ring of out staging tiles: as deep as the 224 KB budget allows, so several TMA stores stay in flight
+  static constexpr int kNumOut = (MODE == EPI_TANGENT) ? 2 : (kHasAux1 ? 4 : (kHasOut2 ? 4 : 8));
+  static constexpr int kOutBytes = kNumOut * kTileBytes * (kHasOut2 ? 2 : 1);
+  static constexpr int kOffAux = kNumStages * kStage;
+  static constexpr int kOffOut = kOffAux + kNumAux * kAuxSlotBytes;
+  static constexpr int kDataBytes = kOffOut + kOutBytes;
+  static constexpr int kSmemBytes = kDataBytes + 1024 + 512;
+  static constexpr int kThreads = 256;
+};
+
+template <int MODE, bool SPLIT>
+__global__ void __launch_bounds__(256, 1)
+gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
+  using Cfg = GemmNTPersistConfig<MODE, SPLIT>;
+  constexpr int NSTAGE = Cfg::kNumStages;
+  constexpr int NAUX = Cfg::kNumAux;
+  constexpr bool kHasAux1 = Cfg::kHasAux1, kHasAux2 = Cfg::kHasAux2, kHasOut2 = Cfg::kHasOut2;
+  constexpr int NCHUNK = 8;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tmem_full = empty_bar + NSTAGE;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint64_t* aux_full = tmem_empty + 2;       // [NAUX]
+  uint64_t* aux_empty = aux_full + (NAUX > 0 ? NAUX : 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + (NAUX > 0 ? NAUX : 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int num_tiles = (p.M + kBlockM - 1) / kBlockM;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB);
+    ptx::prefetch_tmap(&p.tmOut);
+    if (kHasAux1) ptx::prefetch_tmap(&p.tmAux1);
+    if (kHasAux2) ptx::prefetch_tmap(&p.tmAux2);
+    if (kHasOut2) ptx::prefetch_tmap(&p.tmOut2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSTAGE; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&tmem_full[b], 1);
+        ptx::mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
+      }
+      for (int a = 0; a < NAUX; ++a) {
+        ptx::mbar_init(&aux_full[a], 1);
+        ptx::mbar_init(&aux_empty[a], 4);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ A/B producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * kBlockM;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          ptx::mbar_expect_tx(&full_bar[s], Cfg::kStage);
+          uint8_t* sa = smem + s * Cfg::kStage;
+          int ka = kb * kBlockK;
+          if (p.a_k_wrap > 0) ka %= p.a_k_wrap;
+          ptx::tma_load_2d(sa, &p.tmA, &full_bar[s], ka, m0);
+          ptx::tma_load_2d(sa + Cfg::kStageA, &p.tmB, &full_bar[s], kb * kBlockK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, 256, 0, 0);
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        const uint32_t tph = (t >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[buf], tph ^ 1);  // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % NSTAGE;
+          const uint32_t ph = (it / NSTAGE) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * Cfg::kStage);
+          const uint32_t b_addr = a_addr + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * kUmmaK * 4, 0, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
+            ptx::umma_tf32(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+        }
+        ptx::umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ aux producer
+    if (kHasAux1 && lane == 0) {
+      int cc = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = tile * kBlockM;
+        for (int c = 0; c < NCHUNK; ++c) {
+          if (c * 32 >= p.N) break;
+          const int a = cc % NAUX;
+          const uint32_t ph = (cc / NAUX) & 1;
+          ptx::mbar_wait(&aux_empty[a], ph ^ 1);
+          ptx::mbar_expect_tx(&aux_full[a], Cfg::kAuxSlotBytes);
+          uint8_t* slot = smem + Cfg::kOffAux + a * Cfg::kAuxSlotBytes;
+          ptx::tma_load_2d(slot, &p.tmAux1, &aux_full[a], c * 32, m0);
+          if (kHasAux2) ptx::tma_load_2d(slot + kTileBytes, &p.tmAux2, &aux_full[a], c * 32, m0);
+          ++cc;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const bool leader = (warp == 4 && lane == 0);
+    const int swz = r & 7;
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    uint8_t* out_base = smem + Cfg::kOffOut;
+    int cc = 0, t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m0 = tile * kBlockM;
+      const int m = m0 + r;
+      const bool row_ok = m < p.M;
+      const int buf = t & 1;
+      const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[m] : 0.0f;
+      const float rw = (p.colsum_w != nullptr && row_ok) ? p.row_w[m] : 0.0f;
+      const float* gb_row = (p.group_bias != nullptr)
+                                ? p.group_bias + static_cast<size_t>((row_ok ? m : 0) / p.group) * p.ldg
+                                : nullptr;
+      ptx::mbar_wait(&tmem_full[buf], (t >> 1) & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int nc = c * 32;
+        if (nc >= p.N) break;
+        uint32_t accu[32];
+        ptx::tmem_ld_32x32(tmem_base + buf * 256 + (static_cast<uint32_t>(quarter * 32) << 16) + nc, accu);
+        const int a = kHasAux1 ? cc % NAUX : 0;
+        if (kHasAux1) ptx::mbar_wait(&aux_full[a], (cc / NAUX) & 1);
+        ptx::tmem_ld_wait();
+        const uint8_t* slot = smem + Cfg::kOffAux + a * Cfg::kAuxSlotBytes;
+        uint8_t* ob = out_base + (cc % Cfg::kNumOut) * kTileBytes;
+        uint8_t* ob2 = out_base + (Cfg::kNumOut + cc % Cfg::kNumOut) * kTileBytes;
+        float v[32];
+        epilogue_chunk<MODE, SPLIT>(p, accu, slot + row_off, slot + kTileBytes + row_off, ob + row_off,
+                                    ob2 + row_off, swz, nc, rs, gb_row, v);
+        if (kHasAux1) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&aux_empty[a]);  // this warp is done with the aux slot
+        }
+        if (c == NCHUNK - 1 || nc + 32 >= p.N) {
+          // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+        }
+        ptx::fence_proxy_async_smem();
+        // the store of chunk cc-1 must have finished READING its staging buffer before chunk cc+1
+        // overwrites it; waiting here (before the barrier) makes that visible to all 128 threads
+        if (leader) ptx::tma_store_wait_read<Cfg::kNumOut - 2>();
+        ptx::named_bar_sync(1, 128);
+        if (leader) {
+          ptx::tma_store_2d(&p.tmOut, ob, nc, m0);
+          if (kHasOut2) ptx::tma_store_2d(&p.tmOut2, ob2, nc, m0);
+          ptx::tma_store_commit();
+        }
+        epilogue_colsums<MODE>(p, v, ob2 + row_off, swz, nc, row_ok, rw, lane);
+        ++cc;
+      }
+    }
+    if (leader) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 

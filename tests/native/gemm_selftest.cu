@@ -72,6 +72,8 @@ static void report(const char* name, const Cmp& c) {
 }
 
 // mode-generic NT test
+static int g_persist = 0;
+static int g_split = 0;
 static void test_nt(const char* name, int M, int N, int K, int mode, int force_bn, bool use_bias,
                     bool use_group, bool use_rank1, bool use_colsum) {
   const int lda = (K + 3) / 4 * 4, ldb = lda, ldo = (N + 3) / 4 * 4;
@@ -94,6 +96,7 @@ static void test_nt(const char* name, int M, int N, int K, int mode, int force_b
   d.A = dA; d.lda = lda; d.B = dB; d.ldb = ldb; d.out = dout; d.ldo = ldo; d.out2 = dout2; d.ldo2 = ldo;
   d.aux1 = daux1; d.ld1 = ldo; d.aux2 = daux2; d.ld2 = ldo;
   d.M = M; d.N = N; d.K = K; d.mode = mode; d.alpha = 0.75f; d.round_out = 0; d.force_block_n = force_bn;
+  d.persist = g_persist; d.split_out = g_split;
   if (use_bias) d.bias = dbias;
   if (use_group) { d.group_bias = dgb; d.group = group; d.ldg = ldo; }
   if (use_rank1) { d.row_scale = drows; d.col_vec = dcolv; }
@@ -133,9 +136,13 @@ static void test_nt(const char* name, int M, int N, int K, int mode, int force_b
         case EPI_ADJOINT: r1 = pre * s + a2; break;
       }
       double tol = 2e-5 * (mag + std::fabs(pre) + 1.0) * (1.0 + std::fabs(a2));
-      c1.add(out[(size_t)m * ldo + n], r1, tol);
+      if (g_split) {  // out = tf32 hi, out2 = lo: their sum reproduces the fp32 result
+        c1.add((double)out[(size_t)m * ldo + n] + out2[(size_t)m * ldo + n], r1, tol);
+      } else {
+        c1.add(out[(size_t)m * ldo + n], r1, tol);
+      }
       if (mode == EPI_TANGENT) c2.add(out2[(size_t)m * ldo + n], r2, tol);
-      rcs[n] += r1; rcsw[n] += r1 * roww[m];
+      rcs[n] += g_split ? (double)out[(size_t)m * ldo + n] : r1; rcsw[n] += (g_split ? (double)out[(size_t)m * ldo + n] : r1) * roww[m];
     }
   char buf[128];
   snprintf(buf, sizeof(buf), "%s out", name); report(buf, c1);
@@ -201,7 +208,8 @@ static void test_tn(const char* name, int M, int N, int K, bool two) {
   cudaFree(dX0); cudaFree(dY0); cudaFree(dX1); cudaFree(dY1); cudaFree(dO); cudaFree(ws);
 }
 
-static void bench_nt(int M, int N, int K, int mode) {
+static int g_dbg = 0;
+static void bench_nt(int M, int N, int K, int mode, int persist = 0, int split = 0) {
   float *A, *B, *O, *O2, *X1, *X2;
   CK(cudaMalloc(&A, (size_t)M * K * 4)); CK(cudaMalloc(&B, (size_t)N * K * 4));
   CK(cudaMalloc(&O, (size_t)M * N * 4)); CK(cudaMalloc(&O2, (size_t)M * N * 4));
@@ -211,6 +219,7 @@ static void bench_nt(int M, int N, int K, int mode) {
   GemmNTDesc d;
   d.A = A; d.lda = K; d.B = B; d.ldb = K; d.out = O; d.ldo = N; d.out2 = O2; d.ldo2 = N;
   d.aux1 = X1; d.ld1 = N; d.aux2 = X2; d.ld2 = N; d.M = M; d.N = N; d.K = K; d.mode = mode;
+  d.persist = persist; d.split_out = split; d.debug_flags = g_dbg;
   PreparedNT pr;
   if (prepare_gemm_nt(d, &pr)) { printf("bench prepare failed: %s\n", last_error_string().c_str()); return; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -222,7 +231,7 @@ static void bench_nt(int M, int N, int K, int mode) {
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
   int narr = 2 + (mode >= EPI_MUL_SIG) + (mode >= EPI_TANGENT) + (mode == EPI_TANGENT);
   double bytes = (double)M * K * 4 + (double)(narr - 1) * M * N * 4;
-  printf("bench NT M=%d N=%d K=%d mode=%d: %.1f us  %.1f TFLOP/s  %.0f GB/s (%d arrays)\n", M, N, K, mode,
+  printf("bench NT%s M=%d N=%d K=%d mode=%d: %.1f us  %.1f TFLOP/s  %.0f GB/s (%d arrays)\n", persist > 0 ? "(persist)" : "", M, N, K, mode,
          ms * 1e3, 2.0 * M * N * K / ms * 1e-9, bytes / ms * 1e-6, narr);
   cudaFree(A); cudaFree(B); cudaFree(O); cudaFree(O2); cudaFree(X1); cudaFree(X2);
 }
@@ -256,6 +265,17 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 1 && !strcmp(argv[1], "dbg")) {
+    for (int dbg : {0, 1, 2, 3}) {
+      g_dbg = dbg;
+      printf("debug_flags=%d\n", dbg);
+      bench_nt(131072, 256, 32, EPI_SOFTPLUS, -1);
+      bench_nt(131072, 256, 256, EPI_LINEAR, -1);
+      bench_nt(131072, 256, 256, EPI_MUL_SIG, -1);
+      bench_nt(131072, 256, 256, EPI_TANGENT, -1);
+    }
+    return 0;
+  }
   test_nt("NT linear 128x32x32 bn32", 128, 32, 32, EPI_LINEAR, 32, false, false, false, false);
   test_nt("NT linear 128x256x256", 128, 256, 256, EPI_LINEAR, 0, false, false, false, false);
   test_nt("NT linear 256x256x64 bn128", 256, 256, 64, EPI_LINEAR, 128, false, false, false, false);
@@ -271,11 +291,29 @@ int main(int argc, char** argv) {
     test_nt("NT adjoint 384x256x256", 384, 256, 256, EPI_ADJOINT, 0, false, false, false, true);
     test_nt("NT adjoint ragged 100x40x8", 100, 40, 8, EPI_ADJOINT, 0, true, false, false, true);
     test_nt("NT linear K=4 (tiny) 256x256x4", 256, 256, 4, EPI_LINEAR, 0, true, false, true, false);
+    g_persist = 1;
+    test_nt("P NT linear 1000x256x256", 1000, 256, 256, EPI_LINEAR, 0, true, false, false, true);
+    test_nt("P NT softplus grp+rank1 20000x256x64", 20000, 256, 64, EPI_SOFTPLUS, 0, true, true, true, true);
+    test_nt("P NT mul_sig 20000x256x256", 20000, 256, 256, EPI_MUL_SIG, 0, false, false, false, true);
+    test_nt("P NT mul_step 3000x200x96", 3000, 200, 96, EPI_MUL_STEP, 0, false, false, false, true);
+    test_nt("P NT tangent 20000x256x256", 20000, 256, 256, EPI_TANGENT, 0, false, false, false, true);
+    test_nt("P NT adjoint 20000x256x256", 20000, 256, 256, EPI_ADJOINT, 0, true, false, false, true);
+    test_nt("P NT adjoint ragged 20001x200x40", 20001, 200, 40, EPI_ADJOINT, 0, false, false, false, true);
+    g_split = 1;
+    test_nt("P NT softplus split 20000x256x256", 20000, 256, 256, EPI_SOFTPLUS, 0, true, false, false, true);
+    g_persist = -1;
+    test_nt("NT softplus split 500x256x256", 500, 256, 256, EPI_SOFTPLUS, 0, true, false, false, true);
+    g_split = 0; g_persist = 0;
     test_tn("TN two pairs 256x256 K=4096", 256, 256, 4096, true);
     test_tn("TN ragged 300x100 K=500", 300, 100, 500, true);
     test_tn("TN 256x36 K=2048", 256, 36, 2048, false);
     test_tn("TN 784x300 K=512", 784, 300, 512, false);
-    for (int mode : {EPI_LINEAR, EPI_SOFTPLUS, EPI_MUL_SIG, EPI_TANGENT, EPI_ADJOINT}) bench_nt(131072, 256, 256, mode);
+    for (int mode : {EPI_LINEAR, EPI_SOFTPLUS, EPI_MUL_SIG, EPI_TANGENT, EPI_ADJOINT}) {
+      bench_nt(131072, 256, 256, mode, -1);
+      bench_nt(131072, 256, 256, mode, 1);
+    }
+    bench_nt(131072, 256, 768, EPI_SOFTPLUS, -1, 1);
+    bench_nt(131072, 256, 768, EPI_SOFTPLUS, 1, 1);
     bench_nt(131072, 256, 32, EPI_SOFTPLUS);
     bench_nt(131072, 32, 256, EPI_LINEAR);
     bench_tn(256, 256, 131072, false);
