@@ -232,11 +232,11 @@ class ImplicitPosteriorVAE(nn.Module):
             self._plans[key] = (h, ws)
         return key
 
-    def _encode(self, x, noise, nz):
+    def _encode(self, x, noise, nz, slot=0):
         B = x.size(0)
         xf = _lib.require_cuda(x.detach(), 'input').view(B, self.input_dim)
         nf = None if noise is None else _lib.require_cuda(noise.detach(), 'noise')
-        key = self._plan(B, nz, 0)
+        key = self._plan(B, nz, 0, slot)
         z = torch.empty(B * nz, self.z_dim, dtype=torch.float32, device=xf.device)
         _lib.check(_lib.lib().ardae_model_encode(self._plans[key][0], _lib.ptr(xf), _lib.ptr(nf), _lib.ptr(z),
                                                  _lib.stream_ptr()))

@@ -42,6 +42,8 @@ class TrainStep(object):
         self.launches = 0
         self.last_std = None
         self.profile = None  # set to a list to collect (name, start_event, end_event) per segment
+        self.overlap = True
+        self._side = None
 
     class _Seg(object):
         def __init__(self, owner, name):
@@ -66,7 +68,8 @@ class TrainStep(object):
         L = _lib.lib()
         m, c = self.model, self.cdae
         n = 0
-        n += 2 * L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0)][0], 0)        # zbar (x2 minibatches)
+        n += L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0)][0], 0)            # zbar (cdae minibatch)
+        n += L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0, 1)][0], 0)         # zbar (model minibatch)
         n += L.ardae_model_num_launches(m._plans[m._plan(B, self.nz, 0)][0], 0)      # z samples
         n += L.ardae_cdae_num_launches(c._plan(B, self.nz * self.nstd, True))
         n += L.ardae_cdae_num_launches(c._plan(B, self.nzm, False))
@@ -131,16 +134,18 @@ class TrainStep(object):
         self.last_std = std
         return loss
 
-    def model_update(self, x, beta, noise=None):
+    def model_forward(self, x, beta, noise=None):
+        """Everything of the model update that does not depend on the CDAE update of this iteration:
+        ELBO forward (:801), zbar = encode(x, std=0) (:813,:826) and S*(z - zbar) (:827)."""
         L = _lib.lib()
-        m, c = self.model, self.cdae
+        m = self.model
         B = x.size(0)
         d, n = m.z_dim, m.noise_dim
         dev = x.device
         xs = _lib.require_cuda(x, 'x').view(B, -1)
         R = B * self.nzm
         enc = noise['enc_model'] if noise is not None else self._randn(R, n, dev)
-        ar = m._ensure()
+        m._ensure()
         key = m._plan(B, self.nzm, 1)
         hm = m._plans[key][0]
         z = torch.empty(R, d, dtype=torch.float32, device=dev)
@@ -150,34 +155,63 @@ class TrainStep(object):
             _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),
                                              ctypes.c_float(inv_rows), _lib.ptr(z), _lib.ptr(sums), None,
                                              _lib.stream_ptr()))                        # :801
-        zbar = m._encode(xs, None, 1)                                                    # :813,:826
-        xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
-        _lib.check(L.ardae_scaled_diff(_lib.ptr(z), _lib.ptr(zbar), R, self.nzm, d, ctypes.c_float(self.S),
-                                       _lib.ptr(xsd), _lib.stream_ptr()))               # :827
+            zbar = m._encode(xs, None, 1, slot=1)                                        # :813,:826
+            xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
+            _lib.check(L.ardae_scaled_diff(_lib.ptr(z), _lib.ptr(zbar), R, self.nzm, d, ctypes.c_float(self.S),
+                                           _lib.ptr(xsd), _lib.stream_ptr()))           # :827
+        return dict(hm=hm, z=z, sums=sums, zbar=zbar, xsd=xsd, inv_rows=inv_rows, B=B, R=R, enc=enc, xs=xs)
+
+    def model_backward(self, f, beta):
+        """Entropy-gradient estimate with the UPDATED cdae (:829), one backward for :804 + :834, Adam (:846)."""
+        L = _lib.lib()
+        m, c = self.model, self.cdae
+        d = m.z_dim
+        dev = f['z'].device
+        ar = m._ensure()
         c._ensure()
-        hs = c._plan(B, self.nzm, False)
-        zero_sigma = torch.zeros(R, dtype=torch.float32, device=dev)
-        g = torch.empty(R, d, dtype=torch.float32, device=dev)
-        _lib.check(L.ardae_cdae_score(hs, _lib.ptr(xsd), _lib.ptr(zbar), _lib.ptr(zero_sigma), _lib.ptr(g),
-                                      _lib.stream_ptr()))                               # :829
+        hs = c._plan(f['B'], self.nzm, False)
+        zero_sigma = torch.zeros(f['R'], dtype=torch.float32, device=dev)
+        g = torch.empty(f['R'], d, dtype=torch.float32, device=dev)
+        with self._seg('score'):
+            _lib.check(L.ardae_cdae_score(hs, _lib.ptr(f['xsd']), _lib.ptr(f['zbar']), _lib.ptr(zero_sigma),
+                                          _lib.ptr(g), _lib.stream_ptr()))              # :829
         ar.stage_flat.zero_()
-        gz_scale = self.S * beta * inv_rows                                              # :834
+        gz_scale = self.S * beta * f['inv_rows']                                         # :834
         with self._seg('model_bwd'):
-            _lib.check(L.ardae_model_backward(hm, ctypes.c_float(1.0), _lib.ptr(g), ctypes.c_float(gz_scale),
+            _lib.check(L.ardae_model_backward(f['hm'], ctypes.c_float(1.0), _lib.ptr(g), ctypes.c_float(gz_scale),
                                               _lib.stream_ptr()))                       # :804 + :834
         with self._seg('model_allreduce'):
             self._allreduce(ar.stage_flat)
         with self._seg('model_opt'):
             self.mopt.step_flat(ar.stage_flat)                                           # :846
-        return sums, g, z
+        return f['sums'], g, f['z']
+
+    def model_update(self, x, beta, noise=None):
+        return self.model_backward(self.model_forward(x, beta, noise), beta)
 
     def __call__(self, x_cdae, x_model, beta=1.0, noise=None):
         """One iteration.  x_cdae: the minibatch (or list of num_cdae_updates minibatches) for the CDAE
         update(s); x_model: the minibatch of the model update.  Returns device tensors (no sync)."""
         xs = x_cdae if isinstance(x_cdae, (list, tuple)) else [x_cdae] * self.ncu
         closs = None
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            # the ELBO forward of the model update does not depend on this iteration's CDAE update:
+            # run its (latency-bound, B-row) kernels on a side stream underneath the CDAE sweeps
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                fwd = self.model_forward(x_model, beta, noise)
+                for k in ('z', 'sums', 'zbar', 'xsd', 'enc'):
+                    if torch.is_tensor(fwd[k]):
+                        fwd[k].record_stream(main)
         for i in range(self.ncu):
             closs = self.cdae_update(xs[i], noise)
-        sums, g, z = self.model_update(x_model, beta, noise)
+        if self.overlap:
+            main.wait_stream(self._side)
+        else:
+            fwd = self.model_forward(x_model, beta, noise)
+        sums, g, z = self.model_backward(fwd, beta)
         return dict(cdae_loss=closs, model_loss=sums[0:1], recon=sums[1:2], prior=sums[2:3], std=self.last_std,
                     entropy_grad=g, z_model=z)

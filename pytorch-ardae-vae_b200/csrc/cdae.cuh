@@ -204,7 +204,7 @@ struct CdaePlan {
     {
       const Mat vl = V[L - 1].hi(), dpl = DP[L - 1];
       plan.add([=](cudaStream_t s) {
-        cdae_init_delta_kernel<<<grid_for(static_cast<size_t>(N) * H), 256, 0, s>>>(vl.p, vl.ld, wo, dpl.p, dpl.ld, N, H);
+        cdae_init_delta_kernel<<<grid_for(static_cast<size_t>(N) * H / 4), 256, 0, s>>>(vl.p, vl.ld, wo, dpl.p, dpl.ld, N, H);
         return static_cast<int>(cudaGetLastError());
       });
     }
