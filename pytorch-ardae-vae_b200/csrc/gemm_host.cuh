@@ -95,6 +95,8 @@ struct GemmNTDesc {
   int a_k_wrap = 0;
   int force_block_n = 0;
   int persist = 0;     // 0 auto, 1 force the persistent kernel, -1 force the tile-per-CTA kernel
+  int deep = 0;        // 0 auto (small grids), 1 force the deep-pipeline narrow-tile variant, -1 off
+  int multicast = 0;   // 0 auto (2-CTA weight multicast for 256-wide tiles with >= 2 row tiles), 1 on, -1 off
   int debug_flags = 0;
 };
 
@@ -139,26 +141,27 @@ struct PreparedNT {
   dim3 grid;
   int smem = 0;
   int threads = kGemmThreads;
+  int cluster = 1;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool MC, bool DEEP = false>
 inline const void* nt_kernel_for_mode(int mode, int split) {
   if (split) {
     switch (mode) {
-      case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, true>);
-      case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, true>);
-      case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, true>);
+      case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, true, MC, DEEP>);
+      case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, true, MC, DEEP>);
+      case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, true, MC, DEEP>);
       default: return nullptr;
     }
   }
   switch (mode) {
-    case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, false>);
-    case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, false>);
-    case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, false>);
-    case EPI_MUL_SIG: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_SIG, false>);
-    case EPI_MUL_STEP: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_STEP, false>);
-    case EPI_TANGENT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_TANGENT, false>);
-    case EPI_ADJOINT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_ADJOINT, false>);
+    case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, false, MC, DEEP>);
+    case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, false, MC, DEEP>);
+    case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, false, MC, DEEP>);
+    case EPI_MUL_SIG: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_SIG, false, MC, DEEP>);
+    case EPI_MUL_STEP: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_STEP, false, MC, DEEP>);
+    case EPI_TANGENT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_TANGENT, false, MC, DEEP>);
+    case EPI_ADJOINT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_ADJOINT, false, MC, DEEP>);
     default: return nullptr;
   }
 }
@@ -181,7 +184,15 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   if (!d.A || !d.B || !d.out || (has_aux1 && !d.aux1) || (has_aux2 && !d.aux2) ||
       (has_out2 && !d.out2))
     return fail(-2, "gemm_nt: missing operand pointer");
-  const int bn = d.force_block_n ? d.force_block_n : pick_block_n(d.N);
+  int bn = d.force_block_n ? d.force_block_n : pick_block_n(d.N);
+  // small grids (B-row chains) are latency bound: narrow tiles + deep TMA pipeline
+  const int tiles_m_pre = (d.M + kBlockM - 1) / kBlockM;
+  bool deep = false;
+  if (!d.force_block_n && d.persist <= 0 && d.deep >= 0 &&
+      (d.deep > 0 || tiles_m_pre * ((d.N + bn - 1) / bn) * 4 <= num_sms())) {
+    bn = d.N <= 32 ? 32 : 64;
+    deep = true;
+  }
   PreparedNT pr;
   std::memset(&pr.params, 0, sizeof(pr.params));
   GemmNTParams& p = pr.params;
@@ -189,7 +200,11 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   const uint64_t a_inner = d.a_k_wrap > 0 ? d.a_k_wrap : d.K;
   if (d.a_k_wrap > 0 && d.a_k_wrap % kBlockK != 0) return fail(-2, "gemm_nt: a_k_wrap must be a multiple of 32");
   if ((rc = encode_tmap_2d(&p.tmA, d.A, a_inner, d.M, d.lda, kBlockK, kBlockM))) return rc;
-  if ((rc = encode_tmap_2d(&p.tmB, d.B, d.K, d.N, d.ldb, kBlockK, bn))) return rc;
+  const int tiles_m0 = (d.M + kBlockM - 1) / kBlockM;
+  // measured (gemm_selftest): weight multicast does not pay at 2 CTAs/SM (the main loop is bound by
+  // bytes-in-flight x TMA latency, not by L2 bandwidth) -> opt-in only
+  const bool mc = d.persist <= 0 && bn == 256 && d.multicast > 0;
+  if ((rc = encode_tmap_2d(&p.tmB, d.B, d.K, d.N, d.ldb, kBlockK, mc ? bn / 2 : bn))) return rc;
   if ((rc = encode_tmap_2d(&p.tmOut, d.out, d.N, d.M, d.ldo, 32, kBlockM))) return rc;
   if (has_out2 && (rc = encode_tmap_2d(&p.tmOut2, d.out2, d.N, d.M, d.ldo2, 32, kBlockM))) return rc;
   if (has_aux1 && (rc = encode_tmap_2d(&p.tmAux1, d.aux1, d.N, d.M, d.ld1, 32, kBlockM))) return rc;
@@ -205,13 +220,26 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   if (p.row_scale && !p.col_vec) return fail(-2, "gemm_nt: row_scale without col_vec");
   if (p.colsum_w && !p.row_w) return fail(-2, "gemm_nt: colsum_w without row_w");
   switch (bn) {
-    case 32: pr.fn = nt_kernel_for_mode<32>(d.mode, d.split_out); pr.smem = GemmNTConfig<32>::kSmemBytes; break;
-    case 64: pr.fn = nt_kernel_for_mode<64>(d.mode, d.split_out); pr.smem = GemmNTConfig<64>::kSmemBytes; break;
-    case 128: pr.fn = nt_kernel_for_mode<128>(d.mode, d.split_out); pr.smem = GemmNTConfig<128>::kSmemBytes; break;
-    case 256: pr.fn = nt_kernel_for_mode<256>(d.mode, d.split_out); pr.smem = GemmNTConfig<256>::kSmemBytes; break;
+    case 32:
+      if (deep) { pr.fn = nt_kernel_for_mode<32, false, true>(d.mode, d.split_out); pr.smem = GemmNTConfig<32, true>::kSmemBytes; }
+      else { pr.fn = nt_kernel_for_mode<32, false>(d.mode, d.split_out); pr.smem = GemmNTConfig<32>::kSmemBytes; }
+      break;
+    case 64:
+      if (deep) { pr.fn = nt_kernel_for_mode<64, false, true>(d.mode, d.split_out); pr.smem = GemmNTConfig<64, true>::kSmemBytes; }
+      else { pr.fn = nt_kernel_for_mode<64, false>(d.mode, d.split_out); pr.smem = GemmNTConfig<64>::kSmemBytes; }
+      break;
+    case 128: pr.fn = nt_kernel_for_mode<128, false>(d.mode, d.split_out); pr.smem = GemmNTConfig<128>::kSmemBytes; break;
+    case 256:
+      pr.fn = mc ? nt_kernel_for_mode<256, true>(d.mode, d.split_out) : nt_kernel_for_mode<256, false>(d.mode, d.split_out);
+      pr.smem = GemmNTConfig<256>::kSmemBytes;
+      break;
     default: return fail(-2, "gemm_nt: bad BLOCK_N");
   }
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, 1);
+  if (mc) {
+    pr.cluster = 2;
+    pr.grid.x = (pr.grid.x + 1) / 2 * 2;  // an odd tail CTA works on an out-of-range tile (TMA clips)
+  }
   const int tiles_m = (d.M + kBlockM - 1) / kBlockM;
   // measured on B200 (tests/native/gemm_selftest): with the lean epilogue the tile-per-CTA kernel at
   // 2 CTAs/SM is on par with the persistent one, so the persistent kernel is opt-in
@@ -232,6 +260,17 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
 
 inline int launch_prepared_nt(const PreparedNT& pr, cudaStream_t stream) {
   void* args[1] = {const_cast<GemmNTParams*>(&pr.params)};
+  if (pr.cluster > 1) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pr.grid; cfg.blockDim = dim3(pr.threads); cfg.dynamicSmemBytes = pr.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pr.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ARDAE_CUDA_OK(cudaLaunchKernelExC(&cfg, pr.fn, args));
+    return 0;
+  }
   ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(pr.threads), args, pr.smem, stream));
   return 0;
 }

@@ -238,12 +238,15 @@ __device__ __forceinline__ void epilogue_colsums(const GemmNTParams& p, float (&
   }
 }
 
-template <int BLOCK_N>
+// DEEP: latency-optimised variant for grids that cannot fill the GPU (the B-row chains: context
+// branch, encode(std=0), score, model forward/backward).  Narrow tiles (more CTAs, 1-2 epilogue chunks)
+// and 8 TMA stages so the whole K loop of an L2-resident problem is in flight at once; one CTA per SM.
+template <int BLOCK_N, bool DEEP = false>
 struct GemmNTConfig {
   static constexpr int kStageA = kBlockM * kBlockK * 4;
   static constexpr int kStageB = BLOCK_N * kBlockK * 4;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kNumStages = (BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4);
+  static constexpr int kNumStages = DEEP ? 8 : ((BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4));
   static constexpr int kPipeBytes = kStage * kNumStages;
   static constexpr int kEpiBytes = kNumEpiStagingTiles * kTileBytes;
   static constexpr int kDataBytes = kPipeBytes > kEpiBytes ? kPipeBytes : kEpiBytes;
@@ -255,10 +258,13 @@ struct GemmNTConfig {
 //   out = hi = rna(res), out2 = lo = rna(res - hi)
 // so that a following "3xTF32" GEMM (A' = [hi | lo | hi] via a_k_wrap, B' = [W_hi | W_hi | W_lo])
 // reproduces an fp32-accurate product on the tf32 tensor pipe.
-template <int BLOCK_N, int MODE, bool SPLIT>
+// MC: launched as clusters of 2 CTAs (adjacent row tiles).  Each CTA fetches half of every weight
+// (B) k-block and TMA-multicasts it to both, halving the L2->SM weight traffic that bounds the
+// 3xTF32 forward sweep (768 KB of weights per 128-row tile otherwise).
+template <int BLOCK_N, int MODE, bool SPLIT, bool MC, bool DEEP = false>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
-  using Cfg = GemmNTConfig<BLOCK_N>;
+  using Cfg = GemmNTConfig<BLOCK_N, DEEP>;
   constexpr int NSTAGE = Cfg::kNumStages;
   constexpr bool kHasAux1 = MODE >= EPI_MUL_SIG;
   constexpr bool kHasAux2 = MODE >= EPI_TANGENT;
@@ -293,7 +299,7 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
     if (lane == 0) {
       for (int s = 0; s < NSTAGE; ++s) {
         ptx::mbar_init(&full_bar[s], 1);
-        ptx::mbar_init(&empty_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: both CTAs' MMAs release a stage
       }
       ptx::mbar_init(tmem_full_bar, 1);
       for (int a = 0; a < 4; ++a) ptx::mbar_init(&aux_bar[a], 1);
@@ -305,12 +311,14 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      const uint32_t rank = MC ? ptx::cluster_ctarank() : 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % NSTAGE;
         const uint32_t ph = (kb / NSTAGE) & 1;
@@ -320,7 +328,14 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
         int ka = kb * kBlockK;
         if (p.a_k_wrap > 0) ka %= p.a_k_wrap;
         ptx::tma_load_2d(sa, &p.tmA, &full_bar[s], ka, m0);
-        ptx::tma_load_2d(sa + Cfg::kStageA, &p.tmB, &full_bar[s], kb * kBlockK, n0);
+        if (MC) {
+          // this CTA's half of the weight k-block (box = BLOCK_N/2 rows), delivered to both CTAs
+          constexpr int kHalfRows = BLOCK_N / 2;
+          ptx::tma_load_2d_mc(sa + Cfg::kStageA + rank * (kHalfRows * kBlockK * 4), &p.tmB, &full_bar[s],
+                              kb * kBlockK, n0 + static_cast<int>(rank) * kHalfRows, 0x3);
+        } else {
+          ptx::tma_load_2d(sa + Cfg::kStageA, &p.tmB, &full_bar[s], kb * kBlockK, n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -340,7 +355,10 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
           const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
           ptx::umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        if (MC)
+          ptx::umma_commit_mc(&empty_bar[s], 0x3);  // frees this stage in BOTH CTAs' bookkeeping
+        else
+          ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
       }
       ptx::umma_commit(tmem_full_bar);  // accumulator complete (and every stage drained)
     }
@@ -428,6 +446,7 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
