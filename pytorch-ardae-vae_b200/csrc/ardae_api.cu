@@ -57,7 +57,7 @@ ARDAE_API int ardae_cdae_create(const ardae_cdae_config* cfg, float* const* para
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(-11, "workspace must be 256-byte aligned");
   for (int i = 0; i < num_tensors; ++i)
     if (reinterpret_cast<uintptr_t>(params[i]) & 15) return fail(-11, "parameter tensors must be 16-byte aligned");
-  h->p.plan = Plan();
+  h->p.plan.reset();
   h->p.ws = Workspace();
   h->p.ws.dry = false;
   h->p.ws.base = static_cast<uint8_t*>(workspace);
@@ -123,7 +123,7 @@ ARDAE_API int ardae_model_create(const ardae_model_config* cfg, float* const* pa
   if (rc) return rc;
   if (h->p.ws.off + 256 > workspace_bytes) return fail(-3, "model: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(-11, "workspace must be 256-byte aligned");
-  h->p.fwd = Plan(); h->p.bwd_dec = Plan(); h->p.bwd_enc = Plan();
+  h->p.fwd.reset(); h->p.bwd_dec.reset(); h->p.bwd_enc.reset();
   h->p.ws = Workspace();
   h->p.ws.dry = false;
   h->p.ws.base = static_cast<uint8_t*>(workspace);

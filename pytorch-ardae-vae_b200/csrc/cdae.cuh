@@ -137,6 +137,8 @@ struct CdaePlan {
     Mat rmat, gsum;
     float* tn_ws = nullptr;
     size_t tn_ws_bytes = 0;
+    float* ctx_tn_ws = nullptr;
+    size_t ctx_tn_bytes = 0;
     if (train) {
       rmat = ws.mat(N, d);
       gsum = ws.mat(B, H);
@@ -155,8 +157,23 @@ struct CdaePlan {
       }
       tn_ws_bytes = tn_need;
       tn_ws = ws.floats(tn_ws_bytes / 4);
+      ctx_tn_bytes = tn_workspace_bytes(H, H, B);
+      const size_t b2 = tn_workspace_bytes(H, c, B);
+      if (b2 > ctx_tn_bytes) ctx_tn_bytes = b2;
+      ctx_tn_ws = ws.floats(ctx_tn_bytes / 4);
     }
     CdaeBindings* bd = &bind;
+    auto tn2 = [&](const Mat& X0, const Mat& Y0, const Mat* X1, const Mat* Y1, float* dst, int ldo) {
+      GemmTNDesc t;
+      t.X0 = X0.p; t.ldx0 = X0.ld; t.Y0 = Y0.p; t.ldy0 = Y0.ld;
+      if (X1) { t.X1 = X1->p; t.ldx1 = X1->ld; t.Y1 = Y1->p; t.ldy1 = Y1->ld; }
+      t.M = X0.cols; t.N = Y0.cols; t.K = X0.rows; t.out = dst; t.ldo = ldo;
+      t.scale = 1.0f; t.beta = 1.0f;
+      // the side lane (context branch) has its own split-K scratch: both lanes run concurrently
+      t.workspace = plan.cur_lane == 1 ? ctx_tn_ws : tn_ws;
+      t.workspace_bytes = plan.cur_lane == 1 ? ctx_tn_bytes : tn_ws_bytes;
+      plan.tn(t);
+    };
 
     // ---- prologue: sigma copy, x~ = x + sigma*eps (tf32 pair), context pair, exact w_sigma
     {
@@ -172,7 +189,9 @@ struct CdaePlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
-    // ---- context branch on the B distinct rows (reference runs it on all N: graddae/mlp.py:415,426)
+    // ---- context branch on the B distinct rows (reference runs it on all N: graddae/mlp.py:415,426);
+    //      independent of the N-row input branch until layer p_1: side lane
+    plan.fork();
     for (int l = 0; l < L; ++l) {
       GemmNTDesc g = nt3_desc(l == 0 ? ctxp : Cc[l - 1], Cw[l], Cc[l], EPI_SOFTPLUS);
       g.bias = P(iC(l) + 1);
@@ -183,12 +202,14 @@ struct CdaePlan {
       g.bias = P(iW(0) + 1);
       plan.nt(g);
     }
+    plan.cur_lane = 0;  // (still forked: joined right before p_1 needs the per-row bias)
     // ---- sweep 1: primal forward (3xTF32)
     for (int l = 0; l < L; ++l) {
       GemmNTDesc g = nt3_desc(l == 0 ? xt : U[l - 1], Aw[l], U[l], EPI_SOFTPLUS);
       g.bias = P(iA(l) + 1);
       plan.nt(g);
     }
+    plan.join();
     {
       GemmNTDesc g = nt3_desc(U[L - 1], W1u, V[0], EPI_SOFTPLUS);
       g.group_bias = rowbias.p; g.group = S; g.ldg = rowbias.ld;
@@ -268,41 +289,9 @@ struct CdaePlan {
       }
       plan.nt(g);
     }
-    {
-      GemmNTDesc g = nt_desc(TP[0], W1u.T, TA[L - 1], EPI_ADJOINT);
-      set_aux1(g, U[L - 1].hi()); set_aux2(g, TA[L - 1]);
-      g.colsum = G(iA(L - 1) + 1);
-      plan.nt(g);
-    }
-    for (int l = L - 1; l >= 1; --l) {
-      GemmNTDesc g = nt_desc(TA[l], Aw[l].T, TA[l - 1], EPI_ADJOINT);
-      set_aux1(g, U[l - 1].hi()); set_aux2(g, TA[l - 1]);
-      g.colsum = G(iA(l - 1) + 1);
-      plan.nt(g);
-    }
-    // ---- weight gradients: dW = adj^T . act + delta^T . tangent   (accumulated into .grad)
-    auto tn2 = [&](const Mat& X0, const Mat& Y0, const Mat* X1, const Mat* Y1, float* dst, int ldo) {
-      GemmTNDesc t;
-      t.X0 = X0.p; t.ldx0 = X0.ld; t.Y0 = Y0.p; t.ldy0 = Y0.ld;
-      if (X1) { t.X1 = X1->p; t.ldx1 = X1->ld; t.Y1 = Y1->p; t.ldy1 = Y1->ld; }
-      t.M = X0.cols; t.N = Y0.cols; t.K = X0.rows; t.out = dst; t.ldo = ldo;
-      t.scale = 1.0f; t.beta = 1.0f; t.workspace = tn_ws; t.workspace_bytes = tn_ws_bytes;
-      plan.tn(t);
-    };
-    const Mat xt_hi = xt.hi();
-    for (int l = L - 1; l >= 1; --l) {
-      const Mat y = V[l - 1].hi();
-      tn2(TP[l], y, &DP[l], &VD[l - 1], G(iW(l)), H);
-    }
-    {
-      const Mat y = U[L - 1].hi();
-      tn2(TP[0], y, &DP[0], &UD[L - 1], G(iW(0)), ld1);
-    }
-    for (int l = L - 1; l >= 1; --l) {
-      const Mat y = U[l - 1].hi();
-      tn2(TA[l], y, &DA[l], &UD[l - 1], G(iA(l)), H);
-    }
-    tn2(TA[0], xt_hi, &DA[0], &rmat, G(iA(0)), d);
+    // adj p_1 (TP[0]) is final: the context-branch backward (B rows) runs on the side lane underneath
+    // the rest of sweep 4 and the weight-gradient contractions
+    plan.fork();
     // ---- context branch backward (B rows)
     {
       const Mat ap1 = TP[0];
@@ -335,6 +324,35 @@ struct CdaePlan {
       const Mat y = ctxp.hi();
       tn2(DC[0], y, nullptr, nullptr, G(iC(0)), c);
     }
+    plan.cur_lane = 0;
+    {
+      GemmNTDesc g = nt_desc(TP[0], W1u.T, TA[L - 1], EPI_ADJOINT);
+      set_aux1(g, U[L - 1].hi()); set_aux2(g, TA[L - 1]);
+      g.colsum = G(iA(L - 1) + 1);
+      plan.nt(g);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(TA[l], Aw[l].T, TA[l - 1], EPI_ADJOINT);
+      set_aux1(g, U[l - 1].hi()); set_aux2(g, TA[l - 1]);
+      g.colsum = G(iA(l - 1) + 1);
+      plan.nt(g);
+    }
+    // ---- weight gradients: dW = adj^T . act + delta^T . tangent   (accumulated into .grad)
+    const Mat xt_hi = xt.hi();
+    for (int l = L - 1; l >= 1; --l) {
+      const Mat y = V[l - 1].hi();
+      tn2(TP[l], y, &DP[l], &VD[l - 1], G(iW(l)), H);
+    }
+    {
+      const Mat y = U[L - 1].hi();
+      tn2(TP[0], y, &DP[0], &UD[L - 1], G(iW(0)), ld1);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      const Mat y = U[l - 1].hi();
+      tn2(TA[l], y, &DA[l], &UD[l - 1], G(iA(l)), H);
+    }
+    tn2(TA[0], xt_hi, &DA[0], &rmat, G(iA(0)), d);
+    plan.join();
     return plan.error;
   }
 };

@@ -44,15 +44,37 @@ struct Workspace {
 struct Plan {
   bool dry = true;
   int error = 0;
+  // ops carry a lane: 0 = the caller's stream, 1 = a plan-owned side stream used between fork()/join()
+  // for the B-row chains (context branch) that are independent of the N-row sweeps.
   std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<int> lanes;   // per op: 0 main, 1 side, 2 = fork marker, 3 = join marker
+  int cur_lane = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int num_gemm_nt = 0, num_gemm_tn = 0, num_small = 0;
+
+  void fork() {
+    cur_lane = 1;
+    if (dry) return;
+    ops.push_back(nullptr);
+    lanes.push_back(2);
+  }
+  void join() {
+    cur_lane = 0;
+    if (dry) return;
+    ops.push_back(nullptr);
+    lanes.push_back(3);
+  }
 
   void fail_with(int rc) {
     if (error == 0) error = rc;
   }
   void add(std::function<int(cudaStream_t)> f) {
     ++num_small;
-    if (!dry) ops.push_back(std::move(f));
+    if (!dry) {
+      ops.push_back(std::move(f));
+      lanes.push_back(cur_lane);
+    }
   }
   void nt(const GemmNTDesc& d) {
     ++num_gemm_nt;
@@ -61,6 +83,7 @@ struct Plan {
     int rc = prepare_gemm_nt(d, &pr);
     if (rc) return fail_with(rc);
     ops.push_back([pr](cudaStream_t s) { return launch_prepared_nt(pr, s); });
+    lanes.push_back(cur_lane);
   }
   void tn(const GemmTNDesc& d) {
     ++num_gemm_tn;
@@ -69,13 +92,42 @@ struct Plan {
     int rc = prepare_gemm_tn(d, &pr);
     if (rc) return fail_with(rc);
     ops.push_back([pr](cudaStream_t s) { return launch_prepared_tn(pr, s); });
+    lanes.push_back(cur_lane);
   }
-  int run(cudaStream_t s) const {
-    for (const auto& f : ops) {
-      int rc = f(s);
+  int run(cudaStream_t s) {
+    for (size_t i = 0; i < ops.size(); ++i) {
+      const int lane = lanes[i];
+      if (lane == 2) {  // fork: the side stream picks up after everything issued so far
+        if (side == nullptr) {
+          ARDAE_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+          ARDAE_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+          ARDAE_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        ARDAE_CUDA_OK(cudaEventRecord(ev_fork, s));
+        ARDAE_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
+        continue;
+      }
+      if (lane == 3) {  // join: the main stream waits for the side lane
+        ARDAE_CUDA_OK(cudaEventRecord(ev_join, side));
+        ARDAE_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
+        continue;
+      }
+      int rc = ops[i](lane == 1 ? side : s);
       if (rc) return rc;
     }
     return 0;
+  }
+  ~Plan() {
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+  }
+  Plan() = default;
+  Plan(const Plan&) = delete;
+  Plan& operator=(const Plan&) = delete;
+  void reset() {
+    ops.clear(); lanes.clear(); cur_lane = 0; error = 0;
+    num_gemm_nt = num_gemm_tn = num_small = 0;
   }
   int launches() const { return num_gemm_nt + 2 * num_gemm_tn + num_small; }
 };
