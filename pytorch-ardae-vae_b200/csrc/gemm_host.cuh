@@ -96,6 +96,8 @@ struct GemmNTDesc {
   int force_block_n = 0;
   int persist = 0;     // 0 auto, 1 force the persistent kernel, -1 force the tile-per-CTA kernel
   int deep = 0;        // 0 auto (small grids), 1 force the deep-pipeline narrow-tile variant, -1 off
+  int prefetch = 0;    // 0 auto (one resident wave ahead for big grids), -1 off, > 0 explicit distance in row tiles
+  int pair = 0;        // 0 auto, 1 force the CTA-pair (cta_group::2) kernel for 256-wide tiles, -1 off
   int multicast = 0;   // 0 auto (2-CTA weight multicast for 256-wide tiles with >= 2 row tiles), 1 on, -1 off
   int debug_flags = 0;
 };
@@ -144,24 +146,24 @@ struct PreparedNT {
   int cluster = 1;
 };
 
-template <int BLOCK_N, bool MC, bool DEEP = false>
+template <int BLOCK_N, bool MC, bool DEEP = false, bool CG2 = false>
 inline const void* nt_kernel_for_mode(int mode, int split) {
   if (split) {
     switch (mode) {
-      case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, true, MC, DEEP>);
-      case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, true, MC, DEEP>);
-      case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, true, MC, DEEP>);
+      case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, true, MC, DEEP, CG2>);
+      case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, true, MC, DEEP, CG2>);
+      case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, true, MC, DEEP, CG2>);
       default: return nullptr;
     }
   }
   switch (mode) {
-    case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, false, MC, DEEP>);
-    case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, false, MC, DEEP>);
-    case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, false, MC, DEEP>);
-    case EPI_MUL_SIG: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_SIG, false, MC, DEEP>);
-    case EPI_MUL_STEP: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_STEP, false, MC, DEEP>);
-    case EPI_TANGENT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_TANGENT, false, MC, DEEP>);
-    case EPI_ADJOINT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_ADJOINT, false, MC, DEEP>);
+    case EPI_LINEAR: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_LINEAR, false, MC, DEEP, CG2>);
+    case EPI_RELU: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_RELU, false, MC, DEEP, CG2>);
+    case EPI_SOFTPLUS: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_SOFTPLUS, false, MC, DEEP, CG2>);
+    case EPI_MUL_SIG: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_SIG, false, MC, DEEP, CG2>);
+    case EPI_MUL_STEP: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_MUL_STEP, false, MC, DEEP, CG2>);
+    case EPI_TANGENT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_TANGENT, false, MC, DEEP, CG2>);
+    case EPI_ADJOINT: return reinterpret_cast<const void*>(&gemm_nt_kernel<BLOCK_N, EPI_ADJOINT, false, MC, DEEP, CG2>);
     default: return nullptr;
   }
 }
@@ -204,7 +206,9 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
   // measured (gemm_selftest): weight multicast does not pay at 2 CTAs/SM (the main loop is bound by
   // bytes-in-flight x TMA latency, not by L2 bandwidth) -> opt-in only
   const bool mc = d.persist <= 0 && bn == 256 && d.multicast > 0;
-  if ((rc = encode_tmap_2d(&p.tmB, d.B, d.K, d.N, d.ldb, kBlockK, mc ? bn / 2 : bn))) return rc;
+  const bool cg2 = !mc && d.persist <= 0 && bn == 256 &&
+                   (d.pair > 0 || (d.pair == 0 && tiles_m0 >= 2 * num_sms() && d.K >= 512));  // pays for the 3xTF32 sweeps (measured)
+  if ((rc = encode_tmap_2d(&p.tmB, d.B, d.K, d.N, d.ldb, kBlockK, (mc || cg2) ? bn / 2 : bn))) return rc;
   if ((rc = encode_tmap_2d(&p.tmOut, d.out, d.N, d.M, d.ldo, 32, kBlockM))) return rc;
   if (has_out2 && (rc = encode_tmap_2d(&p.tmOut2, d.out2, d.N, d.M, d.ldo2, 32, kBlockM))) return rc;
   if (has_aux1 && (rc = encode_tmap_2d(&p.tmAux1, d.aux1, d.N, d.M, d.ld1, 32, kBlockM))) return rc;
@@ -230,13 +234,14 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
       break;
     case 128: pr.fn = nt_kernel_for_mode<128, false>(d.mode, d.split_out); pr.smem = GemmNTConfig<128>::kSmemBytes; break;
     case 256:
-      pr.fn = mc ? nt_kernel_for_mode<256, true>(d.mode, d.split_out) : nt_kernel_for_mode<256, false>(d.mode, d.split_out);
-      pr.smem = GemmNTConfig<256>::kSmemBytes;
+      pr.fn = cg2 ? nt_kernel_for_mode<256, false, false, true>(d.mode, d.split_out)
+                  : (mc ? nt_kernel_for_mode<256, true>(d.mode, d.split_out) : nt_kernel_for_mode<256, false>(d.mode, d.split_out));
+      pr.smem = cg2 ? GemmNTConfig<256, false, true>::kSmemBytes : GemmNTConfig<256>::kSmemBytes;
       break;
     default: return fail(-2, "gemm_nt: bad BLOCK_N");
   }
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, (d.N + bn - 1) / bn, 1);
-  if (mc) {
+  if (mc || cg2) {
     pr.cluster = 2;
     pr.grid.x = (pr.grid.x + 1) / 2 * 2;  // an odd tail CTA works on an out-of-range tile (TMA clips)
   }
@@ -252,6 +257,12 @@ inline int prepare_gemm_nt(const GemmNTDesc& d, PreparedNT* out) {
     if (fn == nullptr) return fail(-2, "gemm_nt: no persistent kernel for this mode");
     pr.fn = fn; pr.smem = smem; pr.threads = 256;
     pr.grid = dim3(tiles_m < num_sms() ? tiles_m : num_sms(), 1, 1);
+  }
+  pr.params.prefetch_tiles = 0;
+  if (!want_persist) {
+    if (d.prefetch > 0) pr.params.prefetch_tiles = d.prefetch;
+    // auto = off: measured on B200, L2 prefetch of the next wave's tiles slows every sweep by 15-25 %
+    // (extra L2/HBM contention; the kernels are bandwidth-, not latency-limited)
   }
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;

@@ -58,6 +58,7 @@ struct alignas(64) GemmNTParams {
   int a_k_wrap;             // if > 0 the A operand's k coordinate wraps: col = (kb*32) % a_k_wrap
   int debug_flags;          // profiling experiments only: 1 = skip TMA stores, 2 = skip epilogue math
   int vec_ok;               // bias / group_bias / col_vec are 16-byte aligned: float4 broadcast loads
+  int prefetch_tiles;       // > 0: prefetch the A / aux tiles of row tile (this + prefetch_tiles) into L2
 };
 
 struct alignas(64) GemmTNParams {
@@ -241,12 +242,15 @@ __device__ __forceinline__ void epilogue_colsums(const GemmNTParams& p, float (&
 // DEEP: latency-optimised variant for grids that cannot fill the GPU (the B-row chains: context
 // branch, encode(std=0), score, model forward/backward).  Narrow tiles (more CTAs, 1-2 epilogue chunks)
 // and 8 TMA stages so the whole K loop of an L2-resident problem is in flight at once; one CTA per SM.
-template <int BLOCK_N, bool DEEP = false>
+// CG2: CTA-pair (cta_group::2) variant: two CTAs on the SMs of one TPC compute a 256 x BLOCK_N tile;
+// each stages its own 128 rows of A and HALF of the weight k-block, so only half of the weight bytes
+// enter each SM (the NT kernels are bound by the ~68 GB/s per-SM TMA/L2 port, round-1 measurement).
+template <int BLOCK_N, bool DEEP = false, bool CG2 = false>
 struct GemmNTConfig {
   static constexpr int kStageA = kBlockM * kBlockK * 4;
-  static constexpr int kStageB = BLOCK_N * kBlockK * 4;
+  static constexpr int kStageB = (CG2 ? BLOCK_N / 2 : BLOCK_N) * kBlockK * 4;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kNumStages = DEEP ? 8 : ((BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4));
+  static constexpr int kNumStages = DEEP ? 8 : (CG2 ? 3 : ((BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4)));
   static constexpr int kPipeBytes = kStage * kNumStages;
   static constexpr int kEpiBytes = kNumEpiStagingTiles * kTileBytes;
   static constexpr int kDataBytes = kPipeBytes > kEpiBytes ? kPipeBytes : kEpiBytes;
@@ -261,10 +265,11 @@ struct GemmNTConfig {
 // MC: launched as clusters of 2 CTAs (adjacent row tiles).  Each CTA fetches half of every weight
 // (B) k-block and TMA-multicasts it to both, halving the L2->SM weight traffic that bounds the
 // 3xTF32 forward sweep (768 KB of weights per 128-row tile otherwise).
-template <int BLOCK_N, int MODE, bool SPLIT, bool MC, bool DEEP = false>
+template <int BLOCK_N, int MODE, bool SPLIT, bool MC, bool DEEP = false, bool CG2 = false>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
-  using Cfg = GemmNTConfig<BLOCK_N, DEEP>;
+  using Cfg = GemmNTConfig<BLOCK_N, DEEP, CG2>;
+  static_assert(!(MC && CG2), "MC and CG2 are exclusive");
   constexpr int NSTAGE = Cfg::kNumStages;
   constexpr bool kHasAux1 = MODE >= EPI_MUL_SIG;
   constexpr bool kHasAux2 = MODE >= EPI_TANGENT;
@@ -306,27 +311,56 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if (CG2) {
+      ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (MC) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
+  if (MC || CG2) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t pair_rank = (MC || CG2) ? ptx::cluster_ctarank() : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint32_t rank = MC ? ptx::cluster_ctarank() : 0;
+      const uint32_t rank = pair_rank;
+      if (p.prefetch_tiles > 0) {
+        // the CTA that will run on this SM slot a full wave later streams its operands from HBM: pull them
+        // into L2 now so its TMA loads see L2-hit latency instead of a loaded-HBM round trip
+        const int mp = m0 + p.prefetch_tiles * kBlockM;
+        if (mp < p.M) {
+          const int nkb_a = p.a_k_wrap > 0 ? p.a_k_wrap / kBlockK : num_kb;
+          for (int kb = 0; kb < nkb_a; ++kb) ptx::tma_prefetch_l2_2d(&p.tmA, kb * kBlockK, mp);
+          if (kHasAux1 || kHasAux2) {
+            for (int c = 0; c * 32 < BLOCK_N && n0 + c * 32 < p.N; ++c) {
+              if (kHasAux1) ptx::tma_prefetch_l2_2d(&p.tmAux1, n0 + c * 32, mp);
+              if (kHasAux2) ptx::tma_prefetch_l2_2d(&p.tmAux2, n0 + c * 32, mp);
+            }
+          }
+        }
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % NSTAGE;
         const uint32_t ph = (kb / NSTAGE) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        ptx::mbar_expect_tx(&full_bar[s], Cfg::kStage);
         uint8_t* sa = smem + s * Cfg::kStage;
         int ka = kb * kBlockK;
         if (p.a_k_wrap > 0) ka %= p.a_k_wrap;
+        if (CG2) {
+          // both CTAs' tiles complete on the LEADER's full barrier, armed by the leader for both
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], 2 * Cfg::kStage);
+          ptx::tma_load_2d_2sm(sa, &p.tmA, &full_bar[s], ka, m0);
+          ptx::tma_load_2d_2sm(sa + Cfg::kStageA, &p.tmB, &full_bar[s], kb * kBlockK,
+                               n0 + static_cast<int>(rank) * (BLOCK_N / 2));
+          continue;
+        }
+        ptx::mbar_expect_tx(&full_bar[s], Cfg::kStage);
         ptx::tma_load_2d(sa, &p.tmA, &full_bar[s], ka, m0);
         if (MC) {
           // this CTA's half of the weight k-block (box = BLOCK_N/2 rows), delivered to both CTAs
@@ -340,8 +374,8 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, BLOCK_N, 0, 0);
+    if (lane == 0 && (!CG2 || pair_rank == 0)) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(CG2 ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % NSTAGE;
         const uint32_t ph = (kb / NSTAGE) & 1;
@@ -353,14 +387,22 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
           const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * kUmmaK * 4, 0, 1024);
           const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-          ptx::umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (CG2)
+            ptx::umma_tf32_2sm(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          else
+            ptx::umma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        if (MC)
+        if (CG2)
+          ptx::umma_commit_2sm(&empty_bar[s], 0x3);  // frees the stage in both CTAs of the pair
+        else if (MC)
           ptx::umma_commit_mc(&empty_bar[s], 0x3);  // frees this stage in BOTH CTAs' bookkeeping
         else
           ptx::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
       }
-      ptx::umma_commit(tmem_full_bar);  // accumulator complete (and every stage drained)
+      if (CG2)
+        ptx::umma_commit_2sm(tmem_full_bar, 0x3);  // both CTAs' epilogues may read their TMEM halves
+      else
+        ptx::umma_commit(tmem_full_bar);  // accumulator complete (and every stage drained)
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
@@ -446,10 +488,13 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (MC) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers
+  if (MC || CG2) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG2)
+      ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else
+      ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -642,8 +687,9 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
         uint8_t* ob = out_base + (cc % Cfg::kNumOut) * kTileBytes;
         uint8_t* ob2 = out_base + (Cfg::kNumOut + cc % Cfg::kNumOut) * kTileBytes;
         float v[32];
-        epilogue_chunk<MODE, SPLIT>(p, accu, slot + row_off, slot + kTileBytes + row_off, ob + row_off,
-                                    ob2 + row_off, swz, nc, rs, gb_row, v);
+        if (!(p.debug_flags & 2))
+          epilogue_chunk<MODE, SPLIT>(p, accu, slot + row_off, slot + kTileBytes + row_off, ob + row_off,
+                                      ob2 + row_off, swz, nc, rs, gb_row, v);
         if (kHasAux1) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&aux_empty[a]);  // this warp is done with the aux slot
@@ -660,8 +706,10 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
         if (leader) ptx::tma_store_wait_read<Cfg::kNumOut - 2>();
         ptx::named_bar_sync(1, 128);
         if (leader) {
-          ptx::tma_store_2d(&p.tmOut, ob, nc, m0);
-          if (kHasOut2) ptx::tma_store_2d(&p.tmOut2, ob2, nc, m0);
+          if (!(p.debug_flags & 1)) {
+            ptx::tma_store_2d(&p.tmOut, ob, nc, m0);
+            if (kHasOut2) ptx::tma_store_2d(&p.tmOut2, ob2, nc, m0);
+          }
           ptx::tma_store_commit();
         }
         epilogue_colsums<MODE>(p, v, ob2 + row_off, swz, nc, row_ok, rw, lane);

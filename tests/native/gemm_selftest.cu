@@ -76,6 +76,7 @@ static int g_persist = 0;
 static int g_split = 0;
 static int g_mc = -1;
 static int g_deep = -1;
+static int g_pair = -1;
 static void test_nt(const char* name, int M, int N, int K, int mode, int force_bn, bool use_bias,
                     bool use_group, bool use_rank1, bool use_colsum) {
   const int lda = (K + 3) / 4 * 4, ldb = lda, ldo = (N + 3) / 4 * 4;
@@ -98,7 +99,7 @@ static void test_nt(const char* name, int M, int N, int K, int mode, int force_b
   d.A = dA; d.lda = lda; d.B = dB; d.ldb = ldb; d.out = dout; d.ldo = ldo; d.out2 = dout2; d.ldo2 = ldo;
   d.aux1 = daux1; d.ld1 = ldo; d.aux2 = daux2; d.ld2 = ldo;
   d.M = M; d.N = N; d.K = K; d.mode = mode; d.alpha = 0.75f; d.round_out = 0; d.force_block_n = force_bn;
-  d.persist = g_persist; d.split_out = g_split; d.multicast = g_mc; d.deep = g_deep;
+  d.persist = g_persist; d.split_out = g_split; d.multicast = g_mc; d.deep = g_deep; d.pair = g_pair;
   if (use_bias) d.bias = dbias;
   if (use_group) { d.group_bias = dgb; d.group = group; d.ldg = ldo; }
   if (use_rank1) { d.row_scale = drows; d.col_vec = dcolv; }
@@ -211,7 +212,8 @@ static void test_tn(const char* name, int M, int N, int K, bool two) {
 }
 
 static int g_dbg = 0;
-static void bench_nt(int M, int N, int K, int mode, int persist = 0, int split = 0, int mc = -1, int deep = -1) {
+static int g_prefetch = -1;
+static void bench_nt(int M, int N, int K, int mode, int persist = 0, int split = 0, int mc = -1, int deep = -1, int pair = -1) {
   float *A, *B, *O, *O2, *X1, *X2;
   CK(cudaMalloc(&A, (size_t)M * K * 4)); CK(cudaMalloc(&B, (size_t)N * K * 4));
   CK(cudaMalloc(&O, (size_t)M * N * 4)); CK(cudaMalloc(&O2, (size_t)M * N * 4));
@@ -221,7 +223,7 @@ static void bench_nt(int M, int N, int K, int mode, int persist = 0, int split =
   GemmNTDesc d;
   d.A = A; d.lda = K; d.B = B; d.ldb = K; d.out = O; d.ldo = N; d.out2 = O2; d.ldo2 = N;
   d.aux1 = X1; d.ld1 = N; d.aux2 = X2; d.ld2 = N; d.M = M; d.N = N; d.K = K; d.mode = mode;
-  d.persist = persist; d.split_out = split; d.debug_flags = g_dbg; d.multicast = mc; d.deep = deep;
+  d.persist = persist; d.split_out = split; d.debug_flags = g_dbg; d.multicast = mc; d.deep = deep; d.pair = pair; d.prefetch = g_prefetch;
   PreparedNT pr;
   if (prepare_gemm_nt(d, &pr)) { printf("bench prepare failed: %s\n", last_error_string().c_str()); return; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -233,7 +235,7 @@ static void bench_nt(int M, int N, int K, int mode, int persist = 0, int split =
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
   int narr = 2 + (mode >= EPI_MUL_SIG) + (mode >= EPI_TANGENT) + (mode == EPI_TANGENT);
   double bytes = (double)M * K * 4 + (double)(narr - 1) * M * N * 4;
-  printf("bench NT%s%s M=%d N=%d K=%d mode=%d: %.1f us  %.1f TFLOP/s  %.0f GB/s (%d arrays)\n", persist > 0 ? "(persist)" : "", mc > 0 ? "(mc)" : "", M, N, K, mode,
+  printf("bench NT%s%s M=%d N=%d K=%d mode=%d: %.1f us  %.1f TFLOP/s  %.0f GB/s (%d arrays)\n", persist > 0 ? "(persist)" : "", mc > 0 ? "(mc)" : (pair > 0 ? "(cg2)" : ""), M, N, K, mode,
          ms * 1e3, 2.0 * M * N * K / ms * 1e-9, bytes / ms * 1e-6, narr);
   cudaFree(A); cudaFree(B); cudaFree(O); cudaFree(O2); cudaFree(X1); cudaFree(X2);
 }
@@ -267,10 +269,30 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  if (argc > 1 && !strcmp(argv[1], "pf")) {
+    for (int pf : {-1, 148, 296, 444}) {
+      g_prefetch = pf;
+      printf("prefetch distance %d tiles\n", pf);
+      bench_nt(131072, 256, 768, EPI_SOFTPLUS, -1, 1, -1, -1, 1);
+      bench_nt(131072, 256, 256, EPI_LINEAR, -1);
+      bench_nt(131072, 256, 256, EPI_MUL_SIG, -1);
+      bench_nt(131072, 256, 256, EPI_TANGENT, -1);
+      bench_nt(131072, 256, 256, EPI_ADJOINT, -1);
+    }
+    return 0;
+  }
+  if (argc > 5 && !strcmp(argv[1], "one")) {  // one <mode> <K> <split> <pair>: a single bench config (for ncu)
+    bench_nt(131072, 256, atoi(argv[3]), atoi(argv[2]), -1, atoi(argv[4]), -1, -1, atoi(argv[5]));
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "dbg")) {
     for (int dbg : {0, 1, 2, 3}) {
       g_dbg = dbg;
       printf("debug_flags=%d\n", dbg);
+      bench_nt(131072, 256, 768, EPI_SOFTPLUS, -1, 1);
+      bench_nt(131072, 256, 768, EPI_SOFTPLUS, 1, 1);
+      bench_nt(131072, 256, 256, EPI_MUL_SIG, 1);
+      bench_nt(131072, 256, 256, EPI_TANGENT, 1);
       bench_nt(131072, 256, 32, EPI_SOFTPLUS, -1);
       bench_nt(131072, 256, 256, EPI_LINEAR, -1);
       bench_nt(131072, 256, 256, EPI_MUL_SIG, -1);
@@ -313,6 +335,13 @@ int main(int argc, char** argv) {
     g_split = 1;
     test_nt("MC NT softplus split 20000x256x768", 20000, 256, 768, EPI_SOFTPLUS, 0, true, false, false, true);
     g_split = 0; g_mc = -1;
+    g_pair = 1;
+    test_nt("CG2 NT linear 1000x256x256", 1000, 256, 256, EPI_LINEAR, 0, true, false, false, true);
+    test_nt("CG2 NT tangent 20000x256x256", 20000, 256, 256, EPI_TANGENT, 0, false, false, false, true);
+    test_nt("CG2 NT adjoint ragged 2945x200x40", 2945, 200, 40, EPI_ADJOINT, 0, true, false, false, true);
+    g_split = 1;
+    test_nt("CG2 NT softplus split 20000x256x768", 20000, 256, 768, EPI_SOFTPLUS, 0, true, false, false, true);
+    g_split = 0; g_pair = -1;
     g_deep = 0;  // auto: small grids take the deep-pipeline narrow-tile variant
     test_nt("DEEP NT softplus 512x300x784", 512, 300, 784, EPI_SOFTPLUS, 0, true, true, true, true);
     test_nt("DEEP NT tangent 512x256x256", 512, 256, 256, EPI_TANGENT, 0, false, false, false, true);
@@ -332,6 +361,8 @@ int main(int argc, char** argv) {
     bench_nt(131072, 256, 768, EPI_SOFTPLUS, -1, 1);
     bench_nt(131072, 256, 768, EPI_SOFTPLUS, 1, 1);
     bench_nt(131072, 256, 768, EPI_SOFTPLUS, -1, 1, 1);
+    bench_nt(131072, 256, 768, EPI_SOFTPLUS, -1, 1, -1, -1, 1);
+    for (int mode : {EPI_LINEAR, EPI_MUL_SIG, EPI_TANGENT, EPI_ADJOINT}) bench_nt(131072, 256, 256, mode, -1, 0, -1, -1, 1);
     for (int deep : {-1, 1}) {
       printf("small-M chain shapes, deep=%d\n", deep);
       bench_nt(512, 256, 768, EPI_SOFTPLUS, -1, 1, -1, deep);
