@@ -91,6 +91,9 @@ ARDAE_API int ardae_cdae_score(ardae_cdae_t h, const float* x, const float* ctx,
  *   decode.main (n_dec linears), then decode.reparam.{mean_fn,logvar_fn} (toy) | logit_fn (mnist).
  * kind 0 = toy: Gaussian decoder, noise re-concatenated at every fc layer (layers.py:707-724);
  * kind 1 = mnist: x <- 2x-1, noise concatenated once, Bernoulli decoder.
+ * kind 2 = conv: `net.ConvIPVAE` (models/ivae/conv.py:44-304 + models/vae/conv.py:79-136): tensors
+ *   encode.conv1..3, encode.fc4, encode.fc5, decode.fc.layers.0, decode.fc.fc, decode.deconv1, decode.deconv2,
+ *   decode.reparam.logit_fn (n_inp = 3, n_fc = 1, n_dec = 2, h_dim = 800 = fc4 width).
  */
 typedef struct ardae_model_s* ardae_model_t;
 
@@ -101,6 +104,7 @@ typedef struct {
   int act;                /* 0 relu, 1 softplus */
   int batch, nz;          /* B data rows, nz noise samples per row: R = B*nz rows, row index b*nz+k */
   int mode;               /* 0: encode only; 1: forward + backward; 2: IWS log-likelihood */
+  int img_h, img_c;       /* kind 2 (ConvIPVAE): image height (= width) and channels; input_dim = img_c*img_h^2 */
 } ardae_model_config;
 
 ARDAE_API int ardae_model_workspace_bytes(const ardae_model_config* cfg, size_t* bytes);

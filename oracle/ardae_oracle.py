@@ -81,12 +81,65 @@ def mlp_backward(P, keys, tape, dout, nonlin, out_nonlin, G):
     return d
 
 
+# ----------------------------------------------------------------------------- 5x5 stride-2 pad-2 convolutions
+def conv5s2(x, W, b):
+    """nn.Conv2d(Ci, Co, 5, 2, 2) (models/ivae/conv.py:70-72): x [B,Ci,H,H], W [Co,Ci,5,5] -> [B,Co,Ho,Ho]."""
+    B, Ci, H, _ = x.shape
+    Ho = (H + 4 - 5) // 2 + 1
+    xp = np.pad(x, ((0, 0), (0, 0), (2, 2), (2, 2)))
+    out = np.zeros((B, W.shape[0], Ho, Ho), dtype=x.dtype)
+    for kh in range(5):
+        for kw in range(5):
+            out += np.einsum('bchw,oc->bohw', xp[:, :, kh:kh + 2 * Ho:2, kw:kw + 2 * Ho:2], W[:, :, kh, kw])
+    return out + (b[None, :, None, None] if b is not None else 0.0)
+
+
+def conv5s2_backward(x, W, dout):
+    """Returns (dx, dW, db) of conv5s2."""
+    B, Ci, H, _ = x.shape
+    Ho = dout.shape[2]
+    xp = np.pad(x, ((0, 0), (0, 0), (2, 2), (2, 2)))
+    dxp = np.zeros_like(xp)
+    dW = np.zeros_like(W)
+    for kh in range(5):
+        for kw in range(5):
+            patch = xp[:, :, kh:kh + 2 * Ho:2, kw:kw + 2 * Ho:2]
+            dW[:, :, kh, kw] = np.einsum('bohw,bchw->oc', dout, patch)
+            dxp[:, :, kh:kh + 2 * Ho:2, kw:kw + 2 * Ho:2] += np.einsum('bohw,oc->bchw', dout, W[:, :, kh, kw])
+    return dxp[:, :, 2:2 + H, 2:2 + H], dW, dout.sum((0, 2, 3))
+
+
+def deconv5s2(x, W, b):
+    """nn.ConvTranspose2d(Ci, Co, 5, 2, 2, 0) (models/vae/conv.py:112-115): x [B,Ci,H,H], W [Ci,Co,5,5]
+    -> [B,Co,2H-1,2H-1]; it is the adjoint of conv5s2 with the same weight memory."""
+    B, Ci, H, _ = x.shape
+    Hout = 2 * H - 1
+    canvas = np.zeros((B, W.shape[1], Hout + 4, Hout + 4), dtype=x.dtype)
+    for kh in range(5):
+        for kw in range(5):
+            canvas[:, :, kh:kh + 2 * H:2, kw:kw + 2 * H:2] += np.einsum('bchw,co->bohw', x, W[:, :, kh, kw])
+    return canvas[:, :, 2:2 + Hout, 2:2 + Hout] + b[None, :, None, None]
+
+
+def deconv5s2_backward(x, W, dout):
+    B, Ci, H, _ = x.shape
+    dp = np.pad(dout, ((0, 0), (0, 0), (2, 2), (2, 2)))
+    dx = np.zeros_like(x)
+    dW = np.zeros_like(W)
+    for kh in range(5):
+        for kw in range(5):
+            patch = dp[:, :, kh:kh + 2 * H:2, kw:kw + 2 * H:2]
+            dx += np.einsum('bohw,co->bchw', patch, W[:, :, kh, kw])
+            dW[:, :, kh, kw] = np.einsum('bchw,bohw->co', x, patch)
+    return dx, dW, dout.sum((0, 2, 3))
+
+
 # ----------------------------------------------------------------------------- implicit encoders
 class ModelSpec(object):
     """Architecture of an ImplicitPosteriorVAE as built by ivae_ardae.py:295-314."""
 
     def __init__(self, kind, input_dim, noise_dim, h_dim, z_dim, num_hidden_layers, nonlin):
-        assert kind in ('toy', 'mnist')
+        assert kind in ('toy', 'mnist', 'conv')
         self.kind, self.input_dim, self.noise_dim = kind, input_dim, noise_dim
         self.h_dim, self.z_dim, self.n_layers, self.nonlin = h_dim, z_dim, num_hidden_layers, nonlin
         if kind == 'toy':
@@ -94,6 +147,9 @@ class ModelSpec(object):
             self.inp_keys = mlp_keys('encode.inp_encode', num_hidden_layers - 1)
             self.fc_keys = mlp_keys('encode.fc', num_hidden_layers)
             self.dec_keys = mlp_keys('decode.main', num_hidden_layers - 1)
+        elif kind == 'conv':
+            # models/ivae/conv.py:44-136, models/vae/conv.py:79-136; input_dim = C*H*H, h_dim = 800
+            self.dec_keys = mlp_keys('decode.fc', 1)
         else:
             # models/ivae/mnist.py:148-151,180-181,227 (encoder gets num_hidden_layers+1)
             self.inp_keys = mlp_keys('encode.inp_encode', num_hidden_layers + 1)
@@ -106,6 +162,8 @@ def encoder_forward(spec, P, x, eps, nz):
     at every layer); mnist: models/ivae/mnist.py:76-121,161-165 (x <- 2x-1, one concat).
     x [B, D], eps [B*nz, n] (row b*nz+k) -> z [B, nz, d] and a tape for the backward pass."""
     B = x.shape[0]
+    if spec.kind == 'conv':
+        return _conv_encoder_forward(spec, P, x, eps, nz)
     xin = 2.0 * x - 1.0 if spec.kind == 'mnist' else x
     inp, tape_inp = mlp_forward(P, spec.inp_keys, xin, spec.nonlin, True)
     inp_rep = np.repeat(inp, nz, axis=0)  # row b*nz+k  (unsqueeze(1).expand(-1,nz,-1))
@@ -126,6 +184,8 @@ def encoder_forward(spec, P, x, eps, nz):
 
 def encoder_backward(spec, P, tape, dz, nz, G):
     """Backward of encoder_forward for upstream dz [B, nz, d]; accumulates grads into G."""
+    if spec.kind == 'conv':
+        return _conv_encoder_backward(spec, P, tape, dz, nz, G)
     tape_inp, tape_fc, xin = tape
     B = xin.shape[0]
     H = spec.h_dim
@@ -146,11 +206,91 @@ def encoder_backward(spec, P, tape, dz, nz, G):
     mlp_backward(P, spec.inp_keys, tape_inp, dinp, spec.nonlin, True, G)
 
 
+def _img_h(spec):
+    c = getattr(spec, 'img_c', 1)
+    return int(round(math.sqrt(spec.input_dim // c))), c
+
+
+def _conv_encoder_forward(spec, P, x, eps, nz):
+    """models/ivae/conv.py:84-136: x <- 2x-1; conv1..3 + act; flatten (NCHW); fc4([inp, eps]) + act; fc5."""
+    B = x.shape[0]
+    Himg, C = _img_h(spec)
+    x4 = (2.0 * x - 1.0).reshape(B, C, Himg, Himg)
+    maps, pre = [x4], []
+    hcur = x4
+    for k in ('encode.conv1', 'encode.conv2', 'encode.conv3'):
+        a = conv5s2(hcur, P[k + '.weight'], P[k + '.bias'])
+        pre.append(a)
+        hcur = act_fwd(spec.nonlin, a)
+        maps.append(hcur)
+    inp = hcur.reshape(B, -1)
+    cat = np.concatenate([np.repeat(inp, nz, axis=0), eps], axis=1)
+    a4 = cat @ P['encode.fc4.weight'].T + P['encode.fc4.bias']
+    h4 = act_fwd(spec.nonlin, a4)
+    z = h4 @ P['encode.fc5.weight'].T + P['encode.fc5.bias']
+    return z.reshape(B, nz, spec.z_dim), (maps, pre, cat, a4, h4)
+
+
+def _conv_encoder_backward(spec, P, tape, dz, nz, G):
+    maps, pre, cat, a4, h4 = tape
+    B = maps[0].shape[0]
+    d = dz.reshape(B * nz, spec.z_dim)
+    G['encode.fc5.weight'] = G.get('encode.fc5.weight', 0.0) + d.T @ h4
+    G['encode.fc5.bias'] = G.get('encode.fc5.bias', 0.0) + d.sum(0)
+    da4 = (d @ P['encode.fc5.weight']) * act_grad(spec.nonlin, a4)
+    G['encode.fc4.weight'] = G.get('encode.fc4.weight', 0.0) + da4.T @ cat
+    G['encode.fc4.bias'] = G.get('encode.fc4.bias', 0.0) + da4.sum(0)
+    feat = maps[3].reshape(B, -1).shape[1]
+    dinp = (da4 @ P['encode.fc4.weight'])[:, :feat].reshape(B, nz, feat).sum(1)
+    dh = dinp.reshape(maps[3].shape)
+    for i, k in reversed(list(enumerate(('encode.conv1', 'encode.conv2', 'encode.conv3')))):
+        da = dh * act_grad(spec.nonlin, pre[i])
+        dh, dW, db = conv5s2_backward(maps[i], P[k + '.weight'], da)
+        G[k + '.weight'] = G.get(k + '.weight', 0.0) + dW
+        G[k + '.bias'] = G.get(k + '.bias', 0.0) + db
+
+
+def _conv_decoder_head(spec, P, h, tape):
+    """models/vae/conv.py:126-131: view [32,s8,s8] -> act(deconv1) -> ZeroPad2d((0,1,0,1)) -> act(deconv2)
+    -> logit deconv -> crop last row / column."""
+    R = h.shape[0]
+    Himg, C = _img_h(spec)
+    s8 = int(round(math.sqrt(h.shape[1] // 32)))
+    h1 = h.reshape(R, 32, s8, s8)
+    a2 = deconv5s2(h1, P['decode.deconv1.weight'], P['decode.deconv1.bias'])
+    h2 = np.pad(act_fwd(spec.nonlin, a2), ((0, 0), (0, 0), (0, 1), (0, 1)))
+    a3 = deconv5s2(h2, P['decode.deconv2.weight'], P['decode.deconv2.bias'])
+    h3 = act_fwd(spec.nonlin, a3)
+    lg = deconv5s2(h3, P['decode.reparam.logit_fn.weight'], P['decode.reparam.logit_fn.bias'])[:, :, :-1, :-1]
+    assert lg.shape[2] == Himg
+    return (lg.reshape(R, -1),), (h, (tape, h1, a2, h2, a3, h3))
+
+
+def _conv_decoder_head_backward(spec, P, tape_all, dlogit, G):
+    tape, h1, a2, h2, a3, h3 = tape_all
+    R = h1.shape[0]
+    Himg, C = _img_h(spec)
+    dl = np.pad(dlogit.reshape(R, C, Himg, Himg), ((0, 0), (0, 0), (0, 1), (0, 1)))
+    dh3, dW, db = deconv5s2_backward(h3, P['decode.reparam.logit_fn.weight'], dl)
+    G['decode.reparam.logit_fn.weight'] = G.get('decode.reparam.logit_fn.weight', 0.0) + dW
+    G['decode.reparam.logit_fn.bias'] = G.get('decode.reparam.logit_fn.bias', 0.0) + db
+    dh2, dW, db = deconv5s2_backward(h2, P['decode.deconv2.weight'], dh3 * act_grad(spec.nonlin, a3))
+    G['decode.deconv2.weight'] = G.get('decode.deconv2.weight', 0.0) + dW
+    G['decode.deconv2.bias'] = G.get('decode.deconv2.bias', 0.0) + db
+    da2 = dh2[:, :, :-1, :-1] * act_grad(spec.nonlin, a2)
+    dh1, dW, db = deconv5s2_backward(h1, P['decode.deconv1.weight'], da2)
+    G['decode.deconv1.weight'] = G.get('decode.deconv1.weight', 0.0) + dW
+    G['decode.deconv1.bias'] = G.get('decode.deconv1.bias', 0.0) + db
+    return dh1.reshape(R, -1)
+
+
 # ----------------------------------------------------------------------------- decoders + ELBO terms
 def decoder_forward(spec, P, z):
     """toy: models/ivae/toy.py:725-737 + reparam.py:55-58 (mu, logvar heads, no clipping);
     mnist: models/ivae/mnist.py:188-199 + reparam.py:170-172 (logits)."""
     h, tape = mlp_forward(P, spec.dec_keys, z, spec.nonlin, True)
+    if spec.kind == 'conv':
+        return _conv_decoder_head(spec, P, h, tape)
     if spec.kind == 'toy':
         mu = h @ P['decode.reparam.mean_fn.weight'].T + P['decode.reparam.mean_fn.bias']
         lv = h @ P['decode.reparam.logvar_fn.weight'].T + P['decode.reparam.logvar_fn.bias']
@@ -203,11 +343,16 @@ def model_backward(spec, P, tape, beta, nz, dz_extra, G, loss_scale=1.0):
     n = z.shape[0]
     h, tape_main = tape_dec
     hg = recon_rows_grad(spec, heads, xrep)
-    if spec.kind == 'toy':
+    if spec.kind == 'conv':
+        dh = _conv_decoder_head_backward(spec, P, tape_main, hg[0] * (loss_scale / n), G)
+        tape_main = tape_main[0]
+        names, hg = [], []
+    elif spec.kind == 'toy':
         names = ['decode.reparam.mean_fn', 'decode.reparam.logvar_fn']
     else:
         names = ['decode.reparam.logit_fn']
-    dh = 0.0
+    if spec.kind != 'conv':
+        dh = 0.0
     for nm, g in zip(names, hg):
         g = g * (loss_scale / n)
         G[nm + '.weight'] = G.get(nm + '.weight', 0.0) + g.T @ h

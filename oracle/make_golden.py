@@ -36,6 +36,13 @@ CASES = {
                            cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=5, nonlinearity='softplus'),
                            B=5, hp=dict(std_scale=100., delta=0.1, nz_cdae=6, nstd=1, nz_model=2, beta=1.0,
                                         m_lr=1e-3, m_beta1=0.9, d_lr=1e-3, d_momentum=0.9), wscale=3.0),
+    # conv implicit VAE (run_vae_dbmnist.sh:31 shape family, 12x12 images): `lite` = one step, weights
+    # fp32-representable and stored as float32 (the reference hard-codes the 800 / 300 wide fc layers)
+    'conv_small': dict(kind='conv', lite=True,
+                       model=dict(input_height=12, input_channels=1, z_dim=4, noise_dim=5, nonlinearity='softplus'),
+                       cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=3, nonlinearity='softplus'),
+                       B=4, hp=dict(std_scale=10000., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
+                                    m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
 }
 
 
@@ -55,16 +62,24 @@ def make_case(name, c):
                     if p.dim() == 2:
                         p.mul_(c['wscale'])
     hp = c['hp']
+    lite = c.get('lite', False)
+    if lite:  # make every weight exactly fp32-representable
+        with torch.no_grad():
+            for m in (model, cdae):
+                for p in m.parameters():
+                    p.copy_(p.float().double())
     mopt, copt = rh.build_optimizers(model, cdae, hp)
-    B, D, n, d = c['B'], c['model']['input_dim'], c['model']['noise_dim'], c['model']['z_dim']
+    B, n, d = c['B'], c['model']['noise_dim'], c['model']['z_dim']
+    D = c['model']['input_dim'] if 'input_dim' in c['model'] else c['model']['input_channels'] * c['model']['input_height'] ** 2
+    f32 = (lambda a: a.astype(np.float32)) if lite else (lambda a: a)
     nz, nstd, nzm = hp['nz_cdae'], hp['nstd'], hp['nz_model']
     arrays = {}
     for k, v in model.state_dict().items():
-        arrays['m0/' + k] = v.numpy().copy()
+        arrays['m0/' + k] = f32(v.numpy().copy())
     for k, v in cdae.state_dict().items():
-        arrays['c0/' + k] = v.numpy().copy()
-    for step in range(2):
-        if c['kind'] == 'mnist':
+        arrays['c0/' + k] = f32(v.numpy().copy())
+    for step in range(1 if lite else 2):
+        if c['kind'] in ('mnist', 'conv'):
             xc = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
             xm = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
         else:
@@ -85,15 +100,19 @@ def make_case(name, c):
             if v is not None:
                 arrays[p + 'cdae_grads/' + k] = v
         for k, v in t2n(out['model_grads']).items():
-            arrays[p + 'model_grads/' + k] = v
-        for k, v in model.state_dict().items():
-            arrays[p + 'm_after/' + k] = v.numpy().copy()
-        for k, v in cdae.state_dict().items():
-            arrays[p + 'c_after/' + k] = v.numpy().copy()
+            arrays[p + 'model_grads/' + k] = f32(v)
+        if not lite:
+            for k, v in model.state_dict().items():
+                arrays[p + 'm_after/' + k] = v.numpy().copy()
+            for k, v in cdae.state_dict().items():
+                arrays[p + 'c_after/' + k] = v.numpy().copy()
     assert out['cdae_grads']['neglogprob.fc.bias'] is None
     # IWS (evaluate_iws) on the stepped weights
     b, S = 3, 16
-    if c['kind'] == 'mnist':
+    if lite:  # IWS on the INITIAL weights (the stepped ones are not stored)
+        with torch.no_grad():
+            model.load_state_dict({k: torch.from_numpy(arrays['m0/' + k]).double() for k in model.state_dict()})
+    if c['kind'] in ('mnist', 'conv'):
         xe = torch.bernoulli(torch.full((b, D), 0.3, dtype=dt), generator=g)
     else:
         xe = torch.randn(b, D, dtype=dt, generator=g) * 2
@@ -106,11 +125,14 @@ def make_case(name, c):
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + '.npz')
     np.savez_compressed(path, **arrays)
+    last = 's0/' if lite else 's1/'
     print('%s: %d arrays, %.1f KB, cdae_loss=%.6g model_loss=%.6g iws=%.6g' % (
-        name, len(arrays), os.path.getsize(path) / 1024., float(arrays['s1/cdae_loss']),
-        float(arrays['s1/model_loss']), float(arrays['iws/logprob'])))
+        name, len(arrays), os.path.getsize(path) / 1024., float(arrays[last + 'cdae_loss']),
+        float(arrays[last + 'model_loss']), float(arrays['iws/logprob'])))
 
 
 if __name__ == '__main__':
+    only = sys.argv[1:]
     for name, c in CASES.items():
-        make_case(name, c)
+        if not only or name in only:
+            make_case(name, c)

@@ -68,7 +68,10 @@ def build_reference(kind, model_kwargs, cdae_kwargs, dtype=None, seed=0):
     import torch
     _, net = import_reference()
     torch.manual_seed(seed)
-    model = (net.ToyIPVAE if kind == 'toy' else net.MNISTIPVAE)(enc_type='concat', **model_kwargs)
+    if kind == 'conv':
+        model = net.ConvIPVAE(**model_kwargs)
+    else:
+        model = (net.ToyIPVAE if kind == 'toy' else net.MNISTIPVAE)(enc_type='concat', **model_kwargs)
     cdae = net.MLPGradCARDAE(std=1., noise_type='gaussian', enc_ctx=True, enc_input=True, **cdae_kwargs)
     if dtype is not None:
         model, cdae = model.to(dtype), cdae.to(dtype)
@@ -92,7 +95,7 @@ class _NoiseQueue(object):
 
     def __call__(self, batch_size, std=None, device=None):
         import torch
-        std = std if std is not None else self.enc.std
+        std = std if std is not None else getattr(self.enc, 'std', 1.)
         if std == 0:
             w = next(self.enc.parameters())
             return torch.zeros(batch_size, self.enc.noise_dim, dtype=w.dtype, device=w.device)
@@ -110,6 +113,12 @@ def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=
     nz, nstd, nzm, beta = hp['nz_cdae'], hp['nstd'], hp['nz_model'], hp['beta']
     q = _NoiseQueue(model.encode)
     model.encode.sample_noise = q
+    # ConvIPVAE.forward / forward_hidden draw through a module-level sample_noise(sz, std, device)
+    # (ivae/conv.py:24-27,190,207): route that to the same queue
+    cmod = sys.modules.get('_ardae_ref_' + model.__class__.__module__) or sys.modules.get(model.__class__.__module__)
+    c_orig = getattr(cmod, 'sample_noise', None) if cmod is not None else None
+    if c_orig is not None:
+        cmod.sample_noise = lambda sz, std=None, device=None: q(sz[0], std=std, device=device)
     out = {}
     model.train(); cdae.train()
     # ---- update cdae (:713-779)
@@ -147,6 +156,7 @@ def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=
     latent_mean = model.encode(x_model, std=0).detach()                 # :826
     lsm_m = S_ * (latent - latent_mean).detach()                        # :827
     stdmat0 = torch.zeros(Bm, nzm, 1, dtype=x_model.dtype)              # :828
+    latent = latent.view(Bm, nzm, -1)
     grad = cdae.glogprob(lsm_m, context, std=stdmat0, scale=S_).detach()  # :829
     (S_ * (latent - latent_mean)).backward(beta * grad.detach() / float(Bm * nzm))  # :834
     out.update(model_loss=model_loss.detach(), recon=recon_loss, prior=prior_loss, z_model=latent.detach(),
@@ -158,6 +168,8 @@ def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=
             mopt.step()                                                 # :846
     del model.encode.sample_noise
     del cdae.add_noise
+    if c_orig is not None:
+        cmod.sample_noise = c_orig
     return out
 
 

@@ -22,7 +22,7 @@ class CdaeConfig(ctypes.Structure):
 
 class ModelConfig(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int) for k in ('kind', 'input_dim', 'noise_dim', 'h_dim', 'z_dim', 'n_inp', 'n_fc',
-                                            'n_dec', 'act', 'batch', 'nz', 'mode')]
+                                            'n_dec', 'act', 'batch', 'nz', 'mode', 'img_h', 'img_c')]
 
 
 def _declare(lib):

@@ -60,6 +60,19 @@ class BernoulliDistributionLinear(nn.Module):
         return torch.sigmoid(y / temperature)
 
 
+class BernoulliDistributionConvTranspose2d(nn.Module):
+    """models/reparam.py:191-202 (parameter container + the relaxed-Bernoulli sampler :106-120)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, bias=True,
+                 hard=False):
+        super().__init__()
+        self.hard = hard
+        self.logit_fn = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride, padding, output_padding,
+                                           bias=bias)
+
+    sample_logistic_sigmoid = BernoulliDistributionLinear.sample_logistic_sigmoid
+
+
 def _weight_init(m):  # models/ivae/mnist.py:20-25
     if isinstance(m, (nn.Conv2d, nn.Linear)):
         nn.init.xavier_uniform_(m.weight)
@@ -217,9 +230,10 @@ class ImplicitPosteriorVAE(nn.Module):
         if key not in self._plans:
             L = _lib.lib()
             ar = self._ensure()
-            cfg = _lib.ModelConfig(0 if self.KIND == 'toy' else 1, self.input_dim, self.noise_dim, self.h_dim,
-                                   self.z_dim, self._n_inp, self._n_fc, self._n_dec,
-                                   1 if self.nonlinearity == 'softplus' else 0, B, nz, mode)
+            cfg = _lib.ModelConfig({'toy': 0, 'mnist': 1, 'conv': 2}[self.KIND], self.input_dim, self.noise_dim,
+                                   self.h_dim, self.z_dim, self._n_inp, self._n_fc, self._n_dec,
+                                   1 if self.nonlinearity == 'softplus' else 0, B, nz, mode,
+                                   getattr(self, 'input_height', 0), getattr(self, 'input_channels', 0))
             nbytes = ctypes.c_size_t(0)
             _lib.check(L.ardae_model_workspace_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
             ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=ar.flat.device)
@@ -320,3 +334,90 @@ class MNISTIPVAE(ImplicitPosteriorVAE):
                  nonlinearity='softplus', num_hidden_layers=1, init='gaussian', enc_type='concat'):
         super().__init__(energy_func, input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, init,
                          enc_type)
+
+
+class _ConvEncoder(nn.Module):
+    """models/ivae/conv.py:44-136 (parameter container; attribute names = state_dict keys)."""
+
+    def __init__(self, input_height, input_channels, noise_dim, z_dim, nonlinearity):
+        super().__init__()
+        self.input_height, self.input_channels = input_height, input_channels
+        self.noise_dim, self.z_dim, self.nonlinearity, self.enc_noise = noise_dim, z_dim, nonlinearity, False
+        co = lambda hin: int((hin + 2 * 2 - 1 * (5 - 1) - 1) / 2 + 1)  # utils/msc.py:43-45
+        s_h8 = co(co(co(input_height)))
+        self.conv1 = nn.Conv2d(input_channels, 16, 5, 2, 2, bias=True)
+        self.conv2 = nn.Conv2d(16, 32, 5, 2, 2, bias=True)
+        self.conv3 = nn.Conv2d(32, 32, 5, 2, 2, bias=True)
+        self.fc4 = nn.Linear(s_h8 * s_h8 * 32 + noise_dim, 800, bias=True)
+        self.fc5 = nn.Linear(800, z_dim, bias=True)
+        self.nos_encode = Identity()
+        self.s_h8 = s_h8
+
+    def sample_noise(self, batch_size, std=None, device=None):
+        std = std if std is not None else 1
+        device = device if device is not None else next(self.parameters()).device
+        if std == 0:
+            return torch.zeros(batch_size, self.noise_dim, device=device)
+        return std * torch.randn(batch_size, self.noise_dim, device=device)
+
+    def forward(self, x, noise=None, std=None, nz=1):
+        owner = self._owner()
+        batch_size = x.size(0)
+        if noise is None:
+            zero = std is not None and std == 0
+            noise = None if zero else self.sample_noise(batch_size * nz, std=std, device=x.device)
+        else:
+            assert noise.size(0) == batch_size * nz
+            assert noise.size(1) == self.noise_dim
+        return owner._encode(x, noise, nz)
+
+
+class _ConvDecoder(nn.Module):
+    """models/vae/conv.py:79-136 (parameter container)."""
+
+    def __init__(self, input_height, input_channels, z_dim, nonlinearity, s_h8):
+        super().__init__()
+        self.input_height, self.input_channels, self.z_dim, self.nonlinearity = input_height, input_channels, z_dim, nonlinearity
+        self.s_h8 = s_h8
+        self.fc = MLP(z_dim, 300, s_h8 * s_h8 * 32, nonlinearity, 1, True)
+        self.deconv1 = nn.ConvTranspose2d(32, 32, 5, 2, 2, 0, bias=True)
+        self.deconv2 = nn.ConvTranspose2d(32, 16, 5, 2, 2, 0, bias=True)
+        self.reparam = BernoulliDistributionConvTranspose2d(16, input_channels, 5, 2, 2, 0, bias=True)
+
+    def forward(self, z):
+        raise NotImplementedError('the decoder runs inside model.forward / model.logprob on the B200 path')
+
+
+class ConvIPVAE(ImplicitPosteriorVAE):
+    """net.ConvIPVAE (models/ivae/conv.py:138-304): 3x(conv 5x5 s2) + noise-concat fc encoder, fc + 3x deconv
+    Bernoulli decoder.  The conv / deconv layers run as direct fp32 CUDA kernels on the data rows; the
+    per-sample layers (fc4, fc5) and the decoder fc run on the tcgen05 GEMMs."""
+    KIND = 'conv'
+
+    def __init__(self, energy_func=normal_energy_func, input_height=28, input_channels=1, z_dim=32, noise_dim=100,
+                 nonlinearity='softplus', do_xavier=True):
+        nn.Module.__init__(self)
+        if nonlinearity not in ('relu', 'softplus'):
+            raise NotImplementedError("nonlinearity must be 'relu' or 'softplus'")
+        if energy_func is not normal_energy_func:
+            raise NotImplementedError('only the N(0,I) prior energy is fused')
+        self.energy_func = energy_func
+        self.input_height, self.input_channels = input_height, input_channels
+        self.input_dim = input_channels * input_height * input_height
+        self.z_dim, self.latent_dim, self.noise_dim = z_dim, z_dim, noise_dim
+        self.nonlinearity, self.do_xavier = nonlinearity, do_xavier
+        self.h_dim = 800
+        self.encode = _ConvEncoder(input_height, input_channels, noise_dim, z_dim, nonlinearity)
+        self.decode = _ConvDecoder(input_height, input_channels, z_dim, nonlinearity, self.encode.s_h8)
+        if do_xavier:  # models/vae/auxconv.py:18-23: Conv2d and Linear only (not ConvTranspose2d)
+            self.apply(_weight_init)
+        self._n_inp, self._n_fc, self._n_dec = 3, 1, 2
+        object.__setattr__(self.encode, '_owner', weakref.ref(self))
+        self._arena = ParamArena(self)
+        self._plans = {}
+        self.inv_rows_override = None
+
+    def forward(self, input, beta=1.0, eta=0.0, lmbd=0.0, std=None, nz=1, noise=None):
+        out = super().forward(input.reshape(input.size(0), -1), beta, eta, lmbd, std, nz, noise)
+        shp = (-1, self.input_channels, self.input_height, self.input_height)
+        return (out[0].view(shp), out[1].view(shp)) + out[2:]

@@ -97,7 +97,7 @@ ARDAE_API int ardae_cdae_score(ardae_cdae_t h, const float* x, const float* ctx,
 static void to_mcfg(const ardae_model_config* c, ModelConfig* o) {
   o->kind = c->kind; o->D = c->input_dim; o->n = c->noise_dim; o->h = c->h_dim; o->zd = c->z_dim;
   o->n_inp = c->n_inp; o->n_fc = c->n_fc; o->n_dec = c->n_dec; o->act = c->act; o->B = c->batch;
-  o->nz = c->nz; o->mode = c->mode;
+  o->nz = c->nz; o->mode = c->mode; o->img_h = c->img_h; o->img_c = c->img_c;
 }
 
 ARDAE_API int ardae_model_workspace_bytes(const ardae_model_config* cfg, size_t* bytes) {

@@ -11,11 +11,13 @@
 //   mnist: inp_encode (n_inp linears), fc.layers (n_fc), fc.fc, decode.main (n_dec), logit_fn
 #pragma once
 #include "cdae.cuh"
+#include "conv_kernels.cuh"
 
 namespace ardae {
 
 struct ModelConfig {
-  int kind = 0;   // 0 toy (gaussian decoder, noise concatenated at every fc layer), 1 mnist
+  int kind = 0;   // 0 toy (gaussian decoder, noise concatenated at every fc layer), 1 mnist, 2 conv (ConvIPVAE)
+  int img_h = 0, img_c = 0;  // kind 2: image height (= width) and channels; D = img_c*img_h*img_h
   int D = 0, n = 0, h = 0, zd = 0;
   int n_inp = 0, n_fc = 0, n_dec = 0;  // number of linears in inp_encode, hidden fc layers, decode.main
   int act = 1;    // 0 relu, 1 softplus
@@ -51,7 +53,7 @@ struct ModelPlan {
   DeriveList derive;
   size_t tn_need = 0;
 
-  int n_heads() const { return cfg.kind == 0 ? 2 : 1; }
+  int n_heads() const { return cfg.kind == 0 ? 2 : (cfg.kind == 2 ? 3 : 1); }  // kind 2: deconv1, deconv2, logit_fn
   int ntensors() const { return 2 * (cfg.n_inp + cfg.n_fc + 1 + cfg.n_dec + n_heads()); }
 
   int build(float* const* params, float* const* grads) {
@@ -59,7 +61,21 @@ struct ModelPlan {
     const int D = c.D, n = c.n, h = c.h, zd = c.zd, B = c.B, nz = c.nz, R = B * nz;
     if (D <= 0 || n <= 0 || h <= 0 || zd <= 0 || B <= 0 || nz <= 0 || c.n_inp < 1 || c.n_fc < 1 || c.n_dec < 1)
       return fail(-2, "model: bad config");
-    if (c.kind != 0 && c.kind != 1) return fail(-2, "model: kind must be 0 (toy) or 1 (mnist)");
+    if (c.kind < 0 || c.kind > 2) return fail(-2, "model: kind must be 0 (toy), 1 (mnist) or 2 (conv)");
+    const bool conv = c.kind == 2;
+    // conv geometry (models/ivae/conv.py:64-67): three 5x5 stride-2 pad-2 convs
+    auto cos_ = [](int hin) { return (hin + 4 - 5) / 2 + 1; };
+    const int s1 = conv ? c.img_h : 0, s2 = conv ? cos_(s1) : 0, s4 = conv ? cos_(s2) : 0, s8 = conv ? cos_(s4) : 0;
+    const int d7 = conv ? (s8 - 1) * 2 + 1 : 0;         // deconv1 output (7 for 28x28)
+    const int d8 = d7 + 1;                               // after ZeroPad2d((0,1,0,1))
+    const int d15 = conv ? (d8 - 1) * 2 + 1 : 0;        // deconv2 output
+    if (conv) {
+      if (c.img_h <= 0 || c.img_c <= 0 || D != c.img_c * c.img_h * c.img_h) return fail(-2, "model: conv needs D = img_c*img_h^2");
+      if ((d15 - 1) * 2 + 1 - 1 != c.img_h) return fail(-2, "model: conv decoder geometry does not reproduce img_h (28, 12, 20, ... work)");
+      if (c.n_inp != 3 || c.n_fc != 1 || c.n_dec != 2) return fail(-2, "model: conv expects n_inp=3, n_fc=1, n_dec=2");
+    }
+    const int feat = conv ? s8 * s8 * 32 : h;             // width of the per-data-row features fed to fc layer 0
+    auto dwid = [&](int l) { return conv ? (l == 0 ? 300 : feat) : h; };  // decoder fc widths (vae/conv.py:109)
     const bool dry = ws.dry, train = c.mode == 1, dec = c.mode != 0;
     if (c.mode == 2 && (zd > 64 || nz < 2 * zd)) return fail(-2, "iws: need z_dim <= 64 and sample_size >= 2*z_dim (ivae/mnist.py:382)");
     fwd.dry = bwd_dec.dry = bwd_enc.dry = dry;
@@ -78,14 +94,14 @@ struct ModelPlan {
     // ---- derived weights
     derive = DeriveList();
     std::vector<W3> Iw(c.n_inp), Dw(c.n_dec);
-    for (int l = 0; l < c.n_inp; ++l) {
+    for (int l = 0; l < c.n_inp && !conv; ++l) {
       const int in = l == 0 ? D : h;
       Iw[l] = derive.add(ws, P(iI(l)), h, in, in, true, train && l > 0);
     }
-    // fc layer 0: [h, h+n] = [W_inp | W_noise]
-    const int ld0 = h + n;
-    W3 F0i = derive.add(ws, P(iF(0)), h, h, ld0, true, train);
-    W3 F0n = derive.add(ws, P(iF(0)) ? P(iF(0)) + h : nullptr, h, n, ld0, true, false);
+    // fc layer 0: [h, feat+n] = [W_inp | W_noise]
+    const int ld0 = feat + n;
+    W3 F0i = derive.add(ws, P(iF(0)), h, feat, ld0, true, train);
+    W3 F0n = derive.add(ws, P(iF(0)) ? P(iF(0)) + feat : nullptr, h, n, ld0, true, false);
     // later fc layers (toy: input is [hid | eps]; mnist has none) and the final fc.fc
     std::vector<W3> Fw(c.n_fc + 1);
     for (int l = 1; l <= c.n_fc; ++l) {
@@ -94,13 +110,13 @@ struct ModelPlan {
       Fw[l] = derive.add(ws, P(iF(l)), out, in, in, true, train);
     }
     for (int l = 0; l < c.n_dec; ++l) {
-      const int in = l == 0 ? zd : h;
-      if (dec) Dw[l] = derive.add(ws, P(iD(l)), h, in, in, true, train);
+      const int in = l == 0 ? zd : dwid(l - 1);
+      if (dec) Dw[l] = derive.add(ws, P(iD(l)), dwid(l), in, in, true, train);
     }
     // heads: combined [nH*D, h] forward operand and [h, nH*D] transpose
     W3 Hw;
     Hw.in = h; Hw.out = nH * D; Hw.kp = round_up(h, 32);
-    if (dec) {
+    if (dec && !conv) {
       Hw.b3 = Mat(ws.floats(static_cast<size_t>(nH) * D * 3 * Hw.kp), nH * D, 3 * Hw.kp, 3 * Hw.kp);
       if (train) Hw.T = ws.mat(h, nH * Dp);
       for (int k = 0; k < nH; ++k) {
@@ -120,9 +136,19 @@ struct ModelPlan {
     if (rc) return rc;
 
     // ---- buffers
-    Pair xin = make_pair(ws, B, D);
+    Pair xin;
+    if (!conv) xin = make_pair(ws, B, D);
     std::vector<Pair> I(c.n_inp), Fh(c.n_fc + 1), Dh(c.n_dec);
-    for (int l = 0; l < c.n_inp; ++l) I[l] = make_pair(ws, B, h);
+    for (int l = 0; l < c.n_inp && !conv; ++l) I[l] = make_pair(ws, B, h);
+    // conv front end: NCHW fp32 feature maps on the B data rows, then the flattened conv3 output as a pair
+    float *c1 = nullptr, *c2 = nullptr, *c3 = nullptr;
+    if (conv) {
+      c1 = ws.floats(static_cast<size_t>(B) * 16 * s2 * s2);
+      c2 = ws.floats(static_cast<size_t>(B) * 32 * s4 * s4);
+      c3 = ws.floats(static_cast<size_t>(B) * feat);
+      I[c.n_inp - 1] = make_pair(ws, B, feat);
+    }
+    const Pair inp_pair = I[c.n_inp - 1];
     Pair epsp = make_pair(ws, R, n);
     Mat rowbias0 = ws.mat(B, h);
     // fc hidden outputs; for toy they live inside the concat buffer [hid | eps] of the next layer
@@ -135,25 +161,39 @@ struct ModelPlan {
     float* tn_ws = nullptr;
     size_t tn_bytes = 0;
     float *lw0 = nullptr, *wbuf = nullptr;
+    // conv back end (vae/conv.py:126-131): h1 [R,32,s8,s8] -> deconv1 -> pad -> deconv2 -> logit deconv -> crop
+    float *h1 = nullptr, *h2p = nullptr, *h3 = nullptr, *dh3 = nullptr, *dh2 = nullptr, *dh1 = nullptr;
     if (dec) {
-      for (int l = 0; l < c.n_dec; ++l) Dh[l] = make_pair(ws, R, h);
-      heads = ws.mat(R, nH * Dp);
+      for (int l = 0; l < c.n_dec; ++l) Dh[l] = make_pair(ws, R, dwid(l));
+      if (conv) {
+        heads = Mat(ws.floats(static_cast<size_t>(R) * D), R, D, D);
+        h1 = ws.floats(static_cast<size_t>(R) * feat);
+        h2p = ws.floats(static_cast<size_t>(R) * 32 * d8 * d8);   // zero-padded (pad row/col never written)
+        h3 = ws.floats(static_cast<size_t>(R) * 16 * d15 * d15);
+      } else {
+        heads = ws.mat(R, nH * Dp);
+      }
     }
     if (c.mode == 2) {
       lw0 = ws.floats(R);
       wbuf = ws.floats(R);
     }
     if (train) {
-      dheads = ws.mat(R, nH * Dp);
+      dheads = conv ? Mat(ws.floats(static_cast<size_t>(R) * D), R, D, D) : ws.mat(R, nH * Dp);
       dzdec = ws.mat(R, zd);
       dzt = ws.mat(R, zd);
-      for (int l = 0; l < c.n_dec; ++l) dD[l] = ws.mat(R, h);
+      for (int l = 0; l < c.n_dec; ++l) dD[l] = ws.mat(R, dwid(l));
       for (int l = 0; l < c.n_fc; ++l) dF[l] = ws.mat(R, h);
-      for (int l = 0; l < c.n_inp; ++l) dI[l] = ws.mat(B, h);
+      for (int l = 0; l < c.n_inp; ++l) dI[l] = ws.mat(B, (conv && l == c.n_inp - 1) ? feat : (conv ? 4 : h));
       gsum0 = ws.mat(B, h);
+      if (conv) {
+        dh3 = ws.floats(static_cast<size_t>(R) * 16 * d15 * d15);
+        dh2 = ws.floats(static_cast<size_t>(R) * 32 * d8 * d8);
+        dh1 = ws.floats(static_cast<size_t>(R) * feat);
+      }
       if (dry) {
-        const int shapes[8][3] = {{h, h + n, R}, {h, h, R}, {zd, h + n, R}, {nH * D, h, R}, {h, zd, R},
-                                  {h, D, B}, {h, h, B}, {h, n, R}};
+        const int shapes[10][3] = {{h, h + n, R}, {h, h, R}, {zd, h + n, R}, {nH * D, h, R}, {h, zd, R},
+                                   {h, D, B}, {h, h, B}, {h, n, R}, {h, feat, B}, {feat, 300, R}};
         tn_need = 0;
         for (auto& sh : shapes) {
           const size_t b = tn_workspace_bytes(sh[0], sh[1], sh[2]);
@@ -166,9 +206,12 @@ struct ModelPlan {
     ModelBindings* bd = &bind;
 
     // ================================================================= forward
+    const int CACT = c.act ? CONV_ACT_SOFTPLUS : CONV_ACT_RELU;
+    const int IH = c.img_h, IC = c.img_c;
     fwd.add([=](cudaStream_t s) {
-      split2d_kernel<<<grid_for(static_cast<size_t>(B) * D), 256, 0, s>>>(
-          bd->x, D, xin.buf.p, xin.buf.ld, B, D, xin.kp, toy ? 1.0f : 2.0f, toy ? 0.0f : -1.0f);
+      if (!conv)
+        split2d_kernel<<<grid_for(static_cast<size_t>(B) * D), 256, 0, s>>>(
+            bd->x, D, xin.buf.p, xin.buf.ld, B, D, xin.kp, toy ? 1.0f : 2.0f, toy ? 0.0f : -1.0f);
       if (bd->noise != nullptr) {
         split2d_kernel<<<grid_for(static_cast<size_t>(R) * n), 256, 0, s>>>(
             bd->noise, n, epsp.buf.p, epsp.buf.ld, R, n, epsp.kp, 1.0f, 0.0f);
@@ -179,14 +222,29 @@ struct ModelPlan {
       return static_cast<int>(cudaGetLastError());
     });
     // inp_encode on the B data rows
-    for (int l = 0; l < c.n_inp; ++l) {
+    for (int l = 0; l < c.n_inp && !conv; ++l) {
       GemmNTDesc g = nt3_desc(l == 0 ? xin : I[l - 1], Iw[l], I[l], ACT);
       g.bias = P(iI(l) + 1);
       fwd.nt(g);
     }
+    if (conv) {
+      // x <- 2x-1, conv(1->16) -> conv(16->32) -> conv(32->32), all 5x5 s2 p2 + activation (ivae/conv.py:84-96)
+      const float *w1 = P(iI(0)), *b1 = P(iI(0) + 1), *w2 = P(iI(1)), *b2 = P(iI(1) + 1), *w3 = P(iI(2)), *b3 = P(iI(2) + 1);
+      fwd.add([=](cudaStream_t s) {
+        conv5s2_fwd_kernel<<<grid_for(static_cast<size_t>(B) * 16 * s2 * s2), 256, 0, s>>>(
+            bd->x, IC, IH, IH, IH, w1, b1, c1, 16, s2, s2, s2, B, 2.0f, -1.0f, CACT, nullptr);
+        conv5s2_fwd_kernel<<<grid_for(static_cast<size_t>(B) * 32 * s4 * s4), 256, 0, s>>>(
+            c1, 16, s2, s2, s2, w2, b2, c2, 32, s4, s4, s4, B, 1.0f, 0.0f, CACT, nullptr);
+        conv5s2_fwd_kernel<<<grid_for(static_cast<size_t>(B) * 32 * s8 * s8), 256, 0, s>>>(
+            c2, 32, s4, s4, s4, w3, b3, c3, 32, s8, s8, s8, B, 1.0f, 0.0f, CACT, nullptr);
+        split2d_kernel<<<grid_for(static_cast<size_t>(B) * feat), 256, 0, s>>>(
+            c3, feat, inp_pair.buf.p, inp_pair.buf.ld, B, feat, inp_pair.kp, 1.0f, 0.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
     // fc layer 0: input half once per data row (rowbias0), noise half over the R rows
     {
-      GemmNTDesc g = nt3_desc_plain(I[c.n_inp - 1], F0i, rowbias0, EPI_LINEAR);
+      GemmNTDesc g = nt3_desc_plain(inp_pair, F0i, rowbias0, EPI_LINEAR);
       g.bias = P(iF(0) + 1);
       fwd.nt(g);
     }
@@ -248,13 +306,30 @@ struct ModelPlan {
       g.bias = P(iD(l) + 1);
       fwd.nt(g);
     }
-    for (int k = 0; k < nH; ++k) {
+    for (int k = 0; k < nH && !conv; ++k) {
       W3 hk = Hw;
       hk.out = D;
       hk.b3 = Hw.b3.rows_from(k * D, D);
       GemmNTDesc g = nt3_desc_plain(Dh[c.n_dec - 1], hk, heads.cols_from(k * Dp, D), EPI_LINEAR);
       g.bias = P(iH(k) + 1);
       fwd.nt(g);
+    }
+    if (conv) {
+      // deconvs as the adjoint (backward-data) form of the 5x5 s2 p2 conv; the reference pads deconv1's
+      // activated output to d8 x d8 and crops the last row/column of the logits (vae/conv.py:128-131)
+      const Pair hl = Dh[c.n_dec - 1];
+      const float *wd1 = P(iH(0)), *bd1 = P(iH(0) + 1), *wd2 = P(iH(1)), *bd2 = P(iH(1) + 1), *wl = P(iH(2)), *bl = P(iH(2) + 1);
+      fwd.add([=](cudaStream_t s) {
+        pair_sum_kernel<<<grid_for(static_cast<size_t>(R) * feat), 256, 0, s>>>(hl.hi().p, hl.lo().p, hl.buf.ld, h1, feat,
+                                                                              nullptr, R, feat);
+        conv5s2_bwd_data_kernel<<<grid_for(static_cast<size_t>(R) * 32 * d7 * d7), 256, 0, s>>>(
+            h1, 32, s8, s8, s8, wd1, bd1, h2p, 32, d7, d8, d8, R, CACT, nullptr, 0);
+        conv5s2_bwd_data_kernel<<<grid_for(static_cast<size_t>(R) * 16 * d15 * d15), 256, 0, s>>>(
+            h2p, 32, d8, d8, d8, wd2, bd2, h3, 16, d15, d15, d15, R, CACT, nullptr, 0);
+        conv5s2_bwd_data_kernel<<<grid_for(static_cast<size_t>(R) * IC * IH * IH), 256, 0, s>>>(
+            h3, 16, d15, d15, d15, wl, bl, heads.p, IC, IH, IH, IH, R, CONV_ACT_NONE, nullptr, 0);
+        return static_cast<int>(cudaGetLastError());
+      });
     }
     if (c.mode == 2) {
       fwd.add([=](cudaStream_t s) {
@@ -294,16 +369,42 @@ struct ModelPlan {
       });
     };
     // ---- decoder part (skipped when loss_scale == 0)
-    for (int k = 0; k < nH; ++k) {
+    for (int k = 0; k < nH && !conv; ++k) {
       const Mat dh = dheads.cols_from(k * Dp, D);
       tn1(bwd_dec, dh, Dh[c.n_dec - 1].hi(), G(iH(k)), h);
       colsum_op(bwd_dec, dh, G(iH(k) + 1));
     }
-    {
+    if (!conv) {
       GemmNTDesc g = nt_desc(dheads, Hw.T, dD[c.n_dec - 1], DACT);
       set_aux1(g, Dh[c.n_dec - 1].hi());
       g.colsum = G(iD(c.n_dec - 1) + 1);
       bwd_dec.nt(g);
+    } else {
+      float *gwd1 = G(iH(0)), *gbd1 = G(iH(0) + 1), *gwd2 = G(iH(1)), *gbd2 = G(iH(1) + 1), *gwl = G(iH(2)), *gbl = G(iH(2) + 1);
+      const float *wd1 = P(iH(0)), *wd2 = P(iH(1)), *wl = P(iH(2));
+      const Mat dlast = dD[c.n_dec - 1];
+      float* gb_last = G(iD(c.n_dec - 1) + 1);
+      bwd_dec.add([=](cudaStream_t s) {
+        // logit deconv: d h3pre = conv(dlogit) * act'(h3) ; dW = <dlogit (conv input role), h3 (conv output role)>
+        conv5s2_fwd_kernel<<<grid_for(static_cast<size_t>(R) * 16 * d15 * d15), 256, 0, s>>>(
+            dheads.p, IC, IH, IH, IH, wl, nullptr, dh3, 16, d15, d15, d15, R, 1.0f, 0.0f, CACT, h3);
+        conv5s2_bwd_weight_kernel<<<16 * IC, 256, 0, s>>>(dheads.p, IC, IH, IH, IH, h3, 16, d15, d15, d15, gwl, nullptr, R, 1.0f, 0.0f);
+        chan_sum_kernel<<<IC, 256, 0, s>>>(dheads.p, IC, IH, IH, IH, R, gbl);
+        // deconv2
+        conv5s2_fwd_kernel<<<grid_for(static_cast<size_t>(R) * 32 * d8 * d8), 256, 0, s>>>(
+            dh3, 16, d15, d15, d15, wd2, nullptr, dh2, 32, d8, d8, d8, R, 1.0f, 0.0f, CACT, h2p);
+        conv5s2_bwd_weight_kernel<<<32 * 16, 256, 0, s>>>(dh3, 16, d15, d15, d15, h2p, 32, d8, d8, d8, gwd2, nullptr, R, 1.0f, 0.0f);
+        chan_sum_kernel<<<16, 256, 0, s>>>(dh3, 16, d15, d15, d15, R, gbd2);
+        // deconv1 (its input h1 is the activated output of decode.fc: multiply by act' there)
+        conv5s2_fwd_kernel<<<grid_for(static_cast<size_t>(R) * 32 * s8 * s8), 256, 0, s>>>(
+            dh2, 32, d7, d8, d8, wd1, nullptr, dh1, 32, s8, s8, s8, R, 1.0f, 0.0f, CONV_ACT_NONE, nullptr);
+        conv5s2_bwd_weight_kernel<<<32 * 32, 256, 0, s>>>(dh2, 32, d7, d8, d8, h1, 32, s8, s8, s8, gwd1, nullptr, R, 1.0f, 0.0f);
+        chan_sum_kernel<<<32, 256, 0, s>>>(dh2, 32, d7, d8, d8, R, gbd1);
+        mul_dact_kernel<<<grid_for(static_cast<size_t>(R) * feat), 256, 0, s>>>(dh1, h1, dlast.p, static_cast<size_t>(R) * feat, CACT, 1);
+        dim3 grid((feat + 31) / 32, R >= 2048 ? 32 : (R + 63) / 64);
+        colsum_kernel<<<grid, 256, 0, s>>>(dlast.p, dlast.ld, R, feat, gb_last, 1.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
     }
     for (int l = c.n_dec - 1; l >= 1; --l) {
       GemmNTDesc g = nt_desc(dD[l], Dw[l].T, dD[l - 1], DACT);
@@ -311,7 +412,7 @@ struct ModelPlan {
       g.colsum = G(iD(l - 1) + 1);
       bwd_dec.nt(g);
     }
-    for (int l = c.n_dec - 1; l >= 1; --l) tn1(bwd_dec, dD[l], Dh[l - 1].hi(), G(iD(l)), h);
+    for (int l = c.n_dec - 1; l >= 1; --l) tn1(bwd_dec, dD[l], Dh[l - 1].hi(), G(iD(l)), dwid(l - 1));
     tn1(bwd_dec, dD[0], zp.hi(), G(iD(0)), zd);
     {
       GemmNTDesc g = nt_desc(dD[0], Dw[0].T, dzdec, EPI_LINEAR);
@@ -348,7 +449,7 @@ struct ModelPlan {
     }
     for (int l = c.n_fc - 1; l >= 1; --l) tn1(bwd_enc, dF[l], Fh[l - 1].hi(), G(iF(l)), toy ? h + n : h);
     // layer 0: noise half over R rows, input half through the per-data-row sum
-    tn1(bwd_enc, dF[0], epsp.hi(), G(iF(0)) ? G(iF(0)) + h : nullptr, ld0);
+    tn1(bwd_enc, dF[0], epsp.hi(), G(iF(0)) ? G(iF(0)) + feat : nullptr, ld0);
     {
       const Mat d0 = dF[0];
       bwd_enc.add([=](cudaStream_t s) {
@@ -356,12 +457,35 @@ struct ModelPlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
-    tn1(bwd_enc, gsum0, I[c.n_inp - 1].hi(), G(iF(0)), ld0);
+    tn1(bwd_enc, gsum0, inp_pair.hi(), G(iF(0)), ld0);
     {
       GemmNTDesc g = nt_desc(gsum0, F0i.T, dI[c.n_inp - 1], DACT);
-      set_aux1(g, I[c.n_inp - 1].hi());
-      g.colsum = G(iI(c.n_inp - 1) + 1);
+      set_aux1(g, inp_pair.hi());
+      if (!conv) g.colsum = G(iI(c.n_inp - 1) + 1);  // conv: the bias is per channel, summed below
+      if (conv) g.round_out = 0;
       bwd_enc.nt(g);
+    }
+    if (conv) {
+      // back through conv3, conv2, conv1 (dI[last] = d pre-activation of conv3's output, [B, 32*s8*s8])
+      const float* dc3 = dI[c.n_inp - 1].p;
+      const int ldc3 = dI[c.n_inp - 1].ld;
+      float *gw1 = G(iI(0)), *gb1 = G(iI(0) + 1), *gw2 = G(iI(1)), *gb2 = G(iI(1) + 1), *gw3 = G(iI(2)), *gb3 = G(iI(2) + 1);
+      const float *w2 = P(iI(1)), *w3 = P(iI(2));
+      float* dc2 = ws.floats(static_cast<size_t>(B) * 32 * s4 * s4);
+      float* dc1 = ws.floats(static_cast<size_t>(B) * 16 * s2 * s2);
+      float* dc3c = ws.floats(static_cast<size_t>(B) * feat);  // contiguous copy (dI pitch may be padded)
+      bwd_enc.add([=](cudaStream_t s) {
+        unpad_kernel<<<grid_for(static_cast<size_t>(B) * feat), 256, 0, s>>>(dc3, ldc3, dc3c, B, feat, 1.0f);
+        conv5s2_bwd_weight_kernel<<<32 * 32, 256, 0, s>>>(c2, 32, s4, s4, s4, dc3c, 32, s8, s8, s8, gw3, gb3, B, 1.0f, 0.0f);
+        conv5s2_bwd_data_kernel<<<grid_for(static_cast<size_t>(B) * 32 * s4 * s4), 256, 0, s>>>(
+            dc3c, 32, s8, s8, s8, w3, nullptr, dc2, 32, s4, s4, s4, B, CACT, c2, 1);
+        conv5s2_bwd_weight_kernel<<<32 * 16, 256, 0, s>>>(c1, 16, s2, s2, s2, dc2, 32, s4, s4, s4, gw2, gb2, B, 1.0f, 0.0f);
+        conv5s2_bwd_data_kernel<<<grid_for(static_cast<size_t>(B) * 16 * s2 * s2), 256, 0, s>>>(
+            dc2, 32, s4, s4, s4, w2, nullptr, dc1, 16, s2, s2, s2, B, CACT, c1, 1);
+        conv5s2_bwd_weight_kernel<<<16 * IC, 256, 0, s>>>(bd->x, IC, IH, IH, IH, dc1, 16, s2, s2, s2, gw1, gb1, B, 2.0f, -1.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return fwd.error ? fwd.error : (bwd_dec.error ? bwd_dec.error : bwd_enc.error);
     }
     for (int l = c.n_inp - 1; l >= 1; --l) {
       GemmNTDesc g = nt_desc(dI[l], Iw[l].T, dI[l - 1], DACT);

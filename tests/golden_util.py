@@ -5,7 +5,28 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['toy_small', 'mnist_small', 'mnist_small_x3']
+CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small']
+
+
+def model_dims(meta):
+    """(input_dim, noise_dim, h_dim, z_dim, num_hidden_layers, nonlinearity) for any model kind."""
+    m = meta['model']
+    if meta['kind'] == 'conv':
+        return (m['input_channels'] * m['input_height'] ** 2, m['noise_dim'], 800, m['z_dim'], 0, m['nonlinearity'])
+    return (m['input_dim'], m['noise_dim'], m['h_dim'], m['z_dim'], m['num_hidden_layers'], m['nonlinearity'])
+
+
+def build_model(meta):
+    """The drop-in model class of the product package for a fixture's meta."""
+    import ardae
+    m = meta['model']
+    if meta['kind'] == 'conv':
+        return ardae.ConvIPVAE(input_height=m['input_height'], input_channels=m['input_channels'], z_dim=m['z_dim'],
+                               noise_dim=m['noise_dim'], nonlinearity=m['nonlinearity'])
+    cls = ardae.ToyIPVAE if meta['kind'] == 'toy' else ardae.MNISTIPVAE
+    return cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
+               num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',
+               z_dim=m['z_dim'])
 
 
 def load_case(name):

@@ -10,18 +10,16 @@ from golden_util import load_case, sub
 
 def build(meta):
     import ardae
-    m, c = meta['model'], meta['cdae']
-    cls = ardae.ToyIPVAE if meta['kind'] == 'toy' else ardae.MNISTIPVAE
-    model = cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
-                num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',
-                z_dim=m['z_dim'])
+    import golden_util
+    c = meta['cdae']
+    model = golden_util.build_model(meta)
     cdae = ardae.MLPGradCARDAE(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
                                num_hidden_layers=c['num_hidden_layers'], nonlinearity=c['nonlinearity'],
                                noise_type='gaussian', enc_ctx=True, enc_input=True)
     return model, cdae
 
 
-@pytest.mark.parametrize('name', ['toy_small', 'mnist_small'])
+@pytest.mark.parametrize('name', ['toy_small', 'mnist_small', 'conv_small'])
 def test_state_dict_layout_matches_reference(name):
     z, meta = load_case(name)
     model, cdae = build(meta)
@@ -46,6 +44,8 @@ def test_full_size_parameter_counts():
     c1 = ardae.MLPGradCARDAE(input_dim=2, context_dim=2, std=1., h_dim=256, num_hidden_layers=3, nonlinearity='softplus')
     n = lambda mod: sum(p.numel() for p in mod.parameters())
     assert (n(m2), n(c2), n(m1), n(c1)) == (1062816, 938241, 271386, 528129)
+    m4 = ardae.ConvIPVAE(input_height=28, input_channels=1, z_dim=32, noise_dim=100, nonlinearity='softplus')
+    assert n(m4) == 757773
 
 
 def test_init_semantics():

@@ -7,17 +7,13 @@ import torch
 
 import ardae_oracle as orc
 from golden_util import CASES, load_case, sub
+import golden_util
 
 pytestmark = pytest.mark.gpu
 
 
 def build_model(meta, state):
-    import ardae
-    m = meta['model']
-    cls = ardae.ToyIPVAE if meta['kind'] == 'toy' else ardae.MNISTIPVAE
-    model = cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
-                num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',
-                z_dim=m['z_dim'])
+    model = golden_util.build_model(meta)
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)).float() for k, v in state.items()})
     return model.cuda()
 
@@ -29,7 +25,7 @@ def t(a):
 @pytest.mark.parametrize('name', CASES)
 def test_iws_matches_reference_fixture(name):
     z, meta = load_case(name)
-    model = build_model(meta, sub(z, 's1/m_after/'))
+    model = build_model(meta, sub(z, 'm0/' if name == 'conv_small' else 's1/m_after/'))
     val = model.logprob(t(z['iws/x']), sample_size=meta['iws']['S'], noise=t(z['iws/enc_noise']), eta=t(z['iws/eta']))
     ref = float(z['iws/logprob'])
     tol = 0.05 if not name.endswith('_x3') else 0.05 * max(1.0, abs(ref) / 100)

