@@ -204,6 +204,44 @@ struct CdaePlan {
     }
     plan.cur_lane = 0;  // (still forked: joined right before p_1 needs the per-row bias)
     // ---- sweep 1: primal forward (3xTF32)
+    // Fused path: the H -> H layers of each sweep run as ONE launch per chain (chain_sm100.cuh) with the
+    // activation operand resident on chip; only the d -> H first layer / H -> d last layer stay per-layer GEMMs.
+    const bool use_chain = chain_supported(H, 1) && 2 * L - 1 <= kChainMaxLayers;
+    auto chain_of = [&](int mode, const Mat& a0) {
+      ChainDesc cd;
+      cd.mode = mode; cd.M = N; cd.H = H; cd.A0 = a0.p; cd.lda0 = a0.ld; cd.row_scale = sig;
+      return cd;
+    };
+    auto s3_layer = [&](const W3& w, const float* bias, const Pair& out) {
+      ChainLayerDesc q;
+      q.W = w.b3.p; q.ldw = w.b3.ld; q.bias = bias; q.out = out.hi().p; q.ldo = out.buf.ld;
+      return q;
+    };
+    if (use_chain) {
+      {
+        GemmNTDesc g = nt3_desc(xt, Aw[0], U[0], EPI_SOFTPLUS);
+        g.bias = P(iA(0) + 1);
+        plan.nt(g);
+      }
+      if (L > 1) {
+        ChainDesc cd = chain_of(CHAIN_SOFTPLUS3, U[0].hi());
+        cd.A0lo = U[0].lo().p; cd.lda0lo = U[0].buf.ld;
+        for (int l = 1; l < L; ++l) cd.layers.push_back(s3_layer(Aw[l], P(iA(l) + 1), U[l]));
+        cd.layers.back().out_lo = U[L - 1].lo().p;  // the p-chain below restarts from the (hi, lo) pair
+        cd.layers.back().ld_out_lo = U[L - 1].buf.ld;
+        plan.chain(cd);
+      }
+      plan.join();
+      ChainDesc cd = chain_of(CHAIN_SOFTPLUS3, U[L - 1].hi());
+      cd.A0lo = U[L - 1].lo().p; cd.lda0lo = U[L - 1].buf.ld;
+      {
+        ChainLayerDesc q = s3_layer(W1u, nullptr, V[0]);
+        q.group_bias = rowbias.p; q.group = S; q.ldg = rowbias.ld; q.col_vec = wsig;
+        cd.layers.push_back(q);
+      }
+      for (int l = 1; l < L; ++l) cd.layers.push_back(s3_layer(Ww[l], P(iW(l) + 1), V[l]));
+      plan.chain(cd);
+    } else {
     for (int l = 0; l < L; ++l) {
       GemmNTDesc g = nt3_desc(l == 0 ? xt : U[l - 1], Aw[l], U[l], EPI_SOFTPLUS);
       g.bias = P(iA(l) + 1);
@@ -221,6 +259,7 @@ struct CdaePlan {
       g.bias = P(iW(l) + 1);
       plan.nt(g);
     }
+    }
     // ---- sweep 2: score backward (tf32)
     {
       const Mat vl = V[L - 1].hi(), dpl = DP[L - 1];
@@ -229,6 +268,18 @@ struct CdaePlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
+    auto bw_layer = [&](const Mat& wT, const Mat& aux1, const Mat& out) {
+      ChainLayerDesc q;
+      q.W = wT.p; q.ldw = wT.ld; q.aux1 = aux1.p; q.ld1 = aux1.ld; q.out = out.p; q.ldo = out.ld;
+      return q;
+    };
+    if (use_chain) {
+      ChainDesc cd = chain_of(CHAIN_MUL_SIG, DP[L - 1]);
+      for (int l = L - 1; l >= 1; --l) cd.layers.push_back(bw_layer(Ww[l].T, V[l - 1].hi(), DP[l - 1]));
+      cd.layers.push_back(bw_layer(W1u.T, U[L - 1].hi(), DA[L - 1]));
+      for (int l = L - 1; l >= 1; --l) cd.layers.push_back(bw_layer(Aw[l].T, U[l - 1].hi(), DA[l - 1]));
+      plan.chain(cd);
+    } else {
     for (int l = L - 1; l >= 1; --l) {
       GemmNTDesc g = nt_desc(DP[l], Ww[l].T, DP[l - 1], EPI_MUL_SIG);
       set_aux1(g, V[l - 1].hi());
@@ -243,6 +294,7 @@ struct CdaePlan {
       GemmNTDesc g = nt_desc(DA[l], Aw[l].T, DA[l - 1], EPI_MUL_SIG);
       set_aux1(g, U[l - 1].hi());
       plan.nt(g);
+    }
     }
     {
       GemmNTDesc g = nt_desc(DA[0], Aw[0].T, gmat, EPI_LINEAR);
@@ -263,6 +315,25 @@ struct CdaePlan {
       return static_cast<int>(cudaGetLastError());
     });
     // ---- sweep 3: tangent forward (also emits t = delta * tangent_pre * (1 - sig))
+    if (use_chain) {
+      {
+        GemmNTDesc g = nt_desc(rmat, Aw[0].hi(), UD[0], EPI_TANGENT);
+        set_aux1(g, U[0].hi()); set_aux2(g, DA[0]); set_out2(g, TA[0]);
+        plan.nt(g);
+      }
+      auto tg_layer = [&](const Mat& w, const Mat& aux1, const Mat& aux2, const Mat& out, const Mat& out2) {
+        ChainLayerDesc q;
+        q.W = w.p; q.ldw = w.ld; q.aux1 = aux1.p; q.ld1 = aux1.ld; q.aux2 = aux2.p; q.ld2 = aux2.ld;
+        q.out = out.p; q.ldo = out.ld; q.out2 = out2.p; q.ldo2 = out2.ld;
+        return q;
+      };
+      ChainDesc cd = chain_of(CHAIN_TANGENT, UD[0]);
+      for (int l = 1; l < L; ++l) cd.layers.push_back(tg_layer(Aw[l].hi(), U[l].hi(), DA[l], UD[l], TA[l]));
+      for (int l = 0; l < L; ++l) cd.layers.push_back(tg_layer(Ww[l].hi(), V[l].hi(), DP[l], VD[l], TP[l]));
+      cd.layers.back().colsum = G(iW(L)); cd.layers.back().colsum_scale = -1.0f;  // d w_o = -sum_n vdot_L
+      cd.layers.back().colsum2 = G(iW(L - 1) + 1);                                // d beta_L = sum_n adj p_L (= t_L)
+      plan.chain(cd);
+    } else {
     for (int l = 0; l < L; ++l) {
       GemmNTDesc g = nt_desc(l == 0 ? rmat : UD[l - 1], Aw[l].hi(), UD[l], EPI_TANGENT);
       set_aux1(g, U[l].hi()); set_aux2(g, DA[l]); set_out2(g, TA[l]);
@@ -277,20 +348,10 @@ struct CdaePlan {
       }
       plan.nt(g);
     }
-    // ---- sweep 4: adjoint backward (in place over the t buffers)
-    for (int l = L - 1; l >= 1; --l) {
-      GemmNTDesc g = nt_desc(TP[l], Ww[l].T, TP[l - 1], EPI_ADJOINT);
-      set_aux1(g, V[l - 1].hi()); set_aux2(g, TP[l - 1]);
-      g.colsum = G(iW(l - 1) + 1);
-      if (l - 1 == 0) {  // d w_1sigma = sum_n sigma_n * adj p_1
-        g.colsum_w = G(iW(0)) ? G(iW(0)) + 2 * H : nullptr;
-        g.colsum_w_stride = ld1;
-        g.row_w = sig;
-      }
-      plan.nt(g);
     }
-    // adj p_1 (TP[0]) is final: the context-branch backward (B rows) runs on the side lane underneath
-    // the rest of sweep 4 and the weight-gradient contractions
+    // ---- sweep 4: adjoint backward (in place over the t buffers)
+    // context-branch backward (B rows): side lane underneath the rest of the N-row work
+    auto ctx_backward = [&]() {
     plan.fork();
     // ---- context branch backward (B rows)
     {
@@ -325,6 +386,41 @@ struct CdaePlan {
       tn2(DC[0], y, nullptr, nullptr, G(iC(0)), c);
     }
     plan.cur_lane = 0;
+    };
+    if (use_chain) {
+      auto adj_layer = [&](const Mat& wT, const Mat& aux1, const Mat& t, float* colsum) {
+        ChainLayerDesc q;
+        q.W = wT.p; q.ldw = wT.ld; q.aux1 = aux1.p; q.ld1 = aux1.ld; q.aux2 = t.p; q.ld2 = t.ld;
+        q.out = t.p; q.ldo = t.ld; q.colsum = colsum;
+        return q;
+      };
+      ChainDesc cd = chain_of(CHAIN_ADJOINT, TP[L - 1]);
+      for (int l = L - 1; l >= 1; --l) {
+        ChainLayerDesc q = adj_layer(Ww[l].T, V[l - 1].hi(), TP[l - 1], G(iW(l - 1) + 1));
+        if (l - 1 == 0) {  // d w_1sigma = sum_n sigma_n * adj p_1
+          q.colsum_w = G(iW(0)) ? G(iW(0)) + 2 * H : nullptr;
+          q.colsum_w_stride = ld1;
+        }
+        cd.layers.push_back(q);
+      }
+      cd.layers.push_back(adj_layer(W1u.T, U[L - 1].hi(), TA[L - 1], G(iA(L - 1) + 1)));
+      for (int l = L - 1; l >= 1; --l) cd.layers.push_back(adj_layer(Aw[l].T, U[l - 1].hi(), TA[l - 1], G(iA(l - 1) + 1)));
+      plan.chain(cd);
+      ctx_backward();  // adj p_1 (TP[0]) is final only once the chain has finished
+    } else {
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(TP[l], Ww[l].T, TP[l - 1], EPI_ADJOINT);
+      set_aux1(g, V[l - 1].hi()); set_aux2(g, TP[l - 1]);
+      g.colsum = G(iW(l - 1) + 1);
+      if (l - 1 == 0) {  // d w_1sigma = sum_n sigma_n * adj p_1
+        g.colsum_w = G(iW(0)) ? G(iW(0)) + 2 * H : nullptr;
+        g.colsum_w_stride = ld1;
+        g.row_w = sig;
+      }
+      plan.nt(g);
+    }
+    // adj p_1 (TP[0]) is final: the context-branch backward runs underneath the rest of sweep 4
+    ctx_backward();
     {
       GemmNTDesc g = nt_desc(TP[0], W1u.T, TA[L - 1], EPI_ADJOINT);
       set_aux1(g, U[L - 1].hi()); set_aux2(g, TA[L - 1]);
@@ -336,6 +432,7 @@ struct CdaePlan {
       set_aux1(g, U[l - 1].hi()); set_aux2(g, TA[l - 1]);
       g.colsum = G(iA(l - 1) + 1);
       plan.nt(g);
+    }
     }
     // ---- weight gradients: dW = adj^T . act + delta^T . tangent   (accumulated into .grad)
     const Mat xt_hi = xt.hi();

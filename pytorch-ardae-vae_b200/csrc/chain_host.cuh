@@ -1,0 +1,107 @@
+// Host-side preparation (TMA tensor maps) and launch of the fused layer-chain kernel (chain_sm100.cuh).
+#pragma once
+#include <cstdlib>
+#include <vector>
+
+#include "chain_sm100.cuh"
+#include "gemm_host.cuh"
+
+namespace ardae {
+
+struct ChainLayerDesc {
+  const float* W = nullptr; int ldw = 0;      // B operand [H, H] K-major (SOFTPLUS3: [H, 3H] = [Whi | Whi | Wlo])
+  const float* aux1 = nullptr; int ld1 = 0;   // [M, H]
+  const float* aux2 = nullptr; int ld2 = 0;
+  float* out = nullptr; int ldo = 0;          // [M, H]
+  float* out2 = nullptr; int ldo2 = 0;        // TANGENT
+  float* out_lo = nullptr; int ld_out_lo = 0; // SOFTPLUS3: optional lo spill
+  const float* bias = nullptr;                // SOFTPLUS3
+  const float* group_bias = nullptr; int group = 1, ldg = 0;
+  const float* col_vec = nullptr;             // with ChainDesc::row_scale
+  float* colsum = nullptr; float colsum_scale = 1.0f;
+  float* colsum2 = nullptr;
+  float* colsum_w = nullptr; int colsum_w_stride = 1;
+};
+
+struct ChainDesc {
+  int mode = CHAIN_MUL_SIG;
+  int M = 0, H = 0;
+  const float* A0 = nullptr; int lda0 = 0;        // initial activation [M, H] (SOFTPLUS3: hi part)
+  const float* A0lo = nullptr; int lda0lo = 0;    // SOFTPLUS3: lo part
+  const float* row_scale = nullptr;               // [M]
+  std::vector<ChainLayerDesc> layers;
+};
+
+struct PreparedChain {
+  ChainParams params;
+  const void* fn = nullptr;
+  dim3 grid;
+  int smem = 0, threads = 0;
+};
+
+// The chain kernel serves H -> H layers with H a multiple of 32 up to 256 (one k-block ring stage = 256 x 32 floats).
+inline bool chain_supported(int H, int nlayers) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = std::getenv("ARDAE_CHAIN");
+    enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return enabled && H >= 32 && H <= 256 && H % 32 == 0 && nlayers >= 1 && nlayers <= kChainMaxLayers;
+}
+
+inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
+  const int nl = static_cast<int>(d.layers.size());
+  if (d.M <= 0 || !chain_supported(d.H, nl)) return fail(-2, "chain: unsupported shape");
+  if (d.mode < 0 || d.mode >= CHAIN_NUM_MODES) return fail(-2, "chain: bad mode");
+  const bool s3 = d.mode == CHAIN_SOFTPLUS3;
+  const bool aux2 = d.mode == CHAIN_TANGENT || d.mode == CHAIN_ADJOINT, out2 = d.mode == CHAIN_TANGENT;
+  if (!d.A0 || (s3 && !d.A0lo)) return fail(-2, "chain: missing initial activation");
+  PreparedChain pr;
+  std::memset(&pr.params, 0, sizeof(pr.params));
+  ChainParams& p = pr.params;
+  int rc;
+  if ((rc = encode_tmap_2d(&p.tmA0, d.A0, d.H, d.M, d.lda0, 32, kBlockM))) return rc;
+  p.a0_lo = d.A0lo; p.a0_lo_ld = d.lda0lo; p.row_scale = d.row_scale;
+  p.M = d.M; p.H = d.H; p.nlayers = nl;
+  uintptr_t align_or = s3 ? (reinterpret_cast<uintptr_t>(d.A0lo) | static_cast<uintptr_t>(d.lda0lo) * 4) : 0;
+  for (int l = 0; l < nl; ++l) {
+    const ChainLayerDesc& s = d.layers[l];
+    ChainLayerParams& q = p.layer[l];
+    if (!s.W || !s.out || (!s3 && !s.aux1) || (aux2 && !s.aux2) || (out2 && !s.out2))
+      return fail(-2, "chain: missing operand pointer");
+    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * d.H : d.H, d.H, s.ldw, kBlockK, d.H))) return rc;
+    if (!s3 && (rc = encode_tmap_2d(&q.tmAux1, s.aux1, d.H, d.M, s.ld1, 32, kBlockM))) return rc;
+    if (aux2 && (rc = encode_tmap_2d(&q.tmAux2, s.aux2, d.H, d.M, s.ld2, 32, kBlockM))) return rc;
+    if ((rc = encode_tmap_2d(&q.tmOut, s.out, d.H, d.M, s.ldo, 32, kBlockM))) return rc;
+    if (out2 && (rc = encode_tmap_2d(&q.tmOut2, s.out2, d.H, d.M, s.ldo2, 32, kBlockM))) return rc;
+    q.bias = s.bias; q.group_bias = s.group_bias; q.col_vec = s.col_vec;
+    q.group = s.group > 0 ? s.group : 1; q.ldg = s.ldg;
+    q.out_lo = s.out_lo; q.ld_out_lo = s.ld_out_lo;
+    align_or |= reinterpret_cast<uintptr_t>(s.out_lo) | (static_cast<uintptr_t>(s.ld_out_lo) * 4);
+    q.colsum = s.colsum; q.colsum_scale = s.colsum_scale; q.colsum2 = s.colsum2;
+    q.colsum_w = s.colsum_w; q.colsum_w_stride = s.colsum_w_stride;
+    if ((s.col_vec || s.colsum_w) && !d.row_scale) return fail(-2, "chain: col_vec / colsum_w need row_scale");
+    align_or |= reinterpret_cast<uintptr_t>(s.bias) | reinterpret_cast<uintptr_t>(s.group_bias) |
+                reinterpret_cast<uintptr_t>(s.col_vec) | (static_cast<uintptr_t>(s.ldg) * 4);
+  }
+  p.vec_ok = (align_or & 15) == 0 ? 1 : 0;
+  if (s3 && !p.vec_ok) return fail(-2, "chain: SOFTPLUS3 operands must be 16-byte aligned");
+  switch (d.mode) {
+    case CHAIN_MUL_SIG: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_MUL_SIG>); pr.smem = ChainConfig<CHAIN_MUL_SIG>::kSmemBytes; pr.threads = ChainConfig<CHAIN_MUL_SIG>::kThreads; break;
+    case CHAIN_TANGENT: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_TANGENT>); pr.smem = ChainConfig<CHAIN_TANGENT>::kSmemBytes; pr.threads = ChainConfig<CHAIN_TANGENT>::kThreads; break;
+    case CHAIN_ADJOINT: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_ADJOINT>); pr.smem = ChainConfig<CHAIN_ADJOINT>::kSmemBytes; pr.threads = ChainConfig<CHAIN_ADJOINT>::kThreads; break;
+    default: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_SOFTPLUS3>); pr.smem = ChainConfig<CHAIN_SOFTPLUS3>::kSmemBytes; pr.threads = ChainConfig<CHAIN_SOFTPLUS3>::kThreads; break;
+  }
+  pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
+  ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
+  *out = pr;
+  return 0;
+}
+
+inline int launch_prepared_chain(const PreparedChain& pr, cudaStream_t stream) {
+  void* args[1] = {const_cast<ChainParams*>(&pr.params)};
+  ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(pr.threads), args, pr.smem, stream));
+  return 0;
+}
+
+}  // namespace ardae

@@ -1,0 +1,449 @@
+// Fused layer-chain kernel: a run of H -> H layers of one AR-DAE sweep executed by ONE launch, each CTA
+// carrying its 128-row tile through every layer with the activation operand resident ON CHIP.
+//
+//   per layer l:   acc[128, H] = A_l[128, H] . W_l[H, H]^T          (tcgen05.mma kind::tf32, fp32 accumulate in TMEM)
+//                  (out_l, A_{l+1}) = epilogue_l(acc ; aux1_l, aux2_l)   A_{l+1} stays in TMEM / shared memory
+//
+// Why: the layer-per-launch path re-reads every activation tile from HBM as the next layer's A operand and
+// pushes A + W + aux through the ~80 GB/s-per-SM L2 port (round-1 profile: NT kernels at 27-44 % DRAM, 9-21 %
+// tensor pipe).  Here A never leaves the SM; per layer a CTA only streams the (L2-resident) weight, the aux
+// tiles the epilogue needs (softplus outputs of the primal sweep, deltas) and writes the spill the later
+// sweeps / weight-gradient contractions read.
+//
+// Modes (reference math: SURVEY.md 8a-3, models/graddae/mlp.py:400-444 double back-prop):
+//   CHAIN_MUL_SIG   sweep 2 (score backward)  out = acc * sig(aux1)                              A' = out
+//   CHAIN_TANGENT   sweep 3 (tangent forward) out = acc * sig(aux1), out2 = aux2*acc*(1-sig)     A' = out
+//   CHAIN_ADJOINT   sweep 4 (adjoint backward) out = acc * sig(aux1) + aux2                      A' = out
+//   CHAIN_SOFTPLUS3 sweep 1 (primal forward, "3xTF32"): out = softplus(acc + bias terms) split into tf32
+//                   hi/lo; hi lives in shared memory (MMA operand AND TMA-store source of the spill), lo in TMEM;
+//                   acc = hi.Whi + lo.Whi + hi.Wlo  (fp32-accurate products on the tf32 pipe)
+// sig(aux1) = 1 - exp(-u) with u the stored softplus OUTPUT (as in gemm_sm100.cuh).
+//
+// On-chip budget (H = 256): TMEM 512 columns = accumulator [0,256) + A operand [256,512);
+// shared memory 224 KB = 3 x 32 KB weight k-block ring + 64 KB aux ring + 64 KB out staging
+// (SOFTPLUS3: weight ring + 128 KB hi tiles).  One CTA per SM; 12 warps:
+//   warp 0 weight TMA producer | warp 1 MMA issuer + TMEM owner | warp 2 aux / A0 TMA producer | warp 3 idle
+//   warps 4-11 epilogue: two groups of four warps (TMEM lane quarter = warp & 3); group g owns the 32-column
+//   chunks c with c % 2 == g, has its own staging tiles, named barrier and TMA-store issuing thread.
+// MMA and epilogue of one tile are serial (the accumulator is single-buffered); the sweeps this kernel serves are
+// HBM-bound, and the aux ring keeps prefetching under the MMA phase.
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace ardae {
+
+constexpr int kChainMaxLayers = 10;
+enum ChainMode : int { CHAIN_MUL_SIG = 0, CHAIN_TANGENT = 1, CHAIN_ADJOINT = 2, CHAIN_SOFTPLUS3 = 3, CHAIN_NUM_MODES = 4 };
+
+struct alignas(64) ChainLayerParams {
+  CUtensorMap tmW;     // B operand [H rows (out), K] K-major, box {32, H}; SOFTPLUS3: [H, 3H] = [Whi | Whi | Wlo]
+  CUtensorMap tmAux1;  // [M, H], box {32, 128}
+  CUtensorMap tmAux2;
+  CUtensorMap tmOut;
+  CUtensorMap tmOut2;
+  const float* bias;        // SOFTPLUS3: [H] or null
+  const float* group_bias;  // SOFTPLUS3: row m adds group_bias[(m / group) * ldg + n]
+  const float* col_vec;     // SOFTPLUS3: adds row_scale[m] * col_vec[n]
+  float* out_lo;            // SOFTPLUS3: optional spill of the lo part (row pitch ld_out_lo) for a following chain
+  float* colsum;            // colsum[n]  += colsum_scale * sum_m out[m, n]
+  float* colsum2;           // TANGENT: colsum2[n] += sum_m out2[m, n]
+  float* colsum_w;          // colsum_w[n * stride] += sum_m out[m, n] * row_scale[m]
+  float colsum_scale;
+  int colsum_w_stride;
+  int group, ldg;
+  int ld_out_lo;
+};
+
+struct alignas(64) ChainParams {
+  CUtensorMap tmA0;         // initial activation [M, H] (SOFTPLUS3: its hi part), box {32, 128}
+  const float* a0_lo;       // SOFTPLUS3: lo part of the initial activation, row pitch a0_lo_ld
+  const float* row_scale;   // [M] (sigma) or null
+  int a0_lo_ld;
+  int M, H, nlayers;
+  int vec_ok;
+  ChainLayerParams layer[kChainMaxLayers];
+};
+
+template <int MODE>
+struct ChainConfig {
+  static constexpr bool kS3 = MODE == CHAIN_SOFTPLUS3;
+  static constexpr bool kAux2 = MODE == CHAIN_TANGENT || MODE == CHAIN_ADJOINT;
+  static constexpr bool kOut2 = MODE == CHAIN_TANGENT;
+  static constexpr int kGroups = 2;
+  static constexpr int kWStage = 256 * kBlockK * 4;  // 32 KB: one k-block of a [256, K] weight
+  static constexpr int kNumWStages = 3;
+  static constexpr int kAuxSlot = kS3 ? 0 : (kAux2 ? 2 : 1) * kTileBytes;
+  static constexpr int kNumAux = kS3 ? 0 : (kAux2 ? 2 : 4);
+  static constexpr int kOutSlot = (kOut2 ? 2 : 1) * kTileBytes;
+  static constexpr int kNumOutG = kS3 ? 0 : (kOut2 ? 1 : 2);  // staging slots per epilogue group
+  static constexpr int kOffAux = kNumWStages * kWStage;        // SOFTPLUS3: the 8 hi tiles start here
+  static constexpr int kOffOut = kOffAux + kNumAux * kAuxSlot;
+  static constexpr int kDataBytes = kS3 ? kOffAux + 8 * kTileBytes : kOffOut + kGroups * kNumOutG * kOutSlot;
+  static constexpr int kSmemBytes = kDataBytes + 1024 + 512;
+  static constexpr int kThreads = 128 + kGroups * 128;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(ChainConfig<MODE>::kThreads, 1)
+chain_kernel(const __grid_constant__ ChainParams p) {
+  using Cfg = ChainConfig<MODE>;
+  constexpr bool S3 = Cfg::kS3, HAS_AUX2 = Cfg::kAux2, HAS_OUT2 = Cfg::kOut2;
+  constexpr int G = Cfg::kGroups, NW = Cfg::kNumWStages;
+  constexpr int NAUX = Cfg::kNumAux > 0 ? Cfg::kNumAux : 1;
+  constexpr int NOUTG = Cfg::kNumOutG > 0 ? Cfg::kNumOutG : 1;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
+  uint64_t* w_empty = w_full + NW;
+  uint64_t* aux_full = w_empty + NW;   // [4]
+  uint64_t* aux_empty = aux_full + 4;  // [4]
+  uint64_t* acc_full = aux_empty + 4;
+  uint64_t* a_ready = acc_full + 1;
+  uint64_t* a0_full = a_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a0_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int H = p.H;
+  const int NB = H >> 5;  // 32-column chunks == k-blocks
+  const int nl = p.nlayers;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA0);
+    ptx::prefetch_tmap(&p.layer[0].tmW);
+    ptx::prefetch_tmap(&p.layer[0].tmOut);
+    if (!S3) ptx::prefetch_tmap(&p.layer[0].tmAux1);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NW; ++s) {
+        ptx::mbar_init(&w_full[s], 1);
+        ptx::mbar_init(&w_empty[s], 1);
+      }
+      for (int a = 0; a < 4; ++a) {
+        ptx::mbar_init(&aux_full[a], 1);
+        ptx::mbar_init(&aux_empty[a], 4);  // the four warps of the group that consumes the slot
+      }
+      ptx::mbar_init(acc_full, 1);
+      ptx::mbar_init(a_ready, 4 * G);  // every epilogue warp
+      ptx::mbar_init(a0_full, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_t = tmem_base;       // accumulator columns [0, H)
+  const uint32_t a_t = tmem_base + 256;   // A operand (SOFTPLUS3: its lo part) columns [256, 256 + H)
+  uint8_t* hi_tiles = smem + Cfg::kOffAux;  // SOFTPLUS3 only
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      const uint32_t wbytes = static_cast<uint32_t>(H) * kBlockK * 4;
+      int it = 0;
+      for (int l = 0; l < nl; ++l) {
+        const CUtensorMap* tw = &p.layer[l].tmW;
+        const int nst = S3 ? 2 * NB : NB;
+        for (int j = 0; j < nst; ++j, ++it) {
+          const int s = it % NW;
+          const uint32_t ph = (it / NW) & 1;
+          ptx::mbar_wait(&w_empty[s], ph ^ 1);
+          ptx::mbar_expect_tx(&w_full[s], wbytes);
+          // SOFTPLUS3: k-block kb of Whi (columns [0,H)) then of Wlo (columns [2H,3H)); both serve hi, Whi also lo
+          const int kc = S3 ? (((j & 1) ? 2 * H : 0) + (j >> 1) * kBlockK) : j * kBlockK;
+          ptx::tma_load_2d(smem + s * Cfg::kWStage, tw, &w_full[s], kc, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(kBlockM, H, 0, 0);
+      int it = 0;
+      for (int l = 0; l < nl; ++l) {
+        if (S3 && l == 0) ptx::mbar_wait(a0_full, 0);  // hi tiles of the initial activation have landed (TMA)
+        ptx::mbar_wait(a_ready, l & 1);                // A operand of layer l is complete, accumulator is drained
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < NB; ++kb) {
+          {
+            const int s = it % NW;
+            const uint32_t ph = (it / NW) & 1;
+            ptx::mbar_wait(&w_full[s], ph);
+            ptx::tc_fence_after();
+            const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
+            if (S3) {
+              const uint32_t h_addr = ptx::smem_u32(hi_tiles + kb * kTileBytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
+                const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
+                ptx::umma_tf32(acc_t, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
+              ptx::umma_tf32_ts(acc_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, idesc,
+                                (S3 || (kb | k) != 0) ? 1u : 0u);
+            }
+            ptx::umma_commit(&w_empty[s]);
+            ++it;
+          }
+          if (S3) {  // hi . Wlo
+            const int s = it % NW;
+            const uint32_t ph = (it / NW) & 1;
+            ptx::mbar_wait(&w_full[s], ph);
+            ptx::tc_fence_after();
+            const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
+            const uint32_t h_addr = ptx::smem_u32(hi_tiles + kb * kTileBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
+              ptx::umma_tf32(acc_t, adesc, bdesc, idesc, 1u);
+            }
+            ptx::umma_commit(&w_empty[s]);
+            ++it;
+          }
+        }
+        ptx::umma_commit(acc_full);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ aux / initial-activation producer
+    if (lane == 0) {
+      if (S3) {
+        ptx::mbar_expect_tx(a0_full, static_cast<uint32_t>(NB) * kTileBytes);
+        for (int c = 0; c < NB; ++c) ptx::tma_load_2d(hi_tiles + c * kTileBytes, &p.tmA0, a0_full, c * 32, m0);
+      } else {
+        int it = 0;
+        for (int l = -1; l < nl; ++l) {
+          for (int c = 0; c < NB; ++c, ++it) {
+            const int a = it % NAUX;
+            const uint32_t ph = (it / NAUX) & 1;
+            ptx::mbar_wait(&aux_empty[a], ph ^ 1);
+            uint8_t* slot = smem + Cfg::kOffAux + a * Cfg::kAuxSlot;
+            if (l < 0) {
+              ptx::mbar_expect_tx(&aux_full[a], kTileBytes);
+              ptx::tma_load_2d(slot, &p.tmA0, &aux_full[a], c * 32, m0);
+            } else {
+              ptx::mbar_expect_tx(&aux_full[a], Cfg::kAuxSlot);
+              ptx::tma_load_2d(slot, &p.layer[l].tmAux1, &aux_full[a], c * 32, m0);
+              if (HAS_AUX2) ptx::tma_load_2d(slot + kTileBytes, &p.layer[l].tmAux2, &aux_full[a], c * 32, m0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue warps
+    const int g = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int m = m0 + r;
+    const bool row_ok = m < p.M;
+    const bool leader = (quarter == 0 && lane == 0);
+    const int swz = r & 7;
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
+    uint8_t* out_base = smem + Cfg::kOffOut + g * (NOUTG * Cfg::kOutSlot);
+    const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[m] : 0.0f;
+
+    // ---- pseudo-layer -1: bring the initial activation into TMEM
+    for (int c = g; c < NB; c += G) {
+      uint32_t v[32];
+      if (S3) {
+        const float* src = p.a0_lo + static_cast<size_t>(row_ok ? m : 0) * p.a0_lo_ld + c * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok) t = __ldg(reinterpret_cast<const float4*>(src) + q);
+          v[q * 4 + 0] = __float_as_uint(t.x); v[q * 4 + 1] = __float_as_uint(t.y);
+          v[q * 4 + 2] = __float_as_uint(t.z); v[q * 4 + 3] = __float_as_uint(t.w);
+        }
+      } else {
+        const int it = c;
+        const int a = it % NAUX;
+        ptx::mbar_wait(&aux_full[a], (it / NAUX) & 1);
+        const uint8_t* src = smem + Cfg::kOffAux + a * Cfg::kAuxSlot + row_off;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 t = *reinterpret_cast<const uint4*>(src + ((q ^ swz) << 4));
+          v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&aux_empty[a]);
+      }
+      ptx::tmem_st_32x32(a_t + lane_addr + c * 32, v);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(a_ready);
+
+    int gi = 0;  // staging-slot counter of this group
+#pragma unroll 1
+    for (int l = 0; l < nl; ++l) {
+      const ChainLayerParams& L = p.layer[l];
+      const bool last = (l == nl - 1);
+      const float* gb_row = (S3 && L.group_bias != nullptr)
+                                ? L.group_bias + static_cast<size_t>((row_ok ? m : 0) / L.group) * L.ldg
+                                : nullptr;
+      ptx::mbar_wait(acc_full, l & 1);
+      ptx::tc_fence_after();
+      if (S3) {
+        // the hi tiles are rewritten in place: the TMA stores that spilled the previous layer must have read them
+        if (leader) ptx::tma_store_wait_read<0>();
+        ptx::named_bar_sync(bar_a, 128);
+      }
+#pragma unroll 1
+      for (int c = g; c < NB; c += G) {
+        const int nc = c * 32;
+        uint32_t accu[32];
+        ptx::tmem_ld_32x32(acc_t + lane_addr + nc, accu);
+        const int it = NB * (l + 1) + c;
+        const int a = it % NAUX;
+        if (!S3) ptx::mbar_wait(&aux_full[a], (it / NAUX) & 1);
+        ptx::tmem_ld_wait();
+        const uint8_t* a1 = smem + Cfg::kOffAux + a * Cfg::kAuxSlot + row_off;
+        const uint8_t* a2 = a1 + kTileBytes;
+        uint8_t* o1 = S3 ? hi_tiles + c * kTileBytes + row_off : out_base + (gi % NOUTG) * Cfg::kOutSlot + row_off;
+        uint8_t* o2 = o1 + kTileBytes;
+        if (!S3 && NOUTG == 1) {
+          if (leader) ptx::tma_store_wait_read<0>();
+          ptx::named_bar_sync(bar_a, 128);
+        }
+        float v[32];  // A operand of the next layer (tf32): `out`, or the lo part for SOFTPLUS3
+        if (S3) {
+          float add[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) add[j] = 0.0f;
+          const bool vec = p.vec_ok != 0;
+          if (L.bias != nullptr) add_cols32(L.bias + nc, 1.0f, vec, 32, add);
+          if (gb_row != nullptr) add_cols32(gb_row + nc, 1.0f, vec, 32, add);
+          if (L.col_vec != nullptr) add_cols32(L.col_vec + nc, rs, vec, 32, add);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float res = softplus_f(__uint_as_float(accu[q * 4 + j]) + add[q * 4 + j]);
+              const float hi = ptx::round_tf32(res);
+              o[j] = hi;
+              v[q * 4 + j] = ptx::round_tf32(res - hi);
+            }
+            *reinterpret_cast<float4*>(o1 + ((q ^ swz) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          if (L.out_lo != nullptr && row_ok) {  // one layer per step at most: plain row stores
+            float4* dst = reinterpret_cast<float4*>(L.out_lo + static_cast<size_t>(m) * L.ld_out_lo + nc);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t soff = static_cast<uint32_t>((q ^ swz) << 4);
+            const float4 x1 = *reinterpret_cast<const float4*>(a1 + soff);
+            float4 x2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_AUX2) x2 = *reinterpret_cast<const float4*>(a2 + soff);
+            const float u[4] = {x1.x, x1.y, x1.z, x1.w};
+            const float w2[4] = {x2.x, x2.y, x2.z, x2.w};
+            float o[4], ob[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float pre = __uint_as_float(accu[q * 4 + j]);
+              float sg, oms;
+              sig_from_softplus(u[j], sg, oms);
+              float res, res2 = 0.0f;
+              if (MODE == CHAIN_MUL_SIG) {
+                res = pre * sg;
+              } else if (MODE == CHAIN_TANGENT) {
+                res = pre * sg;
+                res2 = ptx::round_tf32(w2[j] * pre * oms);
+              } else {
+                res = fmaf(pre, sg, w2[j]);
+              }
+              res = ptx::round_tf32(res);
+              o[j] = res;
+              ob[j] = res2;
+              v[q * 4 + j] = res;
+            }
+            *reinterpret_cast<float4*>(o1 + soff) = make_float4(o[0], o[1], o[2], o[3]);
+            if (HAS_OUT2) *reinterpret_cast<float4*>(o2 + soff) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&aux_empty[a]);  // this warp is done with the aux slot
+        }
+        if (!last) {
+          uint32_t vu[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vu[j] = __float_as_uint(v[j]);
+          ptx::tmem_st_32x32(a_t + lane_addr + nc, vu);
+        }
+        ptx::fence_proxy_async_smem();
+        if (!S3 && NOUTG >= 2 && leader) ptx::tma_store_wait_read<(NOUTG >= 2 ? NOUTG - 2 : 0)>();
+        ptx::named_bar_sync(bar_b, 128);
+        if (leader) {
+          ptx::tma_store_2d(&L.tmOut, o1 - row_off, nc, m0);
+          if (HAS_OUT2) ptx::tma_store_2d(&L.tmOut2, o2 - row_off, nc, m0);
+          ptx::tma_store_commit();
+        }
+        ++gi;
+        // ---- fused column sums (bias gradients, d w_sigma, d w_o)
+        if (!S3 && (L.colsum != nullptr || L.colsum_w != nullptr || (HAS_OUT2 && L.colsum2 != nullptr))) {
+          if (!row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+          }
+          if (L.colsum_w != nullptr) {
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = v[i] * rs;
+            const float t = warp_transpose_reduce32(w, lane);
+            atomicAdd(L.colsum_w + static_cast<size_t>(nc + lane) * L.colsum_w_stride, t);
+          }
+          if (L.colsum != nullptr) {
+            const float t = warp_transpose_reduce32(v, lane);
+            atomicAdd(L.colsum + nc + lane, L.colsum_scale * t);
+          }
+          if (HAS_OUT2 && L.colsum2 != nullptr) {
+            // re-read this thread's own out2 row from the staging tile (still intact: the next write to it
+            // happens after this thread passes the next barrier)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(o2 + ((q ^ swz) << 4));
+              v[q * 4 + 0] = row_ok ? t4.x : 0.0f; v[q * 4 + 1] = row_ok ? t4.y : 0.0f;
+              v[q * 4 + 2] = row_ok ? t4.z : 0.0f; v[q * 4 + 3] = row_ok ? t4.w : 0.0f;
+            }
+            const float t = warp_transpose_reduce32(v, lane);
+            atomicAdd(L.colsum2 + nc + lane, t);
+          }
+        }
+      }
+      // A operand of layer l+1 written (TMEM stores complete, shared-memory writes fenced), accumulator drained
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_ready);
+    }
+    if (leader) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ardae

@@ -2,8 +2,10 @@
 // and a recorded list of stream-ordered launches (GEMMs with pre-encoded TMA maps + small kernels).
 #pragma once
 #include <functional>
+#include <memory>
 #include <vector>
 
+#include "chain_host.cuh"
 #include "gemm_host.cuh"
 
 namespace ardae {
@@ -51,7 +53,7 @@ struct Plan {
   int cur_lane = 0;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int num_gemm_nt = 0, num_gemm_tn = 0, num_small = 0;
+  int num_gemm_nt = 0, num_gemm_tn = 0, num_small = 0, num_chain = 0;
 
   void fork() {
     cur_lane = 1;
@@ -83,6 +85,16 @@ struct Plan {
     int rc = prepare_gemm_nt(d, &pr);
     if (rc) return fail_with(rc);
     ops.push_back([pr](cudaStream_t s) { return launch_prepared_nt(pr, s); });
+    lanes.push_back(cur_lane);
+  }
+  void chain(const ChainDesc& d) {
+    ++num_chain;
+    if (dry) return;
+    PreparedChain pr;
+    int rc = prepare_chain(d, &pr);
+    if (rc) return fail_with(rc);
+    auto sp = std::make_shared<PreparedChain>(pr);  // ~8 KB of tensor maps: keep one copy
+    ops.push_back([sp](cudaStream_t s) { return launch_prepared_chain(*sp, s); });
     lanes.push_back(cur_lane);
   }
   void tn(const GemmTNDesc& d) {
@@ -127,9 +139,9 @@ struct Plan {
   Plan& operator=(const Plan&) = delete;
   void reset() {
     ops.clear(); lanes.clear(); cur_lane = 0; error = 0;
-    num_gemm_nt = num_gemm_tn = num_small = 0;
+    num_gemm_nt = num_gemm_tn = num_small = num_chain = 0;
   }
-  int launches() const { return num_gemm_nt + 2 * num_gemm_tn + num_small; }
+  int launches() const { return num_gemm_nt + 2 * num_gemm_tn + num_small + num_chain; }
 };
 
 // An activation stored as a tf32 pair: buf[rows, 2*kp] with hi in columns [0,w) and

@@ -1,0 +1,291 @@
+// Stand-alone GPU self-test + micro-benchmark for the fused layer-chain kernel (no Python, no torch).
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
+//              -I pytorch-ardae-vae_b200/csrc tests/native/chain_selftest.cu -o build/chain_selftest
+// Every layer is checked on its own against a CPU double-precision reference that starts from the GPU's
+// own previous-layer output (so tf32 rounding ties cannot cascade); weights are exactly tf32-representable.
+//   chain_selftest            correctness (all modes, ragged M, H = 256 / 64)
+//   chain_selftest bench      + timing at the config-2 shape (M = 131072, H = 256, 9 layers)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "chain_host.cuh"
+
+using namespace ardae;
+
+#define CK(x)                                                                        \
+  do {                                                                               \
+    cudaError_t e = (x);                                                             \
+    if (e != cudaSuccess) {                                                          \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+      exit(2);                                                                       \
+    }                                                                                \
+  } while (0)
+
+static std::mt19937 rng(4321);
+static float tf32_rna(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+static void fill(std::vector<float>& v, float scale, bool tf32) {
+  std::normal_distribution<float> d(0.f, 1.f);
+  for (auto& x : v) { x = scale * d(rng); if (tf32) x = tf32_rna(x); }
+}
+static void fill_pos(std::vector<float>& v) {
+  std::normal_distribution<float> d(0.f, 1.f);
+  for (auto& x : v) x = std::fabs(d(rng)) * 1.5f;
+}
+template <class T>
+static T* dev(const std::vector<T>& h) {
+  T* d;
+  CK(cudaMalloc(&d, h.size() * sizeof(T)));
+  CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+static float* dev_fill(size_t n, int byte) {
+  float* d;
+  CK(cudaMalloc(&d, n * sizeof(float)));
+  CK(cudaMemset(d, byte, n * sizeof(float)));
+  return d;
+}
+static std::vector<float> host(const float* d, size_t n) {
+  std::vector<float> h(n);
+  CK(cudaMemcpy(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return h;
+}
+static double softplus_d(double x) { return x > 20 ? x : std::log1p(std::exp(x)); }
+
+static int g_fail = 0;
+struct Cmp {
+  double max_err = 0, max_ref = 0;
+  long bad = 0;
+  void add(double got, double ref, double tol) {
+    const double e = std::fabs(got - ref);
+    if (e > max_err) max_err = e;
+    if (std::fabs(ref) > max_ref) max_ref = std::fabs(ref);
+    if (!(e <= tol)) ++bad;
+  }
+  void report(const char* what, int mode, int l) {
+    printf("  mode %d layer %d %-8s max_err=%.3e max_ref=%.3e bad=%ld %s\n", mode, l, what, max_err, max_ref, bad,
+           bad ? "FAIL" : "ok");
+    if (bad) ++g_fail;
+  }
+};
+
+static void test_chain(int mode, int M, int H, int nl) {
+  printf("chain mode %d M=%d H=%d layers=%d\n", mode, M, H, nl);
+  const bool s3 = mode == CHAIN_SOFTPLUS3, aux2 = mode == CHAIN_TANGENT || mode == CHAIN_ADJOINT, out2 = mode == CHAIN_TANGENT;
+  const int ldw = s3 ? 3 * H : H;
+  std::vector<float> A0((size_t)M * H), A0lo((size_t)M * H), sigma(M);
+  fill(A0, 1.0f, true);
+  fill(sigma, 1.0f, false);
+  if (s3) {  // a genuine hi/lo pair
+    std::vector<float> full((size_t)M * H);
+    fill(full, 30.0f, false);
+    for (size_t i = 0; i < full.size(); ++i) { A0[i] = tf32_rna(full[i]); A0lo[i] = tf32_rna(full[i] - A0[i]); }
+  }
+  float *dA0 = dev(A0), *dA0lo = dev(A0lo), *dsig = dev(sigma);
+  const int group = 48, ng = (M + group - 1) / group;
+  struct LayerBufs {
+    std::vector<float> W, Wfull, aux1, aux2, bias, gb, colv;
+    float *dW, *daux1, *daux2, *dout, *dout2, *dbias, *dgb, *dcolv, *dcs, *dcs2, *dcsw;
+  };
+  std::vector<LayerBufs> Ls(nl);
+  ChainDesc d;
+  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig;
+  for (int l = 0; l < nl; ++l) {
+    LayerBufs& b = Ls[l];
+    b.Wfull.resize((size_t)H * H);
+    fill(b.Wfull, s3 ? 0.05f : 0.08f, !s3);
+    b.W.assign((size_t)H * ldw, 0.f);
+    for (int o = 0; o < H; ++o)
+      for (int i = 0; i < H; ++i) {
+        const float w = b.Wfull[(size_t)o * H + i];
+        if (s3) {
+          const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+          b.W[(size_t)o * ldw + i] = hi; b.W[(size_t)o * ldw + H + i] = hi; b.W[(size_t)o * ldw + 2 * H + i] = lo;
+        } else {
+          b.W[(size_t)o * ldw + i] = w;
+        }
+      }
+    b.aux1.resize((size_t)M * H); b.aux2.resize((size_t)M * H);
+    fill_pos(b.aux1); fill(b.aux2, 1.0f, false);
+    b.bias.resize(H); b.gb.resize((size_t)ng * H); b.colv.resize(H);
+    fill(b.bias, 1.0f, false); fill(b.gb, 1.0f, false); fill(b.colv, 1.0f, false);
+    b.dW = dev(b.W); b.daux1 = dev(b.aux1); b.daux2 = dev(b.aux2);
+    b.dbias = dev(b.bias); b.dgb = dev(b.gb); b.dcolv = dev(b.colv);
+    b.dout = dev_fill((size_t)M * H, 0xFF); b.dout2 = dev_fill((size_t)M * H, 0xFF);
+    b.dcs = dev_fill(H, 0); b.dcs2 = dev_fill(H, 0); b.dcsw = dev_fill((size_t)H * 3, 0);
+    ChainLayerDesc q;
+    q.W = b.dW; q.ldw = ldw; q.aux1 = b.daux1; q.ld1 = H; q.aux2 = b.daux2; q.ld2 = H;
+    q.out = b.dout; q.ldo = H; q.out2 = b.dout2; q.ldo2 = H;
+    if (s3) {
+      if (l % 2 == 0) q.bias = b.dbias;
+      else { q.group_bias = b.dgb; q.group = group; q.ldg = H; q.col_vec = b.dcolv; }
+    } else {
+      q.colsum = b.dcs; q.colsum_scale = -1.0f;
+      if (out2) q.colsum2 = b.dcs2;
+      if (l == nl - 1) { q.colsum_w = b.dcsw; q.colsum_w_stride = 3; }
+    }
+    d.layers.push_back(q);
+  }
+  PreparedChain pr;
+  int rc = prepare_chain(d, &pr);
+  if (rc) { printf("  prepare failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
+  rc = launch_prepared_chain(pr, 0);
+  if (rc) { printf("  launch failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  kernel error %s\n", cudaGetErrorString(e)); exit(3); }
+
+  std::vector<float> Ain = A0, Ainlo = A0lo;
+  for (int l = 0; l < nl; ++l) {
+    LayerBufs& b = Ls[l];
+    auto out = host(b.dout, (size_t)M * H), o2 = host(b.dout2, (size_t)M * H);
+    auto cs = host(b.dcs, H), cs2 = host(b.dcs2, H), csw = host(b.dcsw, (size_t)H * 3);
+    Cmp c1, c2, c3, c4, c5;
+    std::vector<double> rcs(H, 0.0), rcs2(H, 0.0), rcsw(H, 0.0), mcs(H, 0.0);
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < H; ++n) {
+        double acc = 0, mag = 0;
+        for (int k = 0; k < H; ++k) {
+          const double w = b.Wfull[(size_t)n * H + k];
+          double a = Ain[(size_t)m * H + k];
+          if (s3) {
+            // hi.Whi + lo.Whi + hi.Wlo with the split operands the kernel sees
+            const double whi = b.W[(size_t)n * ldw + k], wlo = b.W[(size_t)n * ldw + 2 * H + k];
+            const double alo = Ainlo[(size_t)m * H + k];
+            acc += a * whi + alo * whi + a * wlo;
+            mag += std::fabs(a * w);
+          } else {
+            acc += a * w;
+            mag += std::fabs(a * w);
+          }
+        }
+        const size_t idx = (size_t)m * H + n;
+        const double u = b.aux1[idx], sg = 1.0 - std::exp(-u), x2 = b.aux2[idx];
+        double ref, ref2 = 0;
+        if (mode == CHAIN_MUL_SIG) ref = acc * sg;
+        else if (mode == CHAIN_TANGENT) { ref = acc * sg; ref2 = x2 * acc * (1.0 - sg); }
+        else if (mode == CHAIN_ADJOINT) ref = acc * sg + x2;
+        else {
+          double pre = acc;
+          if (l % 2 == 0) pre += b.bias[n];
+          else pre += b.gb[(size_t)(m / group) * H + n] + (double)sigma[m] * b.colv[n];
+          ref = softplus_d(pre);
+        }
+        // fp32 accumulation + one tf32 rounding of the stored value (SOFTPLUS3: hi part only -> 2^-11 relative)
+        const double tol = 2e-5 * mag + 6e-4 * std::fabs(ref) + 1e-6;
+        c1.add(out[idx], ref, tol);
+        if (out2) c2.add(o2[idx], ref2, 2e-5 * mag * std::fabs(x2) + 6e-4 * std::fabs(ref2) + 1e-6);
+        rcs[n] += -1.0 * out[idx]; rcs2[n] += o2[idx]; rcsw[n] += (double)out[idx] * sigma[m];
+        mcs[n] += std::fabs(out[idx]) * (1.0 + std::fabs(sigma[m])) + (out2 ? std::fabs(o2[idx]) : 0.0);
+      }
+    c1.report("out", mode, l);
+    if (out2) c2.report("out2", mode, l);
+    if (!s3) {
+      for (int n = 0; n < H; ++n) {
+        c3.add(cs[n], rcs[n], 1e-5 * mcs[n] + 1e-5);
+        if (out2) c4.add(cs2[n], rcs2[n], 1e-5 * mcs[n] + 1e-5);
+        if (l == nl - 1) c5.add(csw[(size_t)n * 3], rcsw[n], 1e-5 * mcs[n] + 1e-5);
+      }
+      c3.report("colsum", mode, l);
+      if (out2) c4.report("colsum2", mode, l);
+      if (l == nl - 1) c5.report("colsum_w", mode, l);
+    }
+    // next layer's reference input = what the GPU produced (SOFTPLUS3: hi from `out`, lo recomputed from the
+    // exact fp32 activation is not observable -> use the CPU value of res - hi, accurate to fp32 rounding)
+    if (s3) {
+      std::vector<float> newlo((size_t)M * H);
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < H; ++n) {
+          double acc = 0;
+          for (int k = 0; k < H; ++k) {
+            const double whi = b.W[(size_t)n * ldw + k], wlo = b.W[(size_t)n * ldw + 2 * H + k];
+            acc += (double)Ain[(size_t)m * H + k] * (whi + wlo) + (double)Ainlo[(size_t)m * H + k] * whi;
+          }
+          double pre = acc;
+          if (l % 2 == 0) pre += b.bias[n];
+          else pre += b.gb[(size_t)(m / group) * H + n] + (double)sigma[m] * b.colv[n];
+          const float res = (float)softplus_d(pre);
+          newlo[(size_t)m * H + n] = tf32_rna(res - out[(size_t)m * H + n]);
+        }
+      Ainlo = newlo;
+    }
+    Ain = out;
+  }
+  for (auto& b : Ls) {
+    cudaFree(b.dW); cudaFree(b.daux1); cudaFree(b.daux2); cudaFree(b.dout); cudaFree(b.dout2); cudaFree(b.dbias);
+    cudaFree(b.dgb); cudaFree(b.dcolv); cudaFree(b.dcs); cudaFree(b.dcs2); cudaFree(b.dcsw);
+  }
+  cudaFree(dA0); cudaFree(dA0lo); cudaFree(dsig);
+}
+
+static void bench_chain(int mode, int M, int H, int nl) {
+  const bool s3 = mode == CHAIN_SOFTPLUS3, aux2 = mode == CHAIN_TANGENT || mode == CHAIN_ADJOINT, out2 = mode == CHAIN_TANGENT;
+  const int ldw = s3 ? 3 * H : H;
+  const size_t n = (size_t)M * H;
+  std::vector<float> W((size_t)H * ldw);
+  fill(W, 0.05f, true);
+  float* dW = dev(W);
+  float *dA0 = dev_fill(n, 0), *dA0lo = dev_fill(n, 0), *dsig = dev_fill(M, 0);
+  ChainDesc d;
+  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig;
+  std::vector<float*> bufs;
+  float* dbias = dev_fill(H, 0);
+  for (int l = 0; l < nl; ++l) {
+    ChainLayerDesc q;
+    float *a1 = dev_fill(n, 0x3c), *a2 = aux2 ? dev_fill(n, 0) : nullptr, *o = dev_fill(n, 0), *o2 = out2 ? dev_fill(n, 0) : nullptr;
+    bufs.push_back(a1); bufs.push_back(a2); bufs.push_back(o); bufs.push_back(o2);
+    q.W = dW; q.ldw = ldw; q.aux1 = a1; q.ld1 = H; q.aux2 = a2; q.ld2 = H; q.out = o; q.ldo = H; q.out2 = o2; q.ldo2 = H;
+    if (s3) q.bias = dbias;
+    d.layers.push_back(q);
+  }
+  PreparedChain pr;
+  int rc = prepare_chain(d, &pr);
+  if (rc) { printf("bench prepare failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 2; ++i) launch_prepared_chain(pr, 0);
+  CK(cudaDeviceSynchronize());
+  const int reps = 5;
+  cudaEventRecord(e0);
+  for (int i = 0; i < reps; ++i) launch_prepared_chain(pr, 0);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= reps;
+  const double arrays = s3 ? 1.0 : (1.0 + (aux2 ? 1 : 0) + 1.0 + (out2 ? 1 : 0));  // per layer: aux reads + out writes
+  const double bytes = (arrays * nl + 1.0 + (s3 ? 1.0 : 0.0)) * n * 4.0;
+  const double flops = 2.0 * M * (double)H * H * nl * (s3 ? 3.0 : 1.0);
+  printf("bench mode %d M=%d H=%d layers=%d: %.3f ms  (%.1f us/layer)  HBM %.0f GB/s  tensor %.0f TFLOP/s (executed)\n",
+         mode, M, H, nl, ms, ms * 1e3 / nl, bytes / ms * 1e-6, flops / ms * 1e-9);
+  for (float* b : bufs) if (b) cudaFree(b);
+  cudaFree(dW); cudaFree(dA0); cudaFree(dA0lo); cudaFree(dsig); cudaFree(dbias);
+}
+
+int main(int argc, char** argv) {
+  const bool bench = argc > 1 && !strcmp(argv[1], "bench");
+  int only = -1;
+  if (argc > 2) only = atoi(argv[2]);
+  for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
+    if (only >= 0 && mode != only) continue;
+    test_chain(mode, 300, 256, 3);
+    test_chain(mode, 128, 64, 2);
+    test_chain(mode, 1000, 96, 4);
+  }
+  if (bench)
+    for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
+      if (only >= 0 && mode != only) continue;
+      bench_chain(mode, 131072, 256, 9);
+      bench_chain(mode, 512, 256, 9);
+    }
+  printf(g_fail ? "CHAIN SELFTEST FAILED (%d)\n" : "CHAIN SELFTEST OK\n", g_fail);
+  return g_fail ? 1 : 0;
+}
