@@ -61,8 +61,47 @@ struct alignas(64) ChainParams {
   int a0_lo_ld;
   int M, H, nlayers;
   int vec_ok;
+  long long* debug_times;   // profiling only: [grid][kChainMaxLayers][8] clock64 stamps (null in production)
   ChainLayerParams layer[kChainMaxLayers];
 };
+
+// ---- lean epilogue arithmetic: the chain epilogues are instruction-issue bound (measured with clock64 stamps:
+// ~2700 cycles per 32-column chunk with __expf/__logf range fix-ups, cvt.rna Inf checks and generic-space LD/ST),
+// so: raw MUFU ex2/lg2, integer round-to-nearest to tf32, explicit shared-space vector accesses.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// round-to-nearest (ties away) to tf32 on finite inputs: 2 integer ops instead of cvt.rna's Inf/NaN handling
+__device__ __forceinline__ float round_tf32_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// sigmoid(a) from u = softplus(a) >= 0:  s = 1 - exp(-u)  (u(1 - u/2) below 2^-7: relative error < 1e-5), 1 - s = exp(-u)
+__device__ __forceinline__ void sig_fast(float u, float& s, float& one_minus_s) {
+  const float e = ex2_ftz(u * -1.4426950408889634f);
+  one_minus_s = e;
+  s = (u < 0.0078125f) ? fmaf(-0.5f * u, u, u) : 1.0f - e;
+}
+// max(x,0) + log1p(exp(-|x|)) == torch softplus (threshold 20) to fp32 rounding
+__device__ __forceinline__ float softplus_fast(float x) {
+  const float e = ex2_ftz(fabsf(x) * -1.4426950408889634f);
+  const float l = (e < 1e-4f) ? fmaf(-0.5f * e, e, e) : lg2_ftz(1.0f + e) * 0.6931471805599453f;
+  return fmaxf(x, 0.0f) + l;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <int MODE>
 struct ChainConfig {
@@ -72,14 +111,15 @@ struct ChainConfig {
   static constexpr int kGroups = 2;
   static constexpr int kWStage = 256 * kBlockK * 4;  // 32 KB: one k-block of a [256, K] weight
   static constexpr int kNumWStages = 3;
+  // One ring serves aux loads AND out stores: a slot receives the aux tile(s) of a chunk by TMA, the epilogue
+  // overwrites them IN PLACE with the out tile(s), the TMA store leaves from the same bytes, and the slot is
+  // recycled once that store has read it.  128 KB of HBM traffic in flight per SM instead of 64.
   static constexpr int kAuxSlot = kS3 ? 0 : (kAux2 ? 2 : 1) * kTileBytes;
-  static constexpr int kNumAux = kS3 ? 0 : (kAux2 ? 2 : 4);
-  static constexpr int kOutSlot = (kOut2 ? 2 : 1) * kTileBytes;
-  static constexpr int kNumOutG = kS3 ? 0 : (kOut2 ? 1 : 2);  // staging slots per epilogue group
+  static constexpr int kNumAux = kS3 ? 0 : (kAux2 ? 4 : 8);
   static constexpr int kOffAux = kNumWStages * kWStage;        // SOFTPLUS3: the 8 hi tiles start here
-  static constexpr int kOffOut = kOffAux + kNumAux * kAuxSlot;
-  static constexpr int kDataBytes = kS3 ? kOffAux + 8 * kTileBytes : kOffOut + kGroups * kNumOutG * kOutSlot;
+  static constexpr int kDataBytes = kOffAux + 8 * kTileBytes;
   static constexpr int kSmemBytes = kDataBytes + 1024 + 512;
+  static_assert(kSmemBytes <= 232448 && kNumAux <= 8, "shared memory budget");
   static constexpr int kThreads = 128 + kGroups * 128;
 };
 
@@ -90,16 +130,15 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   constexpr bool S3 = Cfg::kS3, HAS_AUX2 = Cfg::kAux2, HAS_OUT2 = Cfg::kOut2;
   constexpr int G = Cfg::kGroups, NW = Cfg::kNumWStages;
   constexpr int NAUX = Cfg::kNumAux > 0 ? Cfg::kNumAux : 1;
-  constexpr int NOUTG = Cfg::kNumOutG > 0 ? Cfg::kNumOutG : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + Cfg::kDataBytes);
   uint64_t* w_empty = w_full + NW;
-  uint64_t* aux_full = w_empty + NW;   // [4]
-  uint64_t* aux_empty = aux_full + 4;  // [4]
-  uint64_t* acc_full = aux_empty + 4;
+  uint64_t* aux_full = w_empty + NW;   // [8]
+  uint64_t* aux_empty = aux_full + 8;  // [8]
+  uint64_t* acc_full = aux_empty + 8;
   uint64_t* a_ready = acc_full + 1;
   uint64_t* a0_full = a_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a0_full + 1);
@@ -123,9 +162,9 @@ chain_kernel(const __grid_constant__ ChainParams p) {
         ptx::mbar_init(&w_full[s], 1);
         ptx::mbar_init(&w_empty[s], 1);
       }
-      for (int a = 0; a < 4; ++a) {
+      for (int a = 0; a < 8; ++a) {
         ptx::mbar_init(&aux_full[a], 1);
-        ptx::mbar_init(&aux_empty[a], 4);  // the four warps of the group that consumes the slot
+        ptx::mbar_init(&aux_empty[a], 1);  // the store-issuing thread of the group that consumed the slot
       }
       ptx::mbar_init(acc_full, 1);
       ptx::mbar_init(a_ready, 4 * G);  // every epilogue warp
@@ -170,8 +209,11 @@ chain_kernel(const __grid_constant__ ChainParams p) {
       int it = 0;
       for (int l = 0; l < nl; ++l) {
         if (S3 && l == 0) ptx::mbar_wait(a0_full, 0);  // hi tiles of the initial activation have landed (TMA)
+        long long* dbg = p.debug_times ? p.debug_times + (static_cast<size_t>(blockIdx.x) * kChainMaxLayers + l) * 8 : nullptr;
+        if (dbg) dbg[0] = clock64();
         ptx::mbar_wait(a_ready, l & 1);                // A operand of layer l is complete, accumulator is drained
         ptx::tc_fence_after();
+        if (dbg) dbg[1] = clock64();
         for (int kb = 0; kb < NB; ++kb) {
           {
             const int s = it % NW;
@@ -215,6 +257,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           }
         }
         ptx::umma_commit(acc_full);
+        if (dbg) dbg[2] = clock64();
       }
     }
   } else if (warp == 2) {
@@ -255,7 +298,6 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t bar_a = 1 + 2 * g, bar_b = 2 + 2 * g;
-    uint8_t* out_base = smem + Cfg::kOffOut + g * (NOUTG * Cfg::kOutSlot);
     const float rs = (p.row_scale != nullptr && row_ok) ? p.row_scale[m] : 0.0f;
 
     // ---- pseudo-layer -1: bring the initial activation into TMEM
@@ -274,14 +316,15 @@ chain_kernel(const __grid_constant__ ChainParams p) {
         const int it = c;
         const int a = it % NAUX;
         ptx::mbar_wait(&aux_full[a], (it / NAUX) & 1);
-        const uint8_t* src = smem + Cfg::kOffAux + a * Cfg::kAuxSlot + row_off;
+        const uint32_t src = ptx::smem_u32(smem + Cfg::kOffAux + a * Cfg::kAuxSlot) + row_off;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const uint4 t = *reinterpret_cast<const uint4*>(src + ((q ^ swz) << 4));
-          v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+          const float4 t = lds128(src + ((q ^ swz) << 4));
+          v[q * 4 + 0] = __float_as_uint(t.x); v[q * 4 + 1] = __float_as_uint(t.y);
+          v[q * 4 + 2] = __float_as_uint(t.z); v[q * 4 + 3] = __float_as_uint(t.w);
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&aux_empty[a]);
+        ptx::named_bar_sync(bar_a, 128);  // all four warps have read the slot
+        if (leader) ptx::mbar_arrive(&aux_empty[a]);
       }
       ptx::tmem_st_32x32(a_t + lane_addr + c * 32, v);
     }
@@ -290,7 +333,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(a_ready);
 
-    int gi = 0;  // staging-slot counter of this group
+    int prev_slot = -1;  // slot whose TMA store may still be reading it (released one chunk later)
 #pragma unroll 1
     for (int l = 0; l < nl; ++l) {
       const ChainLayerParams& L = p.layer[l];
@@ -298,8 +341,12 @@ chain_kernel(const __grid_constant__ ChainParams p) {
       const float* gb_row = (S3 && L.group_bias != nullptr)
                                 ? L.group_bias + static_cast<size_t>((row_ok ? m : 0) / L.group) * L.ldg
                                 : nullptr;
+      long long* dbg = (p.debug_times && leader && g == 0)
+                           ? p.debug_times + (static_cast<size_t>(blockIdx.x) * kChainMaxLayers + l) * 8 : nullptr;
+      if (dbg) dbg[3] = clock64();
       ptx::mbar_wait(acc_full, l & 1);
       ptx::tc_fence_after();
+      if (dbg) { dbg[4] = clock64(); dbg[6] = 0; }
       if (S3) {
         // the hi tiles are rewritten in place: the TMA stores that spilled the previous layer must have read them
         if (leader) ptx::tma_store_wait_read<0>();
@@ -312,16 +359,15 @@ chain_kernel(const __grid_constant__ ChainParams p) {
         ptx::tmem_ld_32x32(acc_t + lane_addr + nc, accu);
         const int it = NB * (l + 1) + c;
         const int a = it % NAUX;
+        long long tw0 = 0;
+        if (dbg) tw0 = clock64();
         if (!S3) ptx::mbar_wait(&aux_full[a], (it / NAUX) & 1);
+        if (dbg) dbg[6] += clock64() - tw0;  // time spent waiting for aux tiles
         ptx::tmem_ld_wait();
-        const uint8_t* a1 = smem + Cfg::kOffAux + a * Cfg::kAuxSlot + row_off;
-        const uint8_t* a2 = a1 + kTileBytes;
-        uint8_t* o1 = S3 ? hi_tiles + c * kTileBytes + row_off : out_base + (gi % NOUTG) * Cfg::kOutSlot + row_off;
-        uint8_t* o2 = o1 + kTileBytes;
-        if (!S3 && NOUTG == 1) {
-          if (leader) ptx::tma_store_wait_read<0>();
-          ptx::named_bar_sync(bar_a, 128);
-        }
+        // aux tile(s) in, out tile(s) written over them in place (same thread, same bytes)
+        uint8_t* slot = S3 ? hi_tiles + c * kTileBytes : smem + Cfg::kOffAux + a * Cfg::kAuxSlot;
+        const uint32_t s1 = ptx::smem_u32(slot) + row_off;  // aux1 / out (and hi tile) row of this thread
+        const uint32_t s2 = s1 + kTileBytes;                // aux2 / out2
         float v[32];  // A operand of the next layer (tf32): `out`, or the lo part for SOFTPLUS3
         if (S3) {
           float add[32];
@@ -336,12 +382,12 @@ chain_kernel(const __grid_constant__ ChainParams p) {
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float res = softplus_f(__uint_as_float(accu[q * 4 + j]) + add[q * 4 + j]);
-              const float hi = ptx::round_tf32(res);
+              const float res = softplus_fast(__uint_as_float(accu[q * 4 + j]) + add[q * 4 + j]);
+              const float hi = round_tf32_fast(res);
               o[j] = hi;
-              v[q * 4 + j] = ptx::round_tf32(res - hi);
+              v[q * 4 + j] = round_tf32_fast(res - hi);
             }
-            *reinterpret_cast<float4*>(o1 + ((q ^ swz) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+            sts128(s1 + ((q ^ swz) << 4), o[0], o[1], o[2], o[3]);
           }
           if (L.out_lo != nullptr && row_ok) {  // one layer per step at most: plain row stores
             float4* dst = reinterpret_cast<float4*>(L.out_lo + static_cast<size_t>(m) * L.ld_out_lo + nc);
@@ -350,38 +396,44 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t soff = static_cast<uint32_t>((q ^ swz) << 4);
-            const float4 x1 = *reinterpret_cast<const float4*>(a1 + soff);
-            float4 x2 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (HAS_AUX2) x2 = *reinterpret_cast<const float4*>(a2 + soff);
-            const float u[4] = {x1.x, x1.y, x1.z, x1.w};
-            const float w2[4] = {x2.x, x2.y, x2.z, x2.w};
-            float o[4], ob[4];
+          for (int half = 0; half < 2; ++half) {
+            float4 x1[4], x2[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float pre = __uint_as_float(accu[q * 4 + j]);
-              float sg, oms;
-              sig_from_softplus(u[j], sg, oms);
-              float res, res2 = 0.0f;
-              if (MODE == CHAIN_MUL_SIG) {
-                res = pre * sg;
-              } else if (MODE == CHAIN_TANGENT) {
-                res = pre * sg;
-                res2 = ptx::round_tf32(w2[j] * pre * oms);
-              } else {
-                res = fmaf(pre, sg, w2[j]);
-              }
-              res = ptx::round_tf32(res);
-              o[j] = res;
-              ob[j] = res2;
-              v[q * 4 + j] = res;
+            for (int qq = 0; qq < 4; ++qq) {
+              const uint32_t soff = static_cast<uint32_t>(((half * 4 + qq) ^ swz) << 4);
+              x1[qq] = lds128(s1 + soff);
+              if (HAS_AUX2) x2[qq] = lds128(s2 + soff);
             }
-            *reinterpret_cast<float4*>(o1 + soff) = make_float4(o[0], o[1], o[2], o[3]);
-            if (HAS_OUT2) *reinterpret_cast<float4*>(o2 + soff) = make_float4(ob[0], ob[1], ob[2], ob[3]);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const int q = half * 4 + qq;
+              const uint32_t soff = static_cast<uint32_t>((q ^ swz) << 4);
+              const float u[4] = {x1[qq].x, x1[qq].y, x1[qq].z, x1[qq].w};
+              float o[4], ob[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float w2 = HAS_AUX2 ? (j == 0 ? x2[qq].x : (j == 1 ? x2[qq].y : (j == 2 ? x2[qq].z : x2[qq].w))) : 0.0f;
+                const float pre = __uint_as_float(accu[q * 4 + j]);
+                float sg, oms;
+                sig_fast(u[j], sg, oms);
+                float res, res2 = 0.0f;
+                if (MODE == CHAIN_MUL_SIG) {
+                  res = pre * sg;
+                } else if (MODE == CHAIN_TANGENT) {
+                  res = pre * sg;
+                  res2 = round_tf32_fast(w2 * pre * oms);
+                } else {
+                  res = fmaf(pre, sg, w2);
+                }
+                res = round_tf32_fast(res);
+                o[j] = res;
+                ob[j] = res2;
+                v[q * 4 + j] = res;
+              }
+              sts128(s1 + soff, o[0], o[1], o[2], o[3]);
+              if (HAS_OUT2) sts128(s2 + soff, ob[0], ob[1], ob[2], ob[3]);
+            }
           }
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&aux_empty[a]);  // this warp is done with the aux slot
         }
         if (!last) {
           uint32_t vu[32];
@@ -390,14 +442,19 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           ptx::tmem_st_32x32(a_t + lane_addr + nc, vu);
         }
         ptx::fence_proxy_async_smem();
-        if (!S3 && NOUTG >= 2 && leader) ptx::tma_store_wait_read<(NOUTG >= 2 ? NOUTG - 2 : 0)>();
         ptx::named_bar_sync(bar_b, 128);
         if (leader) {
-          ptx::tma_store_2d(&L.tmOut, o1 - row_off, nc, m0);
-          if (HAS_OUT2) ptx::tma_store_2d(&L.tmOut2, o2 - row_off, nc, m0);
+          ptx::tma_store_2d(&L.tmOut, slot, nc, m0);
+          if (HAS_OUT2) ptx::tma_store_2d(&L.tmOut2, slot + kTileBytes, nc, m0);
           ptx::tma_store_commit();
+          if (!S3) {
+            if (prev_slot >= 0) {  // the previous store of this group has read its slot: hand it back to the producer
+              ptx::tma_store_wait_read<1>();
+              ptx::mbar_arrive(&aux_empty[prev_slot]);
+            }
+            prev_slot = a;
+          }
         }
-        ++gi;
         // ---- fused column sums (bias gradients, d w_sigma, d w_o)
         if (!S3 && (L.colsum != nullptr || L.colsum_w != nullptr || (HAS_OUT2 && L.colsum2 != nullptr))) {
           if (!row_ok) {
@@ -420,7 +477,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
             // happens after this thread passes the next barrier)
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 t4 = *reinterpret_cast<const float4*>(o2 + ((q ^ swz) << 4));
+              const float4 t4 = lds128(s2 + ((q ^ swz) << 4));
               v[q * 4 + 0] = row_ok ? t4.x : 0.0f; v[q * 4 + 1] = row_ok ? t4.y : 0.0f;
               v[q * 4 + 2] = row_ok ? t4.z : 0.0f; v[q * 4 + 3] = row_ok ? t4.w : 0.0f;
             }
@@ -434,6 +491,13 @@ chain_kernel(const __grid_constant__ ChainParams p) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_ready);
+      if (dbg) dbg[5] = clock64();
+      if (HAS_OUT2 && L.colsum2 != nullptr) ptx::named_bar_sync(bar_a, 128);  // colsum2 re-reads of the slot are done
+      if (!S3 && leader && prev_slot >= 0) {  // do not sit on a slot through the MMA phase
+        ptx::tma_store_wait_read<0>();
+        ptx::mbar_arrive(&aux_empty[prev_slot]);
+        prev_slot = -1;
+      }
     }
     if (leader) ptx::tma_store_wait_all<0>();
   }

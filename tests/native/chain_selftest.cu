@@ -249,6 +249,30 @@ static void bench_chain(int mode, int M, int H, int nl) {
   PreparedChain pr;
   int rc = prepare_chain(d, &pr);
   if (rc) { printf("bench prepare failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
+  if (getenv("CHAIN_TIMES")) {
+    const int grid = (M + 127) / 128;
+    long long* dt;
+    CK(cudaMalloc(&dt, (size_t)grid * kChainMaxLayers * 8 * sizeof(long long)));
+    CK(cudaMemset(dt, 0, (size_t)grid * kChainMaxLayers * 8 * sizeof(long long)));
+    pr.params.debug_times = dt;
+    launch_prepared_chain(pr, 0);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h((size_t)grid * kChainMaxLayers * 8);
+    CK(cudaMemcpy(h.data(), dt, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    const int ctas[3] = {0, grid / 2, grid - 1};
+    for (int ci = 0; ci < 3; ++ci) {
+      const int cta = ctas[ci];
+      printf("  times mode %d cta %d (cycles): layer: mma_wait_a  mma_issue  | epi_wait_acc  epi_total  aux_wait | layer_period\n", mode, cta);
+      for (int l = 0; l < nl; ++l) {
+        const long long* t = &h[((size_t)cta * kChainMaxLayers + l) * 8];
+        const long long* tn = &h[((size_t)cta * kChainMaxLayers + l + 1) * 8];
+        printf("    %d: %7lld %7lld | %7lld %7lld %7lld | %7lld\n", l, t[1] - t[0], t[2] - t[1], t[4] - t[3], t[5] - t[4], t[6],
+               l + 1 < nl ? tn[1] - t[1] : 0LL);
+      }
+    }
+    pr.params.debug_times = nullptr;
+    cudaFree(dt);
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 2; ++i) launch_prepared_chain(pr, 0);
