@@ -39,14 +39,14 @@ struct PreparedChain {
   int smem = 0, threads = 0;
 };
 
-// The chain kernel serves H -> H layers with H a multiple of 32 up to 256 (one k-block ring stage = 256 x 32 floats).
+// The chain kernel serves H -> H layers with H a multiple of 64 up to 256 (two N-halves of <= 128 columns each).
 inline bool chain_supported(int H, int nlayers) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = std::getenv("ARDAE_CHAIN");
     enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  return enabled && H >= 32 && H <= 256 && H % 32 == 0 && nlayers >= 1 && nlayers <= kChainMaxLayers;
+  return enabled && H >= 64 && H <= 256 && H % 64 == 0 && nlayers >= 1 && nlayers <= kChainMaxLayers;
 }
 
 inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
@@ -69,7 +69,7 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
     ChainLayerParams& q = p.layer[l];
     if (!s.W || !s.out || (!s3 && !s.aux1) || (aux2 && !s.aux2) || (out2 && !s.out2))
       return fail(-2, "chain: missing operand pointer");
-    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * d.H : d.H, d.H, s.ldw, kBlockK, d.H))) return rc;
+    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * d.H : d.H, d.H, s.ldw, kBlockK, d.H / 2))) return rc;
     if (!s3 && (rc = encode_tmap_2d(&q.tmAux1, s.aux1, d.H, d.M, s.ld1, 32, kBlockM))) return rc;
     if (aux2 && (rc = encode_tmap_2d(&q.tmAux2, s.aux2, d.H, d.M, s.ld2, 32, kBlockM))) return rc;
     if ((rc = encode_tmap_2d(&q.tmOut, s.out, d.H, d.M, s.ldo, 32, kBlockM))) return rc;

@@ -25,8 +25,10 @@
 //   warp 0 weight TMA producer | warp 1 MMA issuer + TMEM owner | warp 2 aux / A0 TMA producer | warp 3 idle
 //   warps 4-11 epilogue: two groups of four warps (TMEM lane quarter = warp & 3); group g owns the 32-column
 //   chunks c with c % 2 == g, has its own staging tiles, named barrier and TMA-store issuing thread.
-// MMA and epilogue of one tile are serial (the accumulator is single-buffered); the sweeps this kernel serves are
-// HBM-bound, and the aux ring keeps prefetching under the MMA phase.
+// Pipelining inside a CTA: every layer's MMA is issued as two N-halves (accumulator columns [0,H/2) then [H/2,H)).
+// The epilogue of half 0 runs underneath the MMA of half 1 (it may overwrite A chunk c only once the half-1 MMAs
+// of k-block c have retired: `kfree[c]`), and the next layer's MMA starts on k-blocks [0,H/64) as soon as the
+// half-0 epilogue has produced them (`a_ready[0]`) while the half-1 epilogue is still running.
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -109,8 +111,8 @@ struct ChainConfig {
   static constexpr bool kAux2 = MODE == CHAIN_TANGENT || MODE == CHAIN_ADJOINT;
   static constexpr bool kOut2 = MODE == CHAIN_TANGENT;
   static constexpr int kGroups = 2;
-  static constexpr int kWStage = 256 * kBlockK * 4;  // 32 KB: one k-block of a [256, K] weight
-  static constexpr int kNumWStages = 3;
+  static constexpr int kWStage = 128 * kBlockK * 4;  // 16 KB: one k-block of one N-half ([<=128, 32] weight rows)
+  static constexpr int kNumWStages = 6;
   // One ring serves aux loads AND out stores: a slot receives the aux tile(s) of a chunk by TMA, the epilogue
   // overwrites them IN PLACE with the out tile(s), the TMA store leaves from the same bytes, and the slot is
   // recycled once that store has read it.  128 KB of HBM traffic in flight per SM instead of 64.
@@ -138,16 +140,19 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   uint64_t* w_empty = w_full + NW;
   uint64_t* aux_full = w_empty + NW;   // [8]
   uint64_t* aux_empty = aux_full + 8;  // [8]
-  uint64_t* acc_full = aux_empty + 8;
-  uint64_t* a_ready = acc_full + 1;
-  uint64_t* a0_full = a_ready + 1;
+  uint64_t* acc_full = aux_empty + 8;  // [2] accumulator half h of the current layer is complete
+  uint64_t* a_ready = acc_full + 2;    // [2] A chunks of half h are written and accumulator half h is drained
+  uint64_t* kfree = a_ready + 2;       // [4] the current layer no longer reads A chunk c (c < NB/2)
+  uint64_t* a0_full = kfree + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a0_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBlockM;
   const int H = p.H;
-  const int NB = H >> 5;  // 32-column chunks == k-blocks
+  const int NB = H >> 5;   // 32-column chunks == k-blocks (even: H is a multiple of 64)
+  const int NB0 = NB >> 1;  // chunks per N-half
+  const int HH = H >> 1;    // columns per N-half
   const int nl = p.nlayers;
 
   if (warp == 0 && lane == 0) {
@@ -166,8 +171,11 @@ chain_kernel(const __grid_constant__ ChainParams p) {
         ptx::mbar_init(&aux_full[a], 1);
         ptx::mbar_init(&aux_empty[a], 1);  // the store-issuing thread of the group that consumed the slot
       }
-      ptx::mbar_init(acc_full, 1);
-      ptx::mbar_init(a_ready, 4 * G);  // every epilogue warp
+      for (int h = 0; h < 2; ++h) {
+        ptx::mbar_init(&acc_full[h], 1);
+        ptx::mbar_init(&a_ready[h], 4 * G);  // every epilogue warp
+      }
+      for (int c = 0; c < 4; ++c) ptx::mbar_init(&kfree[c], 1);
       ptx::mbar_init(a0_full, 1);
       ptx::fence_mbar_init();
     }
@@ -186,77 +194,90 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer
     if (lane == 0) {
-      const uint32_t wbytes = static_cast<uint32_t>(H) * kBlockK * 4;
+      const uint32_t wbytes = static_cast<uint32_t>(HH) * kBlockK * 4;
       int it = 0;
       for (int l = 0; l < nl; ++l) {
         const CUtensorMap* tw = &p.layer[l].tmW;
         const int nst = S3 ? 2 * NB : NB;
-        for (int j = 0; j < nst; ++j, ++it) {
-          const int s = it % NW;
-          const uint32_t ph = (it / NW) & 1;
-          ptx::mbar_wait(&w_empty[s], ph ^ 1);
-          ptx::mbar_expect_tx(&w_full[s], wbytes);
-          // SOFTPLUS3: k-block kb of Whi (columns [0,H)) then of Wlo (columns [2H,3H)); both serve hi, Whi also lo
-          const int kc = S3 ? (((j & 1) ? 2 * H : 0) + (j >> 1) * kBlockK) : j * kBlockK;
-          ptx::tma_load_2d(smem + s * Cfg::kWStage, tw, &w_full[s], kc, 0);
+        for (int h = 0; h < 2; ++h) {
+          for (int j = 0; j < nst; ++j, ++it) {
+            const int s = it % NW;
+            const uint32_t ph = (it / NW) & 1;
+            ptx::mbar_wait(&w_empty[s], ph ^ 1);
+            ptx::mbar_expect_tx(&w_full[s], wbytes);
+            // SOFTPLUS3: k-block kb of Whi (columns [0,H)) then of Wlo (columns [2H,3H)); both serve hi, Whi also lo
+            const int kc = S3 ? (((j & 1) ? 2 * H : 0) + (j >> 1) * kBlockK) : j * kBlockK;
+            ptx::tma_load_2d(smem + s * Cfg::kWStage, tw, &w_full[s], kc, h * HH);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(kBlockM, H, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_tf32(kBlockM, HH, 0, 0);
       int it = 0;
       for (int l = 0; l < nl; ++l) {
-        if (S3 && l == 0) ptx::mbar_wait(a0_full, 0);  // hi tiles of the initial activation have landed (TMA)
         long long* dbg = p.debug_times ? p.debug_times + (static_cast<size_t>(blockIdx.x) * kChainMaxLayers + l) * 8 : nullptr;
         if (dbg) dbg[0] = clock64();
-        ptx::mbar_wait(a_ready, l & 1);                // A operand of layer l is complete, accumulator is drained
-        ptx::tc_fence_after();
-        if (dbg) dbg[1] = clock64();
-        for (int kb = 0; kb < NB; ++kb) {
-          {
-            const int s = it % NW;
-            const uint32_t ph = (it / NW) & 1;
-            ptx::mbar_wait(&w_full[s], ph);
-            ptx::tc_fence_after();
-            const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
-            if (S3) {
+        if (S3 && l == 0) ptx::mbar_wait(a0_full, 0);  // hi tiles of the initial activation have landed (TMA)
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t d_t = acc_t + h * HH;
+          for (int kb = 0; kb < NB; ++kb) {
+            if (h == 0 && kb == 0) {
+              ptx::mbar_wait(&a_ready[0], l & 1);  // A chunks [0, NB/2) written, accumulator half 0 drained
+              ptx::tc_fence_after();
+              if (dbg) dbg[1] = clock64();
+            }
+            if (h == 0 && kb == NB0) {
+              ptx::mbar_wait(&a_ready[1], l & 1);  // A chunks [NB/2, NB) written, accumulator half 1 drained
+              ptx::tc_fence_after();
+            }
+            {
+              const int s = it % NW;
+              const uint32_t ph = (it / NW) & 1;
+              ptx::mbar_wait(&w_full[s], ph);
+              ptx::tc_fence_after();
+              const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
+              if (S3) {
+                const uint32_t h_addr = ptx::smem_u32(hi_tiles + kb * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
+                  const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
+                  ptx::umma_tf32(d_t, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
+                ptx::umma_tf32_ts(d_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, idesc,
+                                  (S3 || (kb | k) != 0) ? 1u : 0u);
+              }
+              ptx::umma_commit(&w_empty[s]);
+              ++it;
+            }
+            if (S3) {  // hi . Wlo
+              const int s = it % NW;
+              const uint32_t ph = (it / NW) & 1;
+              ptx::mbar_wait(&w_full[s], ph);
+              ptx::tc_fence_after();
+              const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
               const uint32_t h_addr = ptx::smem_u32(hi_tiles + kb * kTileBytes);
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
                 const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-                ptx::umma_tf32(acc_t, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_tf32(d_t, adesc, bdesc, idesc, 1u);
               }
+              ptx::umma_commit(&w_empty[s]);
+              ++it;
             }
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-              ptx::umma_tf32_ts(acc_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, idesc,
-                                (S3 || (kb | k) != 0) ? 1u : 0u);
-            }
-            ptx::umma_commit(&w_empty[s]);
-            ++it;
+            // second half: this layer is done with A chunk kb -> the half-0 epilogue may overwrite it
+            if (h == 1 && kb < NB0) ptx::umma_commit(&kfree[kb]);
           }
-          if (S3) {  // hi . Wlo
-            const int s = it % NW;
-            const uint32_t ph = (it / NW) & 1;
-            ptx::mbar_wait(&w_full[s], ph);
-            ptx::tc_fence_after();
-            const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
-            const uint32_t h_addr = ptx::smem_u32(hi_tiles + kb * kTileBytes);
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
-              const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-              ptx::umma_tf32(acc_t, adesc, bdesc, idesc, 1u);
-            }
-            ptx::umma_commit(&w_empty[s]);
-            ++it;
-          }
+          ptx::umma_commit(&acc_full[h]);
         }
-        ptx::umma_commit(acc_full);
         if (dbg) dbg[2] = clock64();
       }
     }
@@ -331,7 +352,10 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     ptx::tmem_st_wait();
     ptx::tc_fence_before();
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(a_ready);
+    if (lane == 0) {
+      ptx::mbar_arrive(&a_ready[0]);
+      ptx::mbar_arrive(&a_ready[1]);
+    }
 
     int prev_slot = -1;  // slot whose TMA store may still be reading it (released one chunk later)
 #pragma unroll 1
@@ -343,18 +367,28 @@ chain_kernel(const __grid_constant__ ChainParams p) {
                                 : nullptr;
       long long* dbg = (p.debug_times && leader && g == 0)
                            ? p.debug_times + (static_cast<size_t>(blockIdx.x) * kChainMaxLayers + l) * 8 : nullptr;
-      if (dbg) dbg[3] = clock64();
-      ptx::mbar_wait(acc_full, l & 1);
-      ptx::tc_fence_after();
-      if (dbg) { dbg[4] = clock64(); dbg[6] = 0; }
-      if (S3) {
+      if (dbg) { dbg[3] = clock64(); dbg[6] = 0; dbg[7] = 0; }
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+      {
+        long long tw0 = 0;
+        if (dbg) tw0 = clock64();
+        ptx::mbar_wait(&acc_full[h], l & 1);
+        ptx::tc_fence_after();
+        if (dbg) { dbg[7] += clock64() - tw0; if (h == 0) dbg[4] = clock64(); }
+      }
+      if (S3 && h == 0) {
         // the hi tiles are rewritten in place: the TMA stores that spilled the previous layer must have read them
         if (leader) ptx::tma_store_wait_read<0>();
         ptx::named_bar_sync(bar_a, 128);
       }
 #pragma unroll 1
-      for (int c = g; c < NB; c += G) {
+      for (int c = h * NB0 + g; c < (h + 1) * NB0; c += G) {
         const int nc = c * 32;
+        if (h == 0) {  // the half-1 MMAs of this layer still read A chunk c until kfree[c] fires
+          ptx::mbar_wait(&kfree[c], l & 1);
+          ptx::tc_fence_after();
+        }
         uint32_t accu[32];
         ptx::tmem_ld_32x32(acc_t + lane_addr + nc, accu);
         const int it = NB * (l + 1) + c;
@@ -486,18 +520,19 @@ chain_kernel(const __grid_constant__ ChainParams p) {
           }
         }
       }
-      // A operand of layer l+1 written (TMEM stores complete, shared-memory writes fenced), accumulator drained
+      // A chunks of this half written (TMEM stores complete, shared-memory writes fenced), accumulator half drained
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_ready);
-      if (dbg) dbg[5] = clock64();
+      if (lane == 0) ptx::mbar_arrive(&a_ready[h]);
+      if (dbg && h == 1) dbg[5] = clock64();
       if (HAS_OUT2 && L.colsum2 != nullptr) ptx::named_bar_sync(bar_a, 128);  // colsum2 re-reads of the slot are done
-      if (!S3 && leader && prev_slot >= 0) {  // do not sit on a slot through the MMA phase
+      if (!S3 && leader && prev_slot >= 0) {  // do not sit on a slot while waiting for the next accumulator half
         ptx::tma_store_wait_read<0>();
         ptx::mbar_arrive(&aux_empty[prev_slot]);
         prev_slot = -1;
       }
+      }  // h
     }
     if (leader) ptx::tma_store_wait_all<0>();
   }

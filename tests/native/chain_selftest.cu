@@ -262,11 +262,11 @@ static void bench_chain(int mode, int M, int H, int nl) {
     const int ctas[3] = {0, grid / 2, grid - 1};
     for (int ci = 0; ci < 3; ++ci) {
       const int cta = ctas[ci];
-      printf("  times mode %d cta %d (cycles): layer: mma_wait_a  mma_issue  | epi_wait_acc  epi_total  aux_wait | layer_period\n", mode, cta);
+      printf("  times mode %d cta %d (cycles): layer: mma_wait_a  mma_issue  | epi_wait_acc(all)  epi_total  aux_wait | layer_period\n", mode, cta);
       for (int l = 0; l < nl; ++l) {
         const long long* t = &h[((size_t)cta * kChainMaxLayers + l) * 8];
         const long long* tn = &h[((size_t)cta * kChainMaxLayers + l + 1) * 8];
-        printf("    %d: %7lld %7lld | %7lld %7lld %7lld | %7lld\n", l, t[1] - t[0], t[2] - t[1], t[4] - t[3], t[5] - t[4], t[6],
+        printf("    %d: %7lld %7lld | %7lld %7lld %7lld | %7lld\n", l, t[1] - t[0], t[2] - t[1], t[7], t[5] - t[4], t[6],
                l + 1 < nl ? tn[1] - t[1] : 0LL);
       }
     }
@@ -302,7 +302,7 @@ int main(int argc, char** argv) {
     if (only >= 0 && mode != only) continue;
     test_chain(mode, 300, 256, 3);
     test_chain(mode, 128, 64, 2);
-    test_chain(mode, 1000, 96, 4);
+    test_chain(mode, 1000, 128, 4);
   }
   if (bench)
     for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
