@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -298,6 +299,7 @@ struct GemmTNDesc {
   float* workspace = nullptr;         // split-K partials
   size_t workspace_bytes = 0;
   int target_ctas = 296;
+  int atomic = 0;                     // 0 auto (ARDAE_TN_ATOMIC, default on), 1 red.global.add epilogue, -1 two-pass reduce
 };
 
 struct PreparedTN {
@@ -309,7 +311,22 @@ struct PreparedTN {
   int nsplit = 0, Mpad = 0, Npad = 0;
   float* out = nullptr; int M = 0, N = 0, ldo = 0;
   float scale = 1.0f, beta = 0.0f;
+  bool atomic = false;
 };
+
+// Split-K combine: L2 reductions straight into the gradient (default) or partial tiles + a reduce launch
+// (ARDAE_TN_ATOMIC=0 / ARDAE_DETERMINISTIC=1: fixed summation order, bit-reproducible gradients).
+inline bool tn_atomic_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("ARDAE_TN_ATOMIC");
+    const char* d = std::getenv("ARDAE_DETERMINISTIC");
+    v = 1;
+    if (e != nullptr && e[0] == '0') v = 0;
+    if (d != nullptr && d[0] == '1') v = 0;
+  }
+  return v != 0;
+}
 
 inline size_t tn_workspace_bytes(int M, int N, int K, int target_ctas = 296) {
   const int bn = pick_block_n(N);
@@ -348,6 +365,12 @@ inline int prepare_gemm_tn(const GemmTNDesc& d, PreparedTN* out) {
     p.npairs = 2;
   }
   p.M = d.M; p.N = d.N; p.K = d.K; p.kb_per_split = kb_per_split; p.partial = d.workspace;
+  // vector reductions need 16-byte aligned rows (the [H, 2H+1] first neglogprob layer keeps the two-pass path)
+  const bool red_vec = (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldo % 4 == 0 && d.N % 4 == 0;
+  pr.atomic = (d.atomic > 0 || (d.atomic == 0 && tn_atomic_default() && red_vec)) && d.scale == 1.0f && d.beta == 1.0f;
+  if (pr.atomic) {
+    p.red_out = d.out; p.red_ld = d.ldo; p.red_vec = red_vec ? 1 : 0;
+  }
   switch (bn) {
     case 32: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<32>); pr.smem = GemmTNConfig<32>::kSmemBytes; break;
     case 64: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<64>); pr.smem = GemmTNConfig<64>::kSmemBytes; break;
@@ -366,6 +389,7 @@ inline int prepare_gemm_tn(const GemmTNDesc& d, PreparedTN* out) {
 inline int launch_prepared_tn(const PreparedTN& pr, cudaStream_t stream) {
   void* args[1] = {const_cast<GemmTNParams*>(&pr.params)};
   ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(kGemmThreads), args, pr.smem, stream));
+  if (pr.atomic) return 0;
   const int total = pr.M * pr.N;
   splitk_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
       pr.params.partial, pr.nsplit, pr.Mpad, pr.Npad, pr.out, pr.M, pr.N, pr.ldo, pr.scale, pr.beta);

@@ -70,6 +70,9 @@ struct alignas(64) GemmTNParams {
   int npairs;        // 1 or 2
   int kb_per_split;  // k-blocks (of 32 rows) handled by one split
   float* partial;    // [nsplit][Mpad][Npad], Mpad = gridDim.y*128, Npad = gridDim.z*BLOCK_N
+  float* red_out;    // non-null: every split adds its tile straight into out[M, N] (pitch red_ld) with
+  int red_ld;        //           red.global.add (no partial buffer, no reduce launch; summation order not fixed)
+  int red_vec;       // rows of red_out are 16-byte aligned: red.global.add.v4.f32
 };
 
 __device__ __forceinline__ float softplus_f(float x) {
@@ -847,6 +850,33 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
+    if (p.red_out != nullptr) {
+      // split-K without a second pass: accumulate this split's tile into the gradient with L2 reductions
+      if (iters > 0) {
+        const bool row_ok = m0 + r < p.M;  // tcgen05.ld is warp-collective: only the reductions are predicated
+        float* orow = p.red_out + static_cast<size_t>(row_ok ? m0 + r : 0) * p.red_ld + n0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          if (n0 + c * 32 >= p.N) break;
+          uint32_t accu[32];
+          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, accu);
+          ptx::tmem_ld_wait();
+          if (!row_ok) continue;
+          if (p.red_vec && n0 + c * 32 + 32 <= p.N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c * 32 + q * 4),
+                           "f"(__uint_as_float(accu[q * 4 + 0])), "f"(__uint_as_float(accu[q * 4 + 1])),
+                           "f"(__uint_as_float(accu[q * 4 + 2])), "f"(__uint_as_float(accu[q * 4 + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c * 32 + j < p.N) atomicAdd(orow + c * 32 + j, __uint_as_float(accu[j]));
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       uint32_t accu[32];
@@ -862,6 +892,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
         *reinterpret_cast<uint4*>(dst + c * 32 + q * 4) =
             make_uint4(accu[q * 4 + 0], accu[q * 4 + 1], accu[q * 4 + 2], accu[q * 4 + 3]);
       }
+    }
     }
   }
 
