@@ -29,6 +29,7 @@ struct ChainDesc {
   const float* A0 = nullptr; int lda0 = 0;        // initial activation [M, H] (SOFTPLUS3: hi part)
   const float* A0lo = nullptr; int lda0lo = 0;    // SOFTPLUS3: lo part
   const float* row_scale = nullptr;               // [M]
+  int pair = 0;   // CTA-pair (cta_group::2) kernel: 1 on, 0 / -1 off (ARDAE_CHAIN_PAIR=1 switches the default)
   std::vector<ChainLayerDesc> layers;
 };
 
@@ -37,6 +38,7 @@ struct PreparedChain {
   const void* fn = nullptr;
   dim3 grid;
   int smem = 0, threads = 0;
+  int cluster = 1;
 };
 
 // The chain kernel serves H -> H layers with H a multiple of 64 up to 256 (two N-halves of <= 128 columns each).
@@ -60,6 +62,13 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
   std::memset(&pr.params, 0, sizeof(pr.params));
   ChainParams& p = pr.params;
   int rc;
+  bool cg2_box;
+  {
+    const char* e = std::getenv("ARDAE_CHAIN_PAIR");
+    const int pe = e ? std::atoi(e) : 0;
+    const int pq = d.pair != 0 ? d.pair : pe;
+    cg2_box = pq > 0;
+  }
   if ((rc = encode_tmap_2d(&p.tmA0, d.A0, d.H, d.M, d.lda0, 32, kBlockM))) return rc;
   p.a0_lo = d.A0lo; p.a0_lo_ld = d.lda0lo; p.row_scale = d.row_scale;
   p.M = d.M; p.H = d.H; p.nlayers = nl;
@@ -69,7 +78,7 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
     ChainLayerParams& q = p.layer[l];
     if (!s.W || !s.out || (!s3 && !s.aux1) || (aux2 && !s.aux2) || (out2 && !s.out2))
       return fail(-2, "chain: missing operand pointer");
-    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * d.H : d.H, d.H, s.ldw, kBlockK, d.H / 2))) return rc;
+    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * d.H : d.H, d.H, s.ldw, kBlockK, cg2_box ? d.H / 4 : d.H / 2))) return rc;
     if (!s3 && (rc = encode_tmap_2d(&q.tmAux1, s.aux1, d.H, d.M, s.ld1, 32, kBlockM))) return rc;
     if (aux2 && (rc = encode_tmap_2d(&q.tmAux2, s.aux2, d.H, d.M, s.ld2, 32, kBlockM))) return rc;
     if ((rc = encode_tmap_2d(&q.tmOut, s.out, d.H, d.M, s.ldo, 32, kBlockM))) return rc;
@@ -86,13 +95,32 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
   }
   p.vec_ok = (align_or & 15) == 0 ? 1 : 0;
   if (s3 && !p.vec_ok) return fail(-2, "chain: SOFTPLUS3 operands must be 16-byte aligned");
-  switch (d.mode) {
-    case CHAIN_MUL_SIG: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_MUL_SIG>); pr.smem = ChainConfig<CHAIN_MUL_SIG>::kSmemBytes; pr.threads = ChainConfig<CHAIN_MUL_SIG>::kThreads; break;
-    case CHAIN_TANGENT: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_TANGENT>); pr.smem = ChainConfig<CHAIN_TANGENT>::kSmemBytes; pr.threads = ChainConfig<CHAIN_TANGENT>::kThreads; break;
-    case CHAIN_ADJOINT: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_ADJOINT>); pr.smem = ChainConfig<CHAIN_ADJOINT>::kSmemBytes; pr.threads = ChainConfig<CHAIN_ADJOINT>::kThreads; break;
-    default: pr.fn = reinterpret_cast<const void*>(&chain_kernel<CHAIN_SOFTPLUS3>); pr.smem = ChainConfig<CHAIN_SOFTPLUS3>::kSmemBytes; pr.threads = ChainConfig<CHAIN_SOFTPLUS3>::kThreads; break;
+  // CTA pairs halve the weight bytes each SM ingests; opt-in (ChainDesc::pair = 1 or ARDAE_CHAIN_PAIR=1)
+  static int pair_env = -2;
+  if (pair_env == -2) {
+    const char* e = std::getenv("ARDAE_CHAIN_PAIR");
+    pair_env = e ? std::atoi(e) : 0;
   }
+  const int pair_req = d.pair != 0 ? d.pair : pair_env;
+  const bool cg2 = pair_req > 0;  // measured on B200: the pair's lock-step costs more than the halved weight stream saves
+#define ARDAE_CHAIN_CASE(MODE_)                                                                      \
+  case MODE_:                                                                                        \
+    if (cg2) { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, true>); pr.smem = ChainConfig<MODE_, true>::kSmemBytes; pr.threads = ChainConfig<MODE_, true>::kThreads; } \
+    else { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, false>); pr.smem = ChainConfig<MODE_, false>::kSmemBytes; pr.threads = ChainConfig<MODE_, false>::kThreads; } \
+    break;
+  switch (d.mode) {
+    ARDAE_CHAIN_CASE(CHAIN_MUL_SIG)
+    ARDAE_CHAIN_CASE(CHAIN_TANGENT)
+    ARDAE_CHAIN_CASE(CHAIN_ADJOINT)
+    default:
+    ARDAE_CHAIN_CASE(CHAIN_SOFTPLUS3)
+  }
+#undef ARDAE_CHAIN_CASE
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
+  if (cg2) {
+    pr.cluster = 2;
+    pr.grid.x = (pr.grid.x + 1) / 2 * 2;  // an odd tail CTA works on an out-of-range tile (TMA clips)
+  }
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;
   return 0;
@@ -100,6 +128,17 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
 
 inline int launch_prepared_chain(const PreparedChain& pr, cudaStream_t stream) {
   void* args[1] = {const_cast<ChainParams*>(&pr.params)};
+  if (pr.cluster > 1) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pr.grid; cfg.blockDim = dim3(pr.threads); cfg.dynamicSmemBytes = pr.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pr.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ARDAE_CUDA_OK(cudaLaunchKernelExC(&cfg, pr.fn, args));
+    return 0;
+  }
   ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(pr.threads), args, pr.smem, stream));
   return 0;
 }

@@ -105,14 +105,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int MODE>
+template <int MODE, bool CG2 = false>
 struct ChainConfig {
   static constexpr bool kS3 = MODE == CHAIN_SOFTPLUS3;
   static constexpr bool kAux2 = MODE == CHAIN_TANGENT || MODE == CHAIN_ADJOINT;
   static constexpr bool kOut2 = MODE == CHAIN_TANGENT;
   static constexpr int kGroups = 2;
-  static constexpr int kWStage = 128 * kBlockK * 4;  // 16 KB: one k-block of one N-half ([<=128, 32] weight rows)
-  static constexpr int kNumWStages = 6;
+  // one k-block of one N-half ([<=128, 32] weight rows); a CTA pair (CG2) stages half of it in each CTA
+  static constexpr int kWStage = (CG2 ? 64 : 128) * kBlockK * 4;
+  static constexpr int kNumWStages = CG2 ? 12 : 6;
   // One ring serves aux loads AND out stores: a slot receives the aux tile(s) of a chunk by TMA, the epilogue
   // overwrites them IN PLACE with the out tile(s), the TMA store leaves from the same bytes, and the slot is
   // recycled once that store has read it.  128 KB of HBM traffic in flight per SM instead of 64.
@@ -125,10 +126,14 @@ struct ChainConfig {
   static constexpr int kThreads = 128 + kGroups * 128;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(ChainConfig<MODE>::kThreads, 1)
+// CG2: launched as clusters of two CTAs (adjacent row tiles).  The leader issues tcgen05.mma.cta_group::2 for the
+// 256-row pair; every weight k-block is staged half in each CTA, so each SM ingests HALF of the weight stream
+// (the 3xTF32 sweep moves 512 KB of weights per tile and layer and is bound by that stream) and the same 96 KB
+// ring holds twice as many k-blocks.
+template <int MODE, bool CG2 = false>
+__global__ void __launch_bounds__(ChainConfig<MODE, CG2>::kThreads, 1)
 chain_kernel(const __grid_constant__ ChainParams p) {
-  using Cfg = ChainConfig<MODE>;
+  using Cfg = ChainConfig<MODE, CG2>;
   constexpr bool S3 = Cfg::kS3, HAS_AUX2 = Cfg::kAux2, HAS_OUT2 = Cfg::kOut2;
   constexpr int G = Cfg::kGroups, NW = Cfg::kNumWStages;
   constexpr int NAUX = Cfg::kNumAux > 0 ? Cfg::kNumAux : 1;
@@ -167,34 +172,43 @@ chain_kernel(const __grid_constant__ ChainParams p) {
         ptx::mbar_init(&w_full[s], 1);
         ptx::mbar_init(&w_empty[s], 1);
       }
+      static_assert(NW <= 12, "barrier area");
       for (int a = 0; a < 8; ++a) {
         ptx::mbar_init(&aux_full[a], 1);
         ptx::mbar_init(&aux_empty[a], 1);  // the store-issuing thread of the group that consumed the slot
       }
       for (int h = 0; h < 2; ++h) {
         ptx::mbar_init(&acc_full[h], 1);
-        ptx::mbar_init(&a_ready[h], 4 * G);  // every epilogue warp
+        ptx::mbar_init(&a_ready[h], (CG2 ? 2 : 1) * 4 * G);  // every epilogue warp (of both CTAs of a pair)
       }
       for (int c = 0; c < 4; ++c) ptx::mbar_init(&kfree[c], 1);
       ptx::mbar_init(a0_full, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if (CG2) {
+      ptx::tmem_alloc_2sm(tmem_slot, 512);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG2) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t rank = CG2 ? ptx::cluster_ctarank() : 0;
   const uint32_t acc_t = tmem_base;       // accumulator columns [0, H)
   const uint32_t a_t = tmem_base + 256;   // A operand (SOFTPLUS3: its lo part) columns [256, 256 + H)
   uint8_t* hi_tiles = smem + Cfg::kOffAux;  // SOFTPLUS3 only
 
   if (warp == 0) {
     // ------------------------------------------------------------ weight producer
-    if (lane == 0) {
-      const uint32_t wbytes = static_cast<uint32_t>(HH) * kBlockK * 4;
+    if (ptx::elect_one()) {  // one elected lane: tcgen05 / TMA issue stays on the uniform datapath
+      const uint32_t wbytes = static_cast<uint32_t>(HH) * kBlockK * 4;  // per pair when CG2 (half lands in each CTA)
+      const int wrows = CG2 ? HH / 2 : HH;
       int it = 0;
       for (int l = 0; l < nl; ++l) {
         const CUtensorMap* tw = &p.layer[l].tmW;
@@ -204,39 +218,61 @@ chain_kernel(const __grid_constant__ ChainParams p) {
             const int s = it % NW;
             const uint32_t ph = (it / NW) & 1;
             ptx::mbar_wait(&w_empty[s], ph ^ 1);
-            ptx::mbar_expect_tx(&w_full[s], wbytes);
             // SOFTPLUS3: k-block kb of Whi (columns [0,H)) then of Wlo (columns [2H,3H)); both serve hi, Whi also lo
             const int kc = S3 ? (((j & 1) ? 2 * H : 0) + (j >> 1) * kBlockK) : j * kBlockK;
-            ptx::tma_load_2d(smem + s * Cfg::kWStage, tw, &w_full[s], kc, h * HH);
+            if (CG2) {
+              // both CTAs' halves complete on the LEADER's full barrier, armed by the leader for both
+              if (rank == 0) ptx::mbar_expect_tx(&w_full[s], wbytes);
+              ptx::tma_load_2d_2sm(smem + s * Cfg::kWStage, tw, &w_full[s], kc, h * HH + static_cast<int>(rank) * wrows);
+            } else {
+              ptx::mbar_expect_tx(&w_full[s], wbytes);
+              ptx::tma_load_2d(smem + s * Cfg::kWStage, tw, &w_full[s], kc, h * HH);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(kBlockM, HH, 0, 0);
+    if (rank == 0 && ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_tf32(CG2 ? 2 * kBlockM : kBlockM, HH, 0, 0);
+      auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        if (CG2) ptx::umma_tf32_2sm(d, a, b, idesc, acc); else ptx::umma_tf32(d, a, b, idesc, acc);
+      };
+      auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
+        if (CG2) ptx::umma_tf32_ts_2sm(d, a, b, idesc, acc); else ptx::umma_tf32_ts(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {  // CG2: the same barrier in both CTAs of the pair
+        if (CG2) ptx::umma_commit_2sm(bar, 0x3); else ptx::umma_commit(bar);
+      };
       int it = 0;
       for (int l = 0; l < nl; ++l) {
         long long* dbg = p.debug_times ? p.debug_times + (static_cast<size_t>(blockIdx.x) * kChainMaxLayers + l) * 8 : nullptr;
         if (dbg) dbg[0] = clock64();
+        long long wait_w = 0, wait_a1 = 0;
         if (S3 && l == 0) ptx::mbar_wait(a0_full, 0);  // hi tiles of the initial activation have landed (TMA)
         for (int h = 0; h < 2; ++h) {
           const uint32_t d_t = acc_t + h * HH;
           for (int kb = 0; kb < NB; ++kb) {
             if (h == 0 && kb == 0) {
+              if (CG2) ptx::mbar_wait_cluster(&a_ready[0], l & 1); else
               ptx::mbar_wait(&a_ready[0], l & 1);  // A chunks [0, NB/2) written, accumulator half 0 drained
               ptx::tc_fence_after();
               if (dbg) dbg[1] = clock64();
             }
             if (h == 0 && kb == NB0) {
+              long long t0 = dbg ? clock64() : 0;
+              if (CG2) ptx::mbar_wait_cluster(&a_ready[1], l & 1); else
               ptx::mbar_wait(&a_ready[1], l & 1);  // A chunks [NB/2, NB) written, accumulator half 1 drained
               ptx::tc_fence_after();
+              if (dbg) wait_a1 += clock64() - t0;
             }
             {
               const int s = it % NW;
               const uint32_t ph = (it / NW) & 1;
+              long long t0 = dbg ? clock64() : 0;
               ptx::mbar_wait(&w_full[s], ph);
+              if (dbg) wait_w += clock64() - t0;
               ptx::tc_fence_after();
               const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
               if (S3) {
@@ -245,16 +281,15 @@ chain_kernel(const __grid_constant__ ChainParams p) {
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                   const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
                   const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-                  ptx::umma_tf32(d_t, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                  mma_ss(d_t, adesc, bdesc, (kb | k) != 0 ? 1u : 0u);
                 }
               }
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-                ptx::umma_tf32_ts(d_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, idesc,
-                                  (S3 || (kb | k) != 0) ? 1u : 0u);
+                mma_ts(d_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, (S3 || (kb | k) != 0) ? 1u : 0u);
               }
-              ptx::umma_commit(&w_empty[s]);
+              commit(&w_empty[s]);
               ++it;
             }
             if (S3) {  // hi . Wlo
@@ -268,25 +303,34 @@ chain_kernel(const __grid_constant__ ChainParams p) {
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                 const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
                 const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-                ptx::umma_tf32(d_t, adesc, bdesc, idesc, 1u);
+                mma_ss(d_t, adesc, bdesc, 1u);
               }
-              ptx::umma_commit(&w_empty[s]);
+              commit(&w_empty[s]);
               ++it;
             }
             // second half: this layer is done with A chunk kb -> the half-0 epilogue may overwrite it
-            if (h == 1 && kb < NB0) ptx::umma_commit(&kfree[kb]);
+            if (h == 1 && kb < NB0) commit(&kfree[kb]);
           }
-          ptx::umma_commit(&acc_full[h]);
+          commit(&acc_full[h]);
         }
-        if (dbg) dbg[2] = clock64();
+        if (dbg) {
+          dbg[2] = clock64();
+          long long* dbg2 = dbg + static_cast<size_t>(gridDim.x) * kChainMaxLayers * 8;
+          dbg2[0] = wait_w; dbg2[1] = wait_a1;
+        }
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ aux / initial-activation producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one elected lane: tcgen05 / TMA issue stays on the uniform datapath
       if (S3) {
-        ptx::mbar_expect_tx(a0_full, static_cast<uint32_t>(NB) * kTileBytes);
-        for (int c = 0; c < NB; ++c) ptx::tma_load_2d(hi_tiles + c * kTileBytes, &p.tmA0, a0_full, c * 32, m0);
+        if (CG2) {  // both CTAs' hi tiles complete on the leader's barrier (its MMA thread is the only consumer)
+          if (rank == 0) ptx::mbar_expect_tx(a0_full, 2u * static_cast<uint32_t>(NB) * kTileBytes);
+          for (int c = 0; c < NB; ++c) ptx::tma_load_2d_2sm(hi_tiles + c * kTileBytes, &p.tmA0, a0_full, c * 32, m0);
+        } else {
+          ptx::mbar_expect_tx(a0_full, static_cast<uint32_t>(NB) * kTileBytes);
+          for (int c = 0; c < NB; ++c) ptx::tma_load_2d(hi_tiles + c * kTileBytes, &p.tmA0, a0_full, c * 32, m0);
+        }
       } else {
         int it = 0;
         for (int l = -1; l < nl; ++l) {
@@ -353,8 +397,13 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      ptx::mbar_arrive(&a_ready[0]);
-      ptx::mbar_arrive(&a_ready[1]);
+      if (CG2) {
+        ptx::mbar_arrive_cluster(&a_ready[0], 0);
+        ptx::mbar_arrive_cluster(&a_ready[1], 0);
+      } else {
+        ptx::mbar_arrive(&a_ready[0]);
+        ptx::mbar_arrive(&a_ready[1]);
+      }
     }
 
     int prev_slot = -1;  // slot whose TMA store may still be reading it (released one chunk later)
@@ -524,7 +573,9 @@ chain_kernel(const __grid_constant__ ChainParams p) {
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&a_ready[h]);
+      if (lane == 0) {
+        if (CG2) ptx::mbar_arrive_cluster(&a_ready[h], 0); else ptx::mbar_arrive(&a_ready[h]);
+      }
       if (dbg && h == 1) dbg[5] = clock64();
       if (HAS_OUT2 && L.colsum2 != nullptr) ptx::named_bar_sync(bar_a, 128);  // colsum2 re-reads of the slot are done
       if (!S3 && leader && prev_slot >= 0) {  // do not sit on a slot while waiting for the next accumulator half
@@ -539,9 +590,10 @@ chain_kernel(const __grid_constant__ ChainParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG2) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers / read its memory
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (CG2) ptx::tmem_dealloc_2sm(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 

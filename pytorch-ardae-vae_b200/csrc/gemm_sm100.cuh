@@ -331,7 +331,7 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one elected lane: tcgen05 / TMA issue stays on the uniform datapath
       const uint32_t rank = pair_rank;
       if (p.prefetch_tiles > 0) {
         // the CTA that will run on this SM slot a full wave later streams its operands from HBM: pull them
@@ -377,7 +377,7 @@ gemm_nt_kernel(const __grid_constant__ GemmNTParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (!CG2 || pair_rank == 0)) {
+    if ((!CG2 || pair_rank == 0) && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_tf32(CG2 ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % NSTAGE;
@@ -591,7 +591,7 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ A/B producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one elected lane: tcgen05 / TMA issue stays on the uniform datapath
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = tile * kBlockM;
@@ -610,7 +610,7 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one elected lane: tcgen05 / TMA issue stays on the uniform datapath
       constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, 256, 0, 0);
       int it = 0, t = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
@@ -797,7 +797,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one elected lane: tcgen05 / TMA issue stays on the uniform datapath
       for (int it = 0; it < iters; ++it) {
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
@@ -818,7 +818,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {  // one elected lane: tcgen05 / TMA issue stays on the uniform datapath
       constexpr uint32_t idesc = ptx::make_idesc_tf32(kBlockM, BLOCK_N, 1, 1);
       for (int it = 0; it < iters; ++it) {
         const int s = it % NSTAGE;

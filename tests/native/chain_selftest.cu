@@ -78,8 +78,8 @@ struct Cmp {
   }
 };
 
-static void test_chain(int mode, int M, int H, int nl) {
-  printf("chain mode %d M=%d H=%d layers=%d\n", mode, M, H, nl);
+static void test_chain(int mode, int M, int H, int nl, int pair) {
+  printf("chain mode %d M=%d H=%d layers=%d pair=%d\n", mode, M, H, nl, pair);
   const bool s3 = mode == CHAIN_SOFTPLUS3, aux2 = mode == CHAIN_TANGENT || mode == CHAIN_ADJOINT, out2 = mode == CHAIN_TANGENT;
   const int ldw = s3 ? 3 * H : H;
   std::vector<float> A0((size_t)M * H), A0lo((size_t)M * H), sigma(M);
@@ -98,7 +98,7 @@ static void test_chain(int mode, int M, int H, int nl) {
   };
   std::vector<LayerBufs> Ls(nl);
   ChainDesc d;
-  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig;
+  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig; d.pair = pair;
   for (int l = 0; l < nl; ++l) {
     LayerBufs& b = Ls[l];
     b.Wfull.resize((size_t)H * H);
@@ -226,7 +226,7 @@ static void test_chain(int mode, int M, int H, int nl) {
   cudaFree(dA0); cudaFree(dA0lo); cudaFree(dsig);
 }
 
-static void bench_chain(int mode, int M, int H, int nl) {
+static void bench_chain(int mode, int M, int H, int nl, int pair) {
   const bool s3 = mode == CHAIN_SOFTPLUS3, aux2 = mode == CHAIN_TANGENT || mode == CHAIN_ADJOINT, out2 = mode == CHAIN_TANGENT;
   const int ldw = s3 ? 3 * H : H;
   const size_t n = (size_t)M * H;
@@ -235,7 +235,7 @@ static void bench_chain(int mode, int M, int H, int nl) {
   float* dW = dev(W);
   float *dA0 = dev_fill(n, 0), *dA0lo = dev_fill(n, 0), *dsig = dev_fill(M, 0);
   ChainDesc d;
-  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig;
+  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig; d.pair = pair;
   std::vector<float*> bufs;
   float* dbias = dev_fill(H, 0);
   for (int l = 0; l < nl; ++l) {
@@ -250,24 +250,25 @@ static void bench_chain(int mode, int M, int H, int nl) {
   int rc = prepare_chain(d, &pr);
   if (rc) { printf("bench prepare failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
   if (getenv("CHAIN_TIMES")) {
-    const int grid = (M + 127) / 128;
+    const int grid = pr.grid.x;
     long long* dt;
-    CK(cudaMalloc(&dt, (size_t)grid * kChainMaxLayers * 8 * sizeof(long long)));
-    CK(cudaMemset(dt, 0, (size_t)grid * kChainMaxLayers * 8 * sizeof(long long)));
+    CK(cudaMalloc(&dt, (size_t)2 * grid * kChainMaxLayers * 8 * sizeof(long long)));
+    CK(cudaMemset(dt, 0, (size_t)2 * grid * kChainMaxLayers * 8 * sizeof(long long)));
     pr.params.debug_times = dt;
     launch_prepared_chain(pr, 0);
     CK(cudaDeviceSynchronize());
-    std::vector<long long> h((size_t)grid * kChainMaxLayers * 8);
+    std::vector<long long> h((size_t)2 * grid * kChainMaxLayers * 8);
     CK(cudaMemcpy(h.data(), dt, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     const int ctas[3] = {0, grid / 2, grid - 1};
     for (int ci = 0; ci < 3; ++ci) {
       const int cta = ctas[ci];
-      printf("  times mode %d cta %d (cycles): layer: mma_wait_a  mma_issue  | epi_wait_acc(all)  epi_total  aux_wait | layer_period\n", mode, cta);
+      printf("  times mode %d cta %d (cycles): layer: mma_wait_a  mma_issue  | epi_wait_acc(all)  epi_total  aux_wait | layer_period | mma_wait_w mma_wait_a1\n", mode, cta);
       for (int l = 0; l < nl; ++l) {
         const long long* t = &h[((size_t)cta * kChainMaxLayers + l) * 8];
         const long long* tn = &h[((size_t)cta * kChainMaxLayers + l + 1) * 8];
-        printf("    %d: %7lld %7lld | %7lld %7lld %7lld | %7lld\n", l, t[1] - t[0], t[2] - t[1], t[7], t[5] - t[4], t[6],
-               l + 1 < nl ? tn[1] - t[1] : 0LL);
+        const long long* t2 = &h[((size_t)(grid + cta) * kChainMaxLayers + l) * 8];
+        printf("    %d: %7lld %7lld | %7lld %7lld %7lld | %7lld | %7lld %7lld\n", l, t[1] - t[0], t[2] - t[1], t[7], t[5] - t[4], t[6],
+               l + 1 < nl ? tn[1] - t[1] : 0LL, t2[0], t2[1]);
       }
     }
     pr.params.debug_times = nullptr;
@@ -288,8 +289,8 @@ static void bench_chain(int mode, int M, int H, int nl) {
   const double arrays = s3 ? 1.0 : (1.0 + (aux2 ? 1 : 0) + 1.0 + (out2 ? 1 : 0));  // per layer: aux reads + out writes
   const double bytes = (arrays * nl + 1.0 + (s3 ? 1.0 : 0.0)) * n * 4.0;
   const double flops = 2.0 * M * (double)H * H * nl * (s3 ? 3.0 : 1.0);
-  printf("bench mode %d M=%d H=%d layers=%d: %.3f ms  (%.1f us/layer)  HBM %.0f GB/s  tensor %.0f TFLOP/s (executed)\n",
-         mode, M, H, nl, ms, ms * 1e3 / nl, bytes / ms * 1e-6, flops / ms * 1e-9);
+  printf("bench mode %d pair=%d M=%d H=%d layers=%d: %.3f ms  (%.1f us/layer)  HBM %.0f GB/s  tensor %.0f TFLOP/s (executed)\n",
+         mode, pair, M, H, nl, ms, ms * 1e3 / nl, bytes / ms * 1e-6, flops / ms * 1e-9);
   for (float* b : bufs) if (b) cudaFree(b);
   cudaFree(dW); cudaFree(dA0); cudaFree(dA0lo); cudaFree(dsig); cudaFree(dbias);
 }
@@ -300,15 +301,19 @@ int main(int argc, char** argv) {
   if (argc > 2) only = atoi(argv[2]);
   for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
     if (only >= 0 && mode != only) continue;
-    test_chain(mode, 300, 256, 3);
-    test_chain(mode, 128, 64, 2);
-    test_chain(mode, 1000, 128, 4);
+    for (int pair = -1; pair <= 1; pair += 2) {
+      test_chain(mode, 300, 256, 3, pair);
+      test_chain(mode, 128, 64, 2, pair);
+      test_chain(mode, 1000, 128, 4, pair);
+    }
   }
   if (bench)
     for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
       if (only >= 0 && mode != only) continue;
-      bench_chain(mode, 131072, 256, 9);
-      bench_chain(mode, 512, 256, 9);
+      for (int pair = -1; pair <= 1; pair += 2) {
+        bench_chain(mode, 131072, 256, 9, pair);
+        bench_chain(mode, 512, 256, 9, pair);
+      }
     }
   printf(g_fail ? "CHAIN SELFTEST FAILED (%d)\n" : "CHAIN SELFTEST OK\n", g_fail);
   return g_fail ? 1 : 0;
