@@ -214,15 +214,21 @@ def main():
     if rank == 0:
         sampler.start()
     step.profile = []
+    from ardae import _lib
+    h_train = cdae._plan(B, c['nz'] * c['nstd'], True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(K):
+        if i == K - 1:  # CUDA events around every launch of the CDAE update of the last timed step
+            _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 1))
         out = step(*resident[i % nb], beta=c['beta'])
     e1.record()
     barrier()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
+    kernel_ms = _lib.read_cdae_profile(h_train)  # per-launch times of the last timed step
+    _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 0))
     prof, step.profile = step.profile, None
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -284,11 +290,44 @@ def main():
     flops = cdae_alg_flops(B, c['nz'] * c['nstd'], c['z'], c['z'], c['cdae_h'], c['cdae_L'])
     ct = seg_ms['cdae_train']
     achieved = flops / ct * 1e-9
-    traffic = None
+    traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('cdae_train_dram_bytes_per_step')
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
     except Exception:
         pass
+    # ---- per-kernel rooflines of the CDAE update (CUDA events around each launch, last timed step)
+    N_, H_, L_ = B * c['nz'] * c['nstd'], c['cdae_h'], c['cdae_L']
+    arr = N_ * H_ * 4.0  # one [N, H] fp32 activation array
+    by_tag = {}
+    for tag, t_ms in kernel_ms:
+        by_tag.setdefault(tag, []).append(t_ms)
+    nlay = 2 * L_ - 1  # fused H->H layers per sweep
+    # algorithmic HBM bytes per launch: aux reads + spill writes per fused layer, + the initial activation
+    alg_bytes = {'chain_mul_sig': (2 * nlay + 1) * arr, 'chain_tangent': (4 * nlay + 1) * arr,
+                 'chain_adjoint': (3 * nlay + 1) * arr, 'gemm_tn': 4 * arr}
+    kernels = []
+    for tag in ('chain_tangent', 'chain_adjoint', 'chain_mul_sig', 'gemm_tn'):
+        ts = sorted(t for t in by_tag.get(tag, []) if t > 0.02)  # the big (N-row) launches only
+        if not ts:
+            continue
+        med = ts[len(ts) // 2]
+        ts = [t for t in ts if 0.8 * med <= t <= 1.25 * med]  # gemm_tn: the 2L-1 [H,H] contractions (not d-wide / two-pass ones)
+        avg = sum(ts) / len(ts)
+        a = alg_bytes[tag] / avg * 1e-6
+        kernels.append(dict(kernel=tag, bound='hbm', launches=len(ts), ms_per_launch=avg, achieved=a, peak=hbm_peak,
+                            unit='GB/s', frac=a / hbm_peak, algorithmic_bytes_per_launch=alg_bytes[tag],
+                            traffic=traffic.get(tag)))
+    ts3 = [t for t in by_tag.get('chain_softplus3', []) if t > 0.02]
+    if ts3:
+        # the two 3xTF32 chains together run nlay layers: algorithmic 2*N*H*H per layer (executed: 3x)
+        tot = sum(ts3)
+        a = 2.0 * N_ * H_ * H_ * nlay / tot * 1e-9
+        kernels.append(dict(kernel='chain_softplus3', bound='tensor', launches=len(ts3), ms_per_launch=tot / len(ts3),
+                            achieved=a, peak=tf32_peak, unit='TFLOP/s', frac=a / tf32_peak, executed_tflops=3 * a,
+                            executed_frac=3 * a / tf32_peak,
+                            note='3xTF32: three tensor-core products per algorithmic product (fp32-accurate forward)',
+                            traffic=traffic.get('chain_softplus3')))
+    dominant = max(kernels, key=lambda k: k['ms_per_launch'] * k['launches']) if kernels else None
     n_cdae = sum(p.numel() for p in cdae.parameters())
     n_model = sum(p.numel() for p in model.parameters())
     opt_bytes_c, opt_bytes_m = 28.0 * cdae._arena.total, 28.0 * model._arena.total
@@ -309,10 +348,15 @@ def main():
                  h2d_bytes_per_step=2 * B * c['D'] * 4, d2h_bytes_per_step=16),
         gpu_launches=step.count_launches(B) * K,
         segments_ms={k: round(v, 4) for k, v in seg_ms.items()},
-        roofline=dict(bound='tensor', kernel='cdae_train plan: gemm_nt_kernel x%d + gemm_tn_kernel (tcgen05 kind::tf32)' % (6 * 2 * c['cdae_L']),
-                      achieved=achieved, peak=tf32_peak, unit='TFLOP/s', frac=achieved / tf32_peak,
-                      peak_source='torch.matmul tf32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: %s burst)' % peaks.get('bf16_tflops'),
-                      algorithmic_flops_per_launch=flops, ms_per_launch=ct, traffic=traffic),
+        roofline=(dict(dominant, peak_source=hbm_src + ' (hbm_gbs)',
+                       note='dominant kernel of the step by total time; every kernel of the CDAE update is in roofline_kernels')
+                  if dominant else None),
+        roofline_kernels=kernels,
+        roofline_plan=dict(bound='tensor', kernel='whole cdae_train plan (4 fused chains + %d weight-gradient contractions + first/last layers)' % (2 * c['cdae_L']),
+                           achieved=achieved, peak=tf32_peak, unit='TFLOP/s', frac=achieved / tf32_peak,
+                           peak_source='torch.matmul tf32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: %s burst)' % peaks.get('bf16_tflops'),
+                           algorithmic_flops_per_launch=flops, ms_per_launch=ct,
+                           note='the plan is HBM-bound by its activation spill (see roofline_kernels); this is the north-star tensor figure'),
         roofline_hbm=roof_opt)
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_reference_leg(steps=2, warmup=1)

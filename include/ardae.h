@@ -66,6 +66,11 @@ ARDAE_API int ardae_cdae_create(const ardae_cdae_config* cfg, float* const* para
 ARDAE_API void ardae_cdae_destroy(ardae_cdae_t h);
 /* number of kernel launches one train / score call issues */
 ARDAE_API int ardae_cdae_num_launches(ardae_cdae_t h);
+/* Measurement hook (bench.py roofline, no reference counterpart): when on, every launch of the plan is bracketed by
+ * CUDA events on the stream it is issued to; read_profile synchronises the device and returns, for the LAST call,
+ * one 16-byte tag ("chain_tangent", "gemm_tn", ...) and the elapsed milliseconds per launch. */
+ARDAE_API int ardae_cdae_set_profile(ardae_cdae_t h, int on);
+ARDAE_API int ardae_cdae_read_profile(ardae_cdae_t h, int max_ops, char* tags, float* ms, int* num_ops);
 
 /* Replaces ConditionalARDAE.forward + cdae_loss.backward() (graddae/mlp.py:400-444,
  * ivae_ardae.py:768-771).  x [N,d] = input flattened, ctx [B,c], sigma [N] (= std, signed),

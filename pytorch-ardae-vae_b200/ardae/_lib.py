@@ -37,6 +37,8 @@ def _declare(lib):
     lib.ardae_cdae_destroy.argtypes = [vp]
     lib.ardae_cdae_destroy.restype = None
     lib.ardae_cdae_num_launches.argtypes = [vp]
+    lib.ardae_cdae_set_profile.argtypes = [vp, i]
+    lib.ardae_cdae_read_profile.argtypes = [vp, i, ctypes.c_char_p, ctypes.POINTER(f), ctypes.POINTER(i)]
     lib.ardae_cdae_train.argtypes = [vp, vp, vp, vp, vp, i, u64, f, vp, vp, vp]
     lib.ardae_cdae_score.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ardae_randn.argtypes = [vp, sz, u64, u32, vp]
@@ -91,3 +93,13 @@ def ptr_array(tensors):
     for k, t in enumerate(tensors):
         arr[k] = t.data_ptr()
     return arr
+
+
+def read_cdae_profile(handle, max_ops=512):
+    """[(tag, ms)] for every launch of the last call of a CDAE plan (ardae_cdae_set_profile must be on)."""
+    tags = ctypes.create_string_buffer(16 * max_ops)
+    ms = (ctypes.c_float * max_ops)()
+    n = ctypes.c_int(0)
+    check(lib().ardae_cdae_read_profile(handle, max_ops, tags, ms, ctypes.byref(n)))
+    raw = tags.raw
+    return [(raw[16 * k:16 * k + 16].split(b'\0')[0].decode(), float(ms[k])) for k in range(n.value)]

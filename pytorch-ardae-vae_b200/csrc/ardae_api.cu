@@ -73,6 +73,23 @@ ARDAE_API int ardae_cdae_create(const ardae_cdae_config* cfg, float* const* para
 ARDAE_API void ardae_cdae_destroy(ardae_cdae_t h) { delete h; }
 ARDAE_API int ardae_cdae_num_launches(ardae_cdae_t h) { return h ? h->p.plan.launches() + 2 : 0; }
 
+ARDAE_API int ardae_cdae_set_profile(ardae_cdae_t h, int on) {
+  if (!h) return fail(-1, "null argument");
+  h->p.plan.profile = on != 0;
+  return 0;
+}
+ARDAE_API int ardae_cdae_read_profile(ardae_cdae_t h, int max_ops, char* tags, float* ms, int* num_ops) {
+  if (!h || !tags || !ms || !num_ops || max_ops <= 0) return fail(-1, "null argument");
+  std::vector<const char*> t(max_ops);
+  const int n = h->p.plan.read_profile(max_ops, t.data(), ms);
+  for (int i = 0; i < n; ++i) {
+    std::strncpy(tags + 16 * i, t[i], 15);
+    tags[16 * i + 15] = 0;
+  }
+  *num_ops = n;
+  return 0;
+}
+
 ARDAE_API int ardae_cdae_train(ardae_cdae_t h, const float* x, const float* ctx, const float* sigma,
                      float* eps, int gen_eps, uint64_t seed, float inv_count, float* loss_out,
                      float* score_out, void* stream) {

@@ -54,6 +54,29 @@ struct Plan {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int num_gemm_nt = 0, num_gemm_tn = 0, num_small = 0, num_chain = 0;
+  // optional per-op timing (bench.py roofline): CUDA events around every op of the LAST run, on the op's stream
+  std::vector<const char*> tags;
+  bool profile = false;
+  std::vector<cudaEvent_t> ev0, ev1;
+
+  void tag_last(const char* t) {
+    if (!dry) tags.resize(ops.size(), "aux"), tags.back() = t;
+  }
+  // elapsed ms of every op of the last run (synchronises the device); returns the number of ops written
+  int read_profile(int max_ops, const char** out_tags, float* out_ms) {
+    if (ev0.size() != ops.size()) return 0;
+    cudaDeviceSynchronize();
+    int n = 0;
+    for (size_t i = 0; i < ops.size() && n < max_ops; ++i) {
+      if (lanes[i] >= 2) continue;
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, ev0[i], ev1[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+      out_tags[n] = i < tags.size() ? tags[i] : "aux";
+      out_ms[n] = ms;
+      ++n;
+    }
+    return n;
+  }
 
   void fork() {
     cur_lane = 1;
@@ -86,6 +109,7 @@ struct Plan {
     if (rc) return fail_with(rc);
     ops.push_back([pr](cudaStream_t s) { return launch_prepared_nt(pr, s); });
     lanes.push_back(cur_lane);
+    tag_last("gemm_nt");
   }
   void chain(const ChainDesc& d) {
     ++num_chain;
@@ -96,6 +120,8 @@ struct Plan {
     auto sp = std::make_shared<PreparedChain>(pr);  // ~8 KB of tensor maps: keep one copy
     ops.push_back([sp](cudaStream_t s) { return launch_prepared_chain(*sp, s); });
     lanes.push_back(cur_lane);
+    static const char* names[CHAIN_NUM_MODES] = {"chain_mul_sig", "chain_tangent", "chain_adjoint", "chain_softplus3"};
+    tag_last(names[d.mode]);
   }
   void tn(const GemmTNDesc& d) {
     ++num_gemm_tn;
@@ -105,8 +131,16 @@ struct Plan {
     if (rc) return fail_with(rc);
     ops.push_back([pr](cudaStream_t s) { return launch_prepared_tn(pr, s); });
     lanes.push_back(cur_lane);
+    tag_last("gemm_tn");
   }
   int run(cudaStream_t s) {
+    if (profile && ev0.size() != ops.size()) {
+      ev0.resize(ops.size()); ev1.resize(ops.size());
+      for (size_t i = 0; i < ops.size(); ++i) {
+        ARDAE_CUDA_OK(cudaEventCreate(&ev0[i]));
+        ARDAE_CUDA_OK(cudaEventCreate(&ev1[i]));
+      }
+    }
     for (size_t i = 0; i < ops.size(); ++i) {
       const int lane = lanes[i];
       if (lane == 2) {  // fork: the side stream picks up after everything issued so far
@@ -124,8 +158,11 @@ struct Plan {
         ARDAE_CUDA_OK(cudaStreamWaitEvent(s, ev_join, 0));
         continue;
       }
-      int rc = ops[i](lane == 1 ? side : s);
+      cudaStream_t st = lane == 1 ? side : s;
+      if (profile) ARDAE_CUDA_OK(cudaEventRecord(ev0[i], st));
+      int rc = ops[i](st);
       if (rc) return rc;
+      if (profile) ARDAE_CUDA_OK(cudaEventRecord(ev1[i], st));
     }
     return 0;
   }
@@ -133,12 +170,14 @@ struct Plan {
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    for (cudaEvent_t e : ev0) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev1) cudaEventDestroy(e);
   }
   Plan() = default;
   Plan(const Plan&) = delete;
   Plan& operator=(const Plan&) = delete;
   void reset() {
-    ops.clear(); lanes.clear(); cur_lane = 0; error = 0;
+    ops.clear(); lanes.clear(); tags.clear(); cur_lane = 0; error = 0;
     num_gemm_nt = num_gemm_tn = num_small = num_chain = 0;
   }
   int launches() const { return num_gemm_nt + 2 * num_gemm_tn + num_small + num_chain; }
