@@ -165,6 +165,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (no CUDA-graph replay of the step)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -192,7 +193,8 @@ def main():
     copt = ardae.RMSprop(cdae.parameters(), lr=c['d_lr'], momentum=c['d_momentum'])
     step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=c['std_scale'], delta=c['delta'], nz_cdae=c['nz'],
                            nstd=c['nstd'], nz_model=c['nz_model'],
-                           process_group=dist.group.WORLD if world > 1 else None, seed=1234)
+                           process_group=dist.group.WORLD if world > 1 else None, seed=1234,
+                           graph=not args.no_graph)
     B = c['B']
     gen = torch.Generator().manual_seed(999 + rank)
     pix = torch.rand(1, c['D'], generator=torch.Generator().manual_seed(5)) * 0.26  # mean ink fraction ~0.13
@@ -206,39 +208,52 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput (`value`)
-    for i in range(W):
+    # ---------------- device-resident throughput (`value`): K iterations (CUDA-graph replays unless --no-graph)
+    for i in range(max(W, 4)):  # >= 2 eager iterations + capture + 1 replay
         step(*resident[i % nb], beta=c['beta'])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    step.profile = []
-    from ardae import _lib
-    h_train = cdae._plan(B, c['nz'] * c['nstd'], True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(K):
-        if i == K - 1:  # CUDA events around every launch of the CDAE update of the last timed step
-            _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 1))
         out = step(*resident[i % nb], beta=c['beta'])
     e1.record()
     barrier()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
-    kernel_ms = _lib.read_cdae_profile(h_train)  # per-launch times of the last timed step
-    _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 0))
-    prof, step.profile = step.profile, None
+    graph_used = bool(step.graph and step._g is not None)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = t.item()
+    final_losses = {k: float(out[k].item()) for k in ('cdae_loss', 'model_loss')}
+
+    # ---------------- profiled pass (eager launches: events cannot sit between the nodes of a graph replay):
+    # K more iterations of the same workload with CUDA events around every segment, and around every launch of the
+    # CDAE update in the last one -> segments_ms and the per-kernel rooflines
+    from ardae import _lib
+    h_train = cdae._plan(B, c['nz'] * c['nstd'], True)
+    step.profile = []
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    for i in range(K):
+        if i == K - 1:
+            _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 1))
+        step(*resident[i % nb], beta=c['beta'])
+    p1.record()
+    barrier()
+    eager_ms = p0.elapsed_time(p1) / K
+    kernel_ms = _lib.read_cdae_profile(h_train)  # per-launch times of the last profiled iteration
+    _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 0))
+    prof, step.profile = step.profile, None
     seg = {}
     for name, a, b in prof:
         seg.setdefault(name, []).append(a.elapsed_time(b))
     seg_ms = {k: sum(v) / K for k, v in seg.items()}
-    final_losses = {k: float(out[k].item()) for k in ('cdae_loss', 'model_loss')}
 
     # ---------------- end-to-end: pinned host inputs -> H2D every step, losses D2H every step
     xbuf = [torch.empty(B, c['D'], device=dev) for _ in range(2)]
@@ -342,12 +357,16 @@ def main():
         config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, cdae_rows_per_gpu=B * c['nz'],
                     parallelism='dp%d' % world, arithmetic='tf32 tensor-core operands, fp32 accumulate; forward sweeps 3xTF32',
                     l2='no flush needed: per-step working set (activation spill) ~7 GB >> 126 MB L2',
+                    launch=('one CUDA-graph replay per step (%d kernels on 3 streams captured)' % step.count_launches(B)
+                            if graph_used else 'eager launches'),
+                    ms_per_step_eager_profiled=eager_ms,
                     noise='in-kernel Philox', final_losses=final_losses),
         clocks=sampler.summary(),
         e2e=dict(value=B * world * K / (e2e_ms * 1e-3), unit='samples/s', ms_per_step=e2e_ms / K,
                  h2d_bytes_per_step=2 * B * c['D'] * 4, d2h_bytes_per_step=16),
         gpu_launches=step.count_launches(B) * K,
-        segments_ms={k: round(v, 4) for k, v in seg_ms.items()},
+        segments_ms=dict({k: round(v, 4) for k, v in seg_ms.items()},
+                         note='eager profiled pass (CUDA events per segment); the timed region replays one graph'),
         roofline=(dict(dominant, peak_source=hbm_src + ' (hbm_gbs)',
                        note='dominant kernel of the step by total time; every kernel of the CDAE update is in roofline_kernels')
                   if dominant else None),

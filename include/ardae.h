@@ -170,6 +170,14 @@ ARDAE_API int ardae_rmsprop_step(float* p, const float* g, float* square_avg, fl
  * Encoder.sample_noise, ivae/toy.py:61-65, which draws on the CPU and copies). */
 ARDAE_API int ardae_randn(float* out, size_t n, uint64_t seed, uint32_t stream_id, void* stream);
 
+/* CUDA-graph support (no reference counterpart: the reference launches eagerly).  While a device counter is set,
+ * every launch issued by this library bakes the POINTER into its arguments: Philox seeds become
+ * seed + counter * golden-ratio and Adam's bias-correction step becomes step + counter, so a captured step draws fresh
+ * noise and advances Adam on every replay.  Set it before capturing, reset it to NULL afterwards (captured launches
+ * keep the pointer; eager calls then run with offset 0); ardae_bump_replay_counter is the last launch of the graph. */
+ARDAE_API int ardae_set_replay_counter(const unsigned long long* device_counter);
+ARDAE_API int ardae_bump_replay_counter(unsigned long long* device_counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,10 @@ Differences from the reference's execution (not from its results):
     summed upstream gradient on z;
   * noise is drawn on the device (Philox) unless injected through `noise=` (parity runs);
   * under data parallelism each rank holds a batch shard, losses/gradients are normalised by the
-    GLOBAL row counts and the two flat gradient buffers are summed with one NCCL allreduce each.
+    GLOBAL row counts and the two flat gradient buffers are summed with one NCCL allreduce each;
+  * `graph=True`: after two eager iterations the whole iteration (~180 launches on three streams) is captured
+    into ONE CUDA graph and replayed; per-replay variation (Philox seeds, Adam's step) comes from a device-resident
+    counter (ardae_set_replay_counter), inputs are copied into static buffers.
 """
 import ctypes
 
@@ -30,7 +33,7 @@ def dp_scales(B_local, nz, nstd, d, nz_model, world):
 
 class TrainStep(object):
     def __init__(self, model, cdae, model_opt, cdae_opt, std_scale=10000., delta=0.1, nz_cdae=256, nstd=1,
-                 nz_model=1, num_cdae_updates=1, process_group=None, seed=1234):
+                 nz_model=1, num_cdae_updates=1, process_group=None, seed=1234, graph=False):
         self.model, self.cdae, self.mopt, self.copt = model, cdae, model_opt, cdae_opt
         self.S, self.delta = float(std_scale), float(delta)
         self.nz, self.nstd, self.nzm, self.ncu = int(nz_cdae), int(nstd), int(nz_model), int(num_cdae_updates)
@@ -44,6 +47,11 @@ class TrainStep(object):
         self.profile = None  # set to a list to collect (name, start_event, end_event) per segment
         self.overlap = True
         self._side = None
+        # CUDA-graph replay of the iteration (opt-in; eager whenever noise is injected or profiling is on)
+        self.graph = bool(graph)
+        self._g = None          # (CUDAGraph, static x_cdae list, static x_model, outputs, beta, shapes)
+        self._g_eager_calls = 0
+        self._g_ctr = None
 
     class _Seg(object):
         def __init__(self, owner, name):
@@ -192,6 +200,85 @@ class TrainStep(object):
     def __call__(self, x_cdae, x_model, beta=1.0, noise=None):
         """One iteration.  x_cdae: the minibatch (or list of num_cdae_updates minibatches) for the CDAE
         update(s); x_model: the minibatch of the model update.  Returns device tensors (no sync)."""
+        if self.graph and noise is None and self.profile is None:
+            return self._call_graph(x_cdae, x_model, beta)
+        out = self._call_eager(x_cdae, x_model, beta, noise)
+        if self._g is not None:  # keep the captured graph's step counter in line with eager iterations in between
+            _lib.check(_lib.lib().ardae_bump_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr()), _lib.stream_ptr()))
+        return out
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _bump_host_steps(self):
+        """What the optimizers' host-side bookkeeping would have done in an eager iteration."""
+        for opt, skip in ((self.copt, (len(self.cdae._arena.params) - 1,)), (self.mopt, ())):
+            ar = opt._setup()
+            for k, p in enumerate(ar.params):
+                if k not in skip:
+                    opt.state[p]['step'] += 1
+
+    def _call_graph(self, x_cdae, x_model, beta):
+        xs = list(x_cdae) if isinstance(x_cdae, (list, tuple)) else [x_cdae] * self.ncu
+        sig = (tuple(tuple(x.shape) for x in xs), tuple(x_model.shape), float(beta), xs[0].device)
+        if self._g is not None and self._g[4] != sig:
+            self._g = None  # shapes / beta changed: capture again
+            self._g_eager_calls = 0
+        if self._g is None:
+            if self._g_eager_calls < 2:  # plans, side streams and allocator pools come to life eagerly
+                self._g_eager_calls += 1
+                return self._call_eager(x_cdae, x_model, beta, None)
+            L = _lib.lib()
+            dev = xs[0].device
+            if self._g_ctr is None:
+                self._g_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._g_ctr.zero_()
+            same = all(x is xs[0] for x in xs)
+            gx0 = torch.empty_like(xs[0])
+            gxs = [gx0] * len(xs) if same else [torch.empty_like(x) for x in xs]
+            gxm = torch.empty_like(x_model)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            _lib.check(L.ardae_set_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr())))
+            steps_before = [[opt.state[p]['step'] for p in opt._setup().params] for opt in (self.copt, self.mopt)]
+            try:
+                with torch.cuda.graph(g):
+                    out = self._call_eager(gxs, gxm, beta, None)
+                    _lib.check(L.ardae_bump_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr()), _lib.stream_ptr()))
+            except Exception as e:  # e.g. a collective that cannot be captured: stay eager, loudly
+                import warnings
+                warnings.warn('ardae.TrainStep: CUDA-graph capture failed (%s); continuing eagerly' % (e,))
+                _lib.check(L.ardae_set_replay_counter(None))
+                for opt, before in zip((self.copt, self.mopt), steps_before):
+                    for p, v in zip(opt._setup().params, before):
+                        opt.state[p]['step'] = v
+                self.graph = False
+                torch.cuda.synchronize()
+                return self._call_eager(x_cdae, x_model, beta, None)
+            finally:
+                _lib.check(L.ardae_set_replay_counter(None))
+            # the captured call advanced the host-side step counters once; undo, replay() re-applies per replay
+            for opt, skip in ((self.copt, (len(self.cdae._arena.params) - 1,)), (self.mopt, ())):
+                ar = opt._setup()
+                for k, p in enumerate(ar.params):
+                    if k not in skip:
+                        opt.state[p]['step'] -= 1
+            # the captured kernels carry step0 = (host step + 1); the counter starts at 0 for the first replay
+            self._g = (g, gxs, gxm, out, sig, same)
+        g, gxs, gxm, out, _, same = self._g
+        if same:
+            if xs[0].data_ptr() != gxs[0].data_ptr():
+                gxs[0].copy_(xs[0], non_blocking=True)
+        else:
+            for dst, src in zip(gxs, xs):
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        if x_model.data_ptr() != gxm.data_ptr():
+            gxm.copy_(x_model, non_blocking=True)
+        g.replay()
+        self._bump_host_steps()
+        self.launches = 1
+        return out
+
+    def _call_eager(self, x_cdae, x_model, beta=1.0, noise=None):
         xs = x_cdae if isinstance(x_cdae, (list, tuple)) else [x_cdae] * self.ncu
         closs = None
         main = torch.cuda.current_stream()

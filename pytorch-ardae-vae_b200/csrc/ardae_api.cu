@@ -207,7 +207,7 @@ ARDAE_API int ardae_sigma_schedule(const float* z, const float* zbar, int B, int
   if (!z || !zbar || !x_out || !sigma_out) return fail(-1, "null argument");
   if (B <= 0 || nz < 2 || d <= 0 || nstd <= 0) return fail(-2, "sigma_schedule: need B>0, nz>=2, d>0, nstd>0");
   sigma_schedule_kernel<<<B, 128, sizeof(float) * 4, static_cast<cudaStream_t>(stream)>>>(
-      z, zbar, nz, d, nstd, S, delta, xi, seed, x_out, sigma_out, std_out);
+      z, zbar, nz, d, nstd, S, delta, xi, seed, x_out, sigma_out, std_out, replay_counter());
   ARDAE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -227,11 +227,9 @@ ARDAE_API int ardae_adam_step(float* p, const float* g, float* exp_avg, float* e
   if (n % 4 != 0 || ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
                       reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15))
     return fail(-11, "optimizer arenas must be 16-byte aligned with n % 4 == 0");
-  const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), step);
-  const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), step);
+  if (step < 1) return fail(-2, "adam: step must be >= 1");
   adam_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, g, exp_avg, exp_avg_sq, n, static_cast<float>(lr / bc1), static_cast<float>(1.0 / std::sqrt(bc2)), beta1,
-      beta2, eps, gscale);
+      p, g, exp_avg, exp_avg_sq, n, lr, step, beta1, beta2, eps, gscale, replay_counter());
   ARDAE_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -251,7 +249,20 @@ ARDAE_API int ardae_rmsprop_step(float* p, const float* g, float* square_avg, fl
 ARDAE_API int ardae_randn(float* out, size_t n, uint64_t seed, uint32_t stream_id, void* stream) {
   if (!out) return fail(-1, "null argument");
   if (n == 0) return 0;
-  randn_kernel<<<grid_for((n + 3) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, stream_id);
+  randn_kernel<<<grid_for((n + 3) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, stream_id,
+                                                                                      replay_counter());
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+ARDAE_API int ardae_set_replay_counter(const unsigned long long* device_counter) {
+  replay_counter() = device_counter;
+  return 0;
+}
+
+ARDAE_API int ardae_bump_replay_counter(unsigned long long* device_counter, void* stream) {
+  if (!device_counter) return fail(-1, "null argument");
+  bump_counter_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(device_counter);
   ARDAE_CUDA_OK(cudaGetLastError());
   return 0;
 }

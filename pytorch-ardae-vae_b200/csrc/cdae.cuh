@@ -182,7 +182,7 @@ struct CdaePlan {
         ARDAE_CUDA_OK(cudaMemcpyAsync(sig, bd->sigma, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
         if (bd->loss_out) ARDAE_CUDA_OK(cudaMemsetAsync(bd->loss_out, 0, sizeof(float), s));
         cdae_perturb_kernel<<<grid_for(static_cast<size_t>(N) * d), 256, 0, s>>>(
-            bd->x, sig, bd->eps, xt.buf.p, N, d, xt.buf.ld, xt.kp, bd->gen_eps, bd->seed);
+            bd->x, sig, bd->eps, xt.buf.p, N, d, xt.buf.ld, xt.kp, bd->gen_eps, bd->seed, replay_counter());
         split2d_kernel<<<grid_for(static_cast<size_t>(B) * c), 256, 0, s>>>(
             bd->ctx, c, ctxp.buf.p, ctxp.buf.ld, B, c, ctxp.kp, 1.0f, 0.0f);
         copy2d_kernel<<<1, 256, 0, s>>>(w1 + 2 * H, ld1, wsig, 1, H, 1, 1, 1.0f, 0.0f, 0);

@@ -33,6 +33,19 @@ __device__ __forceinline__ float block_sum(float v) {
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
+// Replay counter: a CUDA-graph-captured step re-launches the same kernel arguments on every replay, so anything that
+// must change per step (Philox seeds, Adam's bias-correction step) is offset by a device-resident counter that a tiny
+// kernel bumps at the end of each replay.  `ctr == nullptr` (eager calls) means offset 0.
+typedef unsigned long long replay_ctr_t;
+inline const replay_ctr_t*& replay_counter() {
+  static const replay_ctr_t* p = nullptr;
+  return p;
+}
+__device__ __forceinline__ uint64_t replay_seed(uint64_t seed, const replay_ctr_t* ctr) {
+  return ctr != nullptr ? seed + static_cast<uint64_t>(*ctr) * 0x9E3779B97F4A7C15ull : seed;
+}
+__global__ void bump_counter_kernel(replay_ctr_t* ctr) { *ctr += 1ull; }
+
 struct Philox {
   static __device__ __forceinline__ uint4 round4(uint4 c, uint2 k) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
@@ -61,7 +74,9 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   return make_float2(r * c, r * s);
 }
 // out[i] = N(0,1), i < n   (4 normals per Philox call)
-__global__ void randn_kernel(float* __restrict__ out, size_t n, uint64_t seed, uint32_t stream) {
+__global__ void randn_kernel(float* __restrict__ out, size_t n, uint64_t seed, uint32_t stream,
+                             const replay_ctr_t* __restrict__ ctr) {
+  seed = replay_seed(seed, ctr);
   const size_t nq = (n + 3) / 4;
   for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
        q += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -176,7 +191,9 @@ __global__ void group_sum_kernel(const float* __restrict__ in, int in_ld, float*
 // stored; eps == nullptr means "no noise" (glogprob).
 __global__ void cdae_perturb_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                     float* __restrict__ eps, float* __restrict__ xt, int N, int d,
-                                    int ldx, int kp, int gen_eps, uint64_t seed) {
+                                    int ldx, int kp, int gen_eps, uint64_t seed,
+                                    const replay_ctr_t* __restrict__ ctr) {
+  seed = replay_seed(seed, ctr);
   const size_t total = static_cast<size_t>(N) * d;
   for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total;
        e += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -388,7 +405,8 @@ __global__ void sigma_schedule_kernel(const float* __restrict__ z, const float* 
                                       int nz, int d, int nstd, float S, float delta,
                                       const float* __restrict__ xi, uint64_t seed,
                                       float* __restrict__ x_out, float* __restrict__ sigma_out,
-                                      float* __restrict__ std_out) {
+                                      float* __restrict__ std_out, const replay_ctr_t* __restrict__ ctr) {
+  seed = replay_seed(seed, ctr);
   extern __shared__ float sm[];  // [blockDim.x]
   const int b = blockIdx.x;
   const float* zb = z + static_cast<size_t>(b) * nz * d;
@@ -602,8 +620,18 @@ __global__ void iws_logmeanexp_kernel(const float* __restrict__ w, int S, float*
 // Reference Adam (utils/optim.py:59-106, PyTorch-1.2 epsilon placement):
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / ((sqrt(v)+eps)/sqrt(bc2))
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, size_t n, float lr_bc1, float inv_sqrt_bc2,
-                            float b1, float b2, float eps, float gscale) {
+                            float* __restrict__ v, size_t n, float lr, int step0,
+                            float b1, float b2, float eps, float gscale, const replay_ctr_t* __restrict__ ctr) {
+  // bias corrections of step t = step0 + replay counter, in double like the host formula (utils/optim.py:96-98)
+  __shared__ float bc[2];
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(step0) + (ctr != nullptr ? static_cast<double>(*ctr) : 0.0);
+    const double bc1 = 1.0 - pow(static_cast<double>(b1), t), bc2 = 1.0 - pow(static_cast<double>(b2), t);
+    bc[0] = static_cast<float>(static_cast<double>(lr) / bc1);
+    bc[1] = static_cast<float>(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
+  const float lr_bc1 = bc[0], inv_sqrt_bc2 = bc[1];
   const size_t n4 = n / 4;
   float4* p4 = reinterpret_cast<float4*>(p);
   const float4* g4 = reinterpret_cast<const float4*>(g);

@@ -194,3 +194,41 @@ def test_optimizers_match_oracle(kind):
                                                      0.99, 1e-8, 0.5, 1.0, _lib.stream_ptr()))
         torch.cuda.synchronize()
         assert np.max(np.abs(p.cpu().numpy() - P['w'])) <= 2e-6
+
+
+def test_graph_replay_matches_eager():
+    """TrainStep(graph=True): two eager iterations, then the iteration is captured into one CUDA graph and replayed.
+    The first replay runs the very launches (and Philox seeds) the third eager iteration would have issued, so the
+    parameters after three iterations must agree; later replays draw fresh noise through the device counter and
+    keep the host-side optimizer step counters in line."""
+    import ardae
+    z, meta = load_case('mnist_small')
+    hp = meta['hp']
+    xc, xm = t(z['s0/x_cdae']), t(z['s0/x_model'])
+    res = []
+    for graph in (False, True):
+        model, cdae, mopt, copt = build(meta, z)
+        step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=hp['std_scale'], delta=hp['delta'],
+                               nz_cdae=hp['nz_cdae'], nstd=hp['nstd'], nz_model=hp['nz_model'], graph=graph, seed=7)
+        for _ in range(3):
+            step(xc, xm, beta=hp['beta'])
+        torch.cuda.synchronize()
+        p3 = (params_np(model), params_np(cdae))
+        losses = []
+        for _ in range(3):
+            out = step(xc, xm, beta=hp['beta'])
+            losses.append((out['cdae_loss'].item(), out['model_loss'].item()))
+        if graph:
+            assert step._g is not None, 'graph was not captured'
+        t_m = mopt.state[next(iter(model.parameters()))]['step']
+        t_c = copt.state[next(iter(cdae.parameters()))]['step']
+        res.append((p3, losses, t_m, t_c))
+    (pe, le, tme, tce), (pg, lg, tmg, tcg) = res
+    assert (tme, tce) == (tmg, tcg) == (6, 6)
+    for a, b in zip(pe, pg):
+        for k in a:
+            assert rel_err(b[k], a[k]) <= 1e-5, k
+    for (c1, m1), (c2, m2) in zip(le, lg):
+        assert np.isfinite([c1, m1, c2, m2]).all()
+    # fresh noise per replay: the CDAE loss is a noisy estimate, three identical values would mean frozen seeds
+    assert len({round(c, 7) for c, _ in lg}) == 3
