@@ -48,7 +48,8 @@ class TrainStep(object):
         self.overlap = True
         self._side = None
         # CUDA-graph replay of the iteration (opt-in; eager whenever noise is injected or profiling is on)
-        self.graph = bool(graph)
+        # (single process only: capturing the NCCL allreduces hung on the 2-GPU box; data-parallel runs launch eagerly)
+        self.graph = bool(graph) and self.world == 1
         self._g = None          # (CUDAGraph, static x_cdae list, static x_model, outputs, beta, shapes)
         self._g_eager_calls = 0
         self._g_ctr = None
