@@ -170,6 +170,10 @@ def main():
     if args.impl == 'reference':
         return run_reference(args)
 
+    # keep stdout clean for the ONE JSON line (NCCL prints its version banner to stdout): everything else -> stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import ardae
@@ -380,8 +384,11 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_reference_leg(steps=2, warmup=1)
         line['cpu_baseline'] = cb
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
