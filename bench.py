@@ -361,7 +361,9 @@ def main():
         config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, cdae_rows_per_gpu=B * c['nz'],
                     parallelism='dp%d' % world, arithmetic='tf32 tensor-core operands, fp32 accumulate; forward sweeps 3xTF32',
                     l2='no flush needed: per-step working set (activation spill) ~7 GB >> 126 MB L2',
-                    launch=('one CUDA-graph replay per step (%d kernels on 3 streams captured)' % step.count_launches(B)
+                    launch=(('one CUDA-graph replay per step (%d kernels on 3 streams captured)' % step.count_launches(B)
+                             if world == 1 else
+                             '3 CUDA-graph replays + 2 eager NCCL allreduces per step (%d kernels captured)' % step.count_launches(B))
                             if graph_used else 'eager launches'),
                     ms_per_step_eager_profiled=eager_ms,
                     noise='in-kernel Philox', final_losses=final_losses),

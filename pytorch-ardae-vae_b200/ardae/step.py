@@ -48,8 +48,10 @@ class TrainStep(object):
         self.overlap = True
         self._side = None
         # CUDA-graph replay of the iteration (opt-in; eager whenever noise is injected or profiling is on)
-        # (single process only: capturing the NCCL allreduces hung on the 2-GPU box; data-parallel runs launch eagerly)
-        self.graph = bool(graph) and self.world == 1
+        # Under data parallelism the two NCCL allreduces stay eager (capturing them hung on the 2-GPU box): the
+        # iteration is captured as graph segments around them (three replays + two collectives per iteration).
+        self.graph = bool(graph)
+        self._cap = None        # segment recorder while capturing under DP
         self._g = None          # (CUDAGraph, static x_cdae list, static x_model, outputs, beta, shapes)
         self._g_eager_calls = 0
         self._g_ctr = None
@@ -98,8 +100,23 @@ class TrainStep(object):
         return out
 
     def _allreduce(self, flat):
-        if self.world > 1:
-            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        if self.world <= 1:
+            return
+        cap = self._cap
+        if cap is not None:
+            # segment boundary: join the forward side stream, close the graph captured so far, note the collective,
+            # open the next segment (nothing executes during capture, the collective included)
+            main = torch.cuda.current_stream()
+            if cap['side_forked'] and not cap['side_joined']:
+                main.wait_stream(self._side)
+                cap['side_joined'] = True
+            cap['graph'].capture_end()
+            cap['ops'].append(cap['graph'])
+            cap['ops'].append(flat)
+            cap['graph'] = torch.cuda.CUDAGraph()
+            cap['graph'].capture_begin(pool=cap['pool'])
+            return
+        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
 
     def cdae_update(self, x, noise=None):
         L = _lib.lib()
@@ -217,6 +234,38 @@ class TrainStep(object):
                 if k not in skip:
                     opt.state[p]['step'] += 1
 
+    class _Segments(object):
+        """A captured iteration under DP: CUDA graphs alternating with the flat buffers to allreduce eagerly."""
+
+        def __init__(self, owner, ops, out):
+            self.owner, self.ops, self.out = owner, ops, out
+
+        def replay(self):
+            for op in self.ops:
+                if torch.is_tensor(op):
+                    torch.distributed.all_reduce(op, op=torch.distributed.ReduceOp.SUM, group=self.owner.pg)
+                else:
+                    op.replay()
+
+    def _capture_segments(self, gxs, gxm, beta):
+        L = _lib.lib()
+        cs = torch.cuda.Stream()
+        cs.wait_stream(torch.cuda.current_stream())
+        pool = torch.cuda.graph_pool_handle()
+        cap = dict(graph=torch.cuda.CUDAGraph(), ops=[], pool=pool, side_forked=False, side_joined=False)
+        with torch.cuda.stream(cs):
+            cap['graph'].capture_begin(pool=pool)
+            self._cap = cap
+            try:
+                out = self._call_eager(gxs, gxm, beta, None)
+                _lib.check(L.ardae_bump_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr()), _lib.stream_ptr()))
+            finally:
+                self._cap = None
+                cap['graph'].capture_end()
+            cap['ops'].append(cap['graph'])
+        torch.cuda.current_stream().wait_stream(cs)
+        return TrainStep._Segments(self, cap['ops'], out)
+
     def _call_graph(self, x_cdae, x_model, beta):
         xs = list(x_cdae) if isinstance(x_cdae, (list, tuple)) else [x_cdae] * self.ncu
         sig = (tuple(tuple(x.shape) for x in xs), tuple(x_model.shape), float(beta), xs[0].device)
@@ -241,7 +290,11 @@ class TrainStep(object):
             _lib.check(L.ardae_set_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr())))
             steps_before = [[opt.state[p]['step'] for p in opt._setup().params] for opt in (self.copt, self.mopt)]
             try:
-                with torch.cuda.graph(g):
+                if self.world > 1:
+                    g = self._capture_segments(gxs, gxm, beta)
+                    out = g.out
+                else:
+                  with torch.cuda.graph(g):
                     out = self._call_eager(gxs, gxm, beta, None)
                     _lib.check(L.ardae_bump_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr()), _lib.stream_ptr()))
             except Exception as e:  # e.g. a collective that cannot be captured: stay eager, loudly
@@ -289,6 +342,8 @@ class TrainStep(object):
             if self._side is None:
                 self._side = torch.cuda.Stream()
             self._side.wait_stream(main)
+            if self._cap is not None:
+                self._cap['side_forked'] = True
             with torch.cuda.stream(self._side):
                 fwd = self.model_forward(x_model, beta, noise)
                 for k in ('z', 'sums', 'zbar', 'xsd', 'enc'):
@@ -297,7 +352,8 @@ class TrainStep(object):
         for i in range(self.ncu):
             closs = self.cdae_update(xs[i], noise)
         if self.overlap:
-            main.wait_stream(self._side)
+            if self._cap is None or not self._cap['side_joined']:
+                main.wait_stream(self._side)
         else:
             fwd = self.model_forward(x_model, beta, noise)
         sums, g, z = self.model_backward(fwd, beta)
