@@ -130,3 +130,63 @@ def test_cdae_shape_errors():
         m(torch.zeros(8, 4, device='cuda'), torch.zeros(8, 1, 4, device='cuda'))
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 3, 4), torch.zeros(2, 1, 4))  # CPU tensors: no fallback
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Full size (BASELINE.json configs[1]: B=512 data rows x 256 samples = 131072 CDAE rows, d=c=32, H=256, L=5):
+# the oracle cannot run the whole batch in seconds, so parity is checked through size-independent properties.
+FULL = dict(d=32, c=32, H=256, L=5, B=512, S=256)
+
+
+def _full_inputs(seed=3):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    B, S, d, c = FULL['B'], FULL['S'], FULL['d'], FULL['c']
+    x = 30.0 * torch.randn(B, S, d, device='cuda', generator=g)
+    ctx = torch.randn(B, 1, c, device='cuda', generator=g)
+    std = 0.5 * torch.randn(B, S, 1, device='cuda', generator=g)
+    eps = torch.randn(B, S, d, device='cuda', generator=g)
+    return x, ctx, std, eps
+
+
+def test_full_size_rows_match_oracle_on_a_subset():
+    """Rows are independent in sweeps 1-2: the scores of 4 of the 512 data rows taken from the
+    full-size launch (1024 row tiles, fused chains) must equal the oracle run on those rows alone."""
+    m = make_cdae(FULL['d'], FULL['c'], FULL['H'], FULL['L'], seed=5)
+    x, ctx, std, eps = _full_inputs()
+    _, loss = m(x, ctx, std=std, scale=1.0, eps=eps)
+    torch.cuda.synchronize()
+    assert np.isfinite(loss.item())
+    pick = [0, 137, 300, 511]
+    P64 = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in m.state_dict().items()}
+    cs = orc.CdaeSpec(FULL['d'], FULL['c'], FULL['H'], FULL['L'])
+    n = lambda a: a[pick].detach().cpu().numpy().astype(np.float64)
+    loss_o, g_o, _ = orc.cdae_loss_and_grads(cs, P64, n(x), n(ctx), n(std), n(eps))
+    g = m.last_score[pick].cpu().numpy()
+    assert rel_err(g, g_o) <= SCORE_TOL and cosine(g, g_o) >= 0.9999
+    # the subset's own loss term: mean((sigma*g + eps)^2) over the picked rows
+    res = (n(std) * g + n(eps)) ** 2
+    assert abs(res.mean() - loss_o) / abs(loss_o) <= LOSS_TOL
+
+
+def test_full_size_duplicated_halves_give_the_half_batch_gradient():
+    """loss = mean over N*d: a batch whose second half repeats the first has the loss and every parameter gradient
+    of the half batch.  Compares the B=512 launch (1024 tiles) with the B=256 launch (different tiling, different
+    split-K partition of the weight-gradient contractions)."""
+    x, ctx, std, eps = _full_inputs(seed=9)
+    h = FULL['B'] // 2
+    dup = lambda a: torch.cat([a[:h], a[:h]], dim=0).contiguous()
+    m = make_cdae(FULL['d'], FULL['c'], FULL['H'], FULL['L'], seed=6)
+    m.zero_grad()
+    _, l_full = m(dup(x), dup(ctx), std=dup(std), scale=1.0, eps=dup(eps))
+    l_full.backward()
+    g_full = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    _, l_half = m(x[:h].contiguous(), ctx[:h].contiguous(), std=std[:h].contiguous(), scale=1.0, eps=eps[:h].contiguous())
+    l_half.backward()
+    torch.cuda.synchronize()
+    assert abs(l_full.item() - l_half.item()) <= 1e-5 * abs(l_half.item())
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        e = rel_err(g_full[k].cpu().numpy(), p.grad.cpu().numpy())
+        assert e <= 2e-4, (k, e)  # same tf32 products, only the fp32 summation order differs
