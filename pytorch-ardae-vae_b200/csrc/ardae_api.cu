@@ -206,7 +206,7 @@ ARDAE_API int ardae_sigma_schedule(const float* z, const float* zbar, int B, int
                                    float* std_out, void* stream) {
   if (!z || !zbar || !x_out || !sigma_out) return fail(-1, "null argument");
   if (B <= 0 || nz < 2 || d <= 0 || nstd <= 0) return fail(-2, "sigma_schedule: need B>0, nz>=2, d>0, nstd>0");
-  sigma_schedule_kernel<<<B, 128, sizeof(float) * 4, static_cast<cudaStream_t>(stream)>>>(
+  sigma_schedule_kernel<<<B, 256, sizeof(float) * (4 + 256 + d), static_cast<cudaStream_t>(stream)>>>(
       z, zbar, nz, d, nstd, S, delta, xi, seed, x_out, sigma_out, std_out, replay_counter());
   ARDAE_CUDA_OK(cudaGetLastError());
   return 0;

@@ -411,8 +411,41 @@ __global__ void sigma_schedule_kernel(const float* __restrict__ z, const float* 
   const int b = blockIdx.x;
   const float* zb = z + static_cast<size_t>(b) * nz * d;
   const float* zm = zbar + static_cast<size_t>(b) * d;
-  // per-dimension unbiased std over the nz samples; thread t handles dims t, t+blockDim, ...
+  // per-dimension unbiased std over the nz samples (two passes, like torch.std).  Element i = k*d + j of the row's
+  // [nz, d] block is read by thread i % blockDim: coalesced, every thread busy.  When blockDim % d == 0 a thread
+  // always sees the same dimension j, so per-thread partial sums reduce per dimension through shared memory.
   float acc = 0.0f;
+  const int total = nz * d;
+  if (blockDim.x % d == 0 && d <= static_cast<int>(blockDim.x)) {
+    float* red = sm + 4;                 // [blockDim.x]
+    float* stat = sm + 4 + blockDim.x;   // [d]
+    const int j = threadIdx.x % d;
+    const float m0 = zm[j];
+    float s1 = 0.0f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s1 += S * (zb[i] - m0);
+    red[threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < d) {
+      float t = 0.0f;
+      for (int q = threadIdx.x; q < static_cast<int>(blockDim.x); q += d) t += red[q];
+      stat[threadIdx.x] = t / nz;
+    }
+    __syncthreads();
+    const float mean = stat[j];
+    float s2 = 0.0f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const float v = S * (zb[i] - m0) - mean;
+      s2 += v * v;
+    }
+    __syncthreads();
+    red[threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < d) {
+      float t = 0.0f;
+      for (int q = threadIdx.x; q < static_cast<int>(blockDim.x); q += d) t += red[q];
+      acc = sqrtf(t / (nz - 1));
+    }
+  } else {
   for (int j = threadIdx.x; j < d; j += blockDim.x) {
     const float m0 = zm[j];
     float mean = 0.0f;
@@ -424,6 +457,7 @@ __global__ void sigma_schedule_kernel(const float* __restrict__ z, const float* 
       var += v * v;
     }
     acc += sqrtf(var / (nz - 1));
+  }
   }
   acc = block_sum(acc);
   if (threadIdx.x == 0) sm[0] = delta * acc / d;

@@ -253,6 +253,8 @@ struct ModelPlan {
       out.w = h;  // write only the hid columns of the (possibly wider) concat buffer
       GemmNTDesc g = nt3_desc(epsp, F0n, out, ACT);
       g.group_bias = rowbias0.p; g.group = nz; g.ldg = rowbias0.ld;
+      // N-row sampling with 256 < h <= 512: two 256-wide tiles (A read twice) instead of three 128-wide ones
+      if (h > 256 && h <= 512 && R >= 16384) g.force_block_n = 256;
       fwd.nt(g);
     }
     if (toy) {
