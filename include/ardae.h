@@ -58,6 +58,10 @@ typedef struct {
   int batch;             /* B  distinct context rows */
   int samples;           /* S  rows per context row; N = B*S, row index b*S+k */
   int train;             /* 1: loss + gradients (forward + backward); 0: glogprob only */
+  int kind;              /* 0: net.MLPGradCARDAE (--cdae mlp-grad, models/graddae/mlp.py:341-483): energy network, score by
+                          *    back-propagation, double-backprop training gradient;
+                          * 1: net.MLPResCARDAE (--cdae mlp-res, models/resdae/mlp.py:286-413): the last MLP is `dae`
+                          *    ([d, H] output layer) and outputs the score itself; every tensor receives a gradient */
 } ardae_cdae_config;
 
 ARDAE_API int ardae_cdae_workspace_bytes(const ardae_cdae_config* cfg, size_t* bytes);

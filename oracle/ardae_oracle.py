@@ -371,12 +371,43 @@ def model_backward(spec, P, tape, beta, nz, dz_extra, G, loss_scale=1.0):
 class CdaeSpec(object):
     """MLPGradCARDAE as built by ivae_ardae.py:595-606 (enc_ctx = enc_input = True, softplus)."""
 
-    def __init__(self, input_dim, context_dim, h_dim, num_hidden_layers):
+    def __init__(self, input_dim, context_dim, h_dim, num_hidden_layers, kind='grad'):
         self.d, self.c, self.H, self.L = input_dim, context_dim, h_dim, num_hidden_layers
-        # models/graddae/mlp.py:374-378
+        self.kind = kind  # 'grad': MLPGradCARDAE (graddae/mlp.py), 'res': MLPResCARDAE (resdae/mlp.py:286-413)
+        # models/graddae/mlp.py:374-378 ; models/resdae/mlp.py:319-323
         self.ctx_keys = mlp_keys('ctx_encode', num_hidden_layers - 1)
         self.inp_keys = mlp_keys('inp_encode', num_hidden_layers - 1)
-        self.nlp_keys = mlp_keys('neglogprob', num_hidden_layers)
+        self.nlp_keys = mlp_keys('neglogprob' if kind == 'grad' else 'dae', num_hidden_layers)
+
+
+# ----------------------------------------------------------------------------- residual CDAE (mlp-res)
+def _rescdae_forward(cs, P, xt, ctx, std, sample_size):
+    """resdae/mlp.py:373-383 / :403-411: f = dae([inp_encode(xt), ctx_encode(ctx), std]) -- the network outputs the
+    score directly.  xt [N,d], ctx [B,c], std [N,1]."""
+    uL, tape_inp = mlp_forward(P, cs.inp_keys, xt, 'softplus', True)
+    cL, tape_ctx = mlp_forward(P, cs.ctx_keys, ctx, 'softplus', True)
+    hcat = np.concatenate([uL, np.repeat(cL, sample_size, axis=0), std], axis=1)
+    f, tape_dae = mlp_forward(P, cs.nlp_keys, hcat, 'softplus', False)
+    return f, dict(tape_inp=tape_inp, tape_ctx=tape_ctx, tape_dae=tape_dae)
+
+
+def rescdae_loss_and_grads(cs, P, x, ctx, std, eps):
+    """ConditionalARDAE.forward + loss.backward() of the residual CDAE: resdae/mlp.py:353-389,
+    loss = F.mse_loss(std * f, -eps) (:386); plain back-propagation (every parameter gets a gradient)."""
+    B, S, d = x.shape
+    N, H = B * S, cs.H
+    xf, sf, ef = x.reshape(N, d), std.reshape(N, 1), eps.reshape(N, d)
+    xt = xf + sf * ef  # add_gaussian_noise
+    f, T = _rescdae_forward(cs, P, xt, ctx.reshape(B, -1), sf, S)
+    resid = sf * f + ef
+    loss = (resid ** 2).mean()
+    r = (2.0 / (N * d)) * sf * resid
+    G = {}
+    dh = mlp_backward(P, cs.nlp_keys, T['tape_dae'], r, 'softplus', False, G)  # [N, 2H+1]
+    mlp_backward(P, cs.inp_keys, T['tape_inp'], dh[:, :H], 'softplus', True, G)
+    dc = dh[:, H:2 * H].reshape(B, S, H).sum(1)
+    mlp_backward(P, cs.ctx_keys, T['tape_ctx'], dc, 'softplus', True, G)
+    return loss, f.reshape(B, S, d), G
 
 
 def _cdae_primal_and_score(cs, P, xt, ctx, std, sample_size):
@@ -415,6 +446,9 @@ def _cdae_primal_and_score(cs, P, xt, ctx, std, sample_size):
 def cdae_glogprob(cs, P, x, ctx, std):
     """ConditionalARDAE.glogprob: graddae/mlp.py:446-483.  x [B,S,d], ctx [B,1,c], std [B,S,1]."""
     B, S, d = x.shape
+    if cs.kind == 'res':  # resdae/mlp.py:391-413
+        f, _ = _rescdae_forward(cs, P, x.reshape(B * S, d), ctx.reshape(B, -1), std.reshape(B * S, 1), S)
+        return f.reshape(B, S, d)
     g, _ = _cdae_primal_and_score(cs, P, x.reshape(B * S, d), ctx.reshape(B, -1),
                                   std.reshape(B * S, 1), S)
     return g.reshape(B, S, d)
@@ -425,6 +459,8 @@ def cdae_loss_and_grads(cs, P, x, ctx, std, eps):
     The parameter gradient of the double-backprop loss is computed by hand with the
     tangent/adjoint sweeps (3)-(4) of SURVEY.md 8a-3.  Returns loss, score g [B,S,d], grads dict
     (no entry for neglogprob.fc.bias: it never receives a gradient)."""
+    if cs.kind == 'res':
+        return rescdae_loss_and_grads(cs, P, x, ctx, std, eps)
     B, S, d = x.shape
     N, H = B * S, cs.H
     xf, sf, ef = x.reshape(N, d), std.reshape(N, 1), eps.reshape(N, d)

@@ -36,6 +36,12 @@ CASES = {
                            cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=5, nonlinearity='softplus'),
                            B=5, hp=dict(std_scale=100., delta=0.1, nz_cdae=6, nstd=1, nz_model=2, beta=1.0,
                                         m_lr=1e-3, m_beta1=0.9, d_lr=1e-3, d_momentum=0.9), wscale=3.0),
+    # residual CDAE (--cdae mlp-res, run_vae_dbmnist.sh:25: the network outputs the score, plain back-prop), std_scale 100
+    'mnist_small_res': dict(kind='mnist', cdae_kind='res',
+                            model=dict(input_dim=20, noise_dim=5, h_dim=12, num_hidden_layers=2, nonlinearity='softplus', z_dim=4),
+                            cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=5, nonlinearity='softplus'),
+                            B=5, hp=dict(std_scale=100., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
+                                         m_lr=1e-3, m_beta1=0.9, d_lr=1e-4, d_momentum=0.9), wscale=1.0),
     # conv implicit VAE (run_vae_dbmnist.sh:31 shape family, 12x12 images): `lite` = one step, weights
     # fp32-representable and stored as float32 (the reference hard-codes the 800 / 300 wide fc layers)
     'conv_small': dict(kind='conv', lite=True,
@@ -54,7 +60,8 @@ def make_case(name, c):
     import zlib
     g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % (2 ** 31))
     dt = torch.float64
-    model, cdae = rh.build_reference(c['kind'], c['model'], c['cdae'], dtype=dt, seed=1234)
+    model, cdae = rh.build_reference(c['kind'], c['model'], c['cdae'], dtype=dt, seed=1234,
+                                     cdae_kind=c.get('cdae_kind', 'grad'))
     if c['wscale'] != 1.0:
         with torch.no_grad():
             for m in (model, cdae):
@@ -106,7 +113,10 @@ def make_case(name, c):
                 arrays[p + 'm_after/' + k] = v.numpy().copy()
             for k, v in cdae.state_dict().items():
                 arrays[p + 'c_after/' + k] = v.numpy().copy()
-    assert out['cdae_grads']['neglogprob.fc.bias'] is None
+    if c.get('cdae_kind', 'grad') == 'grad':
+        assert out['cdae_grads']['neglogprob.fc.bias'] is None
+    else:
+        assert all(v is not None for v in out['cdae_grads'].values())  # residual CDAE: plain back-prop
     # IWS (evaluate_iws) on the stepped weights
     b, S = 3, 16
     if lite:  # IWS on the INITIAL weights (the stepped ones are not stored)
@@ -120,7 +130,8 @@ def make_case(name, c):
     eta = torch.randn(b, S, d, dtype=dt, generator=g)
     arrays['iws/x'], arrays['iws/enc_noise'], arrays['iws/eta'] = xe.numpy(), enc_noise.numpy(), eta.numpy()
     arrays['iws/logprob'] = rh.ref_iws(model, xe, enc_noise, eta).numpy()
-    meta = dict(kind=c['kind'], model=c['model'], cdae=c['cdae'], B=B, hp=hp, wscale=c['wscale'], iws=dict(b=b, S=S))
+    meta = dict(kind=c['kind'], model=c['model'], cdae=c['cdae'], B=B, hp=hp, wscale=c['wscale'], iws=dict(b=b, S=S),
+                cdae_kind=c.get('cdae_kind', 'grad'))
     arrays['meta'] = np.array(json.dumps(meta))
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + '.npz')

@@ -63,8 +63,9 @@ def import_reference():
     return _REF_MODULES
 
 
-def build_reference(kind, model_kwargs, cdae_kwargs, dtype=None, seed=0):
-    """Construct the reference model + CDAE as ivae_ardae.py:295-314,595-606 does."""
+def build_reference(kind, model_kwargs, cdae_kwargs, dtype=None, seed=0, cdae_kind='grad'):
+    """Construct the reference model + CDAE as ivae_ardae.py:295-314,583-606 does
+    (cdae_kind 'grad' = --cdae mlp-grad, 'res' = --cdae mlp-res)."""
     import torch
     _, net = import_reference()
     torch.manual_seed(seed)
@@ -72,7 +73,8 @@ def build_reference(kind, model_kwargs, cdae_kwargs, dtype=None, seed=0):
         model = net.ConvIPVAE(**model_kwargs)
     else:
         model = (net.ToyIPVAE if kind == 'toy' else net.MNISTIPVAE)(enc_type='concat', **model_kwargs)
-    cdae = net.MLPGradCARDAE(std=1., noise_type='gaussian', enc_ctx=True, enc_input=True, **cdae_kwargs)
+    cls = net.MLPGradCARDAE if cdae_kind == 'grad' else net.MLPResCARDAE
+    cdae = cls(std=1., noise_type='gaussian', enc_ctx=True, enc_input=True, **cdae_kwargs)
     if dtype is not None:
         model, cdae = model.to(dtype), cdae.to(dtype)
     return model, cdae

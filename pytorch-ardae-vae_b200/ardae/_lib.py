@@ -17,7 +17,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 class CdaeConfig(ctypes.Structure):
     _fields_ = [('input_dim', ctypes.c_int), ('context_dim', ctypes.c_int), ('h_dim', ctypes.c_int),
                 ('num_hidden_layers', ctypes.c_int), ('batch', ctypes.c_int), ('samples', ctypes.c_int),
-                ('train', ctypes.c_int)]
+                ('train', ctypes.c_int), ('kind', ctypes.c_int)]
 
 
 class ModelConfig(ctypes.Structure):

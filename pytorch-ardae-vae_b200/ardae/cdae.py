@@ -26,11 +26,14 @@ class _TrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gloss):
         m = ctx.module
-        m._arena.accumulate_staged(gloss, skip=(len(m._arena.params) - 1,))
+        m._arena.accumulate_staged(gloss, skip=m.no_grad_params)
         return (None, None) + (None,) * len(m._arena.params)
 
 
 class ConditionalARDAE(nn.Module):
+    KIND = 0           # ardae_cdae_config.kind: 0 = mlp-grad (energy network), 1 = mlp-res (score network)
+    HEAD = 'neglogprob'  # attribute / state_dict prefix of the last MLP
+
     def __init__(self, input_dim=2, h_dim=128, context_dim=2, std=0.01, num_hidden_layers=1,
                  nonlinearity='tanh', noise_type='gaussian', enc_input=True, enc_ctx=True,
                  std_method='default'):
@@ -49,17 +52,25 @@ class ConditionalARDAE(nn.Module):
                               num_hidden_layers=num_hidden_layers - 1, use_nonlinearity_output=True)
         self.inp_encode = MLP(input_dim, h_dim, h_dim, nonlinearity=nonlinearity,
                               num_hidden_layers=num_hidden_layers - 1, use_nonlinearity_output=True)
-        self.neglogprob = MLP(2 * h_dim + 1, h_dim, 1, nonlinearity=nonlinearity,
-                              num_hidden_layers=num_hidden_layers, use_nonlinearity_output=False)
+        # graddae: neglogprob -> scalar energy (:378); resdae: dae -> the score itself, input_dim wide (resdae/mlp.py:323)
+        setattr(self, self.HEAD, MLP(2 * h_dim + 1, h_dim, 1 if self.KIND == 0 else input_dim, nonlinearity=nonlinearity,
+                                     num_hidden_layers=num_hidden_layers, use_nonlinearity_output=False))
         self._arena = ParamArena(self)
         self._plans = {}
         self.inv_count_override = None  # data parallel: 1 / (global N * d)
         self.last_score = None
 
+    @property
+    def no_grad_params(self):
+        """Indices (arena order) of parameters that never receive a gradient: the energy network's output bias
+        (`neglogprob.fc.bias`, reference: .grad stays None); none for the residual CDAE."""
+        return (len(self._arena.params) - 1,) if self.KIND == 0 else ()
+
     def reset_parameters(self):  # exists in the reference (graddae/mlp.py:380-382); never called there
-        nn.init.normal_(self.neglogprob.fc.weight)
-        for m in self.inp_encode.linears():
-            m.weight.data.mul_(0.001)
+        nn.init.normal_(getattr(self, self.HEAD).fc.weight)
+        if self.KIND == 0:
+            for m in self.inp_encode.linears():
+                m.weight.data.mul_(0.001)
 
     # ------------------------------------------------------------------ plumbing
     def _ensure(self):
@@ -76,7 +87,7 @@ class ConditionalARDAE(nn.Module):
             L = _lib.lib()
             ar = self._ensure()
             cfg = _lib.CdaeConfig(self.input_dim, self.context_dim, self.h_dim, self.num_hidden_layers, B, S,
-                                  1 if train else 0)
+                                  1 if train else 0, self.KIND)
             nbytes = ctypes.c_size_t(0)
             _lib.check(L.ardae_cdae_workspace_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
             ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=ar.flat.device)
@@ -159,3 +170,16 @@ class ConditionalARDAE(nn.Module):
 
 
 MLPGradCARDAE = ConditionalARDAE
+
+
+class ResidualConditionalARDAE(ConditionalARDAE):
+    """Drop-in for net.MLPResCARDAE (= models/resdae/mlp.py:286-413 `ConditionalARDAE`, `--cdae mlp-res`,
+    ivae_ardae.py:583-594): the network `dae([inp_encode(x~), ctx_encode(c), sigma])` outputs the score estimate
+    directly; loss = mse(sigma * f, -eps); plain back-propagation (every parameter receives a gradient).  Same
+    kernels as the energy variant: 3xTF32 forward chain, MUL_SIG backward chain with fused bias-gradient column
+    sums, weight-gradient contractions."""
+    KIND = 1
+    HEAD = 'dae'
+
+
+MLPResCARDAE = ResidualConditionalARDAE

@@ -156,7 +156,7 @@ class TrainStep(object):
         with self._seg('cdae_allreduce'):
             self._allreduce(ar.stage_flat)
         with self._seg('cdae_opt'):
-            self.copt.step_flat(ar.stage_flat, skip=(len(ar.params) - 1,))               # :779
+            self.copt.step_flat(ar.stage_flat, skip=c.no_grad_params)               # :779
         self.last_std = std
         return loss
 
@@ -228,7 +228,7 @@ class TrainStep(object):
     # ------------------------------------------------------------------ CUDA-graph replay
     def _bump_host_steps(self):
         """What the optimizers' host-side bookkeeping would have done in an eager iteration."""
-        for opt, skip in ((self.copt, (len(self.cdae._arena.params) - 1,)), (self.mopt, ())):
+        for opt, skip in ((self.copt, self.cdae.no_grad_params), (self.mopt, ())):
             ar = opt._setup()
             for k, p in enumerate(ar.params):
                 if k not in skip:
@@ -310,7 +310,7 @@ class TrainStep(object):
             finally:
                 _lib.check(L.ardae_set_replay_counter(None))
             # the captured call advanced the host-side step counters once; undo, replay() re-applies per replay
-            for opt, skip in ((self.copt, (len(self.cdae._arena.params) - 1,)), (self.mopt, ())):
+            for opt, skip in ((self.copt, self.cdae.no_grad_params), (self.mopt, ())):
                 ar = opt._setup()
                 for k, p in enumerate(ar.params):
                     if k not in skip:

@@ -29,7 +29,7 @@ ARDAE_API int ardae_check_device(int dev) {
 
 static void to_cfg(const ardae_cdae_config* c, CdaeConfig* o) {
   o->d = c->input_dim; o->c = c->context_dim; o->H = c->h_dim; o->L = c->num_hidden_layers;
-  o->B = c->batch; o->S = c->samples; o->train = c->train;
+  o->B = c->batch; o->S = c->samples; o->train = c->train; o->kind = c->kind;
 }
 
 ARDAE_API int ardae_cdae_workspace_bytes(const ardae_cdae_config* cfg, size_t* bytes) {

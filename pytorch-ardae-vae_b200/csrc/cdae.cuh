@@ -24,6 +24,8 @@ struct CdaeConfig {
   int d = 0, c = 0, H = 0, L = 0;  // input_dim, context_dim, h_dim, num_hidden_layers
   int B = 0, S = 0;                // data rows, samples per data row (N = B*S)
   int train = 1;                   // 0: score-only plan
+  int kind = 0;                    // 0: mlp-grad (energy network, score by back-prop; models/graddae/mlp.py)
+                                   // 1: mlp-res  (network outputs the score; models/resdae/mlp.py:286-413)
 };
 
 struct CdaeBindings {  // per-call user pointers (plain device memory, no TMA)
@@ -117,6 +119,10 @@ struct CdaePlan {
     W3 W1u = derive.add(ws, P(iW(0)), H, H, ld1, true, true);
     W3 W1c = derive.add(ws, P(iW(0)) ? P(iW(0)) + H : nullptr, H, H, ld1, true, train);
     Ww[0] = W1u;
+    const bool res = cfg.kind == 1;
+    if (cfg.kind != 0 && cfg.kind != 1) return fail(-2, "cdae: kind must be 0 (mlp-grad) or 1 (mlp-res)");
+    W3 Wo;  // mlp-res: dae.fc [d, H]
+    if (res) Wo = derive.add(ws, P(iW(L)), d, H, H, true, train);
     int rc = derive.emit(ws, plan);
     if (rc) return rc;
     float* wsig = ws.floats(H);  // exact fp32 copy of W_1[:, 2H]
@@ -142,13 +148,15 @@ struct CdaePlan {
     if (train) {
       rmat = ws.mat(N, d);
       gsum = ws.mat(B, H);
-      for (int l = 0; l < L; ++l) UD[l] = ws.mat(N, H);
-      for (int l = 0; l < L; ++l) VD[l] = ws.mat(N, H);
-      for (int l = 0; l < L; ++l) TA[l] = ws.mat(N, H);
-      for (int l = 0; l < L; ++l) TP[l] = ws.mat(N, H);
+      if (!res) {
+        for (int l = 0; l < L; ++l) UD[l] = ws.mat(N, H);
+        for (int l = 0; l < L; ++l) VD[l] = ws.mat(N, H);
+        for (int l = 0; l < L; ++l) TA[l] = ws.mat(N, H);
+        for (int l = 0; l < L; ++l) TP[l] = ws.mat(N, H);
+      }
       for (int l = 0; l < L; ++l) DC[l] = ws.mat(B, H);
       if (dry) {
-        const int shapes[4][3] = {{H, H, N}, {H, d, N}, {H, H, B}, {H, c, B}};
+        const int shapes[5][3] = {{H, H, N}, {H, d, N}, {H, H, B}, {H, c, B}, {d, H, N}};
         tn_need = 0;
         for (auto& sh : shapes) {
           const size_t b = tn_workspace_bytes(sh[0], sh[1], sh[2]);
@@ -240,6 +248,10 @@ struct CdaePlan {
         cd.layers.push_back(q);
       }
       for (int l = 1; l < L; ++l) cd.layers.push_back(s3_layer(Ww[l], P(iW(l) + 1), V[l]));
+      if (res) {  // the output layer f = v_L Wo^T + b_o runs 3xTF32 on the (hi, lo) pair
+        cd.layers.back().out_lo = V[L - 1].lo().p;
+        cd.layers.back().ld_out_lo = V[L - 1].buf.ld;
+      }
       plan.chain(cd);
     } else {
     for (int l = 0; l < L; ++l) {
@@ -259,6 +271,140 @@ struct CdaePlan {
       g.bias = P(iW(l) + 1);
       plan.nt(g);
     }
+    }
+    if (res) {
+      // =============================================================== mlp-res: plain forward / backward
+      // f = dae.fc(v_L)  [N, d]  (the score estimate itself: resdae/mlp.py:382,411)
+      {
+        GemmNTDesc g = nt3_desc_plain(V[L - 1], Wo, gmat, EPI_LINEAR);
+        g.bias = P(iW(L) + 1);
+        plan.nt(g);
+      }
+      if (!train) {
+        plan.add([=](cudaStream_t s) {
+          unpad_kernel<<<grid_for(static_cast<size_t>(N) * d), 256, 0, s>>>(gmat.p, gmat.ld, bd->score_out, N, d, 1.0f);
+          return static_cast<int>(cudaGetLastError());
+        });
+        return plan.error;
+      }
+      // loss = mean((sigma f + eps)^2) (:386) and r = d loss / d f
+      {
+        float* gbo = G(iW(L) + 1);
+        plan.add([=](cudaStream_t s) {
+          cdae_loss_kernel<<<grid_for(static_cast<size_t>(N) * gmat.ld), 256, 0, s>>>(
+              gmat.p, gmat.ld, sig, bd->eps, rmat.p, N, d, bd->inv_count, bd->loss_out, bd->score_out);
+          dim3 grid((d + 31) / 32, N >= 2048 ? 64 : (N + 63) / 64);
+          colsum_kernel<<<grid, 256, 0, s>>>(rmat.p, rmat.ld, N, d, gbo, 1.0f);  // d b_o = sum_n r
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      // delta p_L = (r Wo) * sig(p_L)
+      {
+        GemmNTDesc g = nt_desc(rmat, Wo.T, DP[L - 1], EPI_MUL_SIG);
+        set_aux1(g, V[L - 1].hi());
+        g.colsum = G(iW(L - 1) + 1);
+        plan.nt(g);
+      }
+      auto bwl = [&](const Mat& wT, const Mat& aux1, const Mat& out, float* colsum) {
+        ChainLayerDesc q;
+        q.W = wT.p; q.ldw = wT.ld; q.aux1 = aux1.p; q.ld1 = aux1.ld; q.out = out.p; q.ldo = out.ld; q.colsum = colsum;
+        return q;
+      };
+      if (use_chain) {
+        ChainDesc cd = chain_of(CHAIN_MUL_SIG, DP[L - 1]);
+        for (int l = L - 1; l >= 1; --l) {
+          ChainLayerDesc q = bwl(Ww[l].T, V[l - 1].hi(), DP[l - 1], G(iW(l - 1) + 1));
+          if (l - 1 == 0) {  // d w_1sigma = sum_n sigma_n * delta p_1
+            q.colsum_w = G(iW(0)) ? G(iW(0)) + 2 * H : nullptr;
+            q.colsum_w_stride = ld1;
+          }
+          cd.layers.push_back(q);
+        }
+        cd.layers.push_back(bwl(W1u.T, U[L - 1].hi(), DA[L - 1], G(iA(L - 1) + 1)));
+        for (int l = L - 1; l >= 1; --l) cd.layers.push_back(bwl(Aw[l].T, U[l - 1].hi(), DA[l - 1], G(iA(l - 1) + 1)));
+        plan.chain(cd);
+      } else {
+        for (int l = L - 1; l >= 1; --l) {
+          GemmNTDesc g = nt_desc(DP[l], Ww[l].T, DP[l - 1], EPI_MUL_SIG);
+          set_aux1(g, V[l - 1].hi());
+          g.colsum = G(iW(l - 1) + 1);
+          if (l - 1 == 0) {
+            g.colsum_w = G(iW(0)) ? G(iW(0)) + 2 * H : nullptr;
+            g.colsum_w_stride = ld1;
+            g.row_w = sig;
+          }
+          plan.nt(g);
+        }
+        {
+          GemmNTDesc g = nt_desc(DP[0], W1u.T, DA[L - 1], EPI_MUL_SIG);
+          set_aux1(g, U[L - 1].hi());
+          g.colsum = G(iA(L - 1) + 1);
+          plan.nt(g);
+        }
+        for (int l = L - 1; l >= 1; --l) {
+          GemmNTDesc g = nt_desc(DA[l], Aw[l].T, DA[l - 1], EPI_MUL_SIG);
+          set_aux1(g, U[l - 1].hi());
+          g.colsum = G(iA(l - 1) + 1);
+          plan.nt(g);
+        }
+      }
+      // context branch backward (B rows) on the side lane, from the per-data-row sums of delta p_1
+      plan.fork();
+      {
+        const Mat dp1 = DP[0];
+        plan.add([=](cudaStream_t s) {
+          group_sum_kernel<<<B, 256, 0, s>>>(dp1.p, dp1.ld, gsum.p, gsum.ld, B, S, H, 1);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      {
+        const Mat y = Cc[L - 1].hi();
+        tn2(gsum, y, nullptr, nullptr, G(iW(0)) ? G(iW(0)) + H : nullptr, ld1);
+      }
+      {
+        GemmNTDesc g = nt_desc(gsum, W1c.T, DC[L - 1], EPI_MUL_SIG);
+        set_aux1(g, Cc[L - 1].hi());
+        g.colsum = G(iC(L - 1) + 1);
+        plan.nt(g);
+      }
+      for (int l = L - 1; l >= 1; --l) {
+        GemmNTDesc g = nt_desc(DC[l], Cw[l].T, DC[l - 1], EPI_MUL_SIG);
+        set_aux1(g, Cc[l - 1].hi());
+        g.colsum = G(iC(l - 1) + 1);
+        plan.nt(g);
+      }
+      for (int l = L - 1; l >= 1; --l) {
+        const Mat y = Cc[l - 1].hi();
+        tn2(DC[l], y, nullptr, nullptr, G(iC(l)), H);
+      }
+      {
+        const Mat y = ctxp.hi();
+        tn2(DC[0], y, nullptr, nullptr, G(iC(0)), c);
+      }
+      plan.cur_lane = 0;
+      // weight gradients: dW = delta^T . activation
+      {
+        const Mat y = V[L - 1].hi();
+        tn2(rmat, y, nullptr, nullptr, G(iW(L)), H);
+      }
+      for (int l = L - 1; l >= 1; --l) {
+        const Mat y = V[l - 1].hi();
+        tn2(DP[l], y, nullptr, nullptr, G(iW(l)), H);
+      }
+      {
+        const Mat y = U[L - 1].hi();
+        tn2(DP[0], y, nullptr, nullptr, G(iW(0)), ld1);
+      }
+      for (int l = L - 1; l >= 1; --l) {
+        const Mat y = U[l - 1].hi();
+        tn2(DA[l], y, nullptr, nullptr, G(iA(l)), H);
+      }
+      {
+        const Mat xh = xt.hi();
+        tn2(DA[0], xh, nullptr, nullptr, G(iA(0)), d);
+      }
+      plan.join();
+      return plan.error;
     }
     // ---- sweep 2: score backward (tf32)
     {

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small']
+CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small', 'mnist_small_res']
 
 
 def model_dims(meta):
@@ -27,6 +27,24 @@ def build_model(meta):
     return cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
                num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',
                z_dim=m['z_dim'])
+
+
+def cdae_spec(meta):
+    """oracle CdaeSpec for a fixture (meta['cdae_kind']: 'grad' = mlp-grad, 'res' = mlp-res)."""
+    import ardae_oracle as orc
+    c = meta['cdae']
+    return orc.CdaeSpec(c['input_dim'], c['context_dim'], c['h_dim'], c['num_hidden_layers'],
+                        kind=meta.get('cdae_kind', 'grad'))
+
+
+def build_cdae(meta):
+    """The drop-in CDAE class of the product package for a fixture's meta."""
+    import ardae
+    c = meta['cdae']
+    cls = ardae.MLPGradCARDAE if meta.get('cdae_kind', 'grad') == 'grad' else ardae.MLPResCARDAE
+    return cls(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
+               num_hidden_layers=c['num_hidden_layers'], nonlinearity=c['nonlinearity'], noise_type='gaussian',
+               enc_ctx=True, enc_input=True)
 
 
 def load_case(name):

@@ -42,7 +42,7 @@ def test_version_and_error_reporting(lib):
 
     class Cfg(ctypes.Structure):
         _fields_ = [(k, ctypes.c_int) for k in ('input_dim', 'context_dim', 'h_dim', 'num_hidden_layers', 'batch',
-                                                'samples', 'train')]
+                                                'samples', 'train', 'kind')]
     n = ctypes.c_size_t(0)
     # a valid config: pure host-side dry build of the plan
     assert lib.ardae_cdae_workspace_bytes(ctypes.byref(Cfg(32, 32, 256, 5, 512, 256, 1)), ctypes.byref(n)) == 0
@@ -56,6 +56,10 @@ def test_version_and_error_reporting(lib):
     assert lib.ardae_cdae_workspace_bytes(ctypes.byref(Cfg(32, 32, 250, 5, 512, 256, 1)), ctypes.byref(n)) < 0
     assert b'multiple of 4' in lib.ardae_last_error()
     assert lib.ardae_cdae_workspace_bytes(None, ctypes.byref(n)) < 0
+    # residual CDAE (kind 1): no tangent / adjoint spill -> smaller workspace than the energy variant
+    assert lib.ardae_cdae_workspace_bytes(ctypes.byref(Cfg(32, 32, 256, 5, 512, 256, 1, 1)), ctypes.byref(n)) == 0
+    assert 0 < n.value < train_bytes
+    assert lib.ardae_cdae_workspace_bytes(ctypes.byref(Cfg(32, 32, 256, 5, 512, 256, 1, 2)), ctypes.byref(n)) < 0
 
 
 def test_model_workspace_query(lib):

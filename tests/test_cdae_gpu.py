@@ -9,18 +9,19 @@ import pytest
 import torch
 
 import ardae_oracle as orc
-from golden_util import CASES, cosine, load_case, rel_err, sub
+from golden_util import CASES, build_cdae, cdae_spec, cosine, load_case, rel_err, sub
 
 pytestmark = pytest.mark.gpu
 
 LOSS_TOL, SCORE_TOL, GRAD_TOL = 2e-3, 1e-2, 2e-2
 
 
-def make_cdae(d, c, H, L, state=None, seed=0):
+def make_cdae(d, c, H, L, state=None, seed=0, kind='grad'):
     import ardae
     torch.manual_seed(seed)
-    m = ardae.MLPGradCARDAE(input_dim=d, context_dim=c, std=1., h_dim=H, num_hidden_layers=L,
-                            nonlinearity='softplus', noise_type='gaussian', enc_ctx=True, enc_input=True)
+    cls = ardae.MLPGradCARDAE if kind == 'grad' else ardae.MLPResCARDAE
+    m = cls(input_dim=d, context_dim=c, std=1., h_dim=H, num_hidden_layers=L,
+            nonlinearity='softplus', noise_type='gaussian', enc_ctx=True, enc_input=True)
     if state is not None:
         m.load_state_dict({k: torch.from_numpy(np.asarray(v)).float() for k, v in state.items()})
     return m.cuda()
@@ -39,9 +40,10 @@ def check_against(m, cs, P64, x, ctx, std, eps, label):
     worst = (0.0, None)
     worst_cos = (1.0, None)
     for k, p in m.named_parameters():
-        if k == 'neglogprob.fc.bias':
+        if k == 'neglogprob.fc.bias':  # energy network: the output bias never receives a gradient
             assert p.grad is None
             continue
+        assert p.grad is not None, k
         e = rel_err(p.grad.cpu().numpy(), G_o[k])
         cth = cosine(p.grad.cpu().numpy(), G_o[k])
         worst = max(worst, (e, k))
@@ -63,9 +65,10 @@ def test_cdae_matches_reference_fixture(name):
     """Same weights / inputs / noise as the reference run that produced the fixture (step 0)."""
     z, meta = load_case(name)
     c = meta['cdae']
-    cs = orc.CdaeSpec(c['input_dim'], c['context_dim'], c['h_dim'], c['num_hidden_layers'])
+    cs = cdae_spec(meta)
     P64 = sub(z, 'c0/')
-    m = make_cdae(c['input_dim'], c['context_dim'], c['h_dim'], c['num_hidden_layers'], state=P64)
+    m = make_cdae(c['input_dim'], c['context_dim'], c['h_dim'], c['num_hidden_layers'], state=P64,
+                  kind=meta.get('cdae_kind', 'grad'))
     hp = meta['hp']
     lsm = hp['std_scale'] * (z['s0/z_cdae'] - z['s0/zbar'])
     lsm = np.repeat(lsm, hp['nstd'], axis=1)
@@ -87,18 +90,24 @@ def test_cdae_matches_reference_fixture(name):
     dict(d=32, c=32, H=256, L=5, B=32, S=256, wscale=1.0),  # config-2 widths, N = 8192
     dict(d=32, c=32, H=256, L=5, B=8, S=128, wscale=3.0),   # saturated activations
     dict(d=5, c=3, H=36, L=2, B=3, S=50, wscale=1.0),       # ragged: N=150, odd dims
+    # residual CDAE (--cdae mlp-res): fused chains (H = 256 / 64) and the per-layer path (H = 36, and H = 512 as in
+    # run_vae_dbmnist.sh:25)
+    dict(d=32, c=32, H=256, L=5, B=32, S=256, wscale=1.0, kind='res'),
+    dict(d=8, c=8, H=64, L=3, B=8, S=32, wscale=3.0, kind='res'),
+    dict(d=5, c=3, H=36, L=2, B=3, S=50, wscale=1.0, kind='res'),
+    dict(d=32, c=32, H=512, L=3, B=4, S=100, wscale=1.0, kind='res'),
 ])
 def test_cdae_matches_oracle(cfg):
     rng = np.random.RandomState(7)
     d, c, H, L, B, S = cfg['d'], cfg['c'], cfg['H'], cfg['L'], cfg['B'], cfg['S']
-    m = make_cdae(d, c, H, L, seed=11)
+    m = make_cdae(d, c, H, L, seed=11, kind=cfg.get('kind', 'grad'))
     if cfg['wscale'] != 1.0:
         with torch.no_grad():
             for p in m.parameters():
                 if p.dim() == 2:
                     p.mul_(cfg['wscale'])
     P64 = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in m.state_dict().items()}
-    cs = orc.CdaeSpec(d, c, H, L)
+    cs = orc.CdaeSpec(d, c, H, L, kind=cfg.get('kind', 'grad'))
     x = rng.randn(B, S, d) * 2.0
     ctx = rng.randn(B, 1, c)
     std = 0.3 * rng.randn(B, S, 1)

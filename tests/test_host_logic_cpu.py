@@ -13,13 +13,11 @@ def build(meta):
     import golden_util
     c = meta['cdae']
     model = golden_util.build_model(meta)
-    cdae = ardae.MLPGradCARDAE(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
-                               num_hidden_layers=c['num_hidden_layers'], nonlinearity=c['nonlinearity'],
-                               noise_type='gaussian', enc_ctx=True, enc_input=True)
+    cdae = golden_util.build_cdae(meta)
     return model, cdae
 
 
-@pytest.mark.parametrize('name', ['toy_small', 'mnist_small', 'conv_small'])
+@pytest.mark.parametrize('name', ['toy_small', 'mnist_small', 'conv_small', 'mnist_small_res'])
 def test_state_dict_layout_matches_reference(name):
     z, meta = load_case(name)
     model, cdae = build(meta)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import ardae_oracle as orc
-from golden_util import CASES, load_case, model_dims, rel_err, sub
+from golden_util import CASES, cdae_spec, load_case, model_dims, rel_err, sub
 
 
 
@@ -12,7 +12,7 @@ def specs(meta):
     c = meta['cdae']
     spec = orc.ModelSpec(meta['kind'], *model_dims(meta))
     spec.img_c = meta['model'].get('input_channels', 1)
-    cs = orc.CdaeSpec(c['input_dim'], c['context_dim'], c['h_dim'], c['num_hidden_layers'])
+    cs = cdae_spec(meta)
     return spec, cs
 
 

@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import CASES, build_model, load_case, rel_err, sub
+from golden_util import CASES, build_cdae, build_model, load_case, rel_err, sub
 
 pytestmark = pytest.mark.gpu
 
@@ -30,8 +30,7 @@ def build(meta, z):
     import ardae
     c, hp = meta['cdae'], meta['hp']
     model = build_model(meta)
-    cdae = ardae.MLPGradCARDAE(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
-                               num_hidden_layers=c['num_hidden_layers'], nonlinearity='softplus')
+    cdae = build_cdae(meta)
     f = lambda d: {k: torch.from_numpy(np.asarray(v)).float() for k, v in d.items()}
     model.load_state_dict(f(sub(z, 'm0/')))
     cdae.load_state_dict(f(sub(z, 'c0/')))
@@ -100,11 +99,14 @@ def test_fused_step_matches_reference_fixture(name):
                 if nme in ref:
                     e = rel_err(ar.view(ar.stage_flat, k).cpu().numpy(), ref[nme])
                     assert e <= gtol, (s, nme, e)
-        assert np.array_equal(c_after['neglogprob.fc.bias'], c_before['neglogprob.fc.bias'])  # never updated
+        if meta.get('cdae_kind', 'grad') == 'grad':
+            assert np.array_equal(c_after['neglogprob.fc.bias'], c_before['neglogprob.fc.bias'])  # never updated
+        else:
+            assert not np.array_equal(c_after['dae.fc.bias'], c_before['dae.fc.bias'])  # residual CDAE: it is
         ref_m_prev, ref_c_prev = ref_m_after, ref_c_after
 
 
-@pytest.mark.parametrize('name', ['toy_small', 'mnist_small', 'conv_small'])
+@pytest.mark.parametrize('name', ['toy_small', 'mnist_small', 'conv_small', 'mnist_small_res'])
 def test_dropin_loop_matches_fused(name):
     """The reference's own step body (ivae_ardae.py:713-846) written against the drop-in module API
     (autograd .backward() calls, optimizer objects) must give what the fused driver gives."""
@@ -167,7 +169,10 @@ def test_dropin_loop_matches_fused(name):
         assert close(pm_d[k], pm_f[k], np.asarray(z['m0/' + k], dtype=np.float32)), (k, rel_err(pm_d[k], pm_f[k]))
     for k in pc_f:
         assert close(pc_d[k], pc_f[k], np.asarray(z['c0/' + k], dtype=np.float32)), (k, rel_err(pc_d[k], pc_f[k]))
-    assert cdae.neglogprob.fc.bias.grad is None
+    if meta.get('cdae_kind', 'grad') == 'grad':
+        assert cdae.neglogprob.fc.bias.grad is None
+    else:
+        assert cdae.dae.fc.bias.grad is not None
 
 
 @pytest.mark.parametrize('kind', ['adam', 'rmsprop'])
