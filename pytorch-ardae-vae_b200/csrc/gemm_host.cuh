@@ -300,6 +300,7 @@ struct GemmTNDesc {
   size_t workspace_bytes = 0;
   int target_ctas = 296;
   int atomic = 0;                     // 0 auto (ARDAE_TN_ATOMIC, default on), 1 red.global.add epilogue, -1 two-pass reduce
+  int full_m = 0;                     // 1: one CTA per SM owns a whole 256 x 256 output (opt-in, also ARDAE_TN_FULL_M=1)
 };
 
 struct PreparedTN {
@@ -328,8 +329,31 @@ inline bool tn_atomic_default() {
   return v != 0;
 }
 
+inline bool tn_full_m(int M, int N, int request) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = std::getenv("ARDAE_TN_FULL_M");
+    env = e ? std::atoi(e) : 0;
+  }
+  const int req = request != 0 ? request : env;
+  // opt-in: measured on B200 it is correct but no faster (98 -> 104 us per [256,256] contraction): the kernel is not
+  // bound by the L2 -> SM path
+  return req > 0 && M > kBlockM && M <= 2 * kBlockM && pick_block_n(N) == 256 && N <= 256;
+}
+
 inline size_t tn_workspace_bytes(int M, int N, int K, int target_ctas = 296) {
   const int bn = pick_block_n(N);
+  if (tn_full_m(M, N, 0)) {  // one CTA per SM
+    const int total_kb = (K + kBlockK - 1) / kBlockK;
+    int nsplit = num_sms();
+    if (nsplit > total_kb) nsplit = total_kb;
+    const size_t full = static_cast<size_t>(nsplit) * 2 * kBlockM * bn * sizeof(float);
+    const int mt2 = 2, nt2 = 1;
+    int ns2 = target_ctas / (mt2 * nt2);
+    if (ns2 > total_kb) ns2 = total_kb;
+    const size_t split = static_cast<size_t>(ns2) * mt2 * kBlockM * nt2 * bn * sizeof(float);
+    return full > split ? full : split;
+  }
   const int mt = (M + kBlockM - 1) / kBlockM, nt = (N + bn - 1) / bn;
   const int total_kb = (K + kBlockK - 1) / kBlockK;
   int nsplit = target_ctas / (mt * nt);
@@ -342,14 +366,16 @@ inline int prepare_gemm_tn(const GemmTNDesc& d, PreparedTN* out) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(-2, "gemm_tn: empty problem");
   if (!d.X0 || !d.Y0 || !d.out || !d.workspace) return fail(-2, "gemm_tn: missing pointer");
   const int bn = pick_block_n(d.N);
-  const int mt = (d.M + kBlockM - 1) / kBlockM, nt = (d.N + bn - 1) / bn;
+  const bool full_m = tn_full_m(d.M, d.N, d.full_m);
+  const int mrows = full_m ? 2 * kBlockM : kBlockM;  // output rows per CTA
+  const int mt = (d.M + mrows - 1) / mrows, nt = (d.N + bn - 1) / bn;
   const int total_kb = (d.K + kBlockK - 1) / kBlockK;
-  int nsplit = d.target_ctas / (mt * nt);
+  int nsplit = (full_m ? num_sms() : d.target_ctas) / (mt * nt);
   if (nsplit < 1) nsplit = 1;
   if (nsplit > total_kb) nsplit = total_kb;
   const int kb_per_split = (total_kb + nsplit - 1) / nsplit;
   nsplit = (total_kb + kb_per_split - 1) / kb_per_split;
-  const size_t need = static_cast<size_t>(nsplit) * mt * kBlockM * nt * bn * sizeof(float);
+  const size_t need = static_cast<size_t>(nsplit) * mt * mrows * nt * bn * sizeof(float);
   if (need > d.workspace_bytes) return fail(-3, "gemm_tn: workspace too small");
   PreparedTN pr;
   std::memset(&pr.params, 0, sizeof(pr.params));
@@ -375,11 +401,14 @@ inline int prepare_gemm_tn(const GemmTNDesc& d, PreparedTN* out) {
     case 32: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<32>); pr.smem = GemmTNConfig<32>::kSmemBytes; break;
     case 64: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<64>); pr.smem = GemmTNConfig<64>::kSmemBytes; break;
     case 128: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<128>); pr.smem = GemmTNConfig<128>::kSmemBytes; break;
-    case 256: pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<256>); pr.smem = GemmTNConfig<256>::kSmemBytes; break;
+    case 256:
+      if (full_m) { pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<256, 2>); pr.smem = GemmTNConfig<256, 2>::kSmemBytes; }
+      else { pr.fn = reinterpret_cast<const void*>(&gemm_tn_kernel<256>); pr.smem = GemmTNConfig<256>::kSmemBytes; }
+      break;
     default: return fail(-2, "gemm_tn: bad BLOCK_N");
   }
   pr.grid = dim3(nsplit, mt, nt);
-  pr.nsplit = nsplit; pr.Mpad = mt * kBlockM; pr.Npad = nt * bn;
+  pr.nsplit = nsplit; pr.Mpad = mt * mrows; pr.Npad = nt * bn;
   pr.out = d.out; pr.M = d.M; pr.N = d.N; pr.ldo = d.ldo; pr.scale = d.scale; pr.beta = d.beta;
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;

@@ -732,22 +732,26 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
 
 // ------------------------------------------------------------------------------------------
 // Weight-gradient contraction: both operands MN-major (TMA boxes of 32 rows x 32 floats).
-template <int BLOCK_N>
+// MT = 2 ("full M", BLOCK_N = 256 only): one CTA owns a 256 x 256 output -- two accumulators fill the 512 TMEM
+// columns, one CTA per SM -- so every X and Y tile enters an SM exactly once (with MT = 1 the two M-tile CTAs both
+// fetch Y: 1.5x the algorithmic bytes through the L2 -> SM path of an HBM-bound kernel).
+template <int BLOCK_N, int MT = 1>
 struct GemmTNConfig {
   static constexpr int kBoxBytes = 32 * 32 * 4;  // 4 KB: 32 k-rows x 32 floats (128 B rows)
-  static constexpr int kStageA = (kBlockM / 32) * kBoxBytes;
+  static constexpr int kStageA = MT * (kBlockM / 32) * kBoxBytes;
   static constexpr int kStageB = (BLOCK_N / 32) * kBoxBytes;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kNumStages = (BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4);
+  static constexpr int kNumStages = MT == 2 ? 3 : ((BLOCK_N >= 256) ? 2 : (BLOCK_N >= 128 ? 3 : 4));
   static constexpr int kDataBytes = kStage * kNumStages;
   static constexpr int kSmemBytes = kDataBytes + 1024 + 256;
-  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int kTmemCols = MT * (BLOCK_N < 32 ? 32 : BLOCK_N);
+  static_assert(MT == 1 || BLOCK_N == 256, "full-M variant: 256 x 256 tiles");
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+template <int BLOCK_N, int MT = 1>
+__global__ void __launch_bounds__(kGemmThreads, MT == 2 ? 1 : 2)
 gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
-  using Cfg = GemmTNConfig<BLOCK_N>;
+  using Cfg = GemmTNConfig<BLOCK_N, MT>;
   constexpr int NSTAGE = Cfg::kNumStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -761,7 +765,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.x;
-  const int m0 = blockIdx.y * kBlockM;
+  const int m0 = blockIdx.y * (MT * kBlockM);
   const int n0 = blockIdx.z * BLOCK_N;
   const int total_kb = (p.K + kBlockK - 1) / kBlockK;
   const int kb_begin = split * p.kb_per_split;
@@ -810,7 +814,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
         uint8_t* sa = smem + s * Cfg::kStage;
         uint8_t* sb = sa + Cfg::kStageA;
 #pragma unroll
-        for (int b = 0; b < kBlockM / 32; ++b)
+        for (int b = 0; b < MT * kBlockM / 32; ++b)
           ptx::tma_load_2d(sa + b * Cfg::kBoxBytes, tx, &full_bar[s], m0 + b * 32, k0);
 #pragma unroll
         for (int b = 0; b < BLOCK_N / 32; ++b)
@@ -835,6 +839,11 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
           const uint64_t adesc = ptx::make_smem_desc(a_addr + k * 1024, Cfg::kBoxBytes, 512, 1);
           const uint64_t bdesc = ptx::make_smem_desc(b_addr + k * 1024, Cfg::kBoxBytes, 512, 1);
           ptx::umma_tf32(tmem_base, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          if (MT == 2) {  // output rows [128, 256): X boxes 4..7, second accumulator
+            const uint64_t adesc2 =
+                ptx::make_smem_desc(a_addr + (kBlockM / 32) * Cfg::kBoxBytes + k * 1024, Cfg::kBoxBytes, 512, 1);
+            ptx::umma_tf32(tmem_base + BLOCK_N, adesc2, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          }
         }
         ptx::umma_commit(&empty_bar[s]);
       }
@@ -842,14 +851,17 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
     }
   } else {
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const int Mpad = gridDim.y * kBlockM;
+    const int Mpad = gridDim.y * (MT * kBlockM);
     const int Npad = gridDim.z * BLOCK_N;
-    float* dst = p.partial + (static_cast<size_t>(split) * Mpad + (m0 + r)) * Npad + n0;
     if (iters > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
+#pragma unroll 1
+    for (int mh = 0; mh < MT; ++mh) {
+    const int r = mh * kBlockM + quarter * 32 + lane;
+    const uint32_t tacc = tmem_base + mh * BLOCK_N;
+    float* dst = p.partial + (static_cast<size_t>(split) * Mpad + (m0 + r)) * Npad + n0;
     if (p.red_out != nullptr) {
       // split-K without a second pass: accumulate this split's tile into the gradient with L2 reductions
       if (iters > 0) {
@@ -859,7 +871,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           if (n0 + c * 32 >= p.N) break;
           uint32_t accu[32];
-          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, accu);
+          ptx::tmem_ld_32x32(tacc + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, accu);
           ptx::tmem_ld_wait();
           if (!row_ok) continue;
           if (p.red_vec && n0 + c * 32 + 32 <= p.N) {
@@ -881,7 +893,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       uint32_t accu[32];
       if (iters > 0) {
-        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, accu);
+        ptx::tmem_ld_32x32(tacc + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, accu);
         ptx::tmem_ld_wait();
       } else {
 #pragma unroll
@@ -894,6 +906,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
       }
     }
     }
+    }  // mh
   }
 
   ptx::tc_fence_before();
