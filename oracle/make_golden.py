@@ -108,6 +108,20 @@ def make_case(name, c):
                 arrays[p + 'cdae_grads/' + k] = v
         for k, v in t2n(out['model_grads']).items():
             arrays[p + 'model_grads/' + k] = f32(v)
+        if name == 'mnist_small' and step == 0:
+            # a REAL reference checkpoint pair after the first iteration, written by the reference's own
+            # utils.save_checkpoint with the dict layout of ivae_ardae.py:1116-1137 (checkpoint-interchange test:
+            # resume on the B200 path, iteration 2 must reproduce s1/*_after)
+            import types
+            utils, _ = rh.import_reference()
+            ck = os.path.join(OUT, 'ref_ckpt_' + name)
+            os.makedirs(ck, exist_ok=True)
+            o = types.SimpleNamespace(path=ck)
+            common = dict(epoch=1, batch_idx=1, train_num_iters_per_epoch=10, best_val_loss=float('inf'), scheduler=None)
+            utils.save_checkpoint(dict(common, model='mnist-concat', state_dict=model.state_dict(), optimizer=mopt.state_dict()),
+                                  o, is_best=False, filename='model-checkpoint.pth.tar')
+            utils.save_checkpoint(dict(common, cdae='mlp-grad', state_dict=cdae.state_dict(), optimizer=copt.state_dict()),
+                                  o, is_best=False, filename='cdae-checkpoint.pth.tar')
         if not lite:
             for k, v in model.state_dict().items():
                 arrays[p + 'm_after/' + k] = v.numpy().copy()

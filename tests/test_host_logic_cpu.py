@@ -103,3 +103,41 @@ def test_optimizer_api():
     assert 'state' in mo.state_dict() and 'param_groups' in co.state_dict()
     with pytest.raises(NotImplementedError):
         ardae.Adam(model.parameters(), amsgrad=True)
+
+
+def test_reference_checkpoint_loads_and_annealing():
+    """Checkpoint interchange: the files under tests/golden/ref_ckpt_mnist_small were written by the
+    reference's own utils.save_checkpoint after one iteration (oracle/make_golden.py)."""
+    import os
+    import ardae
+    from golden_util import GOLDEN_DIR
+    z, meta = load_case('mnist_small')
+    model, cdae = build(meta)
+    hp = meta['hp']
+    mo = ardae.Adam(model.parameters(), lr=hp['m_lr'], betas=(hp['m_beta1'], 0.999))
+    co = ardae.RMSprop(cdae.parameters(), lr=hp['d_lr'], momentum=hp['d_momentum'])
+    ck_dir = os.path.join(GOLDEN_DIR, 'ref_ckpt_mnist_small')
+
+    class Opt(object):
+        path = ck_dir
+    o = Opt()
+    ck = ardae.load_checkpoint(model, mo, o, filename='model-checkpoint.pth.tar')
+    assert ck is not None and (o.start_epoch, o.start_batch_idx, o.train_num_iters_per_epoch) == (1, 1, 10)
+    ardae.load_checkpoint(cdae, co, ck_dir, filename='cdae-checkpoint.pth.tar')
+    for k, v in model.state_dict().items():
+        assert v.dtype == torch.float32
+        assert np.allclose(v.numpy(), z['s0/m_after/' + k], rtol=1e-6, atol=1e-7), k
+    for k, v in cdae.state_dict().items():
+        assert np.allclose(v.numpy(), z['s0/c_after/' + k], rtol=1e-6, atol=1e-7), k
+    p0 = next(iter(model.parameters()))
+    assert set(mo.state[p0]) >= {'step', 'exp_avg', 'exp_avg_sq'} and mo.state[p0]['step'] == 1
+    assert mo.state[p0]['exp_avg'].dtype == torch.float32
+    q0 = next(iter(cdae.parameters()))
+    assert set(co.state[q0]) >= {'step', 'square_avg', 'momentum_buffer'} and co.state[q0]['step'] == 1
+    assert list(cdae.parameters())[-1] not in co.state  # neglogprob.fc.bias never had a gradient: no state in the reference
+    assert ardae.load_checkpoint(model, None, ck_dir, filename='missing.pth.tar') is None
+    # beta annealing (utils/msc.py:53-55)
+    assert ardae.annealing_func(1e-4, 1.0, 50000, 0) == pytest.approx(1e-4)
+    assert ardae.annealing_func(1e-4, 1.0, 50000, 25000) == pytest.approx(1e-4 + (1.0 - 1e-4) * 0.5)
+    assert ardae.annealing_func(1e-4, 1.0, 50000, 10 ** 9) == pytest.approx(1.0)
+    assert ardae.annealing_func(1e-4, 1.0, None, 3) == 1.0

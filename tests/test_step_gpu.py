@@ -237,3 +237,40 @@ def test_graph_replay_matches_eager():
         assert np.isfinite([c1, m1, c2, m2]).all()
     # fresh noise per replay: the CDAE loss is a noisy estimate, three identical values would mean frozen seeds
     assert len({round(c, 7) for c, _ in lg}) == 3
+
+
+def test_resume_from_reference_checkpoint():
+    """Checkpoint interchange: load the files the REFERENCE wrote after its first iteration (weights + utils.Adam /
+    torch RMSprop state), run the second iteration on the B200 path with the fixture's inputs and noise, and land on
+    the parameters the reference reached after ITS second iteration."""
+    import os
+    import ardae
+    from golden_util import GOLDEN_DIR
+    z, meta = load_case('mnist_small')
+    hp = meta['hp']
+    model, cdae = build_model(meta), build_cdae(meta)
+    mopt = ardae.Adam(model.parameters(), lr=hp['m_lr'], betas=(hp['m_beta1'], 0.999))
+    copt = ardae.RMSprop(cdae.parameters(), lr=hp['d_lr'], momentum=hp['d_momentum'])
+    ck = os.path.join(GOLDEN_DIR, 'ref_ckpt_mnist_small')
+    ardae.load_checkpoint(model, mopt, ck, filename='model-checkpoint.pth.tar')
+    ardae.load_checkpoint(cdae, copt, ck, filename='cdae-checkpoint.pth.tar')
+    model, cdae = model.cuda(), cdae.cuda()
+    # optimizer state follows the parameters to the device
+    for opt in (mopt, copt):
+        for st in opt.state.values():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    st[k] = v.cuda()
+    step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=hp['std_scale'], delta=hp['delta'],
+                           nz_cdae=hp['nz_cdae'], nstd=hp['nstd'], nz_model=hp['nz_model'])
+    m_before, c_before = params_np(model), params_np(cdae)
+    noise = {k: t(v) for k, v in sub(z, 's1/noise/').items()}
+    out = step(t(z['s1/x_cdae']), t(z['s1/x_model']), beta=hp['beta'], noise=noise)
+    torch.cuda.synchronize()
+    assert abs(out['cdae_loss'].item() - float(z['s1/cdae_loss'])) <= 2e-3 * abs(float(z['s1/cdae_loss']))
+    assert abs(out['model_loss'].item() - float(z['s1/model_loss'])) <= 2e-3 * abs(float(z['s1/model_loss']))
+    ue_c = update_err(c_before, params_np(cdae), sub(z, 's0/c_after/'), sub(z, 's1/c_after/'))
+    ue_m = update_err(m_before, params_np(model), sub(z, 's0/m_after/'), sub(z, 's1/m_after/'))
+    print('resume: update rel err cdae %.2e model %.2e' % (ue_c, ue_m))
+    assert ue_c <= 5e-2 and ue_m <= 5e-2
+    assert mopt.state[next(iter(model.parameters()))]['step'] == 2
