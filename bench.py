@@ -166,6 +166,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (no CUDA-graph replay of the step)')
+    ap.add_argument('--cdae', default='grad', choices=['grad', 'res'],
+                    help="grad = mlp-grad (BASELINE.json's config, default); res = mlp-res residual CDAE (extra measurement)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -191,8 +193,9 @@ def main():
     torch.manual_seed(1234)  # same weights on every rank (replicated parameters)
     model = ardae.MNISTIPVAE(input_dim=c['D'], noise_dim=c['n'], h_dim=c['h'], num_hidden_layers=c['model_layers'],
                              nonlinearity=c['nonlin'], enc_type='concat', z_dim=c['z']).to(dev)
-    cdae = ardae.MLPGradCARDAE(input_dim=c['z'], context_dim=c['z'], std=1., h_dim=c['cdae_h'],
-                               num_hidden_layers=c['cdae_L'], nonlinearity='softplus').to(dev)
+    cdae_cls = ardae.MLPGradCARDAE if args.cdae == 'grad' else ardae.MLPResCARDAE
+    cdae = cdae_cls(input_dim=c['z'], context_dim=c['z'], std=1., h_dim=c['cdae_h'],
+                    num_hidden_layers=c['cdae_L'], nonlinearity='softplus').to(dev)
     mopt = ardae.Adam(model.parameters(), lr=c['m_lr'], betas=(c['m_beta1'], 0.999))
     copt = ardae.RMSprop(cdae.parameters(), lr=c['d_lr'], momentum=c['d_momentum'])
     step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=c['std_scale'], delta=c['delta'], nz_cdae=c['nz'],
@@ -358,7 +361,8 @@ def main():
         metric='train_samples_per_sec', value=B * world * K / (ms_total * 1e-3), unit='samples/s', n_gpus=world,
         steps=K, warmup=W, ms_per_step=ms_total / K, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='tf32', data='synthetic',
-        config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, cdae_rows_per_gpu=B * c['nz'],
+        config=dict(workload=WORKLOAD if args.cdae == 'grad' else WORKLOAD.replace('mlp-grad', 'mlp-res (residual, NOT the BASELINE config)'),
+                    global_batch=B * world, per_gpu_batch=B, cdae_rows_per_gpu=B * c['nz'],
                     parallelism='dp%d' % world, arithmetic='tf32 tensor-core operands, fp32 accumulate; forward sweeps 3xTF32',
                     l2='no flush needed: per-step working set (activation spill) ~7 GB >> 126 MB L2',
                     launch=(('one CUDA-graph replay per step (%d kernels on 3 streams captured)' % step.count_launches(B)

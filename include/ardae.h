@@ -174,6 +174,10 @@ ARDAE_API int ardae_rmsprop_step(float* p, const float* g, float* square_avg, fl
  * Encoder.sample_noise, ivae/toy.py:61-65, which draws on the CPU and copies). */
 ARDAE_API int ardae_randn(float* out, size_t n, uint64_t seed, uint32_t stream_id, void* stream);
 
+/* out[i] = 1 if u_i < probs[i] else 0 (Philox uniform): dynamic binarisation on the device; replaces the torch.bernoulli
+ * DataLoader transform of datasets/mnist.py:39-40,129. */
+ARDAE_API int ardae_bernoulli(const float* probs, float* out, size_t n, uint64_t seed, void* stream);
+
 /* CUDA-graph support (no reference counterpart: the reference launches eagerly).  While a device counter is set,
  * every launch issued by this library bakes the POINTER into its arguments: Philox seeds become
  * seed + counter * golden-ratio and Adam's bias-correction step becomes step + counter, so a captured step draws fresh

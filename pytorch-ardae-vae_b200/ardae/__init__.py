@@ -3,6 +3,7 @@ from .cdae import ConditionalARDAE, MLPGradCARDAE, MLPResCARDAE, ResidualConditi
 from .ivae import ConvIPVAE, MNISTIPVAE, ToyIPVAE, normal_energy_func  # noqa: F401
 from .optim import Adam, RMSprop  # noqa: F401
 from .step import TrainStep  # noqa: F401
+from .data import MinibatchSampler, dynamic_binarize, toy_exp4  # noqa: F401
 from .checkpoint import annealing_func, load_checkpoint, save_checkpoint  # noqa: F401
 
 

@@ -55,6 +55,7 @@ def _declare(lib):
     lib.ardae_sigma_schedule.argtypes = [vp, vp, i, i, i, i, f, f, vp, u64, vp, vp, vp, vp]
     lib.ardae_scaled_diff.argtypes = [vp, vp, i, i, i, f, vp, vp]
     lib.ardae_adam_step.argtypes = [vp, vp, vp, vp, sz, f, f, f, f, i, f, vp]
+    lib.ardae_bernoulli.argtypes = [vp, vp, sz, u64, vp]
     lib.ardae_set_replay_counter.argtypes = [vp]
     lib.ardae_bump_replay_counter.argtypes = [vp, vp]
     lib.ardae_rmsprop_step.argtypes = [vp, vp, vp, vp, sz, f, f, f, f, f, vp]

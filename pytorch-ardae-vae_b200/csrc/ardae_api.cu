@@ -255,6 +255,15 @@ ARDAE_API int ardae_randn(float* out, size_t n, uint64_t seed, uint32_t stream_i
   return 0;
 }
 
+ARDAE_API int ardae_bernoulli(const float* probs, float* out, size_t n, uint64_t seed, void* stream) {
+  if (!probs || !out) return fail(-1, "null argument");
+  if (n == 0) return 0;
+  bernoulli_kernel<<<grid_for((n + 3) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(probs, out, n, seed,
+                                                                                          replay_counter());
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 ARDAE_API int ardae_set_replay_counter(const unsigned long long* device_counter) {
   replay_counter() = device_counter;
   return 0;

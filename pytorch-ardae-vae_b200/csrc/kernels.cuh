@@ -185,6 +185,22 @@ __global__ void group_sum_kernel(const float* __restrict__ in, int in_ld, float*
   }
 }
 
+// out[i] = (u_i < p[i]) ? 1 : 0, u ~ U[0,1) from Philox: dynamic binarisation of grey-level images on the device
+// (the reference applies torch.bernoulli as a DataLoader transform: datasets/mnist.py:39-40)
+__global__ void bernoulli_kernel(const float* __restrict__ p, float* __restrict__ out, size_t n, uint64_t seed,
+                                 const replay_ctr_t* __restrict__ ctr) {
+  seed = replay_seed(seed, ctr);
+  const size_t nq = (n + 3) / 4;
+  for (size_t q = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; q < nq;
+       q += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 r = Philox::gen(seed, q, 17u);
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < n) out[q * 4 + j] = (static_cast<float>(u[j] >> 8) * 5.9604644775390625e-08f < p[q * 4 + j]) ? 1.0f : 0.0f;
+  }
+}
+
 // ---------------------------------------------------------------- CDAE prologue / epilogues
 // x~[n, j] = x[n, j] + sigma[n] * eps[n, j]  (models/graddae/mlp.py:21-23), stored as the tf32
 // pair xt[n, j] = hi, xt[n, kp + j] = lo.  If gen_eps, eps is first drawn here (Philox) and
