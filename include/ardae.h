@@ -126,6 +126,11 @@ ARDAE_API int ardae_model_num_launches(ardae_model_t h, int which); /* 0 fwd, 1 
  * z_out [R, z_dim] = f(x [B, D], noise [R, n]); noise == NULL means zeros (encode(std=0)). */
 ARDAE_API int ardae_model_encode(ardae_model_t h, const float* x, const float* noise, float* z_out, void* stream);
 
+/* z = encode(x, noise, nz) AND z-bar = encode(x, std=0) [B, z_dim] in one pass: the reference evaluates
+ * model.encode(x, std=0) twice per update next to the sampling pass (ivae_ardae.py:735,748,749), each time recomputing
+ * the input stack; here the mean code is two or three B-row launches on top of the sampling pass. */
+ARDAE_API int ardae_model_encode_with_mean(ardae_model_t h, const float* x, const float* noise, float* z_out,
+                                           float* zbar_out, void* stream);
 /* Replaces ImplicitPosteriorVAE.forward (toy.py:824-858 / mnist.py:267-301, lmbd = 0): encoder,
  * decoder, per-row recon + beta*prior.  sums[3] (device) <- mean loss, recon, prior over
  * 1/inv_rows rows (pass the GLOBAL row count under data parallelism).  heads_out (optional):

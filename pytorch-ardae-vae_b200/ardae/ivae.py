@@ -256,6 +256,18 @@ class ImplicitPosteriorVAE(nn.Module):
                                                  _lib.stream_ptr()))
         return z.view(B, nz, self.z_dim)
 
+    def _encode_with_mean(self, x, noise, nz):
+        """(z [B,nz,d], zbar [B,1,d]) = (encode(x, noise, nz), encode(x, std=0)) from ONE pass over the input stack."""
+        B = x.size(0)
+        xf = _lib.require_cuda(x.detach(), 'input').view(B, self.input_dim)
+        nf = _lib.require_cuda(noise.detach(), 'noise')
+        key = self._plan(B, nz, 0)
+        z = torch.empty(B * nz, self.z_dim, dtype=torch.float32, device=xf.device)
+        zbar = torch.empty(B, self.z_dim, dtype=torch.float32, device=xf.device)
+        _lib.check(_lib.lib().ardae_model_encode_with_mean(self._plans[key][0], _lib.ptr(xf), _lib.ptr(nf), _lib.ptr(z),
+                                                           _lib.ptr(zbar), _lib.stream_ptr()))
+        return z.view(B, nz, self.z_dim), zbar.view(B, 1, self.z_dim)
+
     # ------------------------------------------------------------------ reference API
     def forward_hidden(self, input, std=None, nz=1):
         """toy.py:811-822 / mnist.py:254-265."""

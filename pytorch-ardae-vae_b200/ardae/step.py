@@ -79,7 +79,7 @@ class TrainStep(object):
         L = _lib.lib()
         m, c = self.model, self.cdae
         n = 0
-        n += L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0)][0], 0)            # zbar (cdae minibatch)
+        n += L.ardae_model_num_launches(m._plans[m._plan(B, self.nz, 0)][0], 2)      # zbar (cdae minibatch): mean-code branch
         n += L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0, 1)][0], 0)         # zbar (model minibatch)
         n += L.ardae_model_num_launches(m._plans[m._plan(B, self.nz, 0)][0], 0)      # z samples
         n += L.ardae_cdae_num_launches(c._plan(B, self.nz * self.nstd, True))
@@ -126,9 +126,8 @@ class TrainStep(object):
         dev = x.device
         xs = _lib.require_cuda(x, 'x').view(B, -1)
         with self._seg('encode'):
-            zbar = m._encode(xs, None, 1)                                                # :735,:748
             enc = noise['enc_cdae'] if noise is not None else self._randn(B * self.nz, n, dev)
-            z = m._encode(xs, enc, self.nz)                                              # :749
+            z, zbar = m._encode_with_mean(xs, enc, self.nz)                              # :735,:748 and :749 in one pass
         N = B * self.nz * self.nstd
         xc = torch.empty(N, d, dtype=torch.float32, device=dev)
         sigma = torch.empty(N, dtype=torch.float32, device=dev)

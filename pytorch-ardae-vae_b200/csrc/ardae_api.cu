@@ -140,7 +140,7 @@ ARDAE_API int ardae_model_create(const ardae_model_config* cfg, float* const* pa
   if (rc) return rc;
   if (h->p.ws.off + 256 > workspace_bytes) return fail(-3, "model: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(-11, "workspace must be 256-byte aligned");
-  h->p.fwd.reset(); h->p.bwd_dec.reset(); h->p.bwd_enc.reset();
+  h->p.fwd.reset(); h->p.bwd_dec.reset(); h->p.bwd_enc.reset(); h->p.fwd_mean.reset();
   h->p.ws = Workspace();
   h->p.ws.dry = false;
   h->p.ws.base = static_cast<uint8_t*>(workspace);
@@ -155,6 +155,7 @@ ARDAE_API int ardae_model_create(const ardae_model_config* cfg, float* const* pa
 ARDAE_API void ardae_model_destroy(ardae_model_t h) { delete h; }
 ARDAE_API int ardae_model_num_launches(ardae_model_t h, int which) {
   if (!h) return 0;
+  if (which == 2) return h->p.fwd_mean.launches();
   return which == 0 ? h->p.fwd.launches() + 4 : h->p.bwd_dec.launches() + h->p.bwd_enc.launches();
 }
 
@@ -165,6 +166,18 @@ ARDAE_API int ardae_model_encode(ardae_model_t h, const float* x, const float* n
   b = ModelBindings();
   b.x = x; b.noise = noise; b.z_out = z_out;
   return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_encode_with_mean(ardae_model_t h, const float* x, const float* noise, float* z_out,
+                                           float* zbar_out, void* stream) {
+  if (!h || !x || !z_out || !zbar_out) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 0) return fail(-2, "handle was created with mode = 1 (use ardae_model_forward)");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.x = x; b.noise = noise; b.z_out = z_out; b.zbar_out = zbar_out;
+  int rc = h->p.fwd.run(static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  return h->p.fwd_mean.run(static_cast<cudaStream_t>(stream));
 }
 
 ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* noise, float beta, float inv_rows,

@@ -6,6 +6,7 @@
 
 #include <cstdint>
 
+#include "gemm_sm100.cuh"  // softplus_f
 #include "ptx_sm100.cuh"
 
 namespace ardae {
@@ -198,6 +199,22 @@ __global__ void bernoulli_kernel(const float* __restrict__ p, float* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (q * 4 + j < n) out[q * 4 + j] = (static_cast<float>(u[j] >> 8) * 5.9604644775390625e-08f < p[q * 4 + j]) ? 1.0f : 0.0f;
+  }
+}
+
+// dst pair (hi | lo at +kp) = act(src) : activation of an fp32 [rows, cols] block, stored as a tf32 pair
+// (mean-code branch of the encoder: the noise half of fc layer 0 vanishes for eps = 0)
+__global__ void act_split_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int ldd, int rows,
+                                 int cols, int kp, int act) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<size_t>(r) * cols);
+    const float a = src[static_cast<size_t>(r) * ld + c];
+    const float v = act == 1 ? softplus_f(a) : fmaxf(a, 0.0f);
+    const float hi = ptx::round_tf32(v);
+    dst[static_cast<size_t>(r) * ldd + c] = hi;
+    dst[static_cast<size_t>(r) * ldd + kp + c] = ptx::round_tf32(v - hi);
   }
 }
 

@@ -29,6 +29,7 @@ struct ModelBindings {
   const float* x = nullptr;      // [B, D]
   const float* noise = nullptr;  // [R, n] or null (= zeros: encode(std=0))
   float* z_out = nullptr;        // [R, zd]
+  float* zbar_out = nullptr;     // [B, zd] mean code encode(x, std=0) from the same pass (fwd_mean plan), or null
   float* heads_out = nullptr;    // [R, D] logits | [R, 2D] mu,logvar  (optional)
   float* sums = nullptr;         // [3] loss, recon, prior (device; overwritten)
   float beta = 1.0f;
@@ -48,6 +49,7 @@ struct ModelBindings {
 struct ModelPlan {
   ModelConfig cfg;
   Plan fwd, bwd_dec, bwd_enc;
+  Plan fwd_mean;  // mode 0: z-bar = encode(x, std=0) from the per-data-row bias of the sampling pass (B rows)
   Workspace ws;
   ModelBindings bind;
   DeriveList derive;
@@ -291,6 +293,44 @@ struct ModelPlan {
                                                                             bd->z_out, R, zd);
         return static_cast<int>(cudaGetLastError());
       });
+    }
+    if (c.mode == 0) {
+      // ---- mean code: for eps = 0 the noise half of fc layer 0 contributes nothing, so hid_0 = act(rowbias0) on the
+      // B data rows; the remaining fc layers see [hid | 0].  Reuses the input stack of the sampling pass
+      // (ivae_ardae.py:735,748 recompute it: encode(x, std=0) twice per update).
+      fwd_mean.dry = dry;
+      std::vector<Pair> Fb(c.n_fc);
+      for (int l = 0; l < c.n_fc; ++l) Fb[l] = make_pair(ws, B, toy ? h + n : h);  // eps columns stay zero
+      Pair zbp = make_pair(ws, B, zd);
+      Mat zbb = ws.mat(B, zd);
+      {
+        const Pair f0 = Fb[0];
+        const int ACTI = c.act;
+        fwd_mean.add([=](cudaStream_t s) {
+          act_split_kernel<<<grid_for(static_cast<size_t>(B) * h), 256, 0, s>>>(rowbias0.p, rowbias0.ld, f0.buf.p,
+                                                                               f0.buf.ld, B, h, f0.kp, ACTI);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      for (int l = 1; l < c.n_fc; ++l) {
+        Pair out = Fb[l];
+        out.w = h;
+        GemmNTDesc g = nt3_desc(Fb[l - 1], Fw[l], out, ACT);
+        g.bias = P(iF(l) + 1);
+        fwd_mean.nt(g);
+      }
+      {
+        GemmNTDesc g = nt3_desc(Fb[c.n_fc - 1], Fw[c.n_fc], zbp, EPI_LINEAR);
+        g.bias = P(iF(c.n_fc) + 1);
+        fwd_mean.nt(g);
+        const Mat zh = zbp.hi(), zl = zbp.lo();
+        fwd_mean.add([=](cudaStream_t s) {
+          pair_sum_kernel<<<grid_for(static_cast<size_t>(B) * zd), 256, 0, s>>>(zh.p, zl.p, zh.ld, zbb.p, zbb.ld,
+                                                                              bd->zbar_out, B, zd);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      return fwd.error ? fwd.error : fwd_mean.error;
     }
     if (!dec) return fwd.error;
     if (c.mode == 2) {
