@@ -67,44 +67,6 @@ struct alignas(64) ChainParams {
   ChainLayerParams layer[kChainMaxLayers];
 };
 
-// ---- lean epilogue arithmetic: the chain epilogues are instruction-issue bound (measured with clock64 stamps:
-// ~2700 cycles per 32-column chunk with __expf/__logf range fix-ups, cvt.rna Inf checks and generic-space LD/ST),
-// so: raw MUFU ex2/lg2, integer round-to-nearest to tf32, explicit shared-space vector accesses.
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2_ftz(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// round-to-nearest (ties away) to tf32 on finite inputs: 2 integer ops instead of cvt.rna's Inf/NaN handling
-__device__ __forceinline__ float round_tf32_fast(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
-// sigmoid(a) from u = softplus(a) >= 0:  s = 1 - exp(-u)  (u(1 - u/2) below 2^-7: relative error < 1e-5), 1 - s = exp(-u)
-__device__ __forceinline__ void sig_fast(float u, float& s, float& one_minus_s) {
-  const float e = ex2_ftz(u * -1.4426950408889634f);
-  one_minus_s = e;
-  s = (u < 0.0078125f) ? fmaf(-0.5f * u, u, u) : 1.0f - e;
-}
-// max(x,0) + log1p(exp(-|x|)) == torch softplus (threshold 20) to fp32 rounding
-__device__ __forceinline__ float softplus_fast(float x) {
-  const float e = ex2_ftz(fabsf(x) * -1.4426950408889634f);
-  const float l = (e < 1e-4f) ? fmaf(-0.5f * e, e, e) : lg2_ftz(1.0f + e) * 0.6931471805599453f;
-  return fmaxf(x, 0.0f) + l;
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <int MODE, bool CG2 = false>
 struct ChainConfig {
   static constexpr bool kS3 = MODE == CHAIN_SOFTPLUS3;

@@ -88,6 +88,44 @@ __device__ __forceinline__ void sig_from_softplus(float u, float& s, float& one_
   s = (u < 0.01f) ? u * (1.0f - u * (0.5f - u * (1.0f / 6.0f))) : 1.0f - e;
 }
 
+// ---- lean epilogue arithmetic: the chain epilogues are instruction-issue bound (measured with clock64 stamps:
+// ~2700 cycles per 32-column chunk with __expf/__logf range fix-ups, cvt.rna Inf checks and generic-space LD/ST),
+// so: raw MUFU ex2/lg2, integer round-to-nearest to tf32, explicit shared-space vector accesses.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// round-to-nearest (ties away) to tf32 on finite inputs: 2 integer ops instead of cvt.rna's Inf/NaN handling
+__device__ __forceinline__ float round_tf32_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+// sigmoid(a) from u = softplus(a) >= 0:  s = 1 - exp(-u)  (u(1 - u/2) below 2^-7: relative error < 1e-5), 1 - s = exp(-u)
+__device__ __forceinline__ void sig_fast(float u, float& s, float& one_minus_s) {
+  const float e = ex2_ftz(u * -1.4426950408889634f);
+  one_minus_s = e;
+  s = (u < 0.0078125f) ? fmaf(-0.5f * u, u, u) : 1.0f - e;
+}
+// max(x,0) + log1p(exp(-|x|)) == torch softplus (threshold 20) to fp32 rounding
+__device__ __forceinline__ float softplus_fast(float x) {
+  const float e = ex2_ftz(fabsf(x) * -1.4426950408889634f);
+  const float l = (e < 1e-4f) ? fmaf(-0.5f * e, e, e) : lg2_ftz(1.0f + e) * 0.6931471805599453f;
+  return fmaxf(x, 0.0f) + l;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // After this, lane l holds sum over lanes of v[l] (recursive halving, 31 shuffles).
 __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
 #pragma unroll
@@ -155,12 +193,12 @@ __device__ __forceinline__ void epilogue_chunk_body(const GemmNTParams& p, const
       } else if (MODE == EPI_RELU) {
         res = fmaxf(pre, 0.0f);
       } else if (MODE == EPI_SOFTPLUS) {
-        res = softplus_f(pre);
+        res = softplus_fast(pre);
       } else if (MODE == EPI_MUL_STEP) {
         res = aux1v[j] > 0.0f ? pre : 0.0f;
       } else {
         float sg, oms;
-        sig_from_softplus(aux1v[j], sg, oms);
+        sig_fast(aux1v[j], sg, oms);
         if (MODE == EPI_MUL_SIG) {
           res = pre * sg;
         } else if (MODE == EPI_TANGENT) {
@@ -171,12 +209,12 @@ __device__ __forceinline__ void epilogue_chunk_body(const GemmNTParams& p, const
         }
       }
       if (SPLIT) {
-        const float hi = ptx::round_tf32(res);
-        res2 = ptx::round_tf32(res - hi);
+        const float hi = round_tf32_fast(res);
+        res2 = round_tf32_fast(res - hi);
         res = hi;
       } else if (ROUND) {
-        res = ptx::round_tf32(res);
-        if (kHasOut2) res2 = ptx::round_tf32(res2);
+        res = round_tf32_fast(res);
+        if (kHasOut2) res2 = round_tf32_fast(res2);
       }
       o[j] = res;
       ob[j] = res2;
