@@ -569,13 +569,20 @@ def train_step(spec, cs, Pm, Pc, x_cdae, x_model, noise, hp, opt_state=None):
     B = x_cdae.shape[0]
     n = spec.noise_dim
     out = {}
+    ctx_type = hp.get('ctx_type', 'lt0')  # ivae_ardae.py:729-741: 'lt0' = mean code, 'data' = the input (2x-1 for MNIST)
+
+    def context_of(x, zbar_):
+        if ctx_type == 'data':
+            xx = x.reshape(x.shape[0], 1, -1)
+            return 2.0 * xx - 1.0 if spec.kind in ('mnist', 'conv') else xx
+        return zbar_
     # ---- CDAE update (:713-779)
     zbar, _ = encoder_forward(spec, Pm, x_cdae, np.zeros((B, n), dtype=x_cdae.dtype), 1)  # encode(std=0)
     z, _ = encoder_forward(spec, Pm, x_cdae, noise['enc_cdae'], nz)
     lsm, std = sigma_schedule(z, zbar, S_, delta)
     stdmat = std * noise['xi']
     lsm_e = np.repeat(lsm, nstd, axis=1)  # unsqueeze(2).expand(..nstd..).reshape  (:765-767)
-    closs, g, Gc = cdae_loss_and_grads(cs, Pc, lsm_e, zbar, stdmat, noise['eps_cdae'])
+    closs, g, Gc = cdae_loss_and_grads(cs, Pc, lsm_e, context_of(x_cdae, zbar), stdmat, noise['eps_cdae'])
     out.update(zbar=zbar, z_cdae=z, std=std, cdae_loss=closs, cdae_score=g, cdae_grads=Gc)
     if opt_state is not None:
         rmsprop_step(Pc, Gc, opt_state.setdefault('cdae', {}), hp['d_lr'], hp['d_momentum'])
@@ -584,7 +591,7 @@ def train_step(spec, cs, Pm, Pc, x_cdae, x_model, noise, hp, opt_state=None):
     mo, tape = model_forward(spec, Pm, x_model, noise['enc_model'], beta, nzm)
     zbar_m, _ = encoder_forward(spec, Pm, x_model, np.zeros((Bm, n), dtype=x_model.dtype), 1)
     lsm_m = S_ * (mo['z'] - zbar_m)
-    gm = cdae_glogprob(cs, Pc, lsm_m, zbar_m, np.zeros((Bm, nzm, 1), dtype=x_model.dtype))
+    gm = cdae_glogprob(cs, Pc, lsm_m, context_of(x_model, zbar_m), np.zeros((Bm, nzm, 1), dtype=x_model.dtype))
     dz_extra = S_ * beta * gm / float(Bm * nzm)
     Gm = {}
     model_backward(spec, Pm, tape, beta, nzm, dz_extra, Gm)

@@ -42,6 +42,12 @@ CASES = {
                             cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=5, nonlinearity='softplus'),
                             B=5, hp=dict(std_scale=100., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
                                          m_lr=1e-3, m_beta1=0.9, d_lr=1e-4, d_momentum=0.9), wscale=1.0),
+    # --cdae-ctx-type data: the CDAE is conditioned on the input image (2x-1) instead of the mean code
+    'mnist_small_datactx': dict(kind='mnist', ctx_type='data',
+                                model=dict(input_dim=20, noise_dim=5, h_dim=12, num_hidden_layers=2, nonlinearity='softplus', z_dim=4),
+                                cdae=dict(input_dim=4, context_dim=20, h_dim=16, num_hidden_layers=3, nonlinearity='softplus'),
+                                B=5, hp=dict(std_scale=10000., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
+                                             m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
     # conv implicit VAE (run_vae_dbmnist.sh:31 shape family, 12x12 images): `lite` = one step, weights
     # fp32-representable and stored as float32 (the reference hard-codes the 800 / 300 wide fc layers)
     'conv_small': dict(kind='conv', lite=True,
@@ -96,7 +102,8 @@ def make_case(name, c):
                      xi=torch.randn(B, nz * nstd, 1, dtype=dt, generator=g),
                      eps_cdae=torch.randn(B, nz * nstd, d, dtype=dt, generator=g),
                      enc_model=torch.randn(B * nzm, n, dtype=dt, generator=g))
-        out = rh.ref_train_step(model, cdae, mopt, copt, xc, xm, noise, hp, do_step=True)
+        out = rh.ref_train_step(model, cdae, mopt, copt, xc, xm, noise, hp, do_step=True,
+                                ctx_type=c.get('ctx_type', 'lt0'), mnist_like=c['kind'] in ('mnist', 'conv'))
         p = 's%d/' % step
         arrays[p + 'x_cdae'], arrays[p + 'x_model'] = xc.numpy(), xm.numpy()
         for k, v in noise.items():
@@ -145,7 +152,7 @@ def make_case(name, c):
     arrays['iws/x'], arrays['iws/enc_noise'], arrays['iws/eta'] = xe.numpy(), enc_noise.numpy(), eta.numpy()
     arrays['iws/logprob'] = rh.ref_iws(model, xe, enc_noise, eta).numpy()
     meta = dict(kind=c['kind'], model=c['model'], cdae=c['cdae'], B=B, hp=hp, wscale=c['wscale'], iws=dict(b=b, S=S),
-                cdae_kind=c.get('cdae_kind', 'grad'))
+                cdae_kind=c.get('cdae_kind', 'grad'), ctx_type=c.get('ctx_type', 'lt0'))
     arrays['meta'] = np.array(json.dumps(meta))
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + '.npz')

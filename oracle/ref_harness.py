@@ -106,8 +106,19 @@ class _NoiseQueue(object):
         return std * eps
 
 
-def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=True):
-    """ivae_ardae.py:707-846 with cdae_ctx_type='lt0', num_cdae_updates=1, injected noise.
+def _ref_context(model, x, ctx_type, mnist_like):
+    """ivae_ardae.py:729-741 / :807-819: cdae_ctx_type 'lt0' (latent of the mean code) or 'data' (the input itself)."""
+    if ctx_type == 'data':
+        context = x.unsqueeze(1)
+        if mnist_like:  # "if 'mnist' in opt.dataset"
+            context = 2 * context - 1
+            context = context.view(x.size(0), 1, -1)
+        return context
+    return model.encode(x, std=0).detach()
+
+
+def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=True, ctx_type='lt0', mnist_like=True):
+    """ivae_ardae.py:707-846 with cdae_ctx_type in {'lt0', 'data'}, num_cdae_updates=1, injected noise.
     `noise` holds torch tensors: enc_cdae, xi, eps_cdae, enc_model (see oracle.train_step)."""
     import warnings
     import torch
@@ -126,7 +137,7 @@ def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=
     # ---- update cdae (:713-779)
     copt.zero_grad()
     B = x_cdae.size(0)
-    context = model.encode(x_cdae, std=0).detach()                      # :735
+    context = _ref_context(model, x_cdae, ctx_type, mnist_like)        # :729-741
     latent_mean = model.encode(x_cdae, std=0).detach()                  # :748
     q.q.append(noise['enc_cdae'])
     latent = model.forward_hidden(x_cdae, nz=nz).detach()               # :749
@@ -154,7 +165,7 @@ def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=
     q.q.append(noise['enc_model'])
     _, _, latent, model_loss, recon_loss, prior_loss = model(x_model, beta=beta, eta=0., lmbd=0., nz=nzm)  # :801
     model_loss.backward(retain_graph=True)                              # :804
-    context = model.encode(x_model, std=0).detach()                     # :813
+    context = _ref_context(model, x_model, ctx_type, mnist_like)       # :807-819
     latent_mean = model.encode(x_model, std=0).detach()                 # :826
     lsm_m = S_ * (latent - latent_mean).detach()                        # :827
     stdmat0 = torch.zeros(Bm, nzm, 1, dtype=x_model.dtype)              # :828

@@ -33,10 +33,19 @@ def dp_scales(B_local, nz, nstd, d, nz_model, world):
 
 class TrainStep(object):
     def __init__(self, model, cdae, model_opt, cdae_opt, std_scale=10000., delta=0.1, nz_cdae=256, nstd=1,
-                 nz_model=1, num_cdae_updates=1, process_group=None, seed=1234, graph=False):
+                 nz_model=1, num_cdae_updates=1, process_group=None, seed=1234, graph=False, ctx_type='lt0',
+                 data_ctx_affine=None):
         self.model, self.cdae, self.mopt, self.copt = model, cdae, model_opt, cdae_opt
         self.S, self.delta = float(std_scale), float(delta)
         self.nz, self.nstd, self.nzm, self.ncu = int(nz_cdae), int(nstd), int(nz_model), int(num_cdae_updates)
+        # --cdae-ctx-type (ivae_ardae.py:729-741): 'lt0' = the mean code encode(x, std=0); 'data' = the input itself,
+        # mapped to 2x-1 for the MNIST-like models ("if 'mnist' in opt.dataset"), as is for the toy model
+        if ctx_type not in ('lt0', 'data'):
+            raise NotImplementedError("cdae_ctx_type must be 'lt0' or 'data' ('hidden1a' needs the aux encoders)")
+        self.ctx_type = ctx_type
+        if data_ctx_affine is None:
+            data_ctx_affine = (1.0, 0.0) if getattr(model, 'KIND', 'mnist') == 'toy' else (2.0, -1.0)
+        self.data_ctx_affine = (float(data_ctx_affine[0]), float(data_ctx_affine[1]))
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
@@ -99,6 +108,13 @@ class TrainStep(object):
                                           _lib.stream_ptr()))
         return out
 
+    def _context(self, xs, zbar):
+        """CDAE context rows [B, c] for a minibatch (xs: [B, D] view of the inputs)."""
+        if self.ctx_type == 'data':
+            a, s = self.data_ctx_affine
+            return (xs * a + s) if (a != 1.0 or s != 0.0) else xs.contiguous()
+        return zbar
+
     def _allreduce(self, flat):
         if self.world <= 1:
             return
@@ -149,7 +165,7 @@ class TrainStep(object):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         inv = dp_scales(B, self.nz, self.nstd, d, self.nzm, self.world)['cdae_inv_count']
         with self._seg('cdae_train'):
-            _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(zbar), _lib.ptr(sigma), _lib.ptr(eps), gen,
+            _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(self._context(xs, zbar)), _lib.ptr(sigma), _lib.ptr(eps), gen,
                                           self._next_seed(), ctypes.c_float(inv), _lib.ptr(loss), None,
                                           _lib.stream_ptr()))                           # :768-771
         with self._seg('cdae_allreduce'):
@@ -184,7 +200,8 @@ class TrainStep(object):
             xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
             _lib.check(L.ardae_scaled_diff(_lib.ptr(z), _lib.ptr(zbar), R, self.nzm, d, ctypes.c_float(self.S),
                                            _lib.ptr(xsd), _lib.stream_ptr()))           # :827
-        return dict(hm=hm, z=z, sums=sums, zbar=zbar, xsd=xsd, inv_rows=inv_rows, B=B, R=R, enc=enc, xs=xs)
+        return dict(hm=hm, z=z, sums=sums, zbar=zbar, xsd=xsd, inv_rows=inv_rows, B=B, R=R, enc=enc, xs=xs,
+                    ctx=self._context(xs, zbar))
 
     def model_backward(self, f, beta):
         """Entropy-gradient estimate with the UPDATED cdae (:829), one backward for :804 + :834, Adam (:846)."""
@@ -198,7 +215,7 @@ class TrainStep(object):
         zero_sigma = torch.zeros(f['R'], dtype=torch.float32, device=dev)
         g = torch.empty(f['R'], d, dtype=torch.float32, device=dev)
         with self._seg('score'):
-            _lib.check(L.ardae_cdae_score(hs, _lib.ptr(f['xsd']), _lib.ptr(f['zbar']), _lib.ptr(zero_sigma),
+            _lib.check(L.ardae_cdae_score(hs, _lib.ptr(f['xsd']), _lib.ptr(f['ctx']), _lib.ptr(zero_sigma),
                                           _lib.ptr(g), _lib.stream_ptr()))              # :829
         ar.stage_flat.zero_()
         gz_scale = self.S * beta * f['inv_rows']                                         # :834
@@ -345,7 +362,7 @@ class TrainStep(object):
                 self._cap['side_forked'] = True
             with torch.cuda.stream(self._side):
                 fwd = self.model_forward(x_model, beta, noise)
-                for k in ('z', 'sums', 'zbar', 'xsd', 'enc'):
+                for k in ('z', 'sums', 'zbar', 'xsd', 'enc', 'ctx'):
                     if torch.is_tensor(fwd[k]):
                         fwd[k].record_stream(main)
         for i in range(self.ncu):

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small', 'mnist_small_res']
+CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small', 'mnist_small_res', 'mnist_small_datactx']
 
 
 def model_dims(meta):
@@ -45,6 +45,11 @@ def build_cdae(meta):
     return cls(input_dim=c['input_dim'], context_dim=c['context_dim'], std=1., h_dim=c['h_dim'],
                num_hidden_layers=c['num_hidden_layers'], nonlinearity=c['nonlinearity'], noise_type='gaussian',
                enc_ctx=True, enc_input=True)
+
+
+def hp_of(meta):
+    """Hyper-parameters of a fixture incl. the CDAE context type (ivae_ardae.py:729-741)."""
+    return dict(meta['hp'], ctx_type=meta.get('ctx_type', 'lt0'))
 
 
 def load_case(name):

@@ -74,12 +74,14 @@ def test_cdae_matches_reference_fixture(name):
     lsm = np.repeat(lsm, hp['nstd'], axis=1)
     std = z['s0/std'] * z['s0/noise/xi']
     eps = z['s0/noise/eps_cdae']
+    # context rows: the mean code ('lt0') or the input mapped to 2x-1 ('data'), ivae_ardae.py:729-741
+    ctx = z['s0/zbar'] if meta.get('ctx_type', 'lt0') == 'lt0' else (2.0 * z['s0/x_cdae'] - 1.0)[:, None, :]
     # the fixture's own numbers (reference, fp64) agree with the oracle by test_oracle_golden
-    check_against(m, cs, P64, lsm, z['s0/zbar'], std, eps, name)
+    check_against(m, cs, P64, lsm, ctx, std, eps, name)
     ref_loss = float(z['s0/cdae_loss'])
     m.zero_grad()
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().cuda()
-    _, loss = m(t(lsm), t(z['s0/zbar']), std=t(std), eps=t(eps))
+    _, loss = m(t(lsm), t(ctx), std=t(std), eps=t(eps))
     assert abs(loss.item() - ref_loss) / abs(ref_loss) <= LOSS_TOL
     assert rel_err(m.last_score.cpu().numpy(), z['s0/cdae_score']) <= SCORE_TOL
 

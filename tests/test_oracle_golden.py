@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import ardae_oracle as orc
-from golden_util import CASES, cdae_spec, load_case, model_dims, rel_err, sub
+from golden_util import CASES, cdae_spec, hp_of, load_case, model_dims, rel_err, sub
 
 
 
@@ -30,7 +30,7 @@ def test_train_step_matches_reference(name):
         # 1e-9 fp64 differences of step 0 to ~5e-6 in step 1; step 0 pins the formulas.
         TOL, GTOL = (2e-5, 1e-4) if (name.endswith('_x3') and step == 1) else ((1e-7, 2e-6) if lite else (1e-7, 1e-6))
         out = orc.train_step(spec, cs, Pm, Pc, z[p + 'x_cdae'], z[p + 'x_model'], sub(z, p + 'noise/'),
-                             meta['hp'], opt_state=state)
+                             hp_of(meta), opt_state=state)
         for k in ('zbar', 'z_cdae', 'std', 'cdae_loss', 'cdae_score', 'model_loss', 'recon', 'prior',
                   'z_model', 'entropy_grad'):
             assert rel_err(out[k], z[p + k]) < TOL, (step, k)
