@@ -135,8 +135,19 @@ struct CdaePlan {
     std::vector<Pair> Cc(L), U(L), V(L);
     std::vector<Mat> DA(L), DP(L);
     for (int l = 0; l < L; ++l) Cc[l] = make_pair(ws, B, H);
-    for (int l = 0; l < L; ++l) U[l] = make_pair(ws, N, H);
-    for (int l = 0; l < L; ++l) V[l] = make_pair(ws, N, H);
+    // Fused path: the H -> H layers of each sweep run as ONE launch per chain (chain_sm100.cuh) with the
+    // activation operand resident on chip; only the d -> H first layer / H -> d last layer stay per-layer GEMMs.
+    const bool use_chain = chain_supported(H, 1) && 2 * L - 1 <= kChainMaxLayers;
+    for (int l = 0; l < L; ++l) {
+      // chain plans: dense hi arrays; a lo part only where a chain (re)starts from the (hi, lo) pair
+      if (use_chain) {
+        U[l] = make_pair_split(ws, N, H, l == 0 || l == L - 1);
+        V[l] = (cfg.kind == 1 && l == L - 1) ? make_pair(ws, N, H) : make_pair_split(ws, N, H, false);
+      } else {
+        U[l] = make_pair(ws, N, H);
+        V[l] = make_pair(ws, N, H);
+      }
+    }
     for (int l = 0; l < L; ++l) DA[l] = ws.mat(N, H);
     for (int l = 0; l < L; ++l) DP[l] = ws.mat(N, H);
     std::vector<Mat> UD(L), VD(L), TA(L), TP(L), DC(L);
@@ -212,9 +223,6 @@ struct CdaePlan {
     }
     plan.cur_lane = 0;  // (still forked: joined right before p_1 needs the per-row bias)
     // ---- sweep 1: primal forward (3xTF32)
-    // Fused path: the H -> H layers of each sweep run as ONE launch per chain (chain_sm100.cuh) with the
-    // activation operand resident on chip; only the d -> H first layer / H -> d last layer stay per-layer GEMMs.
-    const bool use_chain = chain_supported(H, 1) && 2 * L - 1 <= kChainMaxLayers;
     auto chain_of = [&](int mode, const Mat& a0) {
       ChainDesc cd;
       cd.mode = mode; cd.M = N; cd.H = H; cd.A0 = a0.p; cd.lda0 = a0.ld; cd.row_scale = sig;
@@ -222,7 +230,7 @@ struct CdaePlan {
     };
     auto s3_layer = [&](const W3& w, const float* bias, const Pair& out) {
       ChainLayerDesc q;
-      q.W = w.b3.p; q.ldw = w.b3.ld; q.bias = bias; q.out = out.hi().p; q.ldo = out.buf.ld;
+      q.W = w.b3.p; q.ldw = w.b3.ld; q.bias = bias; q.out = out.hi().p; q.ldo = out.hi().ld;
       return q;
     };
     if (use_chain) {
@@ -233,15 +241,15 @@ struct CdaePlan {
       }
       if (L > 1) {
         ChainDesc cd = chain_of(CHAIN_SOFTPLUS3, U[0].hi());
-        cd.A0lo = U[0].lo().p; cd.lda0lo = U[0].buf.ld;
+        cd.A0lo = U[0].lo().p; cd.lda0lo = U[0].lo().ld;
         for (int l = 1; l < L; ++l) cd.layers.push_back(s3_layer(Aw[l], P(iA(l) + 1), U[l]));
         cd.layers.back().out_lo = U[L - 1].lo().p;  // the p-chain below restarts from the (hi, lo) pair
-        cd.layers.back().ld_out_lo = U[L - 1].buf.ld;
+        cd.layers.back().ld_out_lo = U[L - 1].lo().ld;
         plan.chain(cd);
       }
       plan.join();
       ChainDesc cd = chain_of(CHAIN_SOFTPLUS3, U[L - 1].hi());
-      cd.A0lo = U[L - 1].lo().p; cd.lda0lo = U[L - 1].buf.ld;
+      cd.A0lo = U[L - 1].lo().p; cd.lda0lo = U[L - 1].lo().ld;
       {
         ChainLayerDesc q = s3_layer(W1u, nullptr, V[0]);
         q.group_bias = rowbias.p; q.group = S; q.ldg = rowbias.ld; q.col_vec = wsig;
@@ -250,7 +258,7 @@ struct CdaePlan {
       for (int l = 1; l < L; ++l) cd.layers.push_back(s3_layer(Ww[l], P(iW(l) + 1), V[l]));
       if (res) {  // the output layer f = v_L Wo^T + b_o runs 3xTF32 on the (hi, lo) pair
         cd.layers.back().out_lo = V[L - 1].lo().p;
-        cd.layers.back().ld_out_lo = V[L - 1].buf.ld;
+        cd.layers.back().ld_out_lo = V[L - 1].lo().ld;
       }
       plan.chain(cd);
     } else {

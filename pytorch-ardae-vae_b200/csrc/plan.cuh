@@ -186,13 +186,27 @@ struct Plan {
 // An activation stored as a tf32 pair: buf[rows, 2*kp] with hi in columns [0,w) and
 // lo = rna(x - hi) in columns [kp, kp+w); kp = w rounded up to the 32-column k-block, pad
 // columns are zero (the workspace is zeroed at plan creation and pads are never written).
+// `split` storage (fused-chain plans): hi and lo are separate dense [rows, w] arrays -- a chain only streams the hi
+// part as aux / spill, and a dense 1 KB row pitch keeps those streams on full DRAM pages (inside the interleaved
+// pair buffer every other KB of a row is the unused lo half); lo exists only where a chain restarts from the pair.
 struct Pair {
   Mat buf;
   int w = 0, kp = 0;
-  Mat hi() const { return buf.cols_from(0, w); }
-  Mat lo() const { return buf.cols_from(kp, w); }
-  Mat a3() const { return Mat(buf.p, buf.rows, 3 * kp, buf.ld); }  // [hi | lo | hi] via a_k_wrap
+  bool split = false;
+  Mat hi_m, lo_m;
+  Mat hi() const { return split ? hi_m : buf.cols_from(0, w); }
+  Mat lo() const { return split ? lo_m : buf.cols_from(kp, w); }
+  Mat a3() const { return Mat(buf.p, buf.rows, 3 * kp, buf.ld); }  // [hi | lo | hi] via a_k_wrap (interleaved storage only)
 };
+inline Pair make_pair_split(Workspace& ws, int rows, int w, bool need_lo) {
+  Pair p;
+  p.w = w;
+  p.kp = round_up(w, 32);
+  p.split = true;
+  p.hi_m = ws.mat(rows, w);
+  if (need_lo) p.lo_m = ws.mat(rows, w);
+  return p;
+}
 inline Pair make_pair(Workspace& ws, int rows, int w) {
   Pair p;
   p.w = w;
