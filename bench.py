@@ -377,7 +377,8 @@ def main():
         gpu_launches=step.count_launches(B) * K,
         segments_ms=dict({k: round(v, 4) for k, v in seg_ms.items()},
                          note='eager profiled pass (CUDA events per segment); the timed region replays one graph'),
-        roofline=(dict(dominant, peak_source=hbm_src + ' (hbm_gbs)',
+        roofline=(dict(dominant, peak_source=(hbm_src + ' (hbm_gbs)' if dominant['bound'] == 'hbm' else
+                                              'torch.matmul tf32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only)'),
                        note='dominant kernel of the step by total time; every kernel of the CDAE update is in roofline_kernels')
                   if dominant else None),
         roofline_kernels=kernels,
