@@ -69,7 +69,7 @@ def synth_batch(gen, p, B, device):
     return torch.bernoulli(p.expand(B, -1), generator=gen).to(device)
 
 
-def cpu_reference_leg(steps, warmup, B_sample=32):
+def cpu_reference_leg(steps, warmup, B_sample=128):
     """The reference's CPU path on the host cores, bounded sample of the same workload.
     kind 'reference': the reference's own modules (when its tree is reachable: build container);
     kind 'port': the numpy oracle restatement (GPU box: the Python reference cannot travel)."""
@@ -389,7 +389,7 @@ def main():
                            note='the plan is HBM-bound by its activation spill (see roofline_kernels); this is the north-star tensor figure'),
         roofline_hbm=roof_opt)
     if not args.no_cpu_baseline and world == 1:
-        cb, _ = cpu_reference_leg(steps=2, warmup=1)
+        cb, _ = cpu_reference_leg(steps=3, warmup=1)  # ~10 s of host work: 4 iterations on 128 of the 512 data rows
         line['cpu_baseline'] = cb
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
