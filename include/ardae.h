@@ -142,6 +142,12 @@ ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* 
  * pass: accumulates d(loss_scale*loss)/dtheta plus the pull-back of gz_scale*gz (an upstream
  * gradient on z, [R, z_dim], may be NULL) into `grads`.  loss_scale == 0 skips the decoder. */
 ARDAE_API int ardae_model_backward(ardae_model_t h, float loss_scale, const float* gz, float gz_scale, void* stream);
+/* The same backward in two calls (decoder + prior half first, then the encoder half with the upstream gradient on z):
+ * model_loss.backward(retain_graph=True) at ivae_ardae.py:804 only needs the ELBO forward, so a driver can issue the
+ * decoder half before the entropy-gradient estimate of :829 exists. */
+ARDAE_API int ardae_model_backward_decoder(ardae_model_t h, float loss_scale, void* stream);
+ARDAE_API int ardae_model_backward_encoder(ardae_model_t h, float loss_scale, const float* gz, float gz_scale,
+                                           void* stream);
 
 /* Replaces ImplicitPosteriorVAE.logprob = logprob_w_cov_gaussian_posterior (toy.py:878-939 /
  * mnist.py:378-437; called by evaluate_iws, ivae_ardae.py:644-673), batched over the images instead

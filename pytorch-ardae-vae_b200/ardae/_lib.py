@@ -52,6 +52,8 @@ def _declare(lib):
     lib.ardae_model_encode_with_mean.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ardae_model_forward.argtypes = [vp, vp, vp, f, f, vp, vp, vp, vp]
     lib.ardae_model_backward.argtypes = [vp, f, vp, f, vp]
+    lib.ardae_model_backward_decoder.argtypes = [vp, f, vp]
+    lib.ardae_model_backward_encoder.argtypes = [vp, f, vp, f, vp]
     lib.ardae_model_iws.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp]
     lib.ardae_sigma_schedule.argtypes = [vp, vp, i, i, i, i, f, f, vp, u64, vp, vp, vp, vp]
     lib.ardae_scaled_diff.argtypes = [vp, vp, i, i, i, f, vp, vp]

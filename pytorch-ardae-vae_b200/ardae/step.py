@@ -200,6 +200,11 @@ class TrainStep(object):
             xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
             _lib.check(L.ardae_scaled_diff(_lib.ptr(z), _lib.ptr(zbar), R, self.nzm, d, ctypes.c_float(self.S),
                                            _lib.ptr(xsd), _lib.stream_ptr()))           # :827
+            # decoder + prior half of the backward (:804): needs only the ELBO forward, so it runs here, underneath
+            # the CDAE update; the encoder half waits for the entropy gradient in model_backward
+            ar = m._ensure()
+            ar.stage_flat.zero_()
+            _lib.check(L.ardae_model_backward_decoder(hm, ctypes.c_float(1.0), _lib.stream_ptr()))
         return dict(hm=hm, z=z, sums=sums, zbar=zbar, xsd=xsd, inv_rows=inv_rows, B=B, R=R, enc=enc, xs=xs,
                     ctx=self._context(xs, zbar))
 
@@ -217,11 +222,10 @@ class TrainStep(object):
         with self._seg('score'):
             _lib.check(L.ardae_cdae_score(hs, _lib.ptr(f['xsd']), _lib.ptr(f['ctx']), _lib.ptr(zero_sigma),
                                           _lib.ptr(g), _lib.stream_ptr()))              # :829
-        ar.stage_flat.zero_()
         gz_scale = self.S * beta * f['inv_rows']                                         # :834
         with self._seg('model_bwd'):
-            _lib.check(L.ardae_model_backward(f['hm'], ctypes.c_float(1.0), _lib.ptr(g), ctypes.c_float(gz_scale),
-                                              _lib.stream_ptr()))                       # :804 + :834
+            _lib.check(L.ardae_model_backward_encoder(f['hm'], ctypes.c_float(1.0), _lib.ptr(g),
+                                                      ctypes.c_float(gz_scale), _lib.stream_ptr()))  # :804 + :834 (encoder half)
         with self._seg('model_allreduce'):
             self._allreduce(ar.stage_flat)
         with self._seg('model_opt'):

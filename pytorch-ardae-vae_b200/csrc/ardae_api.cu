@@ -201,6 +201,25 @@ ARDAE_API int ardae_model_iws(ardae_model_t h, const float* x, const float* nois
   return h->p.fwd.run(static_cast<cudaStream_t>(stream));
 }
 
+// The two halves of ardae_model_backward as separate calls: the decoder half depends only on the ELBO forward, so the
+// fused driver runs it on its side stream underneath the CDAE update; the encoder half needs the entropy gradient.
+ARDAE_API int ardae_model_backward_decoder(ardae_model_t h, float loss_scale, void* stream) {
+  if (!h) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 1) return fail(-2, "handle was created with mode = 0");
+  if (loss_scale == 0.0f) return 0;
+  h->p.bind.loss_scale = loss_scale;
+  return h->p.bwd_dec.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_backward_encoder(ardae_model_t h, float loss_scale, const float* gz, float gz_scale,
+                                           void* stream) {
+  if (!h) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 1) return fail(-2, "handle was created with mode = 0");
+  ModelBindings& b = h->p.bind;
+  b.loss_scale = loss_scale; b.gz = gz; b.gz_scale = gz_scale;
+  return h->p.bwd_enc.run(static_cast<cudaStream_t>(stream));
+}
+
 ARDAE_API int ardae_model_backward(ardae_model_t h, float loss_scale, const float* gz, float gz_scale, void* stream) {
   if (!h) return fail(-1, "null argument");
   if (h->p.cfg.mode != 1) return fail(-2, "handle was created with mode = 0");
