@@ -214,15 +214,22 @@ struct ModelPlan {
       if (!conv)
         split2d_kernel<<<grid_for(static_cast<size_t>(B) * D), 256, 0, s>>>(
             bd->x, D, xin.buf.p, xin.buf.ld, B, D, xin.kp, toy ? 1.0f : 2.0f, toy ? 0.0f : -1.0f);
+      if (bd->sums) ARDAE_CUDA_OK(cudaMemsetAsync(bd->sums, 0, 3 * sizeof(float), s));
+      return static_cast<int>(cudaGetLastError());
+    });
+    // the (HBM-bound, R-row) noise split runs on the plan's side lane underneath the latency-bound B-row input stack;
+    // joined right before the first layer that consumes the noise pair
+    fwd.fork();
+    fwd.add([=](cudaStream_t s) {
       if (bd->noise != nullptr) {
         split2d_kernel<<<grid_for(static_cast<size_t>(R) * n), 256, 0, s>>>(
             bd->noise, n, epsp.buf.p, epsp.buf.ld, R, n, epsp.kp, 1.0f, 0.0f);
       } else {
         ARDAE_CUDA_OK(cudaMemsetAsync(epsp.buf.p, 0, sizeof(float) * R * epsp.buf.ld, s));
       }
-      if (bd->sums) ARDAE_CUDA_OK(cudaMemsetAsync(bd->sums, 0, 3 * sizeof(float), s));
       return static_cast<int>(cudaGetLastError());
     });
+    fwd.cur_lane = 0;
     // inp_encode on the B data rows
     for (int l = 0; l < c.n_inp && !conv; ++l) {
       GemmNTDesc g = nt3_desc(l == 0 ? xin : I[l - 1], Iw[l], I[l], ACT);
@@ -250,6 +257,7 @@ struct ModelPlan {
       g.bias = P(iF(0) + 1);
       fwd.nt(g);
     }
+    fwd.join();
     {
       Pair out = Fh[0];
       out.w = h;  // write only the hid columns of the (possibly wider) concat buffer
