@@ -138,10 +138,13 @@ struct CdaePlan {
     // Fused path: the H -> H layers of each sweep run as ONE launch per chain (chain_sm100.cuh) with the
     // activation operand resident on chip; only the d -> H first layer / H -> d last layer stay per-layer GEMMs.
     const bool use_chain = chain_supported(H, 1) && 2 * L - 1 <= kChainMaxLayers;
+    // primal forward as ONE chain when the N-row first layer is long enough to cover the context branch on the side
+    // lane; small plans (score on B rows) keep two chains so the context branch overlaps the first of them
+    const bool merge_s3 = N >= 16384;
     for (int l = 0; l < L; ++l) {
-      // chain plans: dense hi arrays; a lo part only where a chain (re)starts from the (hi, lo) pair
+      // chain plans: dense hi arrays; a lo part only where the chain starts from the (hi, lo) pair (U[0])
       if (use_chain) {
-        U[l] = make_pair_split(ws, N, H, l == 0 || l == L - 1);
+        U[l] = make_pair_split(ws, N, H, l == 0 || (!merge_s3 && l == L - 1));
         V[l] = (cfg.kind == 1 && l == L - 1) ? make_pair(ws, N, H) : make_pair_split(ws, N, H, false);
       } else {
         U[l] = make_pair(ws, N, H);
@@ -239,17 +242,24 @@ struct CdaePlan {
         g.bias = P(iA(0) + 1);
         plan.nt(g);
       }
-      if (L > 1) {
-        ChainDesc cd = chain_of(CHAIN_SOFTPLUS3, U[0].hi());
-        cd.A0lo = U[0].lo().p; cd.lda0lo = U[0].lo().ld;
-        for (int l = 1; l < L; ++l) cd.layers.push_back(s3_layer(Aw[l], P(iA(l) + 1), U[l]));
-        cd.layers.back().out_lo = U[L - 1].lo().p;  // the p-chain below restarts from the (hi, lo) pair
-        cd.layers.back().ld_out_lo = U[L - 1].lo().ld;
-        plan.chain(cd);
+      // ONE chain for the whole primal forward (inp_encode layers 1..L-1, then p_1 .. p_L) when merge_s3: the context
+      // branch only has to be finished before the chain starts (it runs on the side lane underneath the first-layer
+      // GEMM above), and nothing restarts from an (hi, lo) pair in the middle (no lo spill, no second
+      // initial-activation load).  Otherwise an inp chain, the join, and a p chain restarting from U[L-1].
+      if (!merge_s3 && L > 1) {
+        ChainDesc cu = chain_of(CHAIN_SOFTPLUS3, U[0].hi());
+        cu.A0lo = U[0].lo().p; cu.lda0lo = U[0].lo().ld;
+        for (int l = 1; l < L; ++l) cu.layers.push_back(s3_layer(Aw[l], P(iA(l) + 1), U[l]));
+        cu.layers.back().out_lo = U[L - 1].lo().p;
+        cu.layers.back().ld_out_lo = U[L - 1].lo().ld;
+        plan.chain(cu);
       }
       plan.join();
-      ChainDesc cd = chain_of(CHAIN_SOFTPLUS3, U[L - 1].hi());
-      cd.A0lo = U[L - 1].lo().p; cd.lda0lo = U[L - 1].lo().ld;
+      const Pair& entry = merge_s3 ? U[0] : U[L - 1];
+      ChainDesc cd = chain_of(CHAIN_SOFTPLUS3, entry.hi());
+      cd.A0lo = entry.lo().p; cd.lda0lo = entry.lo().ld;
+      if (merge_s3)
+        for (int l = 1; l < L; ++l) cd.layers.push_back(s3_layer(Aw[l], P(iA(l) + 1), U[l]));
       {
         ChainLayerDesc q = s3_layer(W1u, nullptr, V[0]);
         q.group_bias = rowbias.p; q.group = S; q.ldg = rowbias.ld; q.col_vec = wsig;
