@@ -234,6 +234,13 @@ static void bench_chain(int mode, int M, int H, int nl, int pair) {
   fill(W, 0.05f, true);
   float* dW = dev(W);
   float *dA0 = dev_fill(n, 0), *dA0lo = dev_fill(n, 0), *dsig = dev_fill(M, 0);
+  const bool rnd = getenv("CHAIN_RANDOM") != nullptr;  // random instead of constant operand data
+  std::vector<float> hrnd;
+  if (rnd) {
+    hrnd.resize(n);
+    fill(hrnd, 1.0f, true);
+    CK(cudaMemcpy(dA0, hrnd.data(), n * 4, cudaMemcpyHostToDevice));
+  }
   ChainDesc d;
   d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig; d.pair = pair;
   std::vector<float*> bufs;
@@ -241,6 +248,11 @@ static void bench_chain(int mode, int M, int H, int nl, int pair) {
   for (int l = 0; l < nl; ++l) {
     ChainLayerDesc q;
     float *a1 = dev_fill(n, 0x3c), *a2 = aux2 ? dev_fill(n, 0) : nullptr, *o = dev_fill(n, 0), *o2 = out2 ? dev_fill(n, 0) : nullptr;
+    if (rnd) {
+      for (auto& x : hrnd) x = std::fabs(x) * 1.5f;
+      CK(cudaMemcpy(a1, hrnd.data(), n * 4, cudaMemcpyHostToDevice));
+      if (a2) { fill(hrnd, 1.0f, false); CK(cudaMemcpy(a2, hrnd.data(), n * 4, cudaMemcpyHostToDevice)); }
+    }
     bufs.push_back(a1); bufs.push_back(a2); bufs.push_back(o); bufs.push_back(o2);
     q.W = dW; q.ldw = ldw; q.aux1 = a1; q.ld1 = H; q.aux2 = a2; q.ld2 = H; q.out = o; q.ldo = H; q.out2 = o2; q.ldo2 = H;
     if (s3) q.bias = dbias;
@@ -286,6 +298,20 @@ static void bench_chain(int mode, int M, int H, int nl, int pair) {
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= reps;
+  if (getenv("CHAIN_SINGLE")) {  // one isolated launch after unrelated traffic (what a training step sees)
+    float* junk = dev_fill((size_t)1 << 28, 0);
+    float single = 0;
+    for (int i = 0; i < 3; ++i) {
+      CK(cudaMemsetAsync(junk, i, (size_t)4 << 28, 0));
+      cudaEventRecord(e0);
+      launch_prepared_chain(pr, 0);
+      cudaEventRecord(e1);
+      CK(cudaDeviceSynchronize());
+      cudaEventElapsedTime(&single, e0, e1);
+      printf("  isolated launch %d: %.3f ms\n", i, single);
+    }
+    cudaFree(junk);
+  }
   const double arrays = s3 ? 1.0 : (1.0 + (aux2 ? 1 : 0) + 1.0 + (out2 ? 1 : 0));  // per layer: aux reads + out writes
   const double bytes = (arrays * nl + 1.0 + (s3 ? 1.0 : 0.0)) * n * 4.0;
   const double flops = 2.0 * M * (double)H * H * nl * (s3 ? 3.0 : 1.0);
