@@ -325,10 +325,12 @@ def main():
         by_tag.setdefault(tag, []).append(t_ms)
     nlay = 2 * L_ - 1  # fused H->H layers per sweep
     # algorithmic HBM bytes per launch: aux reads + spill writes per fused layer, + the initial activation
+    nbatch = 2 * (L_ - 1)  # [H,H] weight-gradient contractions batched into one launch (grid.z = layer)
     alg_bytes = {'chain_mul_sig': (2 * nlay + 1) * arr, 'chain_tangent': (4 * nlay + 1) * arr,
-                 'chain_adjoint': (3 * nlay + 1) * arr, 'gemm_tn': 4 * arr}
+                 'chain_adjoint': (3 * nlay + 1) * arr, 'gemm_tn': 4 * arr,
+                 'gemm_tn_batch': nbatch * (4 if args.cdae == 'grad' else 2) * arr}
     kernels = []
-    for tag in ('chain_tangent', 'chain_adjoint', 'chain_mul_sig', 'gemm_tn'):
+    for tag in ('chain_tangent', 'chain_adjoint', 'chain_mul_sig', 'gemm_tn_batch', 'gemm_tn'):
         ts = sorted(t for t in by_tag.get(tag, []) if t > 0.02)  # the big (N-row) launches only
         if not ts:
             continue
@@ -338,7 +340,8 @@ def main():
         a = alg_bytes[tag] / avg * 1e-6
         kernels.append(dict(kernel=tag, bound='hbm', launches=len(ts), ms_per_launch=avg, achieved=a, peak=hbm_peak,
                             unit='GB/s', frac=a / hbm_peak, algorithmic_bytes_per_launch=alg_bytes[tag],
-                            traffic=traffic.get(tag)))
+                            traffic=(traffic.get(tag) if tag != 'gemm_tn_batch' else
+                                     (traffic.get('gemm_tn') * nbatch if traffic.get('gemm_tn') else None))))
     ts3 = [t for t in by_tag.get('chain_softplus3', []) if t > 0.02]
     if ts3:
         # the two 3xTF32 chains together run nlay layers: algorithmic 2*N*H*H per layer (executed: 3x)

@@ -185,7 +185,7 @@ struct CdaePlan {
       ctx_tn_ws = ws.floats(ctx_tn_bytes / 4);
     }
     CdaeBindings* bd = &bind;
-    auto tn2 = [&](const Mat& X0, const Mat& Y0, const Mat* X1, const Mat* Y1, float* dst, int ldo) {
+    auto tn_desc = [&](const Mat& X0, const Mat& Y0, const Mat* X1, const Mat* Y1, float* dst, int ldo) {
       GemmTNDesc t;
       t.X0 = X0.p; t.ldx0 = X0.ld; t.Y0 = Y0.p; t.ldy0 = Y0.ld;
       if (X1) { t.X1 = X1->p; t.ldx1 = X1->ld; t.Y1 = Y1->p; t.ldy1 = Y1->ld; }
@@ -194,7 +194,10 @@ struct CdaePlan {
       // the side lane (context branch) has its own split-K scratch: both lanes run concurrently
       t.workspace = plan.cur_lane == 1 ? ctx_tn_ws : tn_ws;
       t.workspace_bytes = plan.cur_lane == 1 ? ctx_tn_bytes : tn_ws_bytes;
-      plan.tn(t);
+      return t;
+    };
+    auto tn2 = [&](const Mat& X0, const Mat& Y0, const Mat* X1, const Mat* Y1, float* dst, int ldo) {
+      plan.tn(tn_desc(X0, Y0, X1, Y1, dst, ldo));
     };
 
     // ---- prologue: sigma copy, x~ = x + sigma*eps (tf32 pair), context pair, exact w_sigma
@@ -405,17 +408,15 @@ struct CdaePlan {
         const Mat y = V[L - 1].hi();
         tn2(rmat, y, nullptr, nullptr, G(iW(L)), H);
       }
-      for (int l = L - 1; l >= 1; --l) {
-        const Mat y = V[l - 1].hi();
-        tn2(DP[l], y, nullptr, nullptr, G(iW(l)), H);
-      }
       {
         const Mat y = U[L - 1].hi();
         tn2(DP[0], y, nullptr, nullptr, G(iW(0)), ld1);
       }
-      for (int l = L - 1; l >= 1; --l) {
-        const Mat y = U[l - 1].hi();
-        tn2(DA[l], y, nullptr, nullptr, G(iA(l)), H);
+      {  // the 2(L-1) [H, H] contractions as one launch
+        std::vector<GemmTNDesc> batch;
+        for (int l = L - 1; l >= 1; --l) batch.push_back(tn_desc(DP[l], V[l - 1].hi(), nullptr, nullptr, G(iW(l)), H));
+        for (int l = L - 1; l >= 1; --l) batch.push_back(tn_desc(DA[l], U[l - 1].hi(), nullptr, nullptr, G(iA(l)), H));
+        plan.tn_batch(batch);
       }
       {
         const Mat xh = xt.hi();
@@ -600,17 +601,15 @@ struct CdaePlan {
     }
     // ---- weight gradients: dW = adj^T . act + delta^T . tangent   (accumulated into .grad)
     const Mat xt_hi = xt.hi();
-    for (int l = L - 1; l >= 1; --l) {
-      const Mat y = V[l - 1].hi();
-      tn2(TP[l], y, &DP[l], &VD[l - 1], G(iW(l)), H);
-    }
     {
       const Mat y = U[L - 1].hi();
       tn2(TP[0], y, &DP[0], &UD[L - 1], G(iW(0)), ld1);
     }
-    for (int l = L - 1; l >= 1; --l) {
-      const Mat y = U[l - 1].hi();
-      tn2(TA[l], y, &DA[l], &UD[l - 1], G(iA(l)), H);
+    {  // the 2(L-1) two-pair [H, H] contractions as one launch (grid.z = layer)
+      std::vector<GemmTNDesc> batch;
+      for (int l = L - 1; l >= 1; --l) batch.push_back(tn_desc(TP[l], V[l - 1].hi(), &DP[l], &VD[l - 1], G(iW(l)), H));
+      for (int l = L - 1; l >= 1; --l) batch.push_back(tn_desc(TA[l], U[l - 1].hi(), &DA[l], &UD[l - 1], G(iA(l)), H));
+      plan.tn_batch(batch);
     }
     tn2(TA[0], xt_hi, &DA[0], &rmat, G(iA(0)), d);
     plan.join();

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "gemm_sm100.cuh"
 
@@ -409,9 +410,66 @@ inline int prepare_gemm_tn(const GemmTNDesc& d, PreparedTN* out) {
   }
   pr.grid = dim3(nsplit, mt, nt);
   pr.nsplit = nsplit; pr.Mpad = mt * mrows; pr.Npad = nt * bn;
+  p.npad = pr.Npad;
   pr.out = d.out; pr.M = d.M; pr.N = d.N; pr.ldo = d.ldo; pr.scale = d.scale; pr.beta = d.beta;
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;
+  return 0;
+}
+
+// ---- batched weight gradients: same-shape, red.add-combined contractions in ONE launch (grid.z = problem)
+struct PreparedTNBatch {
+  GemmTNBatchParams params;
+  const void* fn = nullptr;
+  dim3 grid;
+  int smem = 0;
+  int count = 0;
+};
+
+// true if `d` can join a batch (vector-reduction epilogue, 256-wide single n tile, no full-M variant)
+inline bool tn_batchable(const GemmTNDesc& d) {
+  static int env = -2;
+  if (env == -2) {
+    // opt-in: measured on B200 the batched launch is SLOWER (116 us vs 102 us per contraction: co-resident CTAs of
+    // different problems interleave their HBM streams), so the default stays one launch per contraction
+    const char* e = std::getenv("ARDAE_TN_BATCH");
+    env = e ? std::atoi(e) : 0;
+  }
+  const bool red_vec = (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldo % 4 == 0 && d.N % 4 == 0;
+  return env > 0 && tn_atomic_default() && red_vec && d.atomic >= 0 && d.scale == 1.0f && d.beta == 1.0f &&
+         pick_block_n(d.N) == 256 && d.N <= 256 && !tn_full_m(d.M, d.N, d.full_m);
+}
+
+inline int prepare_gemm_tn_batch(const std::vector<GemmTNDesc>& ds, PreparedTNBatch* out) {
+  const int n = static_cast<int>(ds.size());
+  if (n < 1 || n > kMaxTNBatch) return fail(-2, "gemm_tn_batch: 1..10 problems");
+  PreparedTNBatch pb;
+  std::memset(&pb.params, 0, sizeof(pb.params));
+  PreparedTN first;
+  for (int i = 0; i < n; ++i) {
+    if (!tn_batchable(ds[i])) return fail(-2, "gemm_tn_batch: problem is not batchable");
+    PreparedTN pr;
+    int rc = prepare_gemm_tn(ds[i], &pr);
+    if (rc) return rc;
+    if (!pr.atomic) return fail(-2, "gemm_tn_batch: needs the red.add epilogue");
+    if (i == 0) first = pr;
+    else if (pr.grid.x != first.grid.x || pr.grid.y != first.grid.y || pr.grid.z != 1 || pr.fn != first.fn)
+      return fail(-2, "gemm_tn_batch: problems must have the same shape");
+    pb.params.prob[i] = pr.params;
+  }
+  if (first.grid.z != 1) return fail(-2, "gemm_tn_batch: single n tile only");
+  pb.fn = reinterpret_cast<const void*>(&gemm_tn_batch_kernel<256>);
+  pb.smem = GemmTNConfig<256>::kSmemBytes;
+  pb.grid = dim3(first.grid.x, first.grid.y, n);
+  pb.count = n;
+  ARDAE_CUDA_OK(cudaFuncSetAttribute(pb.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pb.smem));
+  *out = pb;
+  return 0;
+}
+
+inline int launch_prepared_tn_batch(const PreparedTNBatch& pb, cudaStream_t stream) {
+  void* args[1] = {const_cast<GemmTNBatchParams*>(&pb.params)};
+  ARDAE_CUDA_OK(cudaLaunchKernel(pb.fn, pb.grid, dim3(kGemmThreads), args, pb.smem, stream));
   return 0;
 }
 

@@ -73,6 +73,15 @@ struct alignas(64) GemmTNParams {
   float* red_out;    // non-null: every split adds its tile straight into out[M, N] (pitch red_ld) with
   int red_ld;        //           red.global.add (no partial buffer, no reduce launch; summation order not fixed)
   int red_vec;       // rows of red_out are 16-byte aligned: red.global.add.v4.f32
+  int npad;          // padded N of the partial buffer (n tiles x BLOCK_N)
+};
+
+// Batched launch: grid.z selects one of up to kMaxTNBatch same-shape contractions (the 2L-1 [H,H] weight gradients of
+// a CDAE update).  One launch = one ramp-up and one tail for all of them; CTAs of different problems co-reside, so
+// one CTA's prologue / red.add epilogue overlaps another's main loop and HBM keeps streaming.
+constexpr int kMaxTNBatch = 10;
+struct alignas(64) GemmTNBatchParams {
+  GemmTNParams prob[kMaxTNBatch];
 };
 
 __device__ __forceinline__ float softplus_f(float x) {
@@ -786,9 +795,10 @@ struct GemmTNConfig {
   static_assert(MT == 1 || BLOCK_N == 256, "full-M variant: 256 x 256 tiles");
 };
 
-template <int BLOCK_N, int MT = 1>
-__global__ void __launch_bounds__(kGemmThreads, MT == 2 ? 1 : 2)
-gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
+// Body shared by the single-problem kernel (n-tile = blockIdx.z) and the batched kernel (problem = blockIdx.z).
+// `p` must live in kernel-parameter space (TMA descriptors are taken by address).
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ void gemm_tn_body(const GemmTNParams& p, const int ntile) {
   using Cfg = GemmTNConfig<BLOCK_N, MT>;
   constexpr int NSTAGE = Cfg::kNumStages;
 
@@ -804,7 +814,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.x;
   const int m0 = blockIdx.y * (MT * kBlockM);
-  const int n0 = blockIdx.z * BLOCK_N;
+  const int n0 = ntile * BLOCK_N;
   const int total_kb = (p.K + kBlockK - 1) / kBlockK;
   const int kb_begin = split * p.kb_per_split;
   int kb_end = kb_begin + p.kb_per_split;
@@ -890,7 +900,7 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
   } else {
     const int quarter = warp & 3;
     const int Mpad = gridDim.y * (MT * kBlockM);
-    const int Npad = gridDim.z * BLOCK_N;
+    const int Npad = p.npad;
     if (iters > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
@@ -953,6 +963,18 @@ gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BLOCK_N, int MT = 1>
+__global__ void __launch_bounds__(kGemmThreads, MT == 2 ? 1 : 2)
+gemm_tn_kernel(const __grid_constant__ GemmTNParams p) {
+  gemm_tn_body<BLOCK_N, MT>(p, blockIdx.z);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_tn_batch_kernel(const __grid_constant__ GemmTNBatchParams pb) {
+  gemm_tn_body<BLOCK_N, 1>(pb.prob[blockIdx.z], 0);
 }
 
 // out[m*ld + n] = beta*out + scale * sum_s partial[s][m][n]   (m < M, n < N)

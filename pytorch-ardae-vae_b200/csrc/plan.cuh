@@ -133,6 +133,28 @@ struct Plan {
     lanes.push_back(cur_lane);
     tag_last("gemm_tn");
   }
+  // same-shape weight-gradient contractions as one launch where possible, else one launch each
+  void tn_batch(const std::vector<GemmTNDesc>& ds) {
+    bool ok = ds.size() >= 2 && ds.size() <= static_cast<size_t>(kMaxTNBatch);
+    for (const GemmTNDesc& d : ds) ok = ok && !dry && tn_batchable(d);
+    if (ok && !dry) {
+      for (size_t i = 1; i < ds.size(); ++i)
+        ok = ok && ds[i].M == ds[0].M && ds[i].N == ds[0].N && ds[i].K == ds[0].K &&
+             (ds[i].X1 != nullptr) == (ds[0].X1 != nullptr);
+    }
+    if (!ok) {
+      for (const GemmTNDesc& d : ds) tn(d);
+      return;
+    }
+    ++num_gemm_tn;  // one launch
+    PreparedTNBatch pb;
+    int rc = prepare_gemm_tn_batch(ds, &pb);
+    if (rc) return fail_with(rc);
+    auto sp = std::make_shared<PreparedTNBatch>(pb);
+    ops.push_back([sp](cudaStream_t s) { return launch_prepared_tn_batch(*sp, s); });
+    lanes.push_back(cur_lane);
+    tag_last("gemm_tn_batch");
+  }
   int run(cudaStream_t s) {
     if (profile && ev0.size() != ops.size()) {
       ev0.resize(ops.size()); ev1.resize(ops.size());
