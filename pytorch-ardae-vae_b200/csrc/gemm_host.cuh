@@ -343,6 +343,10 @@ inline bool tn_full_m(int M, int N, int request) {
 }
 
 inline size_t tn_workspace_bytes(int M, int N, int K, int target_ctas = 296) {
+  {
+    const char* e = std::getenv("ARDAE_TN_CTAS");
+    if (e && std::atoi(e) > target_ctas) target_ctas = std::atoi(e);
+  }
   const int bn = pick_block_n(N);
   if (tn_full_m(M, N, 0)) {  // one CTA per SM
     const int total_kb = (K + kBlockK - 1) / kBlockK;
@@ -363,7 +367,18 @@ inline size_t tn_workspace_bytes(int M, int N, int K, int target_ctas = 296) {
   return static_cast<size_t>(nsplit) * mt * kBlockM * nt * bn * sizeof(float);
 }
 
-inline int prepare_gemm_tn(const GemmTNDesc& d, PreparedTN* out) {
+inline int tn_target_ctas(int requested) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("ARDAE_TN_CTAS");
+    env = e ? std::atoi(e) : 0;
+  }
+  return env > 0 ? env : requested;
+}
+
+inline int prepare_gemm_tn(const GemmTNDesc& d_in, PreparedTN* out) {
+  GemmTNDesc d = d_in;
+  d.target_ctas = tn_target_ctas(d.target_ctas);
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(-2, "gemm_tn: empty problem");
   if (!d.X0 || !d.Y0 || !d.out || !d.workspace) return fail(-2, "gemm_tn: missing pointer");
   const int bn = pick_block_n(d.N);
