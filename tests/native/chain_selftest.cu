@@ -254,7 +254,9 @@ static void bench_chain(int mode, int M, int H, int nl, int pair) {
       if (a2) { fill(hrnd, 1.0f, false); CK(cudaMemcpy(a2, hrnd.data(), n * 4, cudaMemcpyHostToDevice)); }
     }
     bufs.push_back(a1); bufs.push_back(a2); bufs.push_back(o); bufs.push_back(o2);
-    q.W = dW; q.ldw = ldw; q.aux1 = a1; q.ld1 = H; q.aux2 = a2; q.ld2 = H; q.out = o; q.ldo = H; q.out2 = o2; q.ldo2 = H;
+    float* wl = dW;
+    if (getenv("CHAIN_WPERLAYER")) { fill(W, 0.05f, true); wl = dev(W); bufs.push_back(wl); }  // a distinct weight per layer
+    q.W = wl; q.ldw = ldw; q.aux1 = a1; q.ld1 = H; q.aux2 = a2; q.ld2 = H; q.out = o; q.ldo = H; q.out2 = o2; q.ldo2 = H;
     if (s3) q.bias = dbias;
     d.layers.push_back(q);
   }
