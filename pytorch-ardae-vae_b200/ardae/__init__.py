@@ -7,13 +7,17 @@ from .data import MinibatchSampler, dynamic_binarize, toy_exp4  # noqa: F401
 from .checkpoint import annealing_func, load_checkpoint, save_checkpoint  # noqa: F401
 
 
-def evaluate_iws(data, model, iws_samples, batch_size=32, process_group=None):
+def evaluate_iws(data, model, iws_samples, batch_size=None, process_group=None):
     """evaluate_iws (ivae_ardae.py:644-673): mean over the images of model.logprob(x, sample_size=iws_samples).
     `data`: an iterable of (x, _) batches like the reference's loader, or one tensor [n, D].  Images are
     processed `batch_size` at a time (the reference scripts use eval batch 1 and a Python loop per image);
     under data parallelism each rank passes its own shard and the partial sums are allreduced."""
     import torch
     total, count = None, 0
+    if batch_size is None:
+        # ~640k decoder rows per call: measured on B200 at 5000 samples, 16 / 32 / 64 / 128 images per call give
+        # 5.9k / 8.4k / 10.1k / 11.7k images/s (launch-bound below that)
+        batch_size = max(1, min(128, 640000 // max(1, int(iws_samples))))
     if torch.is_tensor(data):
         data = [(data[i:i + batch_size], None) for i in range(0, data.size(0), batch_size)]
     for x, _ in data:
