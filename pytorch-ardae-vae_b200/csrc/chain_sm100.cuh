@@ -67,7 +67,7 @@ struct alignas(64) ChainParams {
   ChainLayerParams layer[kChainMaxLayers];
 };
 
-template <int MODE, bool CG2 = false>
+template <int MODE, bool CG2 = false, int MC = 1>
 struct ChainConfig {
   static constexpr bool kS3 = MODE == CHAIN_SOFTPLUS3;
   static constexpr bool kAux2 = MODE == CHAIN_TANGENT || MODE == CHAIN_ADJOINT;
@@ -88,14 +88,21 @@ struct ChainConfig {
   static constexpr int kThreads = 128 + kGroups * 128;
 };
 
+// MC > 1: launched as clusters of MC CTAs (adjacent row tiles, independent MMAs).  Every weight stage is fetched ONCE
+// per cluster: CTA r loads rows [r*HH/MC, (r+1)*HH/MC) of the k-block and TMA-multicasts them into the same stage of
+// all MC CTAs; a stage is recycled when all MC MMA threads have retired it (multicast tcgen05.commit).  The chains
+// re-stream 256 KB (3xTF32: 512 KB) of weights per tile and layer from L2 -- as much L2 -> SM traffic as their HBM
+// data -- so the tf32 sweeps are L2-bandwidth limited; multicast divides that stream by MC.
 // CG2: launched as clusters of two CTAs (adjacent row tiles).  The leader issues tcgen05.mma.cta_group::2 for the
 // 256-row pair; every weight k-block is staged half in each CTA, so each SM ingests HALF of the weight stream
 // (the 3xTF32 sweep moves 512 KB of weights per tile and layer and is bound by that stream) and the same 96 KB
 // ring holds twice as many k-blocks.
-template <int MODE, bool CG2 = false>
-__global__ void __launch_bounds__(ChainConfig<MODE, CG2>::kThreads, 1)
+template <int MODE, bool CG2 = false, int MC = 1>
+__global__ void __launch_bounds__(ChainConfig<MODE, CG2, MC>::kThreads, 1)
 chain_kernel(const __grid_constant__ ChainParams p) {
-  using Cfg = ChainConfig<MODE, CG2>;
+  using Cfg = ChainConfig<MODE, CG2, MC>;
+  static_assert(!(CG2 && MC > 1), "CTA pairs and weight multicast are exclusive");
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << MC) - 1u);
   constexpr bool S3 = Cfg::kS3, HAS_AUX2 = Cfg::kAux2, HAS_OUT2 = Cfg::kOut2;
   constexpr int G = Cfg::kGroups, NW = Cfg::kNumWStages;
   constexpr int NAUX = Cfg::kNumAux > 0 ? Cfg::kNumAux : 1;
@@ -132,7 +139,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     if (lane == 0) {
       for (int s = 0; s < NW; ++s) {
         ptx::mbar_init(&w_full[s], 1);
-        ptx::mbar_init(&w_empty[s], 1);
+        ptx::mbar_init(&w_empty[s], MC);  // MC > 1: every CTA of the cluster retires the (shared) stage
       }
       static_assert(NW <= 12, "barrier area");
       for (int a = 0; a < 8; ++a) {
@@ -158,10 +165,10 @@ chain_kernel(const __grid_constant__ ChainParams p) {
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG2) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
+  if (CG2 || MC > 1) ptx::cluster_sync_all();  // the peers' barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t rank = CG2 ? ptx::cluster_ctarank() : 0;
+  const uint32_t rank = (CG2 || MC > 1) ? ptx::cluster_ctarank() : 0;
   const uint32_t acc_t = tmem_base;       // accumulator columns [0, H)
   const uint32_t a_t = tmem_base + 256;   // A operand (SOFTPLUS3: its lo part) columns [256, 256 + H)
   uint8_t* hi_tiles = smem + Cfg::kOffAux;  // SOFTPLUS3 only
@@ -186,6 +193,13 @@ chain_kernel(const __grid_constant__ ChainParams p) {
               // both CTAs' halves complete on the LEADER's full barrier, armed by the leader for both
               if (rank == 0) ptx::mbar_expect_tx(&w_full[s], wbytes);
               ptx::tma_load_2d_2sm(smem + s * Cfg::kWStage, tw, &w_full[s], kc, h * HH + static_cast<int>(rank) * wrows);
+            } else if (MC > 1) {
+              // this CTA's 1/MC slice of the k-block, delivered to the same stage of every CTA of the cluster; the
+              // local barrier expects the whole stage (MC slices from MC producers)
+              const int srows = HH / MC;
+              ptx::mbar_expect_tx(&w_full[s], wbytes);
+              ptx::tma_load_2d_mc(smem + s * Cfg::kWStage + rank * (srows * kBlockK * 4), tw, &w_full[s], kc,
+                                  h * HH + static_cast<int>(rank) * srows, kMcMask);
             } else {
               ptx::mbar_expect_tx(&w_full[s], wbytes);
               ptx::tma_load_2d(smem + s * Cfg::kWStage, tw, &w_full[s], kc, h * HH);
@@ -196,7 +210,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (rank == 0 && ptx::elect_one()) {
+    if ((!CG2 || rank == 0) && ptx::elect_one()) {  // CG2: the leader issues for the pair; otherwise every CTA
       const uint32_t idesc = ptx::make_idesc_tf32(CG2 ? 2 * kBlockM : kBlockM, HH, 0, 0);
       auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
         if (CG2) ptx::umma_tf32_2sm(d, a, b, idesc, acc); else ptx::umma_tf32(d, a, b, idesc, acc);
@@ -206,6 +220,9 @@ chain_kernel(const __grid_constant__ ChainParams p) {
       };
       auto commit = [&](uint64_t* bar) {  // CG2: the same barrier in both CTAs of the pair
         if (CG2) ptx::umma_commit_2sm(bar, 0x3); else ptx::umma_commit(bar);
+      };
+      auto commit_w = [&](uint64_t* bar) {  // weight stage retired: MC > 1 tells every CTA of the cluster
+        if (MC > 1) ptx::umma_commit_mc(bar, kMcMask); else commit(bar);
       };
       int it = 0;
       for (int l = 0; l < nl; ++l) {
@@ -251,7 +268,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
                 const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
                 mma_ts(d_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, (S3 || (kb | k) != 0) ? 1u : 0u);
               }
-              commit(&w_empty[s]);
+              commit_w(&w_empty[s]);
               ++it;
             }
             if (S3) {  // hi . Wlo
@@ -267,7 +284,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
                 const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
                 mma_ss(d_t, adesc, bdesc, 1u);
               }
-              commit(&w_empty[s]);
+              commit_w(&w_empty[s]);
               ++it;
             }
             // second half: this layer is done with A chunk kb -> the half-0 epilogue may overwrite it
@@ -552,7 +569,7 @@ chain_kernel(const __grid_constant__ ChainParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG2) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers / read its memory
+  if (CG2 || MC > 1) ptx::cluster_sync_all();  // no CTA exits while a peer may still signal its barriers / write its memory
   if (warp == 1) {
     ptx::tc_fence_after();
     if (CG2) ptx::tmem_dealloc_2sm(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
