@@ -30,7 +30,7 @@ struct ChainDesc {
   const float* A0lo = nullptr; int lda0lo = 0;    // SOFTPLUS3: lo part
   const float* row_scale = nullptr;               // [M]
   int pair = 0;   // CTA-pair (cta_group::2) kernel: 1 on, 0 / -1 off (ARDAE_CHAIN_PAIR=1 switches the default)
-  int multicast = 0;  // clusters of 8 CTAs sharing one multicast weight stream: 1 on, -1 off, 0 = default (ARDAE_CHAIN_MC)
+  int multicast = 0;  // clusters of 2 / 4 / 8 CTAs sharing one multicast weight stream (1 = 8), -1 off, 0 = default (ARDAE_CHAIN_MC)
   std::vector<ChainLayerDesc> layers;
 };
 
@@ -76,8 +76,10 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
     mc_env = e ? std::atoi(e) : 0;
   }
   // weight multicast over clusters of 8: needs 8-row-aligned slices (H >= 128) and enough tiles to fill clusters
-  const bool mc8 = !cg2_box && (d.multicast > 0 || (d.multicast == 0 && mc_env > 0)) && d.H % 128 == 0 &&
-                   (d.M + kBlockM - 1) / kBlockM >= 8;
+  int mcs = d.multicast > 0 ? (d.multicast == 1 ? 8 : d.multicast) : (d.multicast == 0 && mc_env > 0 ? (mc_env == 1 ? 8 : mc_env) : 0);
+  if (mcs != 2 && mcs != 4 && mcs != 8) mcs = 0;
+  if (cg2_box || (d.H / 2) % (8 * (mcs ? mcs : 1)) != 0 || (d.M + kBlockM - 1) / kBlockM < mcs) mcs = 0;
+  const bool mc8 = mcs > 0;
   if ((rc = encode_tmap_2d(&p.tmA0, d.A0, d.H, d.M, d.lda0, 32, kBlockM))) return rc;
   p.a0_lo = d.A0lo; p.a0_lo_ld = d.lda0lo; p.row_scale = d.row_scale;
   p.M = d.M; p.H = d.H; p.nlayers = nl;
@@ -87,7 +89,7 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
     ChainLayerParams& q = p.layer[l];
     if (!s.W || !s.out || (!s3 && !s.aux1) || (aux2 && !s.aux2) || (out2 && !s.out2))
       return fail(-2, "chain: missing operand pointer");
-    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * d.H : d.H, d.H, s.ldw, kBlockK, mc8 ? d.H / 16 : (cg2_box ? d.H / 4 : d.H / 2)))) return rc;
+    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * d.H : d.H, d.H, s.ldw, kBlockK, mc8 ? d.H / (2 * mcs) : (cg2_box ? d.H / 4 : d.H / 2)))) return rc;
     if (!s3 && (rc = encode_tmap_2d(&q.tmAux1, s.aux1, d.H, d.M, s.ld1, 32, kBlockM))) return rc;
     if (aux2 && (rc = encode_tmap_2d(&q.tmAux2, s.aux2, d.H, d.M, s.ld2, 32, kBlockM))) return rc;
     if ((rc = encode_tmap_2d(&q.tmOut, s.out, d.H, d.M, s.ldo, 32, kBlockM))) return rc;
@@ -114,7 +116,9 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
   const bool cg2 = pair_req > 0;  // measured on B200: the pair's lock-step costs more than the halved weight stream saves
 #define ARDAE_CHAIN_CASE(MODE_)                                                                      \
   case MODE_:                                                                                        \
-    if (mc8) { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, false, 8>); pr.smem = ChainConfig<MODE_, false, 8>::kSmemBytes; pr.threads = ChainConfig<MODE_, false, 8>::kThreads; } \
+    if (mcs == 8) { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, false, 8>); pr.smem = ChainConfig<MODE_, false, 8>::kSmemBytes; pr.threads = ChainConfig<MODE_, false, 8>::kThreads; } \
+    else if (mcs == 4) { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, false, 4>); pr.smem = ChainConfig<MODE_, false, 4>::kSmemBytes; pr.threads = ChainConfig<MODE_, false, 4>::kThreads; } \
+    else if (mcs == 2) { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, false, 2>); pr.smem = ChainConfig<MODE_, false, 2>::kSmemBytes; pr.threads = ChainConfig<MODE_, false, 2>::kThreads; } \
     else if (cg2) { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, true>); pr.smem = ChainConfig<MODE_, true>::kSmemBytes; pr.threads = ChainConfig<MODE_, true>::kThreads; } \
     else { pr.fn = reinterpret_cast<const void*>(&chain_kernel<MODE_, false>); pr.smem = ChainConfig<MODE_, false>::kSmemBytes; pr.threads = ChainConfig<MODE_, false>::kThreads; } \
     break;
@@ -132,8 +136,8 @@ inline int prepare_chain(const ChainDesc& d, PreparedChain* out) {
     pr.grid.x = (pr.grid.x + 1) / 2 * 2;  // an odd tail CTA works on an out-of-range tile (TMA clips)
   }
   if (mc8) {
-    pr.cluster = 8;
-    pr.grid.x = (pr.grid.x + 7) / 8 * 8;  // tail CTAs work on out-of-range tiles but still serve their weight slices
+    pr.cluster = mcs;
+    pr.grid.x = (pr.grid.x + mcs - 1) / mcs * mcs;  // tail CTAs work on out-of-range tiles but still serve their weight slices
   }
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;

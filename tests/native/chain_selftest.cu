@@ -98,7 +98,7 @@ static void test_chain(int mode, int M, int H, int nl, int pair) {
   };
   std::vector<LayerBufs> Ls(nl);
   ChainDesc d;
-  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig; d.pair = pair == 8 ? -1 : pair; d.multicast = pair == 8 ? 1 : -1;
+  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig; d.pair = pair >= 2 ? -1 : pair; d.multicast = pair >= 2 ? pair : -1;
   for (int l = 0; l < nl; ++l) {
     LayerBufs& b = Ls[l];
     b.Wfull.resize((size_t)H * H);
@@ -242,7 +242,7 @@ static void bench_chain(int mode, int M, int H, int nl, int pair) {
     CK(cudaMemcpy(dA0, hrnd.data(), n * 4, cudaMemcpyHostToDevice));
   }
   ChainDesc d;
-  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig; d.pair = pair == 8 ? -1 : pair; d.multicast = pair == 8 ? 1 : -1;
+  d.mode = mode; d.M = M; d.H = H; d.A0 = dA0; d.lda0 = H; d.A0lo = dA0lo; d.lda0lo = H; d.row_scale = dsig; d.pair = pair >= 2 ? -1 : pair; d.multicast = pair >= 2 ? pair : -1;
   std::vector<float*> bufs;
   float* dbias = dev_fill(H, 0);
   for (int l = 0; l < nl; ++l) {
@@ -336,6 +336,8 @@ int main(int argc, char** argv) {
     }
     test_chain(mode, 1100, 256, 3, 8);   // "pair = 8": clusters of 8 with weight multicast (9 tiles -> 16 CTAs)
     test_chain(mode, 2048, 128, 4, 8);
+    test_chain(mode, 700, 256, 3, 4);
+    test_chain(mode, 700, 256, 3, 2);
   }
   if (bench)
     for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
@@ -345,6 +347,8 @@ int main(int argc, char** argv) {
         bench_chain(mode, 512, 256, 9, pair);
       }
       bench_chain(mode, 131072, 256, 9, 8);
+      bench_chain(mode, 131072, 256, 9, 4);
+      bench_chain(mode, 131072, 256, 9, 2);
     }
   printf(g_fail ? "CHAIN SELFTEST FAILED (%d)\n" : "CHAIN SELFTEST OK\n", g_fail);
   return g_fail ? 1 : 0;
