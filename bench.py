@@ -229,7 +229,6 @@ def main():
         out = step(*resident[i % nb], beta=c['beta'])
     e1.record()
     barrier()
-    sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     graph_used = bool(step.graph and step._g is not None)
     t = torch.tensor([ms], device=dev)
@@ -278,6 +277,7 @@ def main():
         torch.cuda.current_stream().synchronize()  # the caller reads the losses every step
     f1.record()
     barrier()
+    sampler.stop_flag = True  # clocks / throttle reasons sampled across both timed regions (value and e2e)
     t2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
