@@ -276,3 +276,32 @@ def test_resume_from_reference_checkpoint():
     print('resume: update rel err cdae %.2e model %.2e' % (ue_c, ue_m))
     assert ue_c <= 5e-2 and ue_m <= 5e-2
     assert mopt.state[next(iter(model.parameters()))]['step'] == 2
+
+
+def test_two_cdae_updates_per_iteration():
+    """num_cdae_updates = 2 (run_vae_dbmnist.sh:25): the fused driver takes a list of CDAE minibatches; it must equal
+    cdae_update, cdae_update, model_update issued by hand (same injected noise for both)."""
+    import ardae
+    z, meta = load_case('mnist_small')
+    hp = meta['hp']
+    noise = {k: t(v) for k, v in sub(z, 's0/noise/').items()}
+    x1, x2, xm = t(z['s0/x_cdae']), t(z['s1/x_cdae']), t(z['s0/x_model'])
+    res = []
+    for fused in (True, False):
+        model, cdae, mopt, copt = build(meta, z)
+        step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=hp['std_scale'], delta=hp['delta'],
+                               nz_cdae=hp['nz_cdae'], nstd=hp['nstd'], nz_model=hp['nz_model'], num_cdae_updates=2)
+        if fused:
+            step([x1, x2], xm, beta=hp['beta'], noise=noise)
+        else:
+            step.overlap = False
+            step.cdae_update(x1, noise)
+            step.cdae_update(x2, noise)
+            step.model_update(xm, hp['beta'], noise)
+        torch.cuda.synchronize()
+        res.append((params_np(model), params_np(cdae), copt.state[next(iter(cdae.parameters()))]['step']))
+    (pm_a, pc_a, sa), (pm_b, pc_b, sb) = res
+    assert sa == sb == 2
+    for a, b in ((pm_a, pm_b), (pc_a, pc_b)):
+        for k in a:
+            assert rel_err(a[k], b[k]) <= 1e-5, k
