@@ -490,6 +490,26 @@ inline int launch_prepared_tn_batch(const PreparedTNBatch& pb, cudaStream_t stre
 
 inline int launch_prepared_tn(const PreparedTN& pr, cudaStream_t stream) {
   void* args[1] = {const_cast<GemmTNParams*>(&pr.params)};
+  static int pdl_env = -1;
+  if (pdl_env < 0) {
+    const char* e = std::getenv("ARDAE_TN_PDL");
+    pdl_env = e ? std::atoi(e) : 0;
+  }
+  if (pr.atomic && pdl_env > 0) {
+    // overlap this contraction's ramp-up with the tail of the previous launch in the stream (PDL)
+    PreparedTN q = pr;
+    q.params.pdl = 1;
+    void* qargs[1] = {&q.params};
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pr.grid; cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = pr.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ARDAE_CUDA_OK(cudaLaunchKernelExC(&cfg, pr.fn, qargs));
+    return 0;
+  }
   ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(kGemmThreads), args, pr.smem, stream));
   if (pr.atomic) return 0;
   const int total = pr.M * pr.N;

@@ -74,6 +74,8 @@ struct alignas(64) GemmTNParams {
   int red_ld;        //           red.global.add (no partial buffer, no reduce launch; summation order not fixed)
   int red_vec;       // rows of red_out are 16-byte aligned: red.global.add.v4.f32
   int npad;          // padded N of the partial buffer (n tiles x BLOCK_N)
+  long long* dbg;    // profiling only: per CTA [4] clock64 stamps (entry, accumulator complete, epilogue done, -)
+  int pdl;           // launched with programmatic stream serialization (see gemm_tn_body)
 };
 
 // Batched launch: grid.z selects one of up to kMaxTNBatch same-shape contractions (the 2L-1 [H,H] weight gradients of
@@ -821,6 +823,12 @@ __device__ __forceinline__ void gemm_tn_body(const GemmTNParams& p, const int nt
   if (kb_end > total_kb) kb_end = total_kb;
   const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;
   const int iters = nkb * p.npairs;  // pair-major: all k-blocks of pair 0, then pair 1
+  long long* dbg = p.dbg ? p.dbg + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 4 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  // Programmatic dependent launch: consecutive weight-gradient contractions are independent of each other (read-only
+  // inputs, disjoint outputs), so the next one may start filling SM slots as this one's CTAs retire instead of waiting
+  // for the whole grid to drain.  No-ops unless the launch carries the programmatic-serialization attribute.
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmX0);
@@ -905,6 +913,9 @@ __device__ __forceinline__ void gemm_tn_body(const GemmTNParams& p, const int nt
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
+    if (dbg && warp == 2 && lane == 0) dbg[1] = clock64();
+    // stream order for whatever follows: this grid does not finish (its reductions do not land) before its predecessor has
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll 1
     for (int mh = 0; mh < MT; ++mh) {
     const int r = mh * kBlockM + quarter * 32 + lane;
@@ -955,6 +966,7 @@ __device__ __forceinline__ void gemm_tn_body(const GemmTNParams& p, const int nt
     }
     }
     }  // mh
+    if (dbg && warp == 2 && lane == 0) dbg[2] = clock64();
   }
 
   ptx::tc_fence_before();

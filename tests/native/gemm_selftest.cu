@@ -250,8 +250,29 @@ static void bench_tn(int M, int N, int K, bool two) {
   GemmTNDesc d;
   d.X0 = X; d.ldx0 = M; d.Y0 = Y; d.ldy0 = N; if (two) { d.X1 = X1; d.ldx1 = M; d.Y1 = Y1; d.ldy1 = N; }
   d.M = M; d.N = N; d.K = K; d.out = O; d.ldo = N; d.workspace = ws; d.workspace_bytes = wsb;
+  if (getenv("TN_ATOMIC")) { d.scale = 1.0f; d.beta = 1.0f; }  // the red.global.add path of the training plan
   PreparedTN pr;
   if (prepare_gemm_tn(d, &pr)) { printf("bench prepare failed: %s\n", last_error_string().c_str()); return; }
+  if (getenv("TN_TIMES")) {
+    const size_t nc = (size_t)pr.grid.x * pr.grid.y;
+    long long* dt; CK(cudaMalloc(&dt, nc * 4 * sizeof(long long))); CK(cudaMemset(dt, 0, nc * 4 * sizeof(long long)));
+    pr.params.dbg = dt;
+    launch_prepared_tn(pr, 0); CK(cudaDeviceSynchronize());
+    launch_prepared_tn(pr, 0); CK(cudaDeviceSynchronize());
+    std::vector<long long> h(nc * 4);
+    CK(cudaMemcpy(h.data(), dt, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long t0 = h[0], tend = 0; double main_sum = 0, epi_sum = 0; long long main_max = 0, epi_max = 0, start_max = 0;
+    for (size_t c = 0; c < nc; ++c) { if (h[c * 4] < t0) t0 = h[c * 4]; }
+    for (size_t c = 0; c < nc; ++c) {
+      const long long s0 = h[c * 4] - t0, mn = h[c * 4 + 1] - h[c * 4], ep = h[c * 4 + 2] - h[c * 4 + 1];
+      main_sum += mn; epi_sum += ep;
+      if (mn > main_max) main_max = mn; if (ep > epi_max) epi_max = ep; if (s0 > start_max) start_max = s0;
+      if (h[c * 4 + 2] - t0 > tend) tend = h[c * 4 + 2] - t0;
+    }
+    printf("  TN phases (cycles, %zu CTAs; clocks of different SMs are only roughly aligned): latest start %lld, main loop avg %.0f max %lld, "
+           "epilogue avg %.0f max %lld, last end %lld\n", nc, start_max, main_sum / nc, main_max, epi_sum / nc, epi_max, tend);
+    pr.params.dbg = nullptr; cudaFree(dt);
+  }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) launch_prepared_tn(pr, 0);
   cudaEventRecord(e0);
@@ -279,6 +300,10 @@ int main(int argc, char** argv) {
       bench_nt(131072, 256, 256, EPI_TANGENT, -1);
       bench_nt(131072, 256, 256, EPI_ADJOINT, -1);
     }
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "tn")) {  // weight-gradient contraction only (TN_ATOMIC=1 TN_TIMES=1 for the phase stamps)
+    bench_tn(256, 256, 131072, true);
     return 0;
   }
   if (argc > 5 && !strcmp(argv[1], "one")) {  // one <mode> <K> <split> <pair>: a single bench config (for ncu)
