@@ -79,6 +79,11 @@ def cpu_reference_leg(steps, warmup, B_sample=128):
     c = CFG
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    try:  # numpy's BLAS pool too (a launcher may have pinned it to one thread)
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=cores)
+    except Exception:
+        pass
     hp = dict(std_scale=c['std_scale'], delta=c['delta'], nz_cdae=c['nz'], nstd=c['nstd'], nz_model=c['nz_model'],
               beta=c['beta'], m_lr=c['m_lr'], m_beta1=c['m_beta1'], d_lr=c['d_lr'], d_momentum=c['d_momentum'])
     g = torch.Generator().manual_seed(1234)
@@ -147,6 +152,11 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: give the CPU arm every host core back (before numpy / torch
+    # load their BLAS) -- "all the host threads it can use"
+    cores = str(os.cpu_count() or 1)
+    for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[k] = cores
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
     cb, sec = cpu_reference_leg(steps, warmup)
     line = dict(metric='train_samples_per_sec', value=cb['value'], unit='samples/s', impl='reference',
