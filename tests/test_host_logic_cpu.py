@@ -141,3 +141,47 @@ def test_reference_checkpoint_loads_and_annealing():
     assert ardae.annealing_func(1e-4, 1.0, 50000, 25000) == pytest.approx(1e-4 + (1.0 - 1e-4) * 0.5)
     assert ardae.annealing_func(1e-4, 1.0, 50000, 10 ** 9) == pytest.approx(1.0)
     assert ardae.annealing_func(1e-4, 1.0, None, 3) == 1.0
+
+
+def test_checkpoint_written_here_loads_in_the_reference(tmp_path):
+    """The other direction of the interchange: a checkpoint saved by ardae.save_checkpoint (state that came from the
+    reference's files) is read back by the REFERENCE's own utils.load_checkpoint into reference modules / optimizers.
+    Needs the reference tree (build container only)."""
+    import os
+    import sys
+    import types
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    import ref_harness as rh
+    if rh.find_reference() is None:
+        pytest.skip('reference tree not available')
+    import ardae
+    from golden_util import GOLDEN_DIR
+    z, meta = load_case('mnist_small')
+    hp = meta['hp']
+    model, cdae = build(meta)
+    mo = ardae.Adam(model.parameters(), lr=hp['m_lr'], betas=(hp['m_beta1'], 0.999))
+    co = ardae.RMSprop(cdae.parameters(), lr=hp['d_lr'], momentum=hp['d_momentum'])
+    ck_dir = os.path.join(GOLDEN_DIR, 'ref_ckpt_mnist_small')
+    ardae.load_checkpoint(model, mo, ck_dir, filename='model-checkpoint.pth.tar')
+    ardae.load_checkpoint(cdae, co, ck_dir, filename='cdae-checkpoint.pth.tar')
+    out = str(tmp_path)
+    common = dict(epoch=3, batch_idx=7, train_num_iters_per_epoch=10, best_val_loss=1.5, scheduler=None)
+    ardae.save_checkpoint(dict(common, model='mnist-concat', state_dict=model.state_dict(), optimizer=mo.state_dict()),
+                          out, filename='model-checkpoint.pth.tar')
+    ardae.save_checkpoint(dict(common, cdae='mlp-grad', state_dict=cdae.state_dict(), optimizer=co.state_dict()),
+                          out, filename='cdae-checkpoint.pth.tar')
+    utils, _ = rh.import_reference()
+    rmodel, rcdae = rh.build_reference('mnist', meta['model'], meta['cdae'], seed=99)
+    rmo, rco = rh.build_optimizers(rmodel, rcdae, hp)
+    o = types.SimpleNamespace(path=out)
+    utils.load_checkpoint(rmodel, rmo, o, filename='model-checkpoint.pth.tar', verbose=False)
+    utils.load_checkpoint(rcdae, rco, o, filename='cdae-checkpoint.pth.tar', verbose=False)
+    assert (o.start_epoch, o.start_batch_idx, o.best_val_loss) == (3, 7, 1.5)
+    for k, v in rmodel.state_dict().items():
+        assert np.allclose(v.numpy(), z['s0/m_after/' + k], rtol=1e-6, atol=1e-7), k
+    for k, v in rcdae.state_dict().items():
+        assert np.allclose(v.numpy(), z['s0/c_after/' + k], rtol=1e-6, atol=1e-7), k
+    p0 = next(iter(rmodel.parameters()))
+    assert int(rmo.state[p0]['step']) == 1 and rmo.state[p0]['exp_avg'].abs().sum() > 0
+    q0 = next(iter(rcdae.parameters()))
+    assert rco.state[q0]['square_avg'].abs().sum() > 0 and rco.state[q0]['momentum_buffer'].abs().sum() > 0
