@@ -69,7 +69,7 @@ def synth_batch(gen, p, B, device):
     return torch.bernoulli(p.expand(B, -1), generator=gen).to(device)
 
 
-def cpu_reference_leg(steps, warmup, B_sample=128):
+def cpu_reference_leg(steps, warmup, B_sample=int(os.environ.get('ARDAE_BENCH_CPU_ROWS', '128'))):
     """The reference's CPU path on the host cores, bounded sample of the same workload.
     kind 'reference': the reference's own modules (when its tree is reachable: build container);
     kind 'port': the numpy oracle restatement (GPU box: the Python reference cannot travel)."""
