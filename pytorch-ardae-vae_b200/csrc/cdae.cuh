@@ -93,6 +93,256 @@ struct CdaePlan {
 
   int ntensors() const { return 6 * cfg.L + 2; }
 
+  // 16-bit spill plan (chain16_sm100.cuh + gemm_tn16.cuh): mlp-grad training update whose H -> H layers fit the
+  // fused chain kernel.  ARDAE_SPILL16=0 keeps the fp32-spill plan (A/B measurements, parity triage).
+  bool spill16_plan() const {
+    static int env = -1;
+    if (env < 0) {
+      const char* e = std::getenv("ARDAE_SPILL16");
+      env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const int kp = round_up(cfg.d, 32);
+    return env != 0 && cfg.kind == 0 && cfg.train != 0 && chain_supported(cfg.H, 1) && 2 * cfg.L <= kChainMaxLayers &&
+           kp <= cfg.H / 2 && cfg.H % 64 == 0;
+  }
+
+  // The training update of the mlp-grad CDAE as FOUR chain launches (primal 3xTF32 / score / tangent / adjoint, each
+  // carrying its 128-row tile through all 2L layers incl. the d-wide ends) + 2L bf16 weight-gradient contractions.
+  // Every [N, H] array that crosses HBM is bfloat16; [N, d] arrays (x~, g, r, eps) stay fp32.
+  int build16(float* const* params, float* const* grads) {
+    const int d = cfg.d, c = cfg.c, H = cfg.H, L = cfg.L, B = cfg.B, S = cfg.S;
+    const int N = B * S;
+    const bool dry = ws.dry;
+    auto P = [&](int i) -> float* { return dry ? nullptr : params[i]; };
+    auto G = [&](int i) -> float* { return dry ? nullptr : grads[i]; };
+    auto iC = [&](int l) { return 2 * l; };
+    auto iA = [&](int l) { return 2 * L + 2 * l; };
+    auto iW = [&](int l) { return 4 * L + 2 * l; };
+    const int kp = round_up(d, 32), ny = round_up(d, 64);
+
+    derive = DeriveList();
+    std::vector<W3> Cw(L), Aw(L), Ww(L);
+    for (int l = 0; l < L; ++l) Cw[l] = derive.add(ws, P(iC(l)), H, l == 0 ? c : H, l == 0 ? c : H, true, true);
+    for (int l = 0; l < L; ++l) Aw[l] = derive.add(ws, P(iA(l)), H, l == 0 ? d : H, l == 0 ? d : H, true, true);
+    for (int l = 1; l < L; ++l) Ww[l] = derive.add(ws, P(iW(l)), H, H, H, true, true);
+    const int ld1 = 2 * H + 1;
+    W3 W1u = derive.add(ws, P(iW(0)), H, H, ld1, true, true);
+    W3 W1c = derive.add(ws, P(iW(0)) ? P(iW(0)) + H : nullptr, H, H, ld1, true, true);
+    Ww[0] = W1u;
+    int rc = derive.emit(ws, plan);
+    if (rc) return rc;
+    float* wsig = ws.floats(H);
+    const float* wo = P(iW(L));
+
+    // ---- activations
+    Pair xt = make_pair(ws, N, d), ctxp = make_pair(ws, B, c);
+    Mat rowbias = ws.mat(B, H);
+    Mat gmat(ws.floats(static_cast<size_t>(N) * kp), N, d, kp), rmat(ws.floats(static_cast<size_t>(N) * kp), N, d, kp);
+    Mat16 x16h = ws.mat16(N, ny), x16l = ws.mat16(N, ny), r16h = ws.mat16(N, ny), r16l = ws.mat16(N, ny);
+    float* sig = ws.floats(N);
+    std::vector<Pair> Cc(L);
+    for (int l = 0; l < L; ++l) Cc[l] = make_pair(ws, B, H);
+    std::vector<Mat16> U(L), V(L), DA(L), DP(L), UD(L), VD(L), TA(L), TP(L);
+    for (auto* arr : {&U, &V, &DA, &DP, &UD, &VD, &TA, &TP})
+      for (int l = 0; l < L; ++l) (*arr)[l] = ws.mat16(N, H);
+    Mat gsum = ws.mat(B, H);
+    std::vector<Mat> DC(L);
+    for (int l = 0; l < L; ++l) DC[l] = ws.mat(B, H);
+    if (dry) {
+      tn_need = tn16_workspace_bytes(H, H, N);
+      const size_t b2 = tn16_workspace_bytes(H, d, N);
+      if (b2 > tn_need) tn_need = b2;
+    }
+    const size_t tn_ws_bytes = tn_need;
+    float* tn_ws = ws.floats(tn_ws_bytes / 4);
+    size_t ctx_tn_bytes = tn_workspace_bytes(H, H, B);
+    {
+      const size_t b2 = tn_workspace_bytes(H, c, B);
+      if (b2 > ctx_tn_bytes) ctx_tn_bytes = b2;
+    }
+    float* ctx_tn_ws = ws.floats(ctx_tn_bytes / 4);
+    CdaeBindings* bd = &bind;
+
+    // ---- prologue: sigma copy, x~ = x + sigma*eps (tf32 pair + bf16 pair), context pair, exact w_sigma
+    {
+      const float* w1 = P(iW(0));
+      plan.add([=](cudaStream_t s) {
+        ARDAE_CUDA_OK(cudaMemcpyAsync(sig, bd->sigma, sizeof(float) * N, cudaMemcpyDeviceToDevice, s));
+        if (bd->loss_out) ARDAE_CUDA_OK(cudaMemsetAsync(bd->loss_out, 0, sizeof(float), s));
+        split2d_kernel<<<grid_for(static_cast<size_t>(B) * c), 256, 0, s>>>(
+            bd->ctx, c, ctxp.buf.p, ctxp.buf.ld, B, c, ctxp.kp, 1.0f, 0.0f);
+        copy2d_kernel<<<1, 256, 0, s>>>(w1 + 2 * H, ld1, wsig, 1, H, 1, 1, 1.0f, 0.0f, 0);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    // ---- context branch on the B distinct rows (side lane, underneath the perturbation prologue)
+    plan.fork();
+    for (int l = 0; l < L; ++l) {
+      GemmNTDesc g = nt3_desc(l == 0 ? ctxp : Cc[l - 1], Cw[l], Cc[l], EPI_SOFTPLUS);
+      g.bias = P(iC(l) + 1);
+      plan.nt(g);
+    }
+    {
+      GemmNTDesc g = nt3_desc_plain(Cc[L - 1], W1c, rowbias, EPI_LINEAR);
+      g.bias = P(iW(0) + 1);
+      plan.nt(g);
+    }
+    plan.cur_lane = 0;
+    plan.add([=](cudaStream_t s) {
+      cdae_perturb_kernel<<<grid_for(static_cast<size_t>(N) * d), 256, 0, s>>>(
+          bd->x, sig, bd->eps, xt.buf.p, N, d, xt.buf.ld, xt.kp, bd->gen_eps, bd->seed, replay_counter(), x16h.p, x16l.p,
+          x16h.ld);
+      return static_cast<int>(cudaGetLastError());
+    });
+    plan.join();
+    auto base = [&](int mode) {
+      Chain16Desc cd;
+      cd.mode = mode; cd.M = N; cd.H = H; cd.row_scale = sig;
+      return cd;
+    };
+    // ---- sweep 1: primal forward (3xTF32), all 2L layers
+    {
+      Chain16Desc cd = base(CHAIN_SOFTPLUS3);
+      cd.A0_32 = xt.hi().p; cd.lda0_32 = xt.buf.ld; cd.A0lo = xt.lo().p; cd.lda0lo = xt.buf.ld;
+      auto s3 = [&](const W3& w, const float* bias, const Mat16& out, int kin) {
+        Chain16LayerDesc q;
+        q.W = w.b3.p; q.ldw = w.b3.ld; q.kin = kin; q.bias = bias; q.out = out.p; q.ldo = out.ld;
+        return q;
+      };
+      cd.layers.push_back(s3(Aw[0], P(iA(0) + 1), U[0], kp));
+      for (int l = 1; l < L; ++l) cd.layers.push_back(s3(Aw[l], P(iA(l) + 1), U[l], H));
+      {
+        Chain16LayerDesc q = s3(W1u, nullptr, V[0], H);
+        q.group_bias = rowbias.p; q.group = S; q.ldg = rowbias.ld; q.col_vec = wsig;
+        cd.layers.push_back(q);
+      }
+      for (int l = 1; l < L; ++l) cd.layers.push_back(s3(Ww[l], P(iW(l) + 1), V[l], H));
+      plan.chain16(cd);
+    }
+    // ---- sweep 2: score backward, ending in g = delta a_1 . A_1 (fp32 [N, kp])
+    {
+      const Mat16 vl = V[L - 1], dpl = DP[L - 1];
+      plan.add([=](cudaStream_t s) {
+        cdae_init_delta16_kernel<<<grid_for(static_cast<size_t>(N) * H / 8), 256, 0, s>>>(vl.p, vl.ld, wo, dpl.p, dpl.ld, N, H);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    {
+      Chain16Desc cd = base(CHAIN_MUL_SIG);
+      cd.A0_16 = DP[L - 1].p; cd.lda0_16 = DP[L - 1].ld;
+      auto bw = [&](const Mat& wT, const Mat16& aux1, const Mat16& out) {
+        Chain16LayerDesc q;
+        q.W = wT.p; q.ldw = wT.ld; q.aux1 = aux1.p; q.ld1 = aux1.ld; q.out = out.p; q.ldo = out.ld;
+        return q;
+      };
+      for (int l = L - 1; l >= 1; --l) cd.layers.push_back(bw(Ww[l].T, V[l - 1], DP[l - 1]));
+      cd.layers.push_back(bw(W1u.T, U[L - 1], DA[L - 1]));
+      for (int l = L - 1; l >= 1; --l) cd.layers.push_back(bw(Aw[l].T, U[l - 1], DA[l - 1]));
+      {
+        Chain16LayerDesc q;
+        q.W = Aw[0].T.p; q.ldw = Aw[0].T.ld; q.nout = kp; q.w_rows = d; q.out32 = gmat.p; q.ld_out32 = gmat.ld;
+        cd.layers.push_back(q);
+      }
+      plan.chain16(cd);
+    }
+    // ---- loss + residual direction r (fp32 + bf16 pair)
+    plan.add([=](cudaStream_t s) {
+      cdae_loss_kernel<<<grid_for(static_cast<size_t>(N) * gmat.ld), 256, 0, s>>>(
+          gmat.p, gmat.ld, sig, bd->eps, rmat.p, N, d, bd->inv_count, bd->loss_out, bd->score_out, r16h.p, r16l.p, r16h.ld);
+      return static_cast<int>(cudaGetLastError());
+    });
+    // ---- sweep 3: tangent forward from r (also emits t = delta * tangent_pre * (1 - sig))
+    {
+      Chain16Desc cd = base(CHAIN_TANGENT);
+      cd.A0_32 = rmat.p; cd.lda0_32 = rmat.ld;
+      auto tg = [&](const Mat& w, int kin, const Mat16& aux1, const Mat16& aux2, const Mat16& out, const Mat16& out2) {
+        Chain16LayerDesc q;
+        q.W = w.p; q.ldw = w.ld; q.kin = kin; q.aux1 = aux1.p; q.ld1 = aux1.ld; q.aux2 = aux2.p; q.ld2 = aux2.ld;
+        q.out = out.p; q.ldo = out.ld; q.out2 = out2.p; q.ldo2 = out2.ld;
+        return q;
+      };
+      cd.layers.push_back(tg(Aw[0].hi(), kp, U[0], DA[0], UD[0], TA[0]));
+      for (int l = 1; l < L; ++l) cd.layers.push_back(tg(Aw[l].hi(), H, U[l], DA[l], UD[l], TA[l]));
+      for (int l = 0; l < L; ++l) cd.layers.push_back(tg(Ww[l].hi(), H, V[l], DP[l], VD[l], TP[l]));
+      cd.layers.back().colsum = G(iW(L)); cd.layers.back().colsum_scale = -1.0f;  // d w_o = -sum_n vdot_L
+      cd.layers.back().colsum2 = G(iW(L - 1) + 1);                                // d beta_L = sum_n adj p_L (= t_L)
+      plan.chain16(cd);
+    }
+    // ---- sweep 4: adjoint backward (in place over the t buffers)
+    {
+      Chain16Desc cd = base(CHAIN_ADJOINT);
+      cd.A0_16 = TP[L - 1].p; cd.lda0_16 = TP[L - 1].ld;
+      auto adj = [&](const Mat& wT, const Mat16& aux1, const Mat16& t, float* colsum) {
+        Chain16LayerDesc q;
+        q.W = wT.p; q.ldw = wT.ld; q.aux1 = aux1.p; q.ld1 = aux1.ld; q.aux2 = t.p; q.ld2 = t.ld;
+        q.out = t.p; q.ldo = t.ld; q.colsum = colsum;
+        return q;
+      };
+      for (int l = L - 1; l >= 1; --l) {
+        Chain16LayerDesc q = adj(Ww[l].T, V[l - 1], TP[l - 1], G(iW(l - 1) + 1));
+        if (l - 1 == 0) {  // d w_1sigma = sum_n sigma_n * adj p_1
+          q.colsum_w = G(iW(0)) ? G(iW(0)) + 2 * H : nullptr;
+          q.colsum_w_stride = ld1;
+        }
+        cd.layers.push_back(q);
+      }
+      cd.layers.push_back(adj(W1u.T, U[L - 1], TA[L - 1], G(iA(L - 1) + 1)));
+      for (int l = L - 1; l >= 1; --l) cd.layers.push_back(adj(Aw[l].T, U[l - 1], TA[l - 1], G(iA(l - 1) + 1)));
+      plan.chain16(cd);
+    }
+    // ---- context branch backward (B rows, fp32 / tf32) on the side lane underneath the weight-gradient contractions
+    plan.fork();
+    {
+      const Mat16 ap1 = TP[0];
+      plan.add([=](cudaStream_t s) {
+        group_sum16_kernel<<<B, 256, 0, s>>>(ap1.p, ap1.ld, gsum.p, gsum.ld, B, S, H, 1);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    auto ctx_tn = [&](const Mat& X0, const Mat& Y0, float* dst, int ldo) {
+      GemmTNDesc t;
+      t.X0 = X0.p; t.ldx0 = X0.ld; t.Y0 = Y0.p; t.ldy0 = Y0.ld;
+      t.M = X0.cols; t.N = Y0.cols; t.K = X0.rows; t.out = dst; t.ldo = ldo;
+      t.scale = 1.0f; t.beta = 1.0f;
+      t.workspace = ctx_tn_ws; t.workspace_bytes = ctx_tn_bytes;
+      plan.tn(t);
+    };
+    ctx_tn(gsum, Cc[L - 1].hi(), G(iW(0)) ? G(iW(0)) + H : nullptr, ld1);
+    {
+      GemmNTDesc g = nt_desc(gsum, W1c.T, DC[L - 1], EPI_MUL_SIG);
+      set_aux1(g, Cc[L - 1].hi());
+      g.colsum = G(iC(L - 1) + 1);
+      plan.nt(g);
+    }
+    for (int l = L - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(DC[l], Cw[l].T, DC[l - 1], EPI_MUL_SIG);
+      set_aux1(g, Cc[l - 1].hi());
+      g.colsum = G(iC(l - 1) + 1);
+      plan.nt(g);
+    }
+    for (int l = L - 1; l >= 1; --l) ctx_tn(DC[l], Cc[l - 1].hi(), G(iC(l)), H);
+    ctx_tn(DC[0], ctxp.hi(), G(iC(0)), c);
+    plan.cur_lane = 0;
+    // ---- weight gradients: dW = adj^T . act + delta^T . tangent   (accumulated into .grad)
+    auto tn16 = [&](std::initializer_list<std::pair<Mat16, Mat16>> pairs, int Mo, int No, int Ny, float* dst, int ldo) {
+      GemmTN16Desc t;
+      for (const auto& pr : pairs) {
+        t.X[t.npairs] = pr.first.p; t.ldx[t.npairs] = pr.first.ld;
+        t.Y[t.npairs] = pr.second.p; t.ldy[t.npairs] = pr.second.ld;
+        ++t.npairs;
+      }
+      t.M = Mo; t.N = No; t.Ny = Ny; t.K = N; t.out = dst; t.ldo = ldo;
+      t.workspace = tn_ws; t.workspace_bytes = tn_ws_bytes;
+      plan.tn16(t);
+    };
+    tn16({{TP[0], U[L - 1]}, {DP[0], UD[L - 1]}}, H, H, H, G(iW(0)), ld1);
+    for (int l = L - 1; l >= 1; --l) tn16({{TP[l], V[l - 1]}, {DP[l], VD[l - 1]}}, H, H, H, G(iW(l)), H);
+    for (int l = L - 1; l >= 1; --l) tn16({{TA[l], U[l - 1]}, {DA[l], UD[l - 1]}}, H, H, H, G(iA(l)), H);
+    tn16({{TA[0], x16h}, {TA[0], x16l}, {DA[0], r16h}, {DA[0], r16l}}, H, d, ny, G(iA(0)), d);
+    plan.join();
+    return plan.error;
+  }
+
   // returns 0 or error; when ws.dry only measures
   int build(float* const* params, float* const* grads) {
     const int d = cfg.d, c = cfg.c, H = cfg.H, L = cfg.L, B = cfg.B, S = cfg.S;
@@ -101,6 +351,7 @@ struct CdaePlan {
       return fail(-2, "cdae: bad config (need d,c,H,B,S > 0 and num_hidden_layers >= 2)");
     if (H % 4 != 0) return fail(-2, "cdae: h_dim must be a multiple of 4");
     plan.dry = ws.dry;
+    if (spill16_plan()) return build16(params, grads);
     const bool dry = ws.dry;
     const bool train = cfg.train != 0;
     auto P = [&](int i) -> float* { return dry ? nullptr : params[i]; };

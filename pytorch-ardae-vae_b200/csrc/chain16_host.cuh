@@ -1,0 +1,174 @@
+// Host-side preparation (TMA tensor maps) and launch of the 16-bit-spill layer-chain kernel (chain16_sm100.cuh).
+#pragma once
+#include <vector>
+
+#include "chain16_sm100.cuh"
+#include "chain_host.cuh"
+
+namespace ardae {
+
+// 2-D bf16 tensor map.  inner = contiguous dimension (elements); pitch in elements.
+inline int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+                               uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer,
+                               CUtensorMapSwizzle swizzle) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return fail(-10, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
+  if ((pitch_elems * 2) % 16 != 0) return fail(-12, "TMA row pitch not a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (bf16) failed (%d): inner=%llu outer=%llu pitch=%llu box=%ux%u",
+             static_cast<int>(r), (unsigned long long)inner, (unsigned long long)outer,
+             (unsigned long long)pitch_elems, box_inner, box_outer);
+    return fail(-13, buf);
+  }
+  return 0;
+}
+
+// A bf16 [rows, cols] row-major array (pitch in elements).
+struct Mat16 {
+  uint16_t* p = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+  Mat16() {}
+  Mat16(uint16_t* p_, int r, int c, int l) : p(p_), rows(r), cols(c), ld(l) {}
+};
+
+struct Chain16LayerDesc {
+  const float* W = nullptr; int ldw = 0;  // fp32 B operand [nout, kin] K-major (SOFTPLUS3: [H, 3*kin] = [Whi | Whi | Wlo])
+  int kin = 0;                            // 0 = H
+  int nout = 0;                           // 0 = H; < H: narrow linear last layer writing fp32 rows to out32
+  int w_rows = 0;                         // rows of W that exist in memory (0 = nout); missing rows read as zero
+  const uint16_t* aux1 = nullptr; int ld1 = 0;
+  const uint16_t* aux2 = nullptr; int ld2 = 0;
+  uint16_t* out = nullptr; int ldo = 0;
+  uint16_t* out2 = nullptr; int ldo2 = 0;
+  float* out32 = nullptr; int ld_out32 = 0;
+  const float* bias = nullptr;
+  const float* group_bias = nullptr; int group = 1, ldg = 0;
+  const float* col_vec = nullptr;
+  float* colsum = nullptr; float colsum_scale = 1.0f;
+  float* colsum2 = nullptr;
+  float* colsum_w = nullptr; int colsum_w_stride = 1;
+};
+
+struct Chain16Desc {
+  int mode = CHAIN_MUL_SIG;
+  int M = 0, H = 0;
+  // initial activation: either bf16 [M, H] (A0_16) or fp32 [M, kin0] (A0_32; SOFTPLUS3: hi part, with A0lo)
+  const uint16_t* A0_16 = nullptr; int lda0_16 = 0;
+  const float* A0_32 = nullptr; int lda0_32 = 0;
+  const float* A0lo = nullptr; int lda0lo = 0;
+  const float* row_scale = nullptr;
+  std::vector<Chain16LayerDesc> layers;
+};
+
+struct PreparedChain16 {
+  Chain16Params params;
+  const void* fn = nullptr;
+  dim3 grid;
+  int smem = 0, threads = 0;
+};
+
+inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
+  const int nl = static_cast<int>(d.layers.size());
+  if (d.M <= 0 || !chain_supported(d.H, nl)) return fail(-2, "chain16: unsupported shape");
+  if (d.mode < 0 || d.mode >= CHAIN_NUM_MODES) return fail(-2, "chain16: bad mode");
+  const bool s3 = d.mode == CHAIN_SOFTPLUS3;
+  const bool aux2 = d.mode == CHAIN_TANGENT || d.mode == CHAIN_ADJOINT, out2 = d.mode == CHAIN_TANGENT;
+  const int H = d.H;
+  PreparedChain16 pr;
+  std::memset(&pr.params, 0, sizeof(pr.params));
+  Chain16Params& p = pr.params;
+  int rc;
+  const int kin0 = d.layers[0].kin > 0 ? d.layers[0].kin : H;
+  if (kin0 % 32 != 0 || kin0 > H) return fail(-2, "chain16: first-layer input width must be a multiple of 32, <= H");
+  uintptr_t align_or = 0;
+  if (s3) {
+    if (!d.A0_32 || !d.A0lo) return fail(-2, "chain16: SOFTPLUS3 needs the fp32 (hi, lo) initial activation");
+    if ((rc = encode_tmap_2d(&p.tmA0, d.A0_32, kin0, d.M, d.lda0_32, 32, kBlockM))) return rc;
+    p.a0_f32 = d.A0lo; p.a0_ld = d.lda0lo; p.a0_mode = 0;
+    align_or |= reinterpret_cast<uintptr_t>(d.A0lo) | (static_cast<uintptr_t>(d.lda0lo) * 4);
+  } else if (d.A0_16) {
+    if (kin0 != H) return fail(-2, "chain16: a bf16 initial activation must be H wide");
+    if ((rc = encode_tmap_2d_bf16(&p.tmA0, d.A0_16, H, d.M, d.lda0_16, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    p.a0_mode = 1;
+  } else {
+    if (!d.A0_32) return fail(-2, "chain16: missing initial activation");
+    p.a0_f32 = d.A0_32; p.a0_ld = d.lda0_32; p.a0_mode = 0;
+    if ((reinterpret_cast<uintptr_t>(d.A0_32) & 15) != 0 || d.lda0_32 % 4 != 0)
+      return fail(-2, "chain16: fp32 initial activation must be 16-byte aligned");
+  }
+  p.row_scale = d.row_scale;
+  p.M = d.M; p.H = H; p.nlayers = nl;
+  for (int l = 0; l < nl; ++l) {
+    const Chain16LayerDesc& s = d.layers[l];
+    Chain16LayerParams& q = p.layer[l];
+    const int kin = s.kin > 0 ? s.kin : H, nout = s.nout > 0 ? s.nout : H;
+    if (l > 0 && kin != H) return fail(-2, "chain16: only the first layer may be narrower than H on input");
+    if (nout != H && (l != nl - 1 || s3 || nout % 32 != 0 || nout > H / 2 || d.mode != CHAIN_MUL_SIG || !s.out32))
+      return fail(-2, "chain16: only the last MUL_SIG layer may be narrow (multiple of 32, <= H/2, fp32 out32)");
+    const bool narrow = nout != H;
+    if (!s.W || (!narrow && !s3 && (!s.aux1 || !s.out)) || (!narrow && aux2 && !s.aux2) || (out2 && !s.out2) ||
+        (s3 && !s.out))
+      return fail(-2, "chain16: missing operand pointer");
+    if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * kin : kin, s.w_rows > 0 ? s.w_rows : nout, s.ldw, kBlockK,
+                             narrow ? nout : H / 2)))
+      return rc;
+    if (!narrow && !s3) {
+      if ((rc = encode_tmap_2d_bf16(&q.tmAux1, s.aux1, H, d.M, s.ld1, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+      if (aux2 && (rc = encode_tmap_2d_bf16(&q.tmAux2, s.aux2, H, d.M, s.ld2, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+      if ((rc = encode_tmap_2d_bf16(&q.tmOut, s.out, H, d.M, s.ldo, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+      if (out2 && (rc = encode_tmap_2d_bf16(&q.tmOut2, s.out2, H, d.M, s.ldo2, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    }
+    if (s3) {
+      q.out16 = s.out; q.ld_out16 = s.ldo;
+      if ((reinterpret_cast<uintptr_t>(s.out) & 15) != 0 || (s.ldo * 2) % 16 != 0)
+        return fail(-2, "chain16: SOFTPLUS3 spill rows must be 16-byte aligned");
+    }
+    q.out32 = s.out32; q.ld_out32 = s.ld_out32;
+    if (narrow && ((reinterpret_cast<uintptr_t>(s.out32) & 15) != 0 || s.ld_out32 % 4 != 0 || s.ld_out32 < nout))
+      return fail(-2, "chain16: narrow-layer output rows must be 16-byte aligned and nout wide");
+    q.kin = kin; q.nout = nout;
+    q.bias = s.bias; q.group_bias = s.group_bias; q.col_vec = s.col_vec;
+    q.group = s.group > 0 ? s.group : 1; q.ldg = s.ldg;
+    q.colsum = s.colsum; q.colsum_scale = s.colsum_scale; q.colsum2 = s.colsum2;
+    q.colsum_w = s.colsum_w; q.colsum_w_stride = s.colsum_w_stride;
+    if ((s.col_vec || s.colsum_w) && !d.row_scale) return fail(-2, "chain16: col_vec / colsum_w need row_scale");
+    align_or |= reinterpret_cast<uintptr_t>(s.bias) | reinterpret_cast<uintptr_t>(s.group_bias) |
+                reinterpret_cast<uintptr_t>(s.col_vec) | (static_cast<uintptr_t>(s.ldg) * 4);
+  }
+  p.vec_ok = (align_or & 15) == 0 ? 1 : 0;
+  if (s3 && !p.vec_ok) return fail(-2, "chain16: SOFTPLUS3 operands must be 16-byte aligned");
+#define ARDAE_CHAIN16_CASE(MODE_)                                                                               \
+  case MODE_:                                                                                                   \
+    pr.fn = reinterpret_cast<const void*>(&chain16_kernel<MODE_>);                                              \
+    pr.smem = Chain16Config<MODE_>::kSmemBytes; pr.threads = Chain16Config<MODE_>::kThreads;                   \
+    break;
+  switch (d.mode) {
+    ARDAE_CHAIN16_CASE(CHAIN_MUL_SIG)
+    ARDAE_CHAIN16_CASE(CHAIN_TANGENT)
+    ARDAE_CHAIN16_CASE(CHAIN_ADJOINT)
+    default:
+    ARDAE_CHAIN16_CASE(CHAIN_SOFTPLUS3)
+  }
+#undef ARDAE_CHAIN16_CASE
+  pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
+  ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
+  *out = pr;
+  return 0;
+}
+
+inline int launch_prepared_chain16(const PreparedChain16& pr, cudaStream_t stream) {
+  void* args[1] = {const_cast<Chain16Params*>(&pr.params)};
+  ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(pr.threads), args, pr.smem, stream));
+  return 0;
+}
+
+}  // namespace ardae

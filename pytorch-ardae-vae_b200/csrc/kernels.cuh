@@ -33,6 +33,13 @@ __device__ __forceinline__ float block_sum(float v) {
   return v;
 }
 
+// bfloat16 <-> fp32 (round to nearest even; finite inputs)
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return static_cast<uint16_t>((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+__device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(static_cast<uint32_t>(h) << 16); }
+
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
 // Replay counter: a CUDA-graph-captured step re-launches the same kernel arguments on every replay, so anything that
 // must change per step (Philox seeds, Adam's bias-correction step) is offset by a device-resident counter that a tiny
@@ -225,7 +232,8 @@ __global__ void act_split_kernel(const float* __restrict__ src, int ld, float* _
 __global__ void cdae_perturb_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                     float* __restrict__ eps, float* __restrict__ xt, int N, int d,
                                     int ldx, int kp, int gen_eps, uint64_t seed,
-                                    const replay_ctr_t* __restrict__ ctr) {
+                                    const replay_ctr_t* __restrict__ ctr, uint16_t* __restrict__ x16h = nullptr,
+                                    uint16_t* __restrict__ x16l = nullptr, int ld16 = 0) {
   seed = replay_seed(seed, ctr);
   const size_t total = static_cast<size_t>(N) * d;
   for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < total;
@@ -248,6 +256,50 @@ __global__ void cdae_perturb_kernel(const float* __restrict__ x, const float* __
     const float hi = ptx::round_tf32(v);
     xt[static_cast<size_t>(n) * ldx + j] = hi;
     xt[static_cast<size_t>(n) * ldx + kp + j] = ptx::round_tf32(v - hi);
+    if (x16h != nullptr) {  // bf16 (hi, lo) pair of x~: the Y operand of the first-layer weight-gradient contraction
+      const uint16_t h16 = f32_to_bf16_rn(v);
+      x16h[static_cast<size_t>(n) * ld16 + j] = h16;
+      x16l[static_cast<size_t>(n) * ld16 + j] = f32_to_bf16_rn(v - bf16_to_f32(h16));
+    }
+  }
+}
+
+// bf16 variant of cdae_init_delta_kernel (16-bit spill plans): 8 elements per thread; H % 8 == 0
+__global__ void cdae_init_delta16_kernel(const uint16_t* __restrict__ vL, int ld, const float* __restrict__ wo,
+                                         uint16_t* __restrict__ dp, int ld_dp, int N, int H) {
+  const int H8 = H >> 3;
+  const size_t total = static_cast<size_t>(N) * H8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / H8), j = static_cast<int>(i - static_cast<size_t>(n) * H8) * 8;
+    const uint4 u4 = *reinterpret_cast<const uint4*>(vL + static_cast<size_t>(n) * ld + j);
+    const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float u = __uint_as_float(e ? (uw[k] & 0xFFFF0000u) : (uw[k] << 16));
+        const float ex = __expf(-u);
+        const float s = (u < 0.01f) ? u * (1.0f - u * (0.5f - u * (1.0f / 6.0f))) : 1.0f - ex;
+        o[e] = -__ldg(wo + j + 2 * k + e) * s;
+      }
+      ow[k] = static_cast<uint32_t>(f32_to_bf16_rn(o[0])) | (static_cast<uint32_t>(f32_to_bf16_rn(o[1])) << 16);
+    }
+    *reinterpret_cast<uint4*>(dp + static_cast<size_t>(n) * ld_dp + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
+// out[b, c] = sum_{k<S} in[(b*S+k), c]  with a bf16 input array
+__global__ void group_sum16_kernel(const uint16_t* __restrict__ in, int in_ld, float* __restrict__ out, int out_ld,
+                                   int B, int S, int cols, int round) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float acc = 0.0f;
+    const uint16_t* p = in + static_cast<size_t>(b) * S * in_ld + c;
+    for (int k = 0; k < S; ++k) acc += bf16_to_f32(p[static_cast<size_t>(k) * in_ld]);
+    out[static_cast<size_t>(b) * out_ld + c] = round ? ptx::round_tf32(acc) : acc;
   }
 }
 
@@ -279,7 +331,8 @@ __global__ void cdae_init_delta_kernel(const float* __restrict__ vL, int ld,
 __global__ void cdae_loss_kernel(const float* __restrict__ g, int ld, const float* __restrict__ sigma,
                                  const float* __restrict__ eps, float* __restrict__ r, int N, int d,
                                  float inv_count, float* __restrict__ loss_out,
-                                 float* __restrict__ score_out) {
+                                 float* __restrict__ score_out, uint16_t* __restrict__ r16h = nullptr,
+                                 uint16_t* __restrict__ r16l = nullptr, int ld16 = 0) {
   float acc = 0.0f;
   const size_t total = static_cast<size_t>(N) * ld;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -293,6 +346,11 @@ __global__ void cdae_loss_kernel(const float* __restrict__ g, int ld, const floa
       acc += res * res;
       rv = ptx::round_tf32(2.0f * inv_count * s * res);
       if (score_out) score_out[static_cast<size_t>(n) * d + j] = gv;
+      if (r16h != nullptr) {
+        const uint16_t h16 = f32_to_bf16_rn(rv);
+        r16h[static_cast<size_t>(n) * ld16 + j] = h16;
+        r16l[static_cast<size_t>(n) * ld16 + j] = f32_to_bf16_rn(rv - bf16_to_f32(h16));
+      }
     }
     if (r) r[i] = rv;
   }

@@ -5,8 +5,10 @@
 #include <memory>
 #include <vector>
 
+#include "chain16_host.cuh"
 #include "chain_host.cuh"
 #include "gemm_host.cuh"
+#include "gemm_tn16.cuh"
 
 namespace ardae {
 
@@ -34,6 +36,10 @@ struct Workspace {
                    : reinterpret_cast<float*>(base + off);
     off += n * sizeof(float);
     return p;
+  }
+  // bf16 [rows, cols], dense rows (cols % 8 == 0: 16-byte row pitch for TMA)
+  Mat16 mat16(int rows, int cols) {
+    return Mat16(reinterpret_cast<uint16_t*>(floats((static_cast<size_t>(rows) * cols + 1) / 2)), rows, cols, cols);
   }
   // [rows, cols] with a pitch that satisfies TMA (multiple of 4 floats)
   Mat mat(int rows, int cols) {
@@ -122,6 +128,29 @@ struct Plan {
     lanes.push_back(cur_lane);
     static const char* names[CHAIN_NUM_MODES] = {"chain_mul_sig", "chain_tangent", "chain_adjoint", "chain_softplus3"};
     tag_last(names[d.mode]);
+  }
+  void chain16(const Chain16Desc& d) {
+    ++num_chain;
+    if (dry) return;
+    PreparedChain16 pr;
+    int rc = prepare_chain16(d, &pr);
+    if (rc) return fail_with(rc);
+    auto sp = std::make_shared<PreparedChain16>(pr);
+    ops.push_back([sp](cudaStream_t s) { return launch_prepared_chain16(*sp, s); });
+    lanes.push_back(cur_lane);
+    static const char* names[CHAIN_NUM_MODES] = {"chain_mul_sig", "chain_tangent", "chain_adjoint", "chain_softplus3"};
+    tag_last(names[d.mode]);
+  }
+  void tn16(const GemmTN16Desc& d) {
+    ++num_gemm_tn;
+    if (dry) return;
+    PreparedTN16 pr;
+    int rc = prepare_gemm_tn16(d, &pr);
+    if (rc) return fail_with(rc);
+    auto sp = std::make_shared<PreparedTN16>(pr);
+    ops.push_back([sp](cudaStream_t s) { return launch_prepared_tn16(*sp, s); });
+    lanes.push_back(cur_lane);
+    tag_last("gemm_tn16");
   }
   void tn(const GemmTNDesc& d) {
     ++num_gemm_tn;
