@@ -25,8 +25,18 @@ CFG = dict(  # BASELINE.json configs[1]; hyper-parameters from run_vae_dbmnist.s
     kind='mnist', D=784, n=100, h=300, z=32, model_layers=2, nonlin='softplus',
     cdae_h=256, cdae_L=5, B=512, nz=256, nstd=1, nz_model=1, std_scale=10000., delta=0.1, beta=1.0,
     m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5)
-WORKLOAD = ('configs[1]: dbMNIST-shape ivae_ardae, MNISTIPVAE mlp-concat D=784 h=300 n=100 z=32 + mlp-grad CDAE '
-            'h=256 L=5, batch 512 per GPU, train-nz-cdae 256, Adam(model)+RMSprop(cdae)')
+WORKLOAD = 'configs[1] dbMNIST ivae_ardae MLP z=32 + mlp-grad CDAE nz 256, batch 512 per GPU'  # (< 120 chars)
+WORKLOAD_DETAIL = ('MNISTIPVAE mlp-concat D=784 h=300 n=100 z=32 (2 hidden layers, softplus) + MLPGradCARDAE h=256 L=5, '
+                   'train-nz-cdae 256, nstd 1, std-scale 1e4, delta 0.1, Adam(model, b1 0.5) + RMSprop(cdae, momentum 0.5), '
+                   'lr 1e-4 (run_vae_dbmnist.sh:37)')
+CFG1 = dict(  # BASELINE.json configs[0]: 25gaussians README command (run_vae_25gaussians.sh)
+    kind='toy', D=2, n=10, h=256, z=2, model_layers=2, nonlin='relu',
+    cdae_h=256, cdae_L=3, B=512, nz=256, nstd=1, nz_model=1, std_scale=10000., delta=0.1, beta=1.0,
+    m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5)
+CFG4 = dict(  # BASELINE.json configs[3]: dbMNIST conv implicit encoder / decoder (run_vae_dbmnist.sh:31), 8192 / 8 GPUs
+    kind='conv', D=784, n=100, h=800, z=32, model_layers=0, nonlin='softplus',
+    cdae_h=256, cdae_L=5, B=1024, nz=256, nstd=1, nz_model=1, std_scale=10000., delta=0.1, beta=1.0,
+    m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5)
 
 
 def cdae_alg_flops(B, nz, d, c, H, L):
@@ -35,6 +45,18 @@ def cdae_alg_flops(B, nz, d, c, H, L):
     G = (2 * L - 1) * H * H + d * H + H
     ctx = c * H + (L - 1) * H * H + H * H
     return 6 * 2 * N * G + 3 * 2 * B * ctx
+
+
+def step_alg_flops(c, B):
+    """SURVEY 8d whole-step figure: CDAE update + N-row encoder sampling (as executed) + model update."""
+    cd = cdae_alg_flops(B, c['nz'] * c['nstd'], c['z'], c['z'], c['cdae_h'], c['cdae_L'])
+    if c['kind'] == 'mnist':
+        enc = 2 * B * c['nz'] * ((c['h'] + c['n']) * c['h'] + c['h'] * c['z'])
+        mod = 3 * 2 * B * (c['D'] * c['h'] + 3 * c['h'] * c['h'] + (c['h'] + c['n']) * c['h'] + c['h'] * c['z']
+                           + c['z'] * c['h'] + 2 * c['h'] * c['h'] + c['h'] * c['D'])
+    else:
+        enc, mod = 0, 0
+    return cd + enc + mod
 
 
 class ClockSampler(threading.Thread):
@@ -157,15 +179,209 @@ def run_reference(args):
     cores = str(os.cpu_count() or 1)
     for k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
         os.environ[k] = cores
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    # every step is a bounded sample (128 of the 512 data rows): ~3 s of host work, so the driver's own --steps /
+    # --warmup are honoured as given (25 steps ~ 1.5 minutes)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     cb, sec = cpu_reference_leg(steps, warmup)
     line = dict(metric='train_samples_per_sec', value=cb['value'], unit='samples/s', impl='reference',
                 n_gpus=args.gpus, steps=steps, warmup=warmup, ms_per_step=sec * 1e3, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload=WORKLOAD, note='CPU, bounded sample: ' + cb['sample']),
+                config=dict(workload=WORKLOAD, detail=WORKLOAD_DETAIL, note='CPU, bounded sample: ' + cb['sample']),
                 cpu_baseline=cb,
                 e2e=dict(value=cb['value'], unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def build_models(c, dev, cdae_kind='grad'):
+    import ardae
+    if c['kind'] == 'toy':
+        model = ardae.ToyIPVAE(input_dim=c['D'], noise_dim=c['n'], h_dim=c['h'], num_hidden_layers=c['model_layers'],
+                               nonlinearity=c['nonlin'], enc_type='concat', z_dim=c['z']).to(dev)
+    elif c['kind'] == 'conv':
+        model = ardae.ConvIPVAE(input_height=28, input_channels=1, z_dim=c['z'], noise_dim=c['n'],
+                                nonlinearity=c['nonlin']).to(dev)
+    else:
+        model = ardae.MNISTIPVAE(input_dim=c['D'], noise_dim=c['n'], h_dim=c['h'], num_hidden_layers=c['model_layers'],
+                                 nonlinearity=c['nonlin'], enc_type='concat', z_dim=c['z']).to(dev)
+    cdae_cls = ardae.MLPGradCARDAE if cdae_kind == 'grad' else ardae.MLPResCARDAE
+    cdae = cdae_cls(input_dim=c['z'], context_dim=c['z'], std=1., h_dim=c['cdae_h'],
+                    num_hidden_layers=c['cdae_L'], nonlinearity='softplus').to(dev)
+    mopt = ardae.Adam(model.parameters(), lr=c['m_lr'], betas=(c['m_beta1'], 0.999))
+    copt = ardae.RMSprop(cdae.parameters(), lr=c['d_lr'], momentum=c['d_momentum'])
+    return model, cdae, mopt, copt
+
+
+class Harness(object):
+    """One training configuration on this rank: models, fused step, synthetic resident / pinned minibatches."""
+
+    def __init__(self, c, B, dev, world, rank, graph=True, cdae_kind='grad', nb=8):
+        import torch
+        import torch.distributed as dist
+        import ardae
+        self.c, self.B, self.dev, self.world, self.rank = c, B, dev, world, rank
+        torch.manual_seed(1234)  # same weights on every rank (TrainStep also broadcasts rank 0's replica)
+        self.model, self.cdae, self.mopt, self.copt = build_models(c, dev, cdae_kind)
+        self.step = ardae.TrainStep(self.model, self.cdae, self.mopt, self.copt, std_scale=c['std_scale'],
+                                    delta=c['delta'], nz_cdae=c['nz'], nstd=c['nstd'], nz_model=c['nz_model'],
+                                    process_group=dist.group.WORLD if world > 1 else None, seed=1234, graph=graph)
+        gen = torch.Generator().manual_seed(999 + rank)
+        if c['kind'] == 'toy':   # 25-Gaussians mixture, generated on the device (ardae.toy_exp4)
+            data, _ = ardae.toy_exp4(num_data=50000, seed=1 + rank, device=dev)
+            idx = [torch.randint(0, data.size(0), (B,), generator=gen) for _ in range(2 * nb)]
+            self.host = [(data[idx[2 * i].to(dev)].cpu().pin_memory(), data[idx[2 * i + 1].to(dev)].cpu().pin_memory())
+                         for i in range(nb)]
+        else:                    # dbMNIST-shape: x ~ Bernoulli(p), fixed per-pixel p (mean ink fraction ~0.13)
+            pix = torch.rand(1, c['D'], generator=torch.Generator().manual_seed(5)) * 0.26
+            self.host = [(torch.bernoulli(pix.expand(B, -1), generator=gen).pin_memory(),
+                          torch.bernoulli(pix.expand(B, -1), generator=gen).pin_memory()) for _ in range(nb)]
+        self.resident = [(a.to(dev), b.to(dev)) for a, b in self.host]
+        self.nb = nb
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def time_resident(self, W, K):
+        """K iterations on device-resident minibatches (CUDA-graph replays once captured); ms total, max over ranks."""
+        import torch
+        c = self.c
+        for i in range(max(W, 4)):  # >= 2 eager iterations + capture + 1 replay
+            self.step(*self.resident[i % self.nb], beta=c['beta'])
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for i in range(K):
+            out = self.step(*self.resident[i % self.nb], beta=c['beta'])
+        e1.record()
+        self.barrier()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        return ms, {k: float(out[k].item()) for k in ('cdae_loss', 'model_loss')}
+
+    def time_e2e(self, K):
+        """The same iterations fed from pinned host memory: H2D of both minibatches and a D2H read of the losses every
+        step, synchronised every step (the caller reads the losses)."""
+        import torch
+        c = self.c
+        xbuf = [torch.empty_like(self.resident[0][0]) for _ in range(2)]
+        hloss = torch.empty(4, pin_memory=True)
+        for i in range(2):
+            self.step(*self.resident[i % self.nb], beta=c['beta'])
+        self.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(K):
+            xbuf[0].copy_(self.host[i % self.nb][0], non_blocking=True)
+            xbuf[1].copy_(self.host[i % self.nb][1], non_blocking=True)
+            o = self.step(xbuf[0], xbuf[1], beta=c['beta'])
+            hloss.copy_(torch.cat([o['cdae_loss'], o['model_loss'], o['recon'], o['prior']]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        f1.record()
+        self.barrier()
+        h2d = 2 * self.resident[0][0].numel() * 4
+        return self.max_over_ranks(f0.elapsed_time(f1)), h2d
+
+    def close(self):
+        import gc
+        import torch
+        self.step = self.model = self.cdae = self.mopt = self.copt = None
+        self.resident = self.host = None
+        gc.collect()
+        torch.cuda.empty_cache()
+
+
+def sub_record(c, B, dev, world, rank, W, K, label, with_e2e=True):
+    """A secondary configuration measured the same way as the headline (device-resident value + e2e)."""
+    h = Harness(c, B, dev, world, rank)
+    ms, losses = h.time_resident(W, K)
+    rec = dict(workload=label, per_gpu_batch=B, global_batch=B * world, steps=K, warmup=max(W, 4),
+               value=B * world * K / (ms * 1e-3), unit='samples/s', ms_per_step=ms / K, final_losses=losses,
+               graph=bool(h.step._g is not None), gpu_launches_per_step=h.step.count_launches(B))
+    if with_e2e:
+        e2e_ms, h2d = h.time_e2e(K)
+        rec['e2e'] = dict(value=B * world * K / (e2e_ms * 1e-3), unit='samples/s', ms_per_step=e2e_ms / K,
+                          h2d_bytes_per_step=h2d, d2h_bytes_per_step=16)
+    h.close()
+    return rec
+
+
+def iws_record(dev, world, rank, n_images=10000, S=5000):
+    """BASELINE.json configs[4]: IWS log-likelihood, 5000 importance samples x 10k synthetic MNIST-shape images, images
+    sharded by rank (ardae.evaluate_iws allreduces the partial sums); images/s over the whole job."""
+    import torch
+    import torch.distributed as dist
+    import ardae
+    c = CFG
+    torch.manual_seed(1234)
+    model = ardae.MNISTIPVAE(input_dim=c['D'], noise_dim=c['n'], h_dim=c['h'], num_hidden_layers=c['model_layers'],
+                             nonlinearity=c['nonlin'], z_dim=c['z']).to(dev)
+    with torch.no_grad():
+        model.encode.fc.fc.weight.mul_(0.05)  # a posterior of trained-model width (the N(0,1) init gives |z| ~ 20)
+    per = n_images // world
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    x = (torch.rand(per, c['D'], device=dev, generator=g) < 0.13).float()
+    pg = dist.group.WORLD if world > 1 else None
+    ardae.evaluate_iws(x[:256], model, S, process_group=pg)  # warm-up: plans
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    v = ardae.evaluate_iws(x, model, S, process_group=pg)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    dec_macs = c['z'] * c['h'] + 2 * c['h'] * c['h'] + c['h'] * c['D']
+    enc_macs = c['n'] * c['h'] + c['h'] * c['z']
+    rows = per * world * S
+    del model, x
+    torch.cuda.empty_cache()
+    return dict(workload='configs[4] IWS 5000 importance samples x 10k synthetic MNIST-shape images, sharded by rank',
+                metric='iws_images_per_sec', value=per * world / ms * 1e3, unit='images/s', images=per * world,
+                images_per_gpu=per, iws_samples=S, ms=ms, logprob_nats=float(v.item()),
+                algorithmic_tflops=2.0 * rows * (dec_macs + enc_macs) / ms * 1e-9,
+                note='algorithmic FLOPs: decoder + noise half of the encoder fc on every (image, sample) row (SURVEY 8d)')
+
+
+def measure_tf32_peak(dev, index):
+    """tf32 tensor peak the way MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3, best of 10, CUDA events, with the
+    SM clock sampled around the probe (MEASURED_PEAKS.json itself holds bf16 only)."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device=dev)
+    b = torch.randn(8192, 8192, device=dev)
+    sampler = ClockSampler(index)
+    sampler.start()
+    for _ in range(3):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(10):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(); a @ b; g1.record(); torch.cuda.synchronize()
+        best = min(best, g0.elapsed_time(g1))
+    t_end = time.time() + 0.5   # a few more back-to-back products so the 0.1 s sampler sees the probe under load
+    while time.time() < t_end:
+        a @ b
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    del a, b
+    return 2 * 8192 ** 3 / best * 1e-9, sampler.summary()
 
 
 def main():
@@ -176,6 +392,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (no CUDA-graph replay of the step)')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary records (strong scaling, configs 1 / 4 / 5)')
     ap.add_argument('--cdae', default='grad', choices=['grad', 'res'],
                     help="grad = mlp-grad (BASELINE.json's config, default); res = mlp-res residual CDAE (extra measurement)")
     args = ap.parse_args()
@@ -199,53 +416,16 @@ def main():
     dev = torch.device('cuda', local)
     c = CFG
     W, K = max(3, args.warmup), max(1, args.steps)
-
-    torch.manual_seed(1234)  # same weights on every rank (replicated parameters)
-    model = ardae.MNISTIPVAE(input_dim=c['D'], noise_dim=c['n'], h_dim=c['h'], num_hidden_layers=c['model_layers'],
-                             nonlinearity=c['nonlin'], enc_type='concat', z_dim=c['z']).to(dev)
-    cdae_cls = ardae.MLPGradCARDAE if args.cdae == 'grad' else ardae.MLPResCARDAE
-    cdae = cdae_cls(input_dim=c['z'], context_dim=c['z'], std=1., h_dim=c['cdae_h'],
-                    num_hidden_layers=c['cdae_L'], nonlinearity='softplus').to(dev)
-    mopt = ardae.Adam(model.parameters(), lr=c['m_lr'], betas=(c['m_beta1'], 0.999))
-    copt = ardae.RMSprop(cdae.parameters(), lr=c['d_lr'], momentum=c['d_momentum'])
-    step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=c['std_scale'], delta=c['delta'], nz_cdae=c['nz'],
-                           nstd=c['nstd'], nz_model=c['nz_model'],
-                           process_group=dist.group.WORLD if world > 1 else None, seed=1234,
-                           graph=not args.no_graph)
     B = c['B']
-    gen = torch.Generator().manual_seed(999 + rank)
-    pix = torch.rand(1, c['D'], generator=torch.Generator().manual_seed(5)) * 0.26  # mean ink fraction ~0.13
-    nb = 8
-    host = [(torch.bernoulli(pix.expand(B, -1), generator=gen).pin_memory(),
-             torch.bernoulli(pix.expand(B, -1), generator=gen).pin_memory()) for _ in range(nb)]
-    resident = [(a.to(dev), b.to(dev)) for a, b in host]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput (`value`): K iterations (CUDA-graph replays unless --no-graph)
-    for i in range(max(W, 4)):  # >= 2 eager iterations + capture + 1 replay
-        step(*resident[i % nb], beta=c['beta'])
-    barrier()
+    # ================= headline: configs[1], 512 rows per GPU (weak scaling across --gpus)
+    h = Harness(c, B, dev, world, rank, graph=not args.no_graph, cdae_kind=args.cdae)
+    step, model, cdae = h.step, h.model, h.cdae
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(K):
-        out = step(*resident[i % nb], beta=c['beta'])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_total, final_losses = h.time_resident(W, K)
     graph_used = bool(step.graph and step._g is not None)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
-    final_losses = {k: float(out[k].item()) for k in ('cdae_loss', 'model_loss')}
 
     # ---------------- profiled pass (eager launches: events cannot sit between the nodes of a graph replay):
     # K more iterations of the same workload with CUDA events around every segment, and around every launch of the
@@ -254,14 +434,14 @@ def main():
     h_train = cdae._plan(B, c['nz'] * c['nstd'], True)
     step.profile = []
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    h.barrier()
     p0.record()
     for i in range(K):
         if i == K - 1:
             _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 1))
-        step(*resident[i % nb], beta=c['beta'])
+        step(*h.resident[i % h.nb], beta=c['beta'])
     p1.record()
-    barrier()
+    h.barrier()
     eager_ms = p0.elapsed_time(p1) / K
     kernel_ms = _lib.read_cdae_profile(h_train)  # per-launch times of the last profiled iteration
     _lib.check(_lib.lib().ardae_cdae_set_profile(h_train, 0))
@@ -272,26 +452,60 @@ def main():
     seg_ms = {k: sum(v) / K for k, v in seg.items()}
 
     # ---------------- end-to-end: pinned host inputs -> H2D every step, losses D2H every step
-    xbuf = [torch.empty(B, c['D'], device=dev) for _ in range(2)]
-    hloss = torch.empty(4, pin_memory=True)
-    for i in range(2):
-        step(*resident[i % nb], beta=c['beta'])
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(K):
-        xbuf[0].copy_(host[i % nb][0], non_blocking=True)
-        xbuf[1].copy_(host[i % nb][1], non_blocking=True)
-        o = step(xbuf[0], xbuf[1], beta=c['beta'])
-        hloss.copy_(torch.cat([o['cdae_loss'], o['model_loss'], o['recon'], o['prior']]), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the losses every step
-    f1.record()
-    barrier()
+    e2e_ms, h2d_bytes = h.time_e2e(K)
     sampler.stop_flag = True  # clocks / throttle reasons sampled across both timed regions (value and e2e)
-    t2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_ms = t2.item()
+    launches_per_step = step.count_launches(B)
+    n_cdae = sum(p.numel() for p in cdae.parameters())
+    opt_bytes_c = 28.0 * cdae._arena.total
+
+    # ---------------- optimizer kernels on an HBM-resident arena (the 26 MB arenas of the step are
+    # L2-resident and launch-bound; the same kernels over 256 M parameters = 7.2 GB show their HBM rate)
+    opt_big = None
+    if rank == 0:
+        import ctypes
+        nbig = 256 * 1024 * 1024
+        bufs = [torch.zeros(nbig, device=dev) for _ in range(4)]
+        bufs[1].fill_(1e-3)
+        L = _lib.lib()
+        opt_big = {}
+        for name in ('adam', 'rmsprop'):
+            def call():
+                if name == 'adam':
+                    _lib.check(L.ardae_adam_step(_lib.ptr(bufs[0]), _lib.ptr(bufs[1]), _lib.ptr(bufs[2]), _lib.ptr(bufs[3]),
+                                                 ctypes.c_size_t(nbig), 1e-4, 0.5, 0.999, 1e-8, 1, 1.0, _lib.stream_ptr()))
+                else:
+                    _lib.check(L.ardae_rmsprop_step(_lib.ptr(bufs[0]), _lib.ptr(bufs[1]), _lib.ptr(bufs[2]), _lib.ptr(bufs[3]),
+                                                    ctypes.c_size_t(nbig), 1e-4, 0.99, 1e-8, 0.5, 1.0, _lib.stream_ptr()))
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(5):
+                call()
+            g1.record()
+            torch.cuda.synchronize()
+            opt_big[name] = g0.elapsed_time(g1) / 5
+        del bufs
+        torch.cuda.empty_cache()
+    h.close()
+    del step, model, cdae
+
+    # ================= secondary records (every rank takes part; rank 0 reports)
+    extra = {}
+    if not args.no_extra and args.cdae == 'grad':
+        Ks, Ws = max(5, min(K, 10)), 3
+        # configs[2]: sbMNIST-shape, GLOBAL batch 4096 fixed, split over the ranks (strong scaling)
+        if 4096 % world == 0:
+            extra['strong_scaling'] = sub_record(c, 4096 // world, dev, world, rank, Ws, Ks,
+                                                 'configs[2] sbMNIST-shape MLP z=32, global batch 4096 fixed (per GPU 4096 / n_gpus)',
+                                                 with_e2e=False)
+            extra['strong_scaling']['scaling'] = 'strong'
+        extra['config1_25gaussians'] = sub_record(CFG1, CFG1['B'], dev, world, rank, Ws, Ks,
+                                                  'configs[0] 25gaussians ToyIPVAE z=2 h=256 relu + mlp-grad CDAE h=256 L=3, batch 512 per GPU, nz 256')
+        extra['config4_conv'] = sub_record(CFG4, CFG4['B'], dev, world, rank, Ws, Ks,
+                                           'configs[3] dbMNIST ConvIPVAE 28x28 z=32 + mlp-grad CDAE h=256 L=5, 1024 rows per GPU (8192 over 8), nz 256')
+        extra['config5_iws'] = iws_record(dev, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -305,19 +519,11 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    hbm_src = 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
-    torch.backends.cuda.matmul.allow_tf32 = True
-    a = torch.randn(8192, 8192, device=dev)
-    b = torch.randn(8192, 8192, device=dev)
-    for _ in range(2):
-        a @ b
-    best = 1e9
-    for _ in range(5):
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(); a @ b; g1.record(); torch.cuda.synchronize()
-        best = min(best, g0.elapsed_time(g1))
-    tf32_peak = 2 * 8192 ** 3 / best * 1e-9  # TFLOP/s
-    del a, b
+    hbm_src = 'MEASURED_PEAKS.json (hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    tf32_peak, tf32_clocks = measure_tf32_peak(dev, local)
+    bf16_peak = float(peaks.get('bf16_tflops', 2 * tf32_peak))
+    tf32_src = ('torch.matmul tf32 8192^3, best of 10, measured in this run with its own clock record '
+                '(MEASURED_PEAKS.json holds bf16 only: %s burst; half of it = %.0f)' % (peaks.get('bf16_tflops'), bf16_peak / 2))
 
     flops = cdae_alg_flops(B, c['nz'] * c['nstd'], c['z'], c['z'], c['cdae_h'], c['cdae_L'])
     ct = seg_ms['cdae_train']
@@ -327,80 +533,103 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
     except Exception:
         pass
-    # ---- per-kernel rooflines of the CDAE update (CUDA events around each launch, last timed step)
-    N_, H_, L_ = B * c['nz'] * c['nstd'], c['cdae_h'], c['cdae_L']
-    arr = N_ * H_ * 4.0  # one [N, H] fp32 activation array
+    # ---- per-kernel view of the CDAE update (CUDA events around each launch of the last profiled step).
+    # FLOPs are algorithmic.  The [N, H] activation arrays a kernel streams are SPILL: by SURVEY 8d they are
+    # overhead, not algorithmic bytes -- reported as overhead_bytes with the HBM rate they are moved at.
+    N_, H_, L_, d_ = B * c['nz'] * c['nstd'], c['cdae_h'], c['cdae_L'], c['z']
+    kp = (d_ + 31) // 32 * 32
+    spill16 = args.cdae == 'grad'
+    arr = N_ * H_ * (2.0 if spill16 else 4.0)  # one [N, H] spill array (bf16 in the mlp-grad plan)
+    nl = 2 * L_ - 1
+    sweep_flops = 2.0 * N_ * (nl * H_ * H_ + kp * H_)
     by_tag = {}
     for tag, t_ms in kernel_ms:
         by_tag.setdefault(tag, []).append(t_ms)
-    nlay = 2 * L_ - 1  # fused H->H layers per sweep
-    # algorithmic HBM bytes per launch: aux reads + spill writes per fused layer, + the initial activation
-    nbatch = 2 * (L_ - 1)  # [H,H] weight-gradient contractions batched into one launch (grid.z = layer)
-    alg_bytes = {'chain_mul_sig': (2 * nlay + 1) * arr, 'chain_tangent': (4 * nlay + 1) * arr,
-                 'chain_adjoint': (3 * nlay + 1) * arr, 'gemm_tn': 4 * arr,
-                 'gemm_tn_batch': nbatch * (4 if args.cdae == 'grad' else 2) * arr}
+    info = {
+        'chain_softplus3': dict(flops=sweep_flops, overhead=(nl + 1) * arr, executed=3.0,
+                                note='primal forward, all 2L layers, 3xTF32 (three tensor products per algorithmic product)'),
+        'chain_mul_sig': dict(flops=sweep_flops, overhead=(2 * nl + 1) * arr, executed=1.0, note='score backward incl. g = delta a_1 . A_1'),
+        'chain_tangent': dict(flops=sweep_flops, overhead=4 * (nl + 1) * arr, executed=1.0, note='tangent forward (+ t spill)'),
+        'chain_adjoint': dict(flops=2.0 * N_ * nl * H_ * H_, overhead=(3 * nl + 1) * arr, executed=1.0, note='adjoint backward, in place over t'),
+        'gemm_tn16': dict(flops=2 * 2.0 * N_ * H_ * H_, overhead=4 * arr, executed=1.0, peak=bf16_peak,
+                          note='weight gradient of one [H,H] layer: two bf16 contractions over the N rows'),
+        'gemm_tn': dict(flops=2 * 2.0 * N_ * H_ * H_, overhead=4 * arr, executed=1.0, note='weight gradient (fp32 spill plans)'),
+    }
     kernels = []
-    for tag in ('chain_tangent', 'chain_adjoint', 'chain_mul_sig', 'gemm_tn_batch', 'gemm_tn'):
-        ts = sorted(t for t in by_tag.get(tag, []) if t > 0.02)  # the big (N-row) launches only
+    for tag in ('chain_softplus3', 'chain_tangent', 'chain_adjoint', 'chain_mul_sig', 'gemm_tn16', 'gemm_tn'):
+        ts = sorted(t for t in by_tag.get(tag, []) if t > 0.02)  # the N-row launches only
         if not ts:
             continue
         med = ts[len(ts) // 2]
-        ts = [t for t in ts if 0.8 * med <= t <= 1.25 * med]  # gemm_tn: the 2L-1 [H,H] contractions (not d-wide / two-pass ones)
+        ts = [t for t in ts if 0.7 * med <= t <= 1.4 * med]  # the [H,H] contractions (not the d-wide / odd-pitch ones)
         avg = sum(ts) / len(ts)
-        a = alg_bytes[tag] / avg * 1e-6
-        kernels.append(dict(kernel=tag, bound='hbm', launches=len(ts), ms_per_launch=avg, achieved=a, peak=hbm_peak,
-                            unit='GB/s', frac=a / hbm_peak, algorithmic_bytes_per_launch=alg_bytes[tag],
-                            traffic=(traffic.get(tag) if tag != 'gemm_tn_batch' else
-                                     (traffic.get('gemm_tn') * nbatch if traffic.get('gemm_tn') else None))))
-    ts3 = [t for t in by_tag.get('chain_softplus3', []) if t > 0.02]
-    if ts3:
-        # the two 3xTF32 chains together run nlay layers: algorithmic 2*N*H*H per layer (executed: 3x)
-        tot = sum(ts3)
-        a = 2.0 * N_ * H_ * H_ * nlay / tot * 1e-9
-        kernels.append(dict(kernel='chain_softplus3', bound='tensor', launches=len(ts3), ms_per_launch=tot / len(ts3),
-                            achieved=a, peak=tf32_peak, unit='TFLOP/s', frac=a / tf32_peak, executed_tflops=3 * a,
-                            executed_frac=3 * a / tf32_peak,
-                            note='3xTF32: three tensor-core products per algorithmic product (fp32-accurate forward)',
-                            traffic=traffic.get('chain_softplus3')))
-    dominant = max(kernels, key=lambda k: k['ms_per_launch'] * k['launches']) if kernels else None
-    n_cdae = sum(p.numel() for p in cdae.parameters())
-    n_model = sum(p.numel() for p in model.parameters())
-    opt_bytes_c, opt_bytes_m = 28.0 * cdae._arena.total, 28.0 * model._arena.total
-    roof_opt = dict(bound='hbm', kernel='rmsprop_kernel (flat CDAE arena, %d params)' % n_cdae,
-                    achieved=opt_bytes_c / seg_ms['cdae_opt'] * 1e-6, peak=hbm_peak, unit='GB/s',
-                    frac=opt_bytes_c / seg_ms['cdae_opt'] * 1e-6 / hbm_peak, peak_source=hbm_src,
-                    note='28 B/param; 26 MB arena is L2-resident and launch-latency bound (SURVEY 7.2-8)')
+        i = info[tag]
+        pk = i.get('peak', tf32_peak)
+        tfl = i['flops'] / avg * 1e-9
+        gbs = i['overhead'] / avg * 1e-6
+        kernels.append(dict(kernel=tag, launches=len(ts), ms_per_launch=avg, algorithmic_flops_per_launch=i['flops'],
+                            achieved=tfl, unit='TFLOP/s', peak=pk, frac=tfl / pk, executed_frac=i['executed'] * tfl / pk,
+                            algorithmic_bytes_per_launch=0.0, overhead_bytes_per_launch=i['overhead'],
+                            overhead_gbs=gbs, overhead_hbm_frac=gbs / hbm_peak,
+                            bound=('tensor' if i['executed'] * tfl / pk >= gbs / hbm_peak else 'hbm (activation spill: overhead bytes)'),
+                            traffic=traffic.get(tag), note=i['note']))
+    plan_overhead = sum(k['overhead_bytes_per_launch'] * k['launches'] for k in kernels)
+    plan_traffic = None
+    if traffic.get('cdae_train_total'):
+        plan_traffic = traffic['cdae_train_total']
+    step_flops = step_alg_flops(c, B)
+    ms_step = ms_total / K
     line = dict(
         metric='train_samples_per_sec', value=B * world * K / (ms_total * 1e-3), unit='samples/s', n_gpus=world,
-        steps=K, warmup=W, ms_per_step=ms_total / K, higher_is_better=True, scaling='weak', vs_baseline=None,
+        steps=K, warmup=W, ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='tf32', data='synthetic',
-        config=dict(workload=WORKLOAD if args.cdae == 'grad' else WORKLOAD.replace('mlp-grad', 'mlp-res (residual, NOT the BASELINE config)'),
+        config=dict(workload=WORKLOAD if args.cdae == 'grad' else 'configs[1] shapes with --cdae mlp-res (NOT the BASELINE config)',
+                    detail=WORKLOAD_DETAIL,
                     global_batch=B * world, per_gpu_batch=B, cdae_rows_per_gpu=B * c['nz'],
-                    parallelism='dp%d' % world, arithmetic='tf32 tensor-core operands, fp32 accumulate; forward sweeps 3xTF32',
-                    l2='no flush needed: per-step working set (activation spill) ~7 GB >> 126 MB L2',
-                    launch=(('one CUDA-graph replay per step (%d kernels on 3 streams captured)' % step.count_launches(B)
+                    parallelism='dp%d' % world,
+                    arithmetic='tf32 tensor-core operands, fp32 accumulate; primal forward 3xTF32; [N,H] activation spill stored bf16; weight gradients bf16 x bf16 -> fp32',
+                    l2='no flush needed: per-step working set (activation spill) ~3 GB >> 126 MB L2',
+                    launch=(('one CUDA-graph replay per step (%d kernels on 3 streams captured)' % launches_per_step
                              if world == 1 else
-                             '3 CUDA-graph replays + 2 eager NCCL allreduces per step (%d kernels captured)' % step.count_launches(B))
+                             '3 CUDA-graph replays + 2 eager NCCL allreduces per step (%d kernels captured)' % launches_per_step)
                             if graph_used else 'eager launches'),
                     ms_per_step_eager_profiled=eager_ms,
                     noise='in-kernel Philox', final_losses=final_losses),
         clocks=sampler.summary(),
         e2e=dict(value=B * world * K / (e2e_ms * 1e-3), unit='samples/s', ms_per_step=e2e_ms / K,
-                 h2d_bytes_per_step=2 * B * c['D'] * 4, d2h_bytes_per_step=16),
-        gpu_launches=step.count_launches(B) * K,
+                 h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=16),
+        gpu_launches=launches_per_step * K,
         segments_ms=dict({k: round(v, 4) for k, v in seg_ms.items()},
                          note='eager profiled pass (CUDA events per segment); the timed region replays one graph'),
-        roofline=(dict(dominant, peak_source=(hbm_src + ' (hbm_gbs)' if dominant['bound'] == 'hbm' else
-                                              'torch.matmul tf32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only)'),
-                       note='dominant kernel of the step by total time; every kernel of the CDAE update is in roofline_kernels')
-                  if dominant else None),
+        # the north-star figure: algorithmic FLOPs of the dominant piece of the step, the CDAE update
+        # (4 chain launches + 2L weight-gradient contractions + prologue / loss / context branch), over its duration
+        roofline=dict(bound='tensor', kernel='cdae_train (whole CDAE update: 4 fused chain launches + %d weight-gradient contractions)' % (2 * L_),
+                      achieved=achieved, peak=tf32_peak, unit='TFLOP/s', frac=achieved / tf32_peak,
+                      frac_vs_half_bf16_burst=achieved / (bf16_peak / 2),
+                      algorithmic_flops_per_launch=flops, ms_per_launch=ct, peak_source=tf32_src, peak_probe_clocks=tf32_clocks,
+                      traffic=plan_traffic,
+                      note='SURVEY 8d: 6 x 2 x N x G algorithmic FLOPs; executed tensor work is higher (3xTF32 primal sweep)'),
+        roofline_step=dict(bound='tensor', kernel='whole training step', achieved=step_flops / ms_step * 1e-9, peak=tf32_peak,
+                           unit='TFLOP/s', frac=step_flops / ms_step * 1e-9 / tf32_peak, algorithmic_flops_per_step=step_flops),
         roofline_kernels=kernels,
-        roofline_plan=dict(bound='tensor', kernel='whole cdae_train plan (4 fused chains + %d weight-gradient contractions + first/last layers)' % (2 * c['cdae_L']),
-                           achieved=achieved, peak=tf32_peak, unit='TFLOP/s', frac=achieved / tf32_peak,
-                           peak_source='torch.matmul tf32 8192^3 measured in this run (MEASURED_PEAKS.json holds bf16 only: %s burst)' % peaks.get('bf16_tflops'),
-                           algorithmic_flops_per_launch=flops, ms_per_launch=ct,
-                           note='the plan is HBM-bound by its activation spill (see roofline_kernels); this is the north-star tensor figure'),
-        roofline_hbm=roof_opt)
+        roofline_spill=dict(bound='hbm', kernel='activation spill of the CDAE update (bf16 [N,H] arrays between the sweeps)',
+                            algorithmic_bytes=0.0, overhead_bytes=plan_overhead,
+                            achieved=plan_overhead / ct * 1e-6, peak=hbm_peak, unit='GB/s',
+                            frac=plan_overhead / ct * 1e-6 / hbm_peak, peak_source=hbm_src,
+                            note='by SURVEY 8d per-row activation I/O is overhead, not algorithmic bytes; listed so the remaining gap is visible'),
+        roofline_hbm=dict(bound='hbm', kernel='rmsprop_kernel (flat CDAE arena, %d params)' % n_cdae,
+                          achieved=opt_bytes_c / seg_ms['cdae_opt'] * 1e-6, peak=hbm_peak, unit='GB/s',
+                          frac=opt_bytes_c / seg_ms['cdae_opt'] * 1e-6 / hbm_peak, peak_source=hbm_src,
+                          algorithmic_bytes_per_launch=opt_bytes_c,
+                          note='28 B/param; the 26 MB arena of the step is L2-resident and launch-latency bound (SURVEY 7.2-8)',
+                          hbm_resident_arena=(dict(params=256 * 1024 * 1024, bytes=28.0 * 256 * 1024 * 1024,
+                                                   adam_ms=opt_big['adam'], rmsprop_ms=opt_big['rmsprop'],
+                                                   adam_gbs=28.0 * 256 * 1024 * 1024 / opt_big['adam'] * 1e-6,
+                                                   rmsprop_gbs=28.0 * 256 * 1024 * 1024 / opt_big['rmsprop'] * 1e-6,
+                                                   adam_frac=28.0 * 256 * 1024 * 1024 / opt_big['adam'] * 1e-6 / hbm_peak,
+                                                   rmsprop_frac=28.0 * 256 * 1024 * 1024 / opt_big['rmsprop'] * 1e-6 / hbm_peak)
+                                              if opt_big else None)))
+    line.update(extra)
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_reference_leg(steps=3, warmup=1)  # ~10 s of host work: 4 iterations on 128 of the 512 data rows
         line['cpu_baseline'] = cb

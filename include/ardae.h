@@ -112,7 +112,8 @@ typedef struct {
   int n_inp, n_fc, n_dec; /* linears in inp_encode; hidden layers of encode.fc; linears in decode.main */
   int act;                /* 0 relu, 1 softplus */
   int batch, nz;          /* B data rows, nz noise samples per row: R = B*nz rows, row index b*nz+k */
-  int mode;               /* 0: encode only; 1: forward + backward; 2: IWS log-likelihood */
+  int mode;               /* 0: encode only; 1: forward + backward; 2: IWS log-likelihood;
+                           * 3 / 4 / 5: decode(z) / encode._forward_inp(x) / encode._forward_all(inp, nos) (nz = 1) */
   int img_h, img_c;       /* kind 2 (ConvIPVAE): image height (= width) and channels; input_dim = img_c*img_h^2 */
 } ardae_model_config;
 
@@ -137,6 +138,23 @@ ARDAE_API int ardae_model_encode_with_mean(ardae_model_t h, const float* x, cons
  * head-major [nH][R][D] = logits (mnist) or mu, logvar (toy).  Keeps the tape for backward. */
 ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* noise, float beta, float inv_rows,
                                   float* z_out, float* sums, float* heads_out, void* stream);
+
+/* Sub-module calls of the reference API (SURVEY 8b "must expose"), each on its own plan (nz = 1, batch = rows):
+ *   mode 3  Decoder.forward(z) minus the sampler (ivae/toy.py:725-737, ivae/mnist.py:188-199, vae/conv.py:118-136):
+ *           z [rows, z_dim] -> heads_out, head-major [n_heads][rows][input_dim] (toy: mu, logvar; mnist / conv: logit)
+ *   mode 4  Encoder._forward_inp(x) (ivae/mnist.py:76-86; conv: the flattened conv3 features, ivae/conv.py:84-96):
+ *           x [rows, input_dim] -> inp_out [rows, feat]
+ *   mode 5  ConcatEncoder._forward_all(inp, nos) (ivae/mnist.py:161-165, ivae/toy.py:192-194, ivae/conv.py:107-115):
+ *           inp [rows, feat], nos [rows, noise_dim] (NULL = zeros) -> z_out [rows, z_dim] */
+ARDAE_API int ardae_model_decode(ardae_model_t h, const float* z, float* heads_out, void* stream);
+ARDAE_API int ardae_model_forward_inp(ardae_model_t h, const float* x, float* inp_out, void* stream);
+ARDAE_API int ardae_model_forward_all(ardae_model_t h, const float* inp, const float* noise, float* z_out, void* stream);
+
+/* beta annealing (utils/msc.py:53-55 annealing_func, `--beta-annealing` of ivae_ardae.py:101) under CUDA-graph
+ * replay: when `beta_device` is non-NULL every later forward / backward launch of this handle reads beta from that
+ * device scalar at kernel time -- the float `beta` argument of ardae_model_forward is ignored and the `gz_scale` of
+ * the backward calls must then EXCLUDE beta (the kernels multiply it in).  NULL restores the by-value behaviour. */
+ARDAE_API int ardae_model_set_beta_device(ardae_model_t h, const float* beta_device);
 
 /* Replaces model_loss.backward() and (S*(z - zbar)).backward(grad) (ivae_ardae.py:804,834) in one
  * pass: accumulates d(loss_scale*loss)/dtheta plus the pull-back of gz_scale*gz (an upstream
@@ -191,7 +209,9 @@ ARDAE_API int ardae_bernoulli(const float* probs, float* out, size_t n, uint64_t
 
 /* CUDA-graph support (no reference counterpart: the reference launches eagerly).  While a device counter is set,
  * every launch issued by this library bakes the POINTER into its arguments: Philox seeds become
- * seed + counter * golden-ratio and Adam's bias-correction step becomes step + counter, so a captured step draws fresh
+ * seed + counter * 64 * golden-ratio (the host numbers its draws base + (64 * iteration + k) * golden-ratio, k < 64, so
+ * replayed and eager iterations never share a seed) and Adam's bias-correction step becomes step + counter, so a
+ * captured step draws fresh
  * noise and advances Adam on every replay.  Set it before capturing, reset it to NULL afterwards (captured launches
  * keep the pointer; eager calls then run with offset 0); ardae_bump_replay_counter is the last launch of the graph. */
 ARDAE_API int ardae_set_replay_counter(const unsigned long long* device_counter);

@@ -55,6 +55,14 @@ CASES = {
                        cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=3, nonlinearity='softplus'),
                        B=4, hp=dict(std_scale=10000., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
                                     m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
+    # config 4's model at its real geometry: ConvIPVAE 28x28, z = 32, noise 100 (run_vae_dbmnist.sh:31), two full steps.
+    # `sampled`: tensors with more than 16384 elements are stored (gradients, post-step weights) at 8192 fixed random
+    # positions ('sample_idx/<name>'); the initial weights are stored in full as float32
+    'conv28': dict(kind='conv', lite=True, sampled=True, steps=2,
+                   model=dict(input_height=28, input_channels=1, z_dim=32, noise_dim=100, nonlinearity='softplus'),
+                   cdae=dict(input_dim=32, context_dim=32, h_dim=16, num_hidden_layers=3, nonlinearity='softplus'),
+                   B=4, hp=dict(std_scale=10000., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
+                                m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
 }
 
 
@@ -87,11 +95,21 @@ def make_case(name, c):
     f32 = (lambda a: a.astype(np.float32)) if lite else (lambda a: a)
     nz, nstd, nzm = hp['nz_cdae'], hp['nstd'], hp['nz_model']
     arrays = {}
+    sampled = c.get('sampled', False)
+    nsteps = c.get('steps', 1 if lite else 2)
+    if sampled:
+        rs = np.random.RandomState(zlib.crc32(name.encode()) % (2 ** 31))
+        for k, v in model.state_dict().items():
+            if v.numel() > 16384:
+                arrays['sample_idx/' + k] = np.sort(rs.choice(v.numel(), 8192, replace=False)).astype(np.int64)
+
+    def pick(k, a):  # the stored view of a model tensor: sampled positions for big tensors
+        return a.ravel()[arrays['sample_idx/' + k]] if ('sample_idx/' + k) in arrays else a
     for k, v in model.state_dict().items():
         arrays['m0/' + k] = f32(v.numpy().copy())
     for k, v in cdae.state_dict().items():
         arrays['c0/' + k] = f32(v.numpy().copy())
-    for step in range(1 if lite else 2):
+    for step in range(nsteps):
         if c['kind'] in ('mnist', 'conv'):
             xc = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
             xm = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
@@ -114,7 +132,7 @@ def make_case(name, c):
             if v is not None:
                 arrays[p + 'cdae_grads/' + k] = v
         for k, v in t2n(out['model_grads']).items():
-            arrays[p + 'model_grads/' + k] = f32(v)
+            arrays[p + 'model_grads/' + k] = pick(k, v) if sampled else f32(v)
         if name == 'mnist_small' and step == 0:
             # a REAL reference checkpoint pair after the first iteration, written by the reference's own
             # utils.save_checkpoint with the dict layout of ivae_ardae.py:1116-1137 (checkpoint-interchange test:
@@ -129,6 +147,11 @@ def make_case(name, c):
                                   o, is_best=False, filename='model-checkpoint.pth.tar')
             utils.save_checkpoint(dict(common, cdae='mlp-grad', state_dict=cdae.state_dict(), optimizer=copt.state_dict()),
                                   o, is_best=False, filename='cdae-checkpoint.pth.tar')
+        if sampled:
+            for k, v in model.state_dict().items():
+                arrays[p + 'm_after/' + k] = pick(k, v.numpy().copy())
+            for k, v in cdae.state_dict().items():
+                arrays[p + 'c_after/' + k] = v.numpy().copy()
         if not lite:
             for k, v in model.state_dict().items():
                 arrays[p + 'm_after/' + k] = v.numpy().copy()
@@ -139,7 +162,7 @@ def make_case(name, c):
     else:
         assert all(v is not None for v in out['cdae_grads'].values())  # residual CDAE: plain back-prop
     # IWS (evaluate_iws) on the stepped weights
-    b, S = 3, 16
+    b, S = 3, max(16, 2 * d)
     if lite:  # IWS on the INITIAL weights (the stepped ones are not stored)
         with torch.no_grad():
             model.load_state_dict({k: torch.from_numpy(arrays['m0/' + k]).double() for k in model.state_dict()})
@@ -152,12 +175,13 @@ def make_case(name, c):
     arrays['iws/x'], arrays['iws/enc_noise'], arrays['iws/eta'] = xe.numpy(), enc_noise.numpy(), eta.numpy()
     arrays['iws/logprob'] = rh.ref_iws(model, xe, enc_noise, eta).numpy()
     meta = dict(kind=c['kind'], model=c['model'], cdae=c['cdae'], B=B, hp=hp, wscale=c['wscale'], iws=dict(b=b, S=S),
-                cdae_kind=c.get('cdae_kind', 'grad'), ctx_type=c.get('ctx_type', 'lt0'))
+                cdae_kind=c.get('cdae_kind', 'grad'), ctx_type=c.get('ctx_type', 'lt0'), steps=nsteps, sampled=sampled,
+                lite=lite)
     arrays['meta'] = np.array(json.dumps(meta))
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + '.npz')
     np.savez_compressed(path, **arrays)
-    last = 's0/' if lite else 's1/'
+    last = 's%d/' % (nsteps - 1)
     print('%s: %d arrays, %.1f KB, cdae_loss=%.6g model_loss=%.6g iws=%.6g' % (
         name, len(arrays), os.path.getsize(path) / 1024., float(arrays[last + 'cdae_loss']),
         float(arrays[last + 'model_loss']), float(arrays['iws/logprob'])))

@@ -52,6 +52,10 @@ def _declare(lib):
     lib.ardae_model_encode_with_mean.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ardae_model_forward.argtypes = [vp, vp, vp, f, f, vp, vp, vp, vp]
     lib.ardae_model_backward.argtypes = [vp, f, vp, f, vp]
+    lib.ardae_model_set_beta_device.argtypes = [vp, vp]
+    lib.ardae_model_decode.argtypes = [vp, vp, vp, vp]
+    lib.ardae_model_forward_inp.argtypes = [vp, vp, vp, vp]
+    lib.ardae_model_forward_all.argtypes = [vp, vp, vp, vp, vp]
     lib.ardae_model_backward_decoder.argtypes = [vp, f, vp]
     lib.ardae_model_backward_encoder.argtypes = [vp, f, vp, f, vp]
     lib.ardae_model_iws.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp]

@@ -124,8 +124,19 @@ class ConcatEncoder(nn.Module):
         return owner._encode(x, noise, nz)
 
     def _forward_inp(self, x):
-        raise NotImplementedError('the B200 path evaluates inp_encode inside the fused encode plan; '
-                                  'use model.encode / model.logprob')
+        """ivae/mnist.py:76-86 / ivae/toy.py:67-75: features of the data rows, [B, h_dim]."""
+        return self._owner()._forward_inp(x)
+
+    def _forward_nos(self, batch_size=None, noise=None, std=None, device=None):
+        """ivae/mnist.py:88-97: nos_encode is the identity for enc_type 'concat'."""
+        assert batch_size is not None or noise is not None
+        if noise is None:
+            noise = self.sample_noise(batch_size, std=std, device=device)
+        return noise
+
+    def _forward_all(self, inp, nos):
+        """ivae/mnist.py:161-165 / ivae/toy.py:192-194: z = fc([inp, nos]) on already expanded rows."""
+        return self._owner()._forward_all(inp, nos)
 
 
 class Decoder(nn.Module):
@@ -143,8 +154,15 @@ class Decoder(nn.Module):
             self.main = MLP(z_dim, h_dim, h_dim, nonlinearity, num_hidden_layers, True)
             self.reparam = BernoulliDistributionLinear(h_dim, input_dim)
 
+    def sample(self, *heads):
+        if self.kind == 'toy':
+            return self.reparam.sample_gaussian(*heads)
+        return self.reparam.sample_logistic_sigmoid(*heads)
+
     def forward(self, z):
-        raise NotImplementedError('the decoder runs inside model.forward / model.logprob on the B200 path')
+        """ivae/toy.py:725-737 -> (x, mu, logvar); ivae/mnist.py:188-199 -> (x, logit)."""
+        heads = self._owner()._decode_heads(z)
+        return (self.sample(*heads),) + tuple(heads)
 
 
 class _ForwardFn(torch.autograd.Function):
@@ -203,6 +221,7 @@ class ImplicitPosteriorVAE(nn.Module):
                 self.encode.reset_parameters()
             self._n_inp, self._n_fc, self._n_dec = num_hidden_layers + 2, 1, num_hidden_layers + 1
         object.__setattr__(self.encode, '_owner', weakref.ref(self))
+        object.__setattr__(self.decode, '_owner', weakref.ref(self))
         self._arena = ParamArena(self)
         self._plans = {}
         self.inv_rows_override = None  # data parallel: 1 / global row count
@@ -268,7 +287,52 @@ class ImplicitPosteriorVAE(nn.Module):
                                                            _lib.ptr(zbar), _lib.stream_ptr()))
         return z.view(B, nz, self.z_dim), zbar.view(B, 1, self.z_dim)
 
+    def _feat_dim(self):
+        return self.encode.s_h8 * self.encode.s_h8 * 32 if self.KIND == 'conv' else self.h_dim
+
+    def _decode_heads(self, z):
+        """Decoder heads for given latents (mode-3 plan): toy -> (mu, logvar), mnist / conv -> (logit,)."""
+        R = z.size(0)
+        zf = _lib.require_cuda(z.detach(), 'z').reshape(R, self.z_dim)
+        self._ensure()
+        key = self._plan(R, 1, 3)
+        nH = 2 if self.KIND == 'toy' else 1
+        heads = torch.empty(nH, R, self.input_dim, dtype=torch.float32, device=zf.device)
+        _lib.check(_lib.lib().ardae_model_decode(self._plans[key][0], _lib.ptr(zf), _lib.ptr(heads), _lib.stream_ptr()))
+        if self.KIND == 'conv':
+            return (heads[0].view(R, self.input_channels, self.input_height, self.input_height),)
+        return tuple(heads[k] for k in range(nH))
+
+    def _forward_inp(self, x):
+        B = x.size(0)
+        xf = _lib.require_cuda(x.detach(), 'input').reshape(B, self.input_dim)
+        self._ensure()
+        key = self._plan(B, 1, 4)
+        out = torch.empty(B, self._feat_dim(), dtype=torch.float32, device=xf.device)
+        _lib.check(_lib.lib().ardae_model_forward_inp(self._plans[key][0], _lib.ptr(xf), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def _forward_all(self, inp, nos):
+        R = inp.size(0)
+        f = _lib.require_cuda(inp.detach(), 'inp').reshape(R, self._feat_dim())
+        nf = None if nos is None else _lib.require_cuda(nos.detach(), 'nos').reshape(R, self.noise_dim)
+        self._ensure()
+        key = self._plan(R, 1, 5)
+        z = torch.empty(R, self.z_dim, dtype=torch.float32, device=f.device)
+        _lib.check(_lib.lib().ardae_model_forward_all(self._plans[key][0], _lib.ptr(f), _lib.ptr(nf), _lib.ptr(z),
+                                                      _lib.stream_ptr()))
+        return z
+
     # ------------------------------------------------------------------ reference API
+    def generate(self, batch_size=1):
+        """ivae/toy.py:860-873 -> (x, mu, z); ivae/mnist.py:303-316 / ivae/conv.py:232-245 -> (x, sigmoid(logit), z)."""
+        dev = next(self.parameters()).device
+        z = torch.randn(batch_size, self.z_dim, device=dev)
+        out = self.decode(z)
+        if self.KIND == 'toy':
+            return out[0], out[1], z
+        return out[0], torch.sigmoid(out[1]), z
+
     def forward_hidden(self, input, std=None, nz=1):
         """toy.py:811-822 / mnist.py:254-265."""
         batch_size = input.size(0)
@@ -383,6 +447,16 @@ class _ConvEncoder(nn.Module):
             assert noise.size(1) == self.noise_dim
         return owner._encode(x, noise, nz)
 
+    def _forward_inp(self, x):
+        """ivae/conv.py:84-96: flattened conv3 features, [B, 32 * s_h8^2]."""
+        return self._owner()._forward_inp(x)
+
+    _forward_nos = ConcatEncoder._forward_nos
+
+    def _forward_all(self, inp, nos):
+        """ivae/conv.py:107-115."""
+        return self._owner()._forward_all(inp, nos)
+
 
 class _ConvDecoder(nn.Module):
     """models/vae/conv.py:79-136 (parameter container)."""
@@ -396,8 +470,13 @@ class _ConvDecoder(nn.Module):
         self.deconv2 = nn.ConvTranspose2d(32, 16, 5, 2, 2, 0, bias=True)
         self.reparam = BernoulliDistributionConvTranspose2d(16, input_channels, 5, 2, 2, 0, bias=True)
 
+    def sample(self, logit):
+        return self.reparam.sample_logistic_sigmoid(logit)
+
     def forward(self, z):
-        raise NotImplementedError('the decoder runs inside model.forward / model.logprob on the B200 path')
+        """vae/conv.py:118-136 -> (x, logit), both [rows, C, H, W]."""
+        (logit,) = self._owner()._decode_heads(z)
+        return self.sample(logit), logit
 
 
 class ConvIPVAE(ImplicitPosteriorVAE):
@@ -425,6 +504,7 @@ class ConvIPVAE(ImplicitPosteriorVAE):
             self.apply(_weight_init)
         self._n_inp, self._n_fc, self._n_dec = 3, 1, 2
         object.__setattr__(self.encode, '_owner', weakref.ref(self))
+        object.__setattr__(self.decode, '_owner', weakref.ref(self))
         self._arena = ParamArena(self)
         self._plans = {}
         self.inv_rows_override = None

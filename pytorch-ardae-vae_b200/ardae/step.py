@@ -9,9 +9,15 @@ Differences from the reference's execution (not from its results):
   * noise is drawn on the device (Philox) unless injected through `noise=` (parity runs);
   * under data parallelism each rank holds a batch shard, losses/gradients are normalised by the
     GLOBAL row counts and the two flat gradient buffers are summed with one NCCL allreduce each;
-  * `graph=True`: after two eager iterations the whole iteration (~180 launches on three streams) is captured
+  * `graph=True`: after two eager iterations the whole iteration (~150 launches on three streams) is captured
     into ONE CUDA graph and replayed; per-replay variation (Philox seeds, Adam's step) comes from a device-resident
-    counter (ardae_set_replay_counter), inputs are copied into static buffers.
+    counter (ardae_set_replay_counter), beta from a device scalar (annealing does not re-capture), inputs are
+    copied into static buffers.  Optimizer hyper-parameters (lr, betas, momentum, ...) are part of the capture
+    signature: changing them re-captures.  In graph mode the returned tensors are STATIC buffers that the next
+    replay overwrites -- clone them if they are read later than the next call.
+
+Noise: draw k of iteration t uses the Philox seed  base + (64 t + k) * golden-ratio  (k < 64), on the host for eager
+launches and through the device counter for replays, so no two draws of a run share a seed.
 """
 import ctypes
 
@@ -50,8 +56,16 @@ class TrainStep(object):
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
         self.seed = int(seed) * 1000003 + self.rank * 7919
-        self.counter = 0
+        self.iter = 0      # iteration index t (advanced by __call__)
+        self.draw = 0      # draw index k inside the iteration
         self.launches = 0
+        # keep_noise: remember the device tensors of the noise this iteration drew (parity tests feed them to the
+        # oracle); in graph mode they are static buffers overwritten by the next replay
+        self.keep_noise = False
+        self.last_noise = {}
+        self._beta_dev = None   # device scalar holding beta (graph mode)
+        if process_group is not None:
+            self._sync_replicas()
         self.last_std = None
         self.profile = None  # set to a list to collect (name, start_event, end_event) per segment
         self.overlap = True
@@ -98,9 +112,35 @@ class TrainStep(object):
         n += 2 + 1 + 1 + 2 + 2  # randn x2, sigma schedule, scaled diff, optimizers, stage memsets
         return n
 
+    SEED_STRIDE = 64  # == kReplaySeedStride (csrc/kernels.cuh)
+
     def _next_seed(self):
-        self.counter += 1
-        return ctypes.c_uint64((self.seed + self.counter * 0x9E3779B97F4A7C15) & ((1 << 64) - 1))
+        self.draw += 1
+        if self.draw >= self.SEED_STRIDE:  # sub-steps driven by hand (drop-in loops) without __call__
+            self.iter += 1
+            self.draw = 1
+        k = self.iter * self.SEED_STRIDE + self.draw
+        return ctypes.c_uint64((self.seed + k * 0x9E3779B97F4A7C15) & ((1 << 64) - 1))
+
+    def _sync_replicas(self):
+        """Data parallelism assumes bit-identical replicas: broadcast rank 0's parameters and optimizer state."""
+        dist = torch.distributed
+        src = dist.get_global_rank(self.pg, 0) if hasattr(dist, 'get_global_rank') else 0
+        for mod, opt in ((self.model, self.mopt), (self.cdae, self.copt)):
+            ar = mod._ensure()
+            dist.broadcast(ar.flat, src=src, group=self.pg)
+            opt._setup()
+            for buf in opt._bufs:
+                dist.broadcast(buf, src=src, group=self.pg)
+            steps = torch.tensor([float(opt.state[p]['step']) for p in ar.params], device=ar.flat.device)
+            dist.broadcast(steps, src=src, group=self.pg)
+            for p, v in zip(ar.params, steps.tolist()):
+                opt.state[p]['step'] = int(v)
+
+    def _set_beta(self, beta, dev):
+        if self._beta_dev is None:
+            self._beta_dev = torch.empty(1, dtype=torch.float32, device=dev)
+        self._beta_dev.fill_(float(beta))
 
     def _randn(self, rows, cols, dev):
         out = torch.empty(rows, cols, dtype=torch.float32, device=dev)
@@ -173,6 +213,8 @@ class TrainStep(object):
         with self._seg('cdae_opt'):
             self.copt.step_flat(ar.stage_flat, skip=c.no_grad_params)               # :779
         self.last_std = std
+        if self.keep_noise:
+            self.last_noise.update(enc_cdae=enc, sigma=sigma, std=std, eps_cdae=eps, z_cdae=z, zbar_cdae=zbar)
         return loss
 
     def model_forward(self, x, beta, noise=None):
@@ -192,11 +234,18 @@ class TrainStep(object):
         z = torch.empty(R, d, dtype=torch.float32, device=dev)
         sums = torch.empty(3, dtype=torch.float32, device=dev)
         inv_rows = dp_scales(B, self.nz, self.nstd, d, self.nzm, self.world)['model_inv_rows']
+        if self.keep_noise:
+            self.last_noise.update(enc_model=enc)
+        if self.graph and self._beta_dev is None:  # sub-step driven by hand before the first __call__
+            self._set_beta(beta, dev)
+        _lib.check(L.ardae_model_set_beta_device(hm, _lib.ptr(self._beta_dev) if self.graph else None))
         with self._seg('model_fwd'):
             _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),
                                              ctypes.c_float(inv_rows), _lib.ptr(z), _lib.ptr(sums), None,
                                              _lib.stream_ptr()))                        # :801
             zbar = m._encode(xs, None, 1, slot=1)                                        # :813,:826
+            if self.keep_noise:
+                self.last_noise.update(zbar_model=zbar)
             xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
             _lib.check(L.ardae_scaled_diff(_lib.ptr(z), _lib.ptr(zbar), R, self.nzm, d, ctypes.c_float(self.S),
                                            _lib.ptr(xsd), _lib.stream_ptr()))           # :827
@@ -222,7 +271,8 @@ class TrainStep(object):
         with self._seg('score'):
             _lib.check(L.ardae_cdae_score(hs, _lib.ptr(f['xsd']), _lib.ptr(f['ctx']), _lib.ptr(zero_sigma),
                                           _lib.ptr(g), _lib.stream_ptr()))              # :829
-        gz_scale = self.S * beta * f['inv_rows']                                         # :834
+        # :834 (with beta in a device scalar the kernels multiply it in)
+        gz_scale = self.S * f['inv_rows'] * (1.0 if self.graph else beta)
         with self._seg('model_bwd'):
             _lib.check(L.ardae_model_backward_encoder(f['hm'], ctypes.c_float(1.0), _lib.ptr(g),
                                                       ctypes.c_float(gz_scale), _lib.stream_ptr()))  # :804 + :834 (encoder half)
@@ -238,6 +288,11 @@ class TrainStep(object):
     def __call__(self, x_cdae, x_model, beta=1.0, noise=None):
         """One iteration.  x_cdae: the minibatch (or list of num_cdae_updates minibatches) for the CDAE
         update(s); x_model: the minibatch of the model update.  Returns device tensors (no sync)."""
+        self.iter += 1
+        self.draw = 0
+        if self.graph:
+            x0 = x_cdae[0] if isinstance(x_cdae, (list, tuple)) else x_cdae
+            self._set_beta(beta, x0.device)
         if self.graph and noise is None and self.profile is None:
             return self._call_graph(x_cdae, x_model, beta)
         out = self._call_eager(x_cdae, x_model, beta, noise)
@@ -288,9 +343,12 @@ class TrainStep(object):
 
     def _call_graph(self, x_cdae, x_model, beta):
         xs = list(x_cdae) if isinstance(x_cdae, (list, tuple)) else [x_cdae] * self.ncu
-        sig = (tuple(tuple(x.shape) for x in xs), tuple(x_model.shape), float(beta), xs[0].device)
+        hyper = tuple(tuple(sorted((k, v) for k, v in opt.param_groups[0].items() if k != 'params'))
+                      for opt in (self.copt, self.mopt))
+        sig = (tuple(tuple(x.shape) for x in xs), tuple(x_model.shape), xs[0].device, hyper, self.S, self.delta,
+               self.keep_noise)
         if self._g is not None and self._g[4] != sig:
-            self._g = None  # shapes / beta changed: capture again
+            self._g = None  # shapes / optimizer hyper-parameters changed: capture again (beta lives in a device scalar)
             self._g_eager_calls = 0
         if self._g is None:
             if self._g_eager_calls < 2:  # plans, side streams and allocator pools come to life eagerly

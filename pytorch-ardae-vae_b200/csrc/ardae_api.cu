@@ -12,6 +12,7 @@ struct ardae_cdae_s {
 };
 struct ardae_model_s {
   ModelPlan p;
+  const float* beta_dev = nullptr;
 };
 
 extern "C" {
@@ -187,8 +188,43 @@ ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* 
   ModelBindings& b = h->p.bind;
   b = ModelBindings();
   b.x = x; b.noise = noise; b.z_out = z_out; b.sums = sums; b.heads_out = heads_out; b.beta = beta;
+  b.beta_dev = h->beta_dev;
   b.inv_rows = inv_rows;
   return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_decode(ardae_model_t h, const float* z, float* heads_out, void* stream) {
+  if (!h || !z || !heads_out) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 3) return fail(-2, "handle was not created with mode = 3 (decode)");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.z_in = z; b.heads_out = heads_out;
+  return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_forward_inp(ardae_model_t h, const float* x, float* inp_out, void* stream) {
+  if (!h || !x || !inp_out) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 4) return fail(-2, "handle was not created with mode = 4 (_forward_inp)");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.x = x; b.inp_out = inp_out;
+  return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_forward_all(ardae_model_t h, const float* inp, const float* noise, float* z_out, void* stream) {
+  if (!h || !inp || !z_out) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 5) return fail(-2, "handle was not created with mode = 5 (_forward_all)");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.inp_in = inp; b.noise = noise; b.z_out = z_out;
+  return h->p.fwd.run(static_cast<cudaStream_t>(stream));
+}
+
+ARDAE_API int ardae_model_set_beta_device(ardae_model_t h, const float* beta_device) {
+  if (!h) return fail(-1, "null argument");
+  h->beta_dev = beta_device;
+  h->p.bind.beta_dev = beta_device;
+  return 0;
 }
 
 ARDAE_API int ardae_model_iws(ardae_model_t h, const float* x, const float* noise, const float* eta, uint64_t seed,

@@ -49,8 +49,12 @@ inline const replay_ctr_t*& replay_counter() {
   static const replay_ctr_t* p = nullptr;
   return p;
 }
+// The host derives the seed of draw k of iteration t as base + (t * kReplaySeedStride + k) * GOLDEN (k < stride);
+// a replay advances t by the counter, so replayed and eager iterations draw from disjoint seed sets (a stride of 1
+// made draw k+1 of replay r collide with draw k of replay r+1).
+constexpr unsigned long long kReplaySeedStride = 64ull;
 __device__ __forceinline__ uint64_t replay_seed(uint64_t seed, const replay_ctr_t* ctr) {
-  return ctr != nullptr ? seed + static_cast<uint64_t>(*ctr) * 0x9E3779B97F4A7C15ull : seed;
+  return ctr != nullptr ? seed + static_cast<uint64_t>(*ctr) * (0x9E3779B97F4A7C15ull * kReplaySeedStride) : seed;
 }
 __global__ void bump_counter_kernel(replay_ctr_t* ctr) { *ctr += 1ull; }
 
@@ -409,7 +413,8 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ld, int rows, int
 __global__ void bern_elbo_kernel(const float* __restrict__ logit, int ldl, const float* __restrict__ x,
                                  int D, const float* __restrict__ z, int ldz, int zd, int nz, float beta,
                                  float inv_rows, float* __restrict__ sums, float* __restrict__ dlogit,
-                                 int ldd) {
+                                 int ldd, const float* __restrict__ beta_dev = nullptr) {
+  if (beta_dev != nullptr) beta = *beta_dev;
   const int r = blockIdx.x;
   const float* l = logit + static_cast<size_t>(r) * ldl;
   const float* xr = x + static_cast<size_t>(r / nz) * D;
@@ -444,7 +449,8 @@ __global__ void gauss_elbo_kernel(const float* __restrict__ heads, int ldh, int 
                                   const float* __restrict__ x,
                                   int D, const float* __restrict__ z, int ldz, int zd, int nz, float beta,
                                   float inv_rows, float* __restrict__ sums, float* __restrict__ dheads,
-                                  int ldd) {
+                                  int ldd, const float* __restrict__ beta_dev = nullptr) {
+  if (beta_dev != nullptr) beta = *beta_dev;
   const int r = blockIdx.x;
   const float* hrow = heads + static_cast<size_t>(r) * ldh;
   const float* xr = x + static_cast<size_t>(r / nz) * D;
@@ -475,7 +481,14 @@ __global__ void gauss_elbo_kernel(const float* __restrict__ heads, int ldh, int 
 __global__ void dz_total_kernel(const float* __restrict__ dz_dec, int ld_dec, const float* __restrict__ z,
                                 int ldz, const float* __restrict__ gz, float gz_scale, float loss_scale,
                                 float beta_inv_rows,
-                                float* __restrict__ out, int ld_out, int R, int zd) {
+                                float* __restrict__ out, int ld_out, int R, int zd,
+                                const float* __restrict__ beta_dev = nullptr, float inv_rows = 0.0f) {
+  // beta_dev: beta lives in a device scalar (annealing under CUDA-graph replay); gz_scale then excludes beta
+  if (beta_dev != nullptr) {
+    const float b = *beta_dev;
+    beta_inv_rows = b * inv_rows;
+    gz_scale *= b;
+  }
   const size_t total = static_cast<size_t>(R) * zd;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {

@@ -22,7 +22,8 @@ struct ModelConfig {
   int n_inp = 0, n_fc = 0, n_dec = 0;  // number of linears in inp_encode, hidden fc layers, decode.main
   int act = 1;    // 0 relu, 1 softplus
   int B = 0, nz = 1;
-  int mode = 0;   // 0 encode only, 1 forward + backward, 2 IWS log-likelihood (forward only)
+  int mode = 0;   // 0 encode only, 1 forward + backward, 2 IWS log-likelihood (forward only),
+                  // 3 decode(z) only, 4 encode._forward_inp(x) only, 5 encode._forward_all(inp, nos) only (nz = 1)
 };
 
 struct ModelBindings {
@@ -33,6 +34,7 @@ struct ModelBindings {
   float* heads_out = nullptr;    // [R, D] logits | [R, 2D] mu,logvar  (optional)
   float* sums = nullptr;         // [3] loss, recon, prior (device; overwritten)
   float beta = 1.0f;
+  const float* beta_dev = nullptr;  // non-null: beta is read from this device scalar at kernel time (graph replay + annealing)
   float inv_rows = 0.0f;         // 1 / R_global
   // backward
   float loss_scale = 0.0f;
@@ -43,6 +45,10 @@ struct ModelBindings {
   uint64_t seed = 0;
   float* iws_out = nullptr;      // [B] per-image log p_hat(x)
   float* iws_total = nullptr;    // device scalar, += sum over images
+  // sub-module calls (modes 3-5)
+  const float* z_in = nullptr;   // [R, zd]   decode(z)
+  const float* inp_in = nullptr; // [R, feat] encode._forward_all(inp, nos)
+  float* inp_out = nullptr;      // [B, feat] encode._forward_inp(x)
   int* status = nullptr;         // set to 1+image if a covariance is not positive definite
 };
 
@@ -78,7 +84,11 @@ struct ModelPlan {
     }
     const int feat = conv ? s8 * s8 * 32 : h;             // width of the per-data-row features fed to fc layer 0
     auto dwid = [&](int l) { return conv ? (l == 0 ? 300 : feat) : h; };  // decoder fc widths (vae/conv.py:109)
-    const bool dry = ws.dry, train = c.mode == 1, dec = c.mode != 0;
+    if (c.mode < 0 || c.mode > 5) return fail(-2, "model: bad mode");
+    if (c.mode >= 3 && nz != 1) return fail(-2, "model: sub-module plans (modes 3-5) take nz = 1");
+    const bool dry = ws.dry, train = c.mode == 1, dec = c.mode >= 1 && c.mode <= 3;
+    const bool enc_inp = c.mode != 3 && c.mode != 5;  // the input stack runs
+    const bool enc_fc = c.mode != 3 && c.mode != 4;   // the fc stack runs
     if (c.mode == 2 && (zd > 64 || nz < 2 * zd)) return fail(-2, "iws: need z_dim <= 64 and sample_size >= 2*z_dim (ivae/mnist.py:382)");
     fwd.dry = bwd_dec.dry = bwd_enc.dry = dry;
     const int ACT = c.act ? EPI_SOFTPLUS : EPI_RELU;
@@ -211,7 +221,7 @@ struct ModelPlan {
     const int CACT = c.act ? CONV_ACT_SOFTPLUS : CONV_ACT_RELU;
     const int IH = c.img_h, IC = c.img_c;
     fwd.add([=](cudaStream_t s) {
-      if (!conv)
+      if (!conv && enc_inp)
         split2d_kernel<<<grid_for(static_cast<size_t>(B) * D), 256, 0, s>>>(
             bd->x, D, xin.buf.p, xin.buf.ld, B, D, xin.kp, toy ? 1.0f : 2.0f, toy ? 0.0f : -1.0f);
       if (bd->sums) ARDAE_CUDA_OK(cudaMemsetAsync(bd->sums, 0, 3 * sizeof(float), s));
@@ -219,8 +229,8 @@ struct ModelPlan {
     });
     // the (HBM-bound, R-row) noise split runs on the plan's side lane underneath the latency-bound B-row input stack;
     // joined right before the first layer that consumes the noise pair
-    fwd.fork();
-    fwd.add([=](cudaStream_t s) {
+    if (enc_fc) fwd.fork();
+    if (enc_fc) fwd.add([=](cudaStream_t s) {
       if (bd->noise != nullptr) {
         split2d_kernel<<<grid_for(static_cast<size_t>(R) * n), 256, 0, s>>>(
             bd->noise, n, epsp.buf.p, epsp.buf.ld, R, n, epsp.kp, 1.0f, 0.0f);
@@ -230,13 +240,20 @@ struct ModelPlan {
       return static_cast<int>(cudaGetLastError());
     });
     fwd.cur_lane = 0;
+    if (c.mode == 5) {  // encode._forward_all(inp, nos): the per-row features are given
+      fwd.add([=](cudaStream_t s) {
+        split2d_kernel<<<grid_for(static_cast<size_t>(B) * feat), 256, 0, s>>>(
+            bd->inp_in, feat, inp_pair.buf.p, inp_pair.buf.ld, B, feat, inp_pair.kp, 1.0f, 0.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
     // inp_encode on the B data rows
-    for (int l = 0; l < c.n_inp && !conv; ++l) {
+    for (int l = 0; l < c.n_inp && !conv && enc_inp; ++l) {
       GemmNTDesc g = nt3_desc(l == 0 ? xin : I[l - 1], Iw[l], I[l], ACT);
       g.bias = P(iI(l) + 1);
       fwd.nt(g);
     }
-    if (conv) {
+    if (conv && enc_inp) {
       // x <- 2x-1, conv(1->16) -> conv(16->32) -> conv(32->32), all 5x5 s2 p2 + activation (ivae/conv.py:84-96)
       const float *w1 = P(iI(0)), *b1 = P(iI(0) + 1), *w2 = P(iI(1)), *b2 = P(iI(1) + 1), *w3 = P(iI(2)), *b3 = P(iI(2) + 1);
       fwd.add([=](cudaStream_t s) {
@@ -251,14 +268,24 @@ struct ModelPlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
+    if (c.mode == 4) {  // encode._forward_inp(x): the features of the data rows
+      const Mat ih = inp_pair.hi(), il = inp_pair.lo();
+      Mat ibuf = ws.mat(B, feat);
+      fwd.add([=](cudaStream_t s) {
+        pair_sum_kernel<<<grid_for(static_cast<size_t>(B) * feat), 256, 0, s>>>(ih.p, il.p, ih.ld, ibuf.p, ibuf.ld,
+                                                                              bd->inp_out, B, feat);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return fwd.error;
+    }
     // fc layer 0: input half once per data row (rowbias0), noise half over the R rows
-    {
+    if (enc_fc) {
       GemmNTDesc g = nt3_desc_plain(inp_pair, F0i, rowbias0, EPI_LINEAR);
       g.bias = P(iF(0) + 1);
       fwd.nt(g);
     }
-    fwd.join();
-    {
+    if (enc_fc) fwd.join();
+    if (enc_fc) {
       Pair out = Fh[0];
       out.w = h;  // write only the hid columns of the (possibly wider) concat buffer
       GemmNTDesc g = nt3_desc(epsp, F0n, out, ACT);
@@ -267,7 +294,7 @@ struct ModelPlan {
       if (h > 256 && h <= 512 && R >= 16384) g.force_block_n = 256;
       fwd.nt(g);
     }
-    if (toy) {
+    if (toy && enc_fc) {
       // append eps to every concat buffer: columns [h, h+n) of hi and lo halves
       fwd.add([=](cudaStream_t s) {
         for (int l = 0; l < c.n_fc; ++l) {
@@ -283,14 +310,21 @@ struct ModelPlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
-    for (int l = 1; l < c.n_fc; ++l) {
+    for (int l = 1; l < c.n_fc && enc_fc; ++l) {
       Pair out = Fh[l];
       out.w = h;
       GemmNTDesc g = nt3_desc(Fh[l - 1], Fw[l], out, ACT);
       g.bias = P(iF(l) + 1);
       fwd.nt(g);
     }
-    {  // z = fc.fc([hid | eps])  (plain fp32 to the user buffer layout, and as a tf32 pair)
+    if (c.mode == 3) {  // decode(z): the latent rows are given
+      fwd.add([=](cudaStream_t s) {
+        split2d_kernel<<<grid_for(static_cast<size_t>(R) * zd), 256, 0, s>>>(bd->z_in, zd, zp.buf.p, zp.buf.ld, R, zd,
+                                                                           zp.kp, 1.0f, 0.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    if (enc_fc) {  // z = fc.fc([hid | eps])  (plain fp32 to the user buffer layout, and as a tf32 pair)
       GemmNTDesc g = nt3_desc(Fh[c.n_fc - 1], Fw[c.n_fc], zp, EPI_LINEAR);
       g.bias = P(iF(c.n_fc) + 1);
       fwd.nt(g);
@@ -381,6 +415,15 @@ struct ModelPlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
+    if (c.mode == 3) {  // head-major [nH][R][D] logits / (mu, logvar) to the caller
+      fwd.add([=](cudaStream_t s) {
+        for (int k = 0; k < (conv ? 1 : nH); ++k)
+          unpad_kernel<<<grid_for(static_cast<size_t>(R) * D), 256, 0, s>>>(
+              heads.p + k * Dp, heads.ld, bd->heads_out + static_cast<size_t>(k) * R * D, R, D, 1.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return fwd.error;
+    }
     if (c.mode == 2) {
       fwd.add([=](cudaStream_t s) {
         iws_loglik_kernel<<<R, 128, 0, s>>>(heads.p, heads.ld, Dp, bd->x, D, nz, toy ? 0 : 1, lw0, wbuf);
@@ -392,10 +435,10 @@ struct ModelPlan {
     fwd.add([=](cudaStream_t s) {
       if (toy)
         gauss_elbo_kernel<<<R, 128, 0, s>>>(heads.p, heads.ld, Dp, bd->x, D, zbuf.p, zbuf.ld, zd, nz, bd->beta,
-                                            bd->inv_rows, bd->sums, dheads.p, dheads.ld);
+                                            bd->inv_rows, bd->sums, dheads.p, dheads.ld, bd->beta_dev);
       else
         bern_elbo_kernel<<<R, 256, 0, s>>>(heads.p, heads.ld, bd->x, D, zbuf.p, zbuf.ld, zd, nz, bd->beta,
-                                           bd->inv_rows, bd->sums, dheads.p, dheads.ld);
+                                           bd->inv_rows, bd->sums, dheads.p, dheads.ld, bd->beta_dev);
       if (bd->heads_out)  // head-major [nH][R][D]
         for (int k = 0; k < nH; ++k)
           unpad_kernel<<<grid_for(static_cast<size_t>(R) * D), 256, 0, s>>>(
@@ -472,7 +515,8 @@ struct ModelPlan {
     // ---- encoder part
     bwd_enc.add([=](cudaStream_t s) {
       dz_total_kernel<<<grid_for(static_cast<size_t>(R) * zd), 256, 0, s>>>(
-          dzdec.p, dzdec.ld, zbuf.p, zbuf.ld, bd->gz, bd->gz_scale, bd->loss_scale, bd->beta * bd->inv_rows, dzt.p, dzt.ld, R, zd);
+          dzdec.p, dzdec.ld, zbuf.p, zbuf.ld, bd->gz, bd->gz_scale, bd->loss_scale, bd->beta * bd->inv_rows, dzt.p, dzt.ld, R, zd, bd->beta_dev,
+          bd->inv_rows);
       return static_cast<int>(cudaGetLastError());
     });
     {

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small', 'mnist_small_res', 'mnist_small_datactx']
+CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small', 'mnist_small_res', 'mnist_small_datactx', 'conv28']
 
 
 def model_dims(meta):
@@ -56,6 +56,21 @@ def load_case(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'))
     meta = json.loads(str(z['meta']))
     return z, meta
+
+
+def is_lite(name, meta):
+    """lite fixtures store float32 weights / gradients (looser oracle tolerance); older files carry no flag."""
+    return bool(meta.get('lite', name == 'conv_small'))
+
+
+def num_steps(name, meta):
+    return int(meta.get('steps', 1 if is_lite(name, meta) else 2))
+
+
+def pick(z, name, a):
+    """The stored view of a model tensor: `sampled` fixtures keep big tensors at fixed random positions."""
+    k = 'sample_idx/' + name
+    return np.asarray(a).ravel()[z[k]] if k in z.files else np.asarray(a)
 
 
 def sub(z, prefix):

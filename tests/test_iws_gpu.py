@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import ardae_oracle as orc
-from golden_util import CASES, load_case, sub
+from golden_util import CASES, is_lite, load_case, sub
 import golden_util
 
 pytestmark = pytest.mark.gpu
@@ -25,7 +25,7 @@ def t(a):
 @pytest.mark.parametrize('name', CASES)
 def test_iws_matches_reference_fixture(name):
     z, meta = load_case(name)
-    model = build_model(meta, sub(z, 'm0/' if name == 'conv_small' else 's1/m_after/'))
+    model = build_model(meta, sub(z, 'm0/' if is_lite(name, meta) else 's1/m_after/'))
     val = model.logprob(t(z['iws/x']), sample_size=meta['iws']['S'], noise=t(z['iws/enc_noise']), eta=t(z['iws/eta']))
     ref = float(z['iws/logprob'])
     tol = 0.05 if not name.endswith('_x3') else 0.05 * max(1.0, abs(ref) / 100)

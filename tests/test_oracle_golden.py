@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import ardae_oracle as orc
-from golden_util import CASES, cdae_spec, hp_of, load_case, model_dims, rel_err, sub
+from golden_util import CASES, cdae_spec, hp_of, is_lite, load_case, model_dims, num_steps, pick, rel_err, sub
 
 
 
@@ -23,8 +23,8 @@ def test_train_step_matches_reference(name):
     f64 = lambda d: {k: np.asarray(v, dtype=np.float64) for k, v in d.items()}
     Pm, Pc = f64(sub(z, 'm0/')), f64(sub(z, 'c0/'))
     state = {}
-    lite = name == 'conv_small'  # one step, weights / gradients stored as float32
-    for step in range(1 if lite else 2):
+    lite = is_lite(name, meta)  # weights / gradients stored as float32
+    for step in range(num_steps(name, meta)):
         p = 's%d/' % step
         # x3 weights (saturated, ill-conditioned) + RMSprop's g/(|g|+eps) normalisation amplify the
         # 1e-9 fp64 differences of step 0 to ~5e-6 in step 1; step 0 pins the formulas.
@@ -41,12 +41,12 @@ def test_train_step_matches_reference(name):
         ref_mg = sub(z, p + 'model_grads/')
         assert set(ref_mg) == set(out['model_grads'])
         for k, v in ref_mg.items():
-            assert rel_err(out['model_grads'][k], v) < GTOL, (step, 'model_grad', k)
-        if lite:
+            assert rel_err(pick(z, k, out['model_grads'][k]), v) < GTOL, (step, 'model_grad', k)
+        if lite and not meta.get('sampled'):
             continue
         # optimizer semantics: reference Adam (eps placement) and torch RMSprop w/ momentum
         for k, v in sub(z, p + 'm_after/').items():
-            assert rel_err(Pm[k], v) < TOL, (step, 'adam', k)
+            assert rel_err(pick(z, k, Pm[k]), v) < (1e-6 if lite else TOL), (step, 'adam', k)
         for k, v in sub(z, p + 'c_after/').items():
             assert rel_err(Pc[k], v) < TOL, (step, 'rmsprop', k)
 
@@ -55,9 +55,10 @@ def test_train_step_matches_reference(name):
 def test_iws_matches_reference(name):
     z, meta = load_case(name)
     spec, _ = specs(meta)
-    Pm = sub(z, 's1/m_after/') if 's1/m_after/encode.fc5.weight' in z.files or name != 'conv_small' else None
-    if name == 'conv_small':
+    if is_lite(name, meta):  # IWS on the initial weights (the stepped ones are not stored in full)
         Pm = {k: np.asarray(v, dtype=np.float64) for k, v in sub(z, 'm0/').items()}
+    else:
+        Pm = sub(z, 's1/m_after/')
     val, per = orc.iws_logprob(spec, Pm, z['iws/x'], z['iws/enc_noise'], z['iws/eta'])
     assert abs(val - float(z['iws/logprob'])) < 1e-8 * max(1.0, abs(val))
     assert per.shape == (meta['iws']['b'],)

@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import CASES, build_cdae, build_model, load_case, rel_err, sub
+from golden_util import CASES, build_cdae, build_model, is_lite, load_case, num_steps, pick, rel_err, sub
 
 pytestmark = pytest.mark.gpu
 
@@ -64,8 +64,11 @@ def test_fused_step_matches_reference_fixture(name):
                            nz_cdae=hp['nz_cdae'], nstd=hp['nstd'], nz_model=hp['nz_model'],
                            ctx_type=meta.get('ctx_type', 'lt0'))
     ref_m_prev, ref_c_prev = sub(z, 'm0/'), sub(z, 'c0/')
-    lite = name == 'conv_small'  # fixture holds one step and no post-step weights
-    for s in range(1 if lite else 2):
+    lite = is_lite(name, meta) and not meta.get('sampled')  # fixture holds one step and no post-step weights
+    def pk(d):  # `sampled` fixtures keep big model tensors at fixed positions (idempotent: already-picked arrays pass)
+        return {k: (v if ('sample_idx/' + k) in z.files and np.asarray(v).size == z['sample_idx/' + k].size
+                    else pick(z, k, v)) for k, v in d.items()}
+    for s in range(num_steps(name, meta)):
         p = 's%d/' % s
         noise = {k: t(v) for k, v in sub(z, p + 'noise/').items()}
         m_before, c_before = params_np(model), params_np(cdae)
@@ -79,7 +82,7 @@ def test_fused_step_matches_reference_fixture(name):
             assert e <= ltol, (s, k, e)
         assert rel_err(out['std'].cpu().numpy(), z[p + 'std'].ravel()) <= (1e-2 if loose else 1e-4)
         # step >= 1 starts from parameters that carry the (tf32-level, Adam-normalised) update error of the step before
-        assert rel_err(out['z_model'].cpu().numpy().ravel(), z[p + 'z_model'].ravel()) <= (1e-3 if loose else (1e-5 if s == 0 else 1e-4))
+        assert rel_err(out['z_model'].cpu().numpy().ravel(), z[p + 'z_model'].ravel()) <= (1e-3 if loose else ((2e-5 if meta['kind'] == 'conv' else 1e-5) if s == 0 else (2e-4 if meta['kind'] == 'conv' else 1e-4)))
         eg = rel_err(out['entropy_grad'].cpu().numpy().ravel(), z[p + 'entropy_grad'].ravel())
         assert eg <= (5e-2 if loose else 1e-2), (s, 'entropy_grad', eg)
         m_after, c_after = params_np(model), params_np(cdae)
@@ -88,7 +91,7 @@ def test_fused_step_matches_reference_fixture(name):
         else:
             ref_m_after, ref_c_after = sub(z, p + 'm_after/'), sub(z, p + 'c_after/')
             ue_c = update_err(c_before, c_after, ref_c_prev, ref_c_after)
-            ue_m = update_err(m_before, m_after, ref_m_prev, ref_m_after)
+            ue_m = update_err(pk(m_before), pk(m_after), pk(ref_m_prev), ref_m_after)
         print('%s step %d: cdae_loss %.6g (ref %.6g) model_loss %.6g (ref %.6g) entropy_grad rel %.2e '
               'update rel: cdae %.2e model %.2e' % (name, s, out['cdae_loss'].item(), float(z[p + 'cdae_loss']),
                                                     out['model_loss'].item(), float(z[p + 'model_loss']), eg, ue_c, ue_m))
@@ -99,7 +102,8 @@ def test_fused_step_matches_reference_fixture(name):
             ar, ref = mod._arena, sub(z, p + pref)
             for k, nme in enumerate(ar.names):
                 if nme in ref:
-                    e = rel_err(ar.view(ar.stage_flat, k).cpu().numpy(), ref[nme])
+                    got = ar.view(ar.stage_flat, k).cpu().numpy()
+                    e = rel_err(pick(z, nme, got) if mod is model else got, ref[nme])
                     assert e <= gtol, (s, nme, e)
         if meta.get('cdae_kind', 'grad') == 'grad':
             assert np.array_equal(c_after['neglogprob.fc.bias'], c_before['neglogprob.fc.bias'])  # never updated
