@@ -4,7 +4,8 @@ from .ivae import ConvIPVAE, MNISTIPVAE, ToyIPVAE, normal_energy_func  # noqa: F
 from .optim import Adam, RMSprop  # noqa: F401
 from .step import TrainStep  # noqa: F401
 from .data import MinibatchSampler, dynamic_binarize, toy_exp4  # noqa: F401
-from .checkpoint import annealing_func, load_checkpoint, save_checkpoint  # noqa: F401
+from .checkpoint import (EndIterError, annealing_func, final_mode_should_stop, load_checkpoint, load_end_iter,  # noqa: F401
+                         save_checkpoint)
 
 
 def evaluate_iws(data, model, iws_samples, batch_size=None, process_group=None):

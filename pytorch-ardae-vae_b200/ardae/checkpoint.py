@@ -67,3 +67,27 @@ def load_checkpoint(model, optimizer, opt, filename='checkpoint.pth.tar', verbos
     if scheduler is not None and ck.get('scheduler') is not None:
         scheduler.load_state_dict(ck['scheduler'])
     return ck
+
+
+def load_end_iter(opt, filename='best-checkpoint.pth.tar', verbose=False, device=None):
+    """utils/msc.py:98-110: "final"-mode replay (ivae_ardae.py:284-285,699-700,1142,1167).  The iteration index at
+    which the best validation checkpoint of the train/val run was written, i.e. where the re-run on train+val data
+    stops: (epoch - 1) * train_num_iters_per_epoch + batch_idx - 1."""
+    path = os.path.join(_path(opt), filename)
+    if not os.path.isfile(path):
+        raise ValueError("=> no checkpoint found at '{}'".format(path))
+    if verbose:
+        print("=> loading checkpoint '{}'".format(path))
+    ck = torch.load(path, map_location=device if device is not None else 'cpu')
+    i_ep = (ck['epoch'] - 1) * ck['train_num_iters_per_epoch'] + ck['batch_idx']
+    return i_ep - 1
+
+
+class EndIterError(Exception):
+    """utils/msc.py:112-113: raised by the training loop when the "final"-mode run reaches `end_iter`."""
+    pass
+
+
+def final_mode_should_stop(i_ep, end_iter, train_mode='final'):
+    """The stop test of the reference's loop (ivae_ardae.py:699-700): `i_ep` is the 0-based iteration about to run."""
+    return train_mode == 'final' and end_iter is not None and (i_ep + 1) > end_iter

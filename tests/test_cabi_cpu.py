@@ -79,3 +79,55 @@ def test_no_gpu_means_loud_failure(lib):
     if torch.cuda.is_available():
         pytest.skip('GPU present')
     assert lib.ardae_check_device(0) != 0  # CUDA error code, not a crash and not a silent fallback
+
+
+def header_struct_fields(name):
+    """Field names of `typedef struct { ... } name;` in include/ardae.h (all members are `int`)."""
+    src = open(HDR).read()
+    m = re.search(r'typedef\s+struct\s*\{([^{}]*)\}\s*' + name + r'\s*;', src, re.S)
+    assert m, name
+    body = re.sub(r'/\*.*?\*/', '', m.group(1), flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        assert decl.startswith('int '), decl
+        fields += [f.strip() for f in decl[4:].split(',')]
+    return fields
+
+
+def test_ctypes_structs_match_the_header():
+    """The ctypes mirrors (product binding, INTEGRATION.md stub) must have exactly the header's fields, in order: a short
+    struct makes the library read past the caller's memory (round-1 INTEGRATION.md declared 7 of the 8 ints)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'pytorch-ardae-vae_b200'))
+    from ardae import _lib
+    cfields = header_struct_fields('ardae_cdae_config')
+    mfields = header_struct_fields('ardae_model_config')
+    assert [f for f, _ in _lib.CdaeConfig._fields_] == cfields
+    assert [f for f, _ in _lib.ModelConfig._fields_] == mfields
+    assert all(t is ctypes.c_int for _, t in _lib.CdaeConfig._fields_ + _lib.ModelConfig._fields_)
+    assert ctypes.sizeof(_lib.CdaeConfig) == 4 * len(cfields) and ctypes.sizeof(_lib.ModelConfig) == 4 * len(mfields)
+    # the stub a reference maintainer would paste (INTEGRATION.md)
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    m = re.search(r'class CdaeCfg\(ctypes\.Structure\):\s*_fields_ = \[\(k, ctypes\.c_int\) for k in\s*\((.*?)\)\]', doc, re.S)
+    assert m, 'INTEGRATION.md: CdaeCfg stub not found'
+    assert re.findall(r"'(\w+)'", m.group(1)) == cfields
+
+
+def test_load_end_iter(tmp_path):
+    """utils/msc.py:98-110 on a checkpoint with the reference's dict layout (ivae_ardae.py:1116-1137)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'pytorch-ardae-vae_b200'))
+    import ardae
+    torch.save(dict(epoch=3, batch_idx=17, train_num_iters_per_epoch=100, best_val_loss=1.0, state_dict={}, optimizer={}),
+               os.path.join(str(tmp_path), 'best-model-checkpoint.pth.tar'))
+    end = ardae.load_end_iter(str(tmp_path), filename='best-model-checkpoint.pth.tar')
+    assert end == (3 - 1) * 100 + 17 - 1
+    assert not ardae.final_mode_should_stop(end - 1, end) and ardae.final_mode_should_stop(end, end)
+    assert not ardae.final_mode_should_stop(10 ** 9, end, train_mode='train')
+    with pytest.raises(ValueError):
+        ardae.load_end_iter(str(tmp_path), filename='missing.pth.tar')
+    assert issubclass(ardae.EndIterError, Exception)
