@@ -553,10 +553,12 @@ def main():
         'chain_adjoint': dict(flops=2.0 * N_ * nl * H_ * H_, overhead=(3 * nl + 1) * arr, executed=1.0, note='adjoint backward, in place over t'),
         'gemm_tn16': dict(flops=2 * 2.0 * N_ * H_ * H_, overhead=4 * arr, executed=1.0, peak=bf16_peak,
                           note='weight gradient of one [H,H] layer: two bf16 contractions over the N rows'),
+        'gemm_tn16_multi': dict(flops=2 * (L_ - 1) * 2 * 2.0 * N_ * H_ * H_, overhead=2 * (L_ - 1) * 4 * arr, executed=1.0,
+                                peak=bf16_peak, note='weight gradients of the 2(L-1) [H,H] layers in one launch (bf16 x bf16 -> fp32)'),
         'gemm_tn': dict(flops=2 * 2.0 * N_ * H_ * H_, overhead=4 * arr, executed=1.0, note='weight gradient (fp32 spill plans)'),
     }
     kernels = []
-    for tag in ('chain_softplus3', 'chain_tangent', 'chain_adjoint', 'chain_mul_sig', 'gemm_tn16', 'gemm_tn'):
+    for tag in ('chain_softplus3', 'chain_tangent', 'chain_adjoint', 'chain_mul_sig', 'gemm_tn16_multi', 'gemm_tn16', 'gemm_tn'):
         ts = sorted(t for t in by_tag.get(tag, []) if t > 0.02)  # the N-row launches only
         if not ts:
             continue

@@ -45,7 +45,7 @@ struct DeriveList {
   std::vector<DeriveItem> host;
   int blocks = 0;
   // W[rows(out), cols(in)] at src (pitch src_ld).  want3: forward 3xTF32 operand; wantT: transpose.
-  W3 add(Workspace& ws, const float* src, int rows, int cols, int src_ld, bool want3, bool wantT) {
+  W3 add(Workspace& ws, const float* src, int rows, int cols, int src_ld, bool want3, bool wantT, bool want16 = false) {
     W3 w;
     w.in = cols; w.out = rows; w.kp = round_up(cols, 32);
     DeriveItem it;
@@ -58,6 +58,11 @@ struct DeriveList {
     if (wantT) {
       w.T = ws.mat(cols, rows);
       it.dstT = w.T.p; it.ldT = w.T.ld;
+    }
+    if (want16) {
+      w.k16 = round_up(cols, 64);
+      w.h16 = ws.mat16(rows, 2 * w.k16);
+      it.dst16 = w.h16.p; it.k16 = w.k16;
     }
     it.first_block = blocks;
     it.tiles_x = (cols + 31) / 32;
@@ -93,8 +98,8 @@ struct CdaePlan {
 
   int ntensors() const { return 6 * cfg.L + 2; }
 
-  // 16-bit spill plan (chain16_sm100.cuh + gemm_tn16.cuh): mlp-grad training update whose H -> H layers fit the
-  // fused chain kernel.  ARDAE_SPILL16=0 keeps the fp32-spill plan (A/B measurements, parity triage).
+  // 16-bit spill plan (chain16_sm100.cuh + gemm_tn16.cuh): mlp-grad plans (training update, or score only: sweeps 1-2)
+  // whose H -> H layers fit the fused chain kernel.  ARDAE_SPILL16=0 keeps the fp32-spill plan (A/B measurements, parity triage).
   bool spill16_plan() const {
     static int env = -1;
     if (env < 0) {
@@ -102,7 +107,7 @@ struct CdaePlan {
       env = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     const int kp = round_up(cfg.d, 32);
-    return env != 0 && cfg.kind == 0 && cfg.train != 0 && chain_supported(cfg.H, 1) && 2 * cfg.L <= kChainMaxLayers &&
+    return env != 0 && cfg.kind == 0 && chain_supported(cfg.H, 1) && 2 * cfg.L <= kChainMaxLayers &&
            kp <= cfg.H / 2 && cfg.H % 64 == 0;
   }
 
@@ -113,8 +118,9 @@ struct CdaePlan {
     const int d = cfg.d, c = cfg.c, H = cfg.H, L = cfg.L, B = cfg.B, S = cfg.S;
     const int N = B * S;
     const bool dry = ws.dry;
+    const bool train = cfg.train != 0;
     auto P = [&](int i) -> float* { return dry ? nullptr : params[i]; };
-    auto G = [&](int i) -> float* { return dry ? nullptr : grads[i]; };
+    auto G = [&](int i) -> float* { return (dry || !train) ? nullptr : grads[i]; };
     auto iC = [&](int l) { return 2 * l; };
     auto iA = [&](int l) { return 2 * L + 2 * l; };
     auto iW = [&](int l) { return 4 * L + 2 * l; };
@@ -123,10 +129,11 @@ struct CdaePlan {
     derive = DeriveList();
     std::vector<W3> Cw(L), Aw(L), Ww(L);
     for (int l = 0; l < L; ++l) Cw[l] = derive.add(ws, P(iC(l)), H, l == 0 ? c : H, l == 0 ? c : H, true, true);
-    for (int l = 0; l < L; ++l) Aw[l] = derive.add(ws, P(iA(l)), H, l == 0 ? d : H, l == 0 ? d : H, true, true);
-    for (int l = 1; l < L; ++l) Ww[l] = derive.add(ws, P(iW(l)), H, H, H, true, true);
+    const bool s3h = s3h_supported(H);  // primal sweep on the fp16 pipe
+    for (int l = 0; l < L; ++l) Aw[l] = derive.add(ws, P(iA(l)), H, l == 0 ? d : H, l == 0 ? d : H, true, true, s3h);
+    for (int l = 1; l < L; ++l) Ww[l] = derive.add(ws, P(iW(l)), H, H, H, true, true, s3h);
     const int ld1 = 2 * H + 1;
-    W3 W1u = derive.add(ws, P(iW(0)), H, H, ld1, true, true);
+    W3 W1u = derive.add(ws, P(iW(0)), H, H, ld1, true, true, s3h);
     W3 W1c = derive.add(ws, P(iW(0)) ? P(iW(0)) + H : nullptr, H, H, ld1, true, true);
     Ww[0] = W1u;
     int rc = derive.emit(ws, plan);
@@ -143,8 +150,11 @@ struct CdaePlan {
     std::vector<Pair> Cc(L);
     for (int l = 0; l < L; ++l) Cc[l] = make_pair(ws, B, H);
     std::vector<Mat16> U(L), V(L), DA(L), DP(L), UD(L), VD(L), TA(L), TP(L);
-    for (auto* arr : {&U, &V, &DA, &DP, &UD, &VD, &TA, &TP})
+    for (auto* arr : {&U, &V, &DA, &DP})
       for (int l = 0; l < L; ++l) (*arr)[l] = ws.mat16(N, H);
+    if (train)
+      for (auto* arr : {&UD, &VD, &TA, &TP})
+        for (int l = 0; l < L; ++l) (*arr)[l] = ws.mat16(N, H);
     Mat gsum = ws.mat(B, H);
     std::vector<Mat> DC(L);
     for (int l = 0; l < L; ++l) DC[l] = ws.mat(B, H);
@@ -207,6 +217,7 @@ struct CdaePlan {
       auto s3 = [&](const W3& w, const float* bias, const Mat16& out, int kin) {
         Chain16LayerDesc q;
         q.W = w.b3.p; q.ldw = w.b3.ld; q.kin = kin; q.bias = bias; q.out = out.p; q.ldo = out.ld;
+        q.W16 = w.h16.p; q.ldw16 = w.h16.ld; q.kin16 = w.k16;
         return q;
       };
       cd.layers.push_back(s3(Aw[0], P(iA(0) + 1), U[0], kp));
@@ -217,7 +228,7 @@ struct CdaePlan {
         cd.layers.push_back(q);
       }
       for (int l = 1; l < L; ++l) cd.layers.push_back(s3(Ww[l], P(iW(l) + 1), V[l], H));
-      plan.chain16(cd);
+      if (s3h) plan.chain_s3h(cd); else plan.chain16(cd);
     }
     // ---- sweep 2: score backward, ending in g = delta a_1 . A_1 (fp32 [N, kp])
     {
@@ -244,6 +255,13 @@ struct CdaePlan {
         cd.layers.push_back(q);
       }
       plan.chain16(cd);
+    }
+    if (!train) {  // glogprob: sweeps 1-2 only
+      plan.add([=](cudaStream_t s) {
+        unpad_kernel<<<grid_for(static_cast<size_t>(N) * d), 256, 0, s>>>(gmat.p, gmat.ld, bd->score_out, N, d, 1.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return plan.error;
     }
     // ---- loss + residual direction r (fp32 + bf16 pair)
     plan.add([=](cudaStream_t s) {
@@ -324,7 +342,7 @@ struct CdaePlan {
     ctx_tn(DC[0], ctxp.hi(), G(iC(0)), c);
     plan.cur_lane = 0;
     // ---- weight gradients: dW = adj^T . act + delta^T . tangent   (accumulated into .grad)
-    auto tn16 = [&](std::initializer_list<std::pair<Mat16, Mat16>> pairs, int Mo, int No, int Ny, float* dst, int ldo) {
+    auto tn16_desc = [&](std::initializer_list<std::pair<Mat16, Mat16>> pairs, int Mo, int No, int Ny, float* dst, int ldo) {
       GemmTN16Desc t;
       for (const auto& pr : pairs) {
         t.X[t.npairs] = pr.first.p; t.ldx[t.npairs] = pr.first.ld;
@@ -333,12 +351,16 @@ struct CdaePlan {
       }
       t.M = Mo; t.N = No; t.Ny = Ny; t.K = N; t.out = dst; t.ldo = ldo;
       t.workspace = tn_ws; t.workspace_bytes = tn_ws_bytes;
-      plan.tn16(t);
+      return t;
     };
-    tn16({{TP[0], U[L - 1]}, {DP[0], UD[L - 1]}}, H, H, H, G(iW(0)), ld1);
-    for (int l = L - 1; l >= 1; --l) tn16({{TP[l], V[l - 1]}, {DP[l], VD[l - 1]}}, H, H, H, G(iW(l)), H);
-    for (int l = L - 1; l >= 1; --l) tn16({{TA[l], U[l - 1]}, {DA[l], UD[l - 1]}}, H, H, H, G(iA(l)), H);
-    tn16({{TA[0], x16h}, {TA[0], x16l}, {DA[0], r16h}, {DA[0], r16l}}, H, d, ny, G(iA(0)), d);
+    plan.tn16(tn16_desc({{TP[0], U[L - 1]}, {DP[0], UD[L - 1]}}, H, H, H, G(iW(0)), ld1));
+    {  // the 2(L-1) [H,H] layers: one launch walking them in order
+      std::vector<GemmTN16Desc> batch;
+      for (int l = L - 1; l >= 1; --l) batch.push_back(tn16_desc({{TP[l], V[l - 1]}, {DP[l], VD[l - 1]}}, H, H, H, G(iW(l)), H));
+      for (int l = L - 1; l >= 1; --l) batch.push_back(tn16_desc({{TA[l], U[l - 1]}, {DA[l], UD[l - 1]}}, H, H, H, G(iA(l)), H));
+      plan.tn16_multi(batch);
+    }
+    plan.tn16(tn16_desc({{TA[0], x16h}, {TA[0], x16l}, {DA[0], r16h}, {DA[0], r16l}}, H, d, ny, G(iA(0)), d));
     plan.join();
     return plan.error;
   }

@@ -4,13 +4,14 @@
 
 #include "chain16_sm100.cuh"
 #include "chain_host.cuh"
+#include "chain_s3h_sm100.cuh"
 
 namespace ardae {
 
 // 2-D bf16 tensor map.  inner = contiguous dimension (elements); pitch in elements.
 inline int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
                                uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer,
-                               CUtensorMapSwizzle swizzle) {
+                               CUtensorMapSwizzle swizzle, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   PFN_encodeTiled fn = get_encode_fn();
   if (fn == nullptr) return fail(-10, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
@@ -19,7 +20,7 @@ inline int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner
   cuuint64_t gstride[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = fn(tm, dtype, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -56,6 +57,8 @@ struct Chain16LayerDesc {
   float* colsum = nullptr; float colsum_scale = 1.0f;
   float* colsum2 = nullptr;
   float* colsum_w = nullptr; int colsum_w_stride = 1;
+  // SOFTPLUS3 on the fp16 pipe (chain_s3h_sm100.cuh): fp16 [H, 2*kin16] = [Whi | Wlo], scaled by 2^4
+  const uint16_t* W16 = nullptr; int ldw16 = 0; int kin16 = 0;
 };
 
 struct Chain16Desc {
@@ -68,6 +71,74 @@ struct Chain16Desc {
   const float* row_scale = nullptr;
   std::vector<Chain16LayerDesc> layers;
 };
+
+// The fp16-pipe primal sweep serves H = 128 / 256 (64-wide k-blocks split evenly over the two N-halves).
+// ARDAE_S3_FP16=0 keeps the tf32 variant (A/B measurements).
+inline bool s3h_supported(int H) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("ARDAE_S3_FP16");
+    env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return env != 0 && (H == 128 || H == 256);
+}
+
+struct PreparedChainS3h {
+  ChainS3hParams params;
+  dim3 grid;
+};
+
+// SOFTPLUS3 chain on the fp16 pipe: A0_32 / A0lo = the tf32 (hi, lo) pair of the initial activation [M, kin0]
+inline int prepare_chain_s3h(const Chain16Desc& d, PreparedChainS3h* out) {
+  const int nl = static_cast<int>(d.layers.size());
+  if (d.M <= 0 || d.mode != CHAIN_SOFTPLUS3 || !s3h_supported(d.H) || nl < 1 || nl > kChainMaxLayers)
+    return fail(-2, "chain_s3h: unsupported shape");
+  if (!d.A0_32 || !d.A0lo || d.lda0_32 != d.lda0lo) return fail(-2, "chain_s3h: needs the fp32 (hi, lo) initial activation");
+  PreparedChainS3h pr;
+  std::memset(&pr.params, 0, sizeof(pr.params));
+  ChainS3hParams& p = pr.params;
+  const int H = d.H;
+  const int kin0 = d.layers[0].kin > 0 ? d.layers[0].kin : H;
+  if (kin0 % 32 != 0 || kin0 > H) return fail(-2, "chain_s3h: first-layer input width must be a multiple of 32, <= H");
+  p.a0_hi = d.A0_32; p.a0_lo = d.A0lo; p.a0_ld = d.lda0_32; p.kin0 = kin0;
+  p.row_scale = d.row_scale; p.M = d.M; p.H = H; p.nlayers = nl;
+  uintptr_t align_or = reinterpret_cast<uintptr_t>(d.A0_32) | reinterpret_cast<uintptr_t>(d.A0lo) |
+                       (static_cast<uintptr_t>(d.lda0_32) * 4);
+  int rc;
+  for (int l = 0; l < nl; ++l) {
+    const Chain16LayerDesc& s = d.layers[l];
+    ChainS3hLayerParams& q = p.layer[l];
+    const int kin = s.kin > 0 ? s.kin : H;
+    const int kin16 = (kin + 63) / 64 * 64;
+    if (l > 0 && kin != H) return fail(-2, "chain_s3h: only the first layer may be narrower than H on input");
+    if (!s.W16 || s.kin16 != kin16 || !s.out) return fail(-2, "chain_s3h: missing fp16 weight operand / output");
+    if ((rc = encode_tmap_2d_bf16(&q.tmW, s.W16, 2 * kin16, H, s.ldw16, kS3hBlockK, H / 2, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_DATA_TYPE_FLOAT16)))
+      return rc;
+    q.kin16 = kin16;
+    q.bias = s.bias; q.group_bias = s.group_bias; q.col_vec = s.col_vec;
+    q.group = s.group > 0 ? s.group : 1; q.ldg = s.ldg;
+    q.out16 = s.out; q.ld_out16 = s.ldo;
+    if (s.col_vec && !d.row_scale) return fail(-2, "chain_s3h: col_vec needs row_scale");
+    align_or |= reinterpret_cast<uintptr_t>(s.bias) | reinterpret_cast<uintptr_t>(s.group_bias) |
+                reinterpret_cast<uintptr_t>(s.col_vec) | (static_cast<uintptr_t>(s.ldg) * 4) |
+                reinterpret_cast<uintptr_t>(s.out) | (static_cast<uintptr_t>(s.ldo) * 2);
+  }
+  if ((align_or & 15) != 0) return fail(-2, "chain_s3h: operands must be 16-byte aligned");
+  p.vec_ok = 1;
+  pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
+  ARDAE_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(&chain_s3h_kernel),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, ChainS3hConfig::kSmemBytes));
+  *out = pr;
+  return 0;
+}
+
+inline int launch_prepared_chain_s3h(const PreparedChainS3h& pr, cudaStream_t stream) {
+  void* args[1] = {const_cast<ChainS3hParams*>(&pr.params)};
+  ARDAE_CUDA_OK(cudaLaunchKernel(reinterpret_cast<const void*>(&chain_s3h_kernel), pr.grid,
+                                 dim3(ChainS3hConfig::kThreads), args, ChainS3hConfig::kSmemBytes, stream));
+  return 0;
+}
 
 struct PreparedChain16 {
   Chain16Params params;

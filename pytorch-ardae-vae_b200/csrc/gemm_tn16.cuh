@@ -213,6 +213,189 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_tn16_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Several same-shape contractions (the 2(L-1) [H,H] weight gradients of one update) in ONE launch: every CTA keeps its
+// (split, m-tile) slot and walks the problems in order.  The TMA producer runs ahead into the next problem while the
+// epilogue warps drain the accumulator (and the co-resident CTA keeps streaming), so launch, ramp-up, tail and the
+// red.add burst are paid once instead of once per layer (round-1 profile: ~25 us of a 100 us contraction).
+constexpr int kTN16MaxProbs = 10;
+struct alignas(64) GemmTN16Prob {
+  CUtensorMap tmX[2];
+  CUtensorMap tmY[2];
+  float* red_out;
+  int red_ld;
+  int npairs;
+};
+struct alignas(64) GemmTN16MultiParams {
+  GemmTN16Prob prob[kTN16MaxProbs];
+  int nprob;
+  int M, N, K;
+  int kb_per_split;
+};
+
+// One CTA per SM, four 48 KB stages (192 KB of HBM traffic in flight per SM) and a DOUBLE-BUFFERED accumulator (2 x BLOCK_N
+// TMEM columns): the MMAs of problem q+1 fill one buffer while the epilogue warps drain problem q from the other, so the
+// operand stream never pauses for the red.add epilogue.
+template <int BLOCK_N>
+struct GemmTN16MultiConfig {
+  using Base = GemmTN16Config<BLOCK_N>;
+  static constexpr int kNumStages = BLOCK_N >= 256 ? 4 : 6;
+  static constexpr int kDataBytes = Base::kStage * kNumStages;
+  static constexpr int kSmemBytes = kDataBytes + 1024 + 256;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn16_multi_kernel(const __grid_constant__ GemmTN16MultiParams p) {
+  using Cfg = GemmTN16Config<BLOCK_N>;
+  using MCfg = GemmTN16MultiConfig<BLOCK_N>;
+  constexpr int NSTAGE = MCfg::kNumStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + MCfg::kDataBytes);
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tmem_full_bar = empty_bar + NSTAGE;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int m0 = blockIdx.y * kBlockM;
+  const int n0 = blockIdx.z * BLOCK_N;
+  const int total_kb = (p.K + kTN16BlockK - 1) / kTN16BlockK;
+  const int kb_begin = split * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > total_kb) kb_end = total_kb;
+  const int nkb = kb_end > kb_begin ? kb_end - kb_begin : 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.prob[0].tmX[0]);
+    ptx::prefetch_tmap(&p.prob[0].tmY[0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSTAGE; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&tmem_full_bar[b], 1);
+        ptx::mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, MCfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (nkb == 0) {  // (only when there are more splits than k-blocks) nothing to add
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, MCfg::kTmemCols);
+    return;
+  }
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int it = 0;
+      for (int q = 0; q < p.nprob; ++q) {
+        const GemmTN16Prob& pr = p.prob[q];
+        if (q + 1 < p.nprob) {
+          ptx::prefetch_tmap(&p.prob[q + 1].tmX[0]);
+          ptx::prefetch_tmap(&p.prob[q + 1].tmY[0]);
+        }
+        for (int pair = 0; pair < pr.npairs; ++pair) {
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % NSTAGE;
+            const int k0 = (kb_begin + kb) * kTN16BlockK;
+            ptx::mbar_wait(&empty_bar[s], ((it / NSTAGE) & 1) ^ 1);
+            ptx::mbar_expect_tx(&full_bar[s], Cfg::kStage);
+            uint8_t* sa = smem + s * Cfg::kStage;
+            uint8_t* sb = sa + Cfg::kStageA;
+#pragma unroll
+            for (int b = 0; b < kBlockM / 64; ++b)
+              ptx::tma_load_2d(sa + b * Cfg::kBoxBytes, &pr.tmX[pair], &full_bar[s], m0 + b * 64, k0);
+#pragma unroll
+            for (int b = 0; b < BLOCK_N / 64; ++b)
+              ptx::tma_load_2d(sb + b * Cfg::kBoxBytes, &pr.tmY[pair], &full_bar[s], n0 + b * 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);
+      int it = 0;
+      for (int q = 0; q < p.nprob; ++q) {
+        const int iters = nkb * p.prob[q].npairs;
+        const int buf = q & 1;
+        const uint32_t d_t = tmem_base + buf * BLOCK_N;
+        ptx::mbar_wait(&tmem_empty_bar[buf], ((q >> 1) & 1) ^ 1);  // the epilogue has drained this buffer (problem q-2)
+        ptx::tc_fence_after();
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % NSTAGE;
+          ptx::mbar_wait(&full_bar[s], (it / NSTAGE) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * Cfg::kStage);
+          const uint32_t b_addr = a_addr + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < kTN16BlockK / 16; ++k) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(a_addr + k * 2048, Cfg::kBoxBytes, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * 2048, Cfg::kBoxBytes, 1024);
+            ptx::umma_bf16(d_t, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[s]);
+        }
+        ptx::umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const bool row_ok = m0 + r < p.M;
+    for (int q = 0; q < p.nprob; ++q) {
+      const GemmTN16Prob& pr = p.prob[q];
+      const int buf = q & 1;
+      ptx::mbar_wait(&tmem_full_bar[buf], (q >> 1) & 1);
+      ptx::tc_fence_after();
+      float* orow = pr.red_out + static_cast<size_t>(row_ok ? m0 + r : 0) * pr.red_ld + n0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        if (n0 + c * 32 >= p.N) break;
+        uint32_t accu[32];
+        ptx::tmem_ld_32x32(tmem_base + buf * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, accu);
+        ptx::tmem_ld_wait();
+        if (c == BLOCK_N / 32 - 1 || n0 + (c + 1) * 32 >= p.N) {  // last TMEM read: hand the buffer back
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        if (!row_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c * 32 + j * 4),
+                       "f"(__uint_as_float(accu[j * 4 + 0])), "f"(__uint_as_float(accu[j * 4 + 1])),
+                       "f"(__uint_as_float(accu[j * 4 + 2])), "f"(__uint_as_float(accu[j * 4 + 3]))
+                       : "memory");
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, MCfg::kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 struct GemmTN16Desc {
   const uint16_t* X[kTN16MaxPairs] = {nullptr, nullptr, nullptr, nullptr}; int ldx[kTN16MaxPairs] = {0, 0, 0, 0};  // [K, M]
@@ -304,6 +487,78 @@ inline int launch_prepared_tn16(const PreparedTN16& pr, cudaStream_t stream) {
   splitk_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(pr.params.partial, pr.nsplit, pr.Mpad, pr.Npad, pr.out,
                                                                  pr.M, pr.N, pr.ldo, 1.0f, 1.0f);
   ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ardae
+
+namespace ardae {
+
+struct PreparedTN16Multi {
+  GemmTN16MultiParams params;
+  const void* fn = nullptr;
+  dim3 grid;
+  int smem = 0;
+};
+
+// One launch for same-shape, <= 2-pair, vector-reducible contractions (ARDAE_TN_MULTI=0: one launch each).
+inline bool tn16_multi_ok(const std::vector<GemmTN16Desc>& ds) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("ARDAE_TN_MULTI");
+    env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (!env || !tn_atomic_default() || ds.size() < 2 || ds.size() > static_cast<size_t>(kTN16MaxProbs)) return false;
+  for (const GemmTN16Desc& d : ds) {
+    const bool red_vec = (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldo % 4 == 0 && d.N % 32 == 0;
+    if (!red_vec || d.atomic < 0 || d.npairs < 1 || d.npairs > 2 || d.M != ds[0].M || d.N != ds[0].N || d.K != ds[0].K ||
+        (d.Ny > 0 && d.Ny != d.N))
+      return false;
+  }
+  return true;
+}
+
+inline int prepare_gemm_tn16_multi(const std::vector<GemmTN16Desc>& ds, PreparedTN16Multi* out) {
+  if (!tn16_multi_ok(ds)) return fail(-2, "gemm_tn16_multi: problems are not batchable");
+  const GemmTN16Desc& d0 = ds[0];
+  const int bn = tn16_block_n(d0.N);
+  const int mt = (d0.M + kBlockM - 1) / kBlockM, nt = (d0.N + bn - 1) / bn;
+  const int total_kb = (d0.K + kTN16BlockK - 1) / kTN16BlockK;
+  int nsplit = num_sms() / (mt * nt);  // one CTA per SM
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > total_kb) nsplit = total_kb;
+  const int kb_per_split = (total_kb + nsplit - 1) / nsplit;
+  nsplit = (total_kb + kb_per_split - 1) / kb_per_split;
+  PreparedTN16Multi pr;
+  std::memset(&pr.params, 0, sizeof(pr.params));
+  GemmTN16MultiParams& p = pr.params;
+  int rc;
+  for (size_t i = 0; i < ds.size(); ++i) {
+    const GemmTN16Desc& d = ds[i];
+    GemmTN16Prob& q = p.prob[i];
+    for (int k = 0; k < d.npairs; ++k) {
+      if (!d.X[k] || !d.Y[k]) return fail(-2, "gemm_tn16_multi: missing operand");
+      if ((rc = encode_tmap_2d_bf16(&q.tmX[k], d.X[k], d.M, d.K, d.ldx[k], 64, kTN16BlockK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+      if ((rc = encode_tmap_2d_bf16(&q.tmY[k], d.Y[k], d.N, d.K, d.ldy[k], 64, kTN16BlockK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+    q.npairs = d.npairs; q.red_out = d.out; q.red_ld = d.ldo;
+  }
+  p.nprob = static_cast<int>(ds.size());
+  p.M = d0.M; p.N = d0.N; p.K = d0.K; p.kb_per_split = kb_per_split;
+  switch (bn) {
+    case 64: pr.fn = reinterpret_cast<const void*>(&gemm_tn16_multi_kernel<64>); pr.smem = GemmTN16MultiConfig<64>::kSmemBytes; break;
+    case 128: pr.fn = reinterpret_cast<const void*>(&gemm_tn16_multi_kernel<128>); pr.smem = GemmTN16MultiConfig<128>::kSmemBytes; break;
+    default: pr.fn = reinterpret_cast<const void*>(&gemm_tn16_multi_kernel<256>); pr.smem = GemmTN16MultiConfig<256>::kSmemBytes; break;
+  }
+  pr.grid = dim3(nsplit, mt, nt);
+  ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
+  *out = pr;
+  return 0;
+}
+
+inline int launch_prepared_tn16_multi(const PreparedTN16Multi& pr, cudaStream_t stream) {
+  void* args[1] = {const_cast<GemmTN16MultiParams*>(&pr.params)};
+  ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(kGemmThreads), args, pr.smem, stream));
   return 0;
 }
 

@@ -2,6 +2,7 @@
 // transposes), noise / perturbation prologues, loss epilogues, reductions, optimizers.
 // All are grid-stride, coalesced over the contiguous dimension, vectorised where rows allow it.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -115,6 +116,8 @@ struct DeriveItem {
   int rows, cols, src_ld, ld, ldT, kp, ld3;
   int first_block;  // prefix sum over 32x32 tiles
   int tiles_x;      // ceil(ld/32)
+  uint16_t* dst16;  // fp16 [rows, 2*k16] = [W_hi | W_lo] of w * 2^4 (chain_s3h_sm100.cuh), pad columns zero
+  int k16;
 };
 __global__ void derive_weights_kernel(const DeriveItem* __restrict__ items, int nitems) {
   __shared__ float tile[32][33];
@@ -137,6 +140,14 @@ __global__ void derive_weights_kernel(const DeriveItem* __restrict__ items, int 
         o[0] = v;
         o[d.kp] = v;
         o[2 * d.kp] = ptx::round_tf32(w - v);
+      }
+      if (d.dst16 != nullptr) {
+        const float ws = fminf(fmaxf(w * 16.0f, -65000.0f), 65000.0f);
+        const __half hi = __float2half_rn(ws);
+        const __half lo = __float2half_rn(ws - __half2float(hi));
+        uint16_t* o = d.dst16 + static_cast<size_t>(r) * (2 * d.k16) + c;
+        o[0] = __half_as_ushort(hi);
+        o[d.k16] = __half_as_ushort(lo);
       }
     }
     tile[ly + j][lx] = v;

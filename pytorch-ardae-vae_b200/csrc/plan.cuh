@@ -141,6 +141,17 @@ struct Plan {
     static const char* names[CHAIN_NUM_MODES] = {"chain_mul_sig", "chain_tangent", "chain_adjoint", "chain_softplus3"};
     tag_last(names[d.mode]);
   }
+  void chain_s3h(const Chain16Desc& d) {
+    ++num_chain;
+    if (dry) return;
+    PreparedChainS3h pr;
+    int rc = prepare_chain_s3h(d, &pr);
+    if (rc) return fail_with(rc);
+    auto sp = std::make_shared<PreparedChainS3h>(pr);
+    ops.push_back([sp](cudaStream_t s) { return launch_prepared_chain_s3h(*sp, s); });
+    lanes.push_back(cur_lane);
+    tag_last("chain_softplus3");
+  }
   void tn16(const GemmTN16Desc& d) {
     ++num_gemm_tn;
     if (dry) return;
@@ -151,6 +162,21 @@ struct Plan {
     ops.push_back([sp](cudaStream_t s) { return launch_prepared_tn16(*sp, s); });
     lanes.push_back(cur_lane);
     tag_last("gemm_tn16");
+  }
+  // same-shape bf16 contractions as one launch where possible, else one launch each
+  void tn16_multi(const std::vector<GemmTN16Desc>& ds) {
+    if (dry || !tn16_multi_ok(ds)) {
+      for (const GemmTN16Desc& d : ds) tn16(d);
+      return;
+    }
+    ++num_gemm_tn;
+    PreparedTN16Multi pr;
+    int rc = prepare_gemm_tn16_multi(ds, &pr);
+    if (rc) return fail_with(rc);
+    auto sp = std::make_shared<PreparedTN16Multi>(pr);
+    ops.push_back([sp](cudaStream_t s) { return launch_prepared_tn16_multi(*sp, s); });
+    lanes.push_back(cur_lane);
+    tag_last("gemm_tn16_multi");
   }
   void tn(const GemmTNDesc& d) {
     ++num_gemm_tn;
@@ -267,6 +293,8 @@ inline Pair make_pair(Workspace& ws, int rows, int w) {
 }
 // A weight in the layouts the kernels consume.
 struct W3 {
+  Mat16 h16;   // fp16 [out, 2*k16] = [W_hi | W_lo] of w * 2^4 (fp16-pipe primal sweep), k16 = in rounded up to 64
+  int k16 = 0;
   Mat b3;  // [out, 3*kp]  = [W_hi | W_hi | W_lo]  (3xTF32 B operand of the forward GEMMs)
   Mat T;   // [in, out]    tf32-rounded transpose   (B operand of the backward-data GEMMs)
   int in = 0, out = 0, kp = 0;

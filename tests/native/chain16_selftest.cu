@@ -13,6 +13,8 @@
 #include <random>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "chain16_host.cuh"
 #include "gemm_tn16.cuh"
 
@@ -84,6 +86,7 @@ static std::vector<T> host(const T* d, size_t n) {
 static double softplus_d(double x) { return x > 20 ? x : std::log1p(std::exp(x)); }
 
 static int g_fail = 0;
+static float time_it(const std::function<void()>& f, int reps);
 struct Cmp {
   double max_err = 0, max_ref = 0;
   long bad = 0, n = 0;
@@ -283,6 +286,97 @@ static void test_chain16(int mode, int M, int H, int nl, int kin0, int dn) {
   cudaFree(dA0f); cudaFree(dA0lo); cudaFree(dA016); cudaFree(dsig);
 }
 
+// ---- primal sweep on the fp16 pipe (chain_s3h_sm100.cuh): checked against the EXACT double-precision chain (the
+// three-product scheme is fp32-accurate: relative error ~2^-21 of sum |a w|), bf16 rounding of the stored value on top
+static uint16_t f16_bits(float x) {
+  __half h = __float2half_rn(x);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+static float f16_val(uint16_t u) {
+  __half h;
+  memcpy(&h, &u, 2);
+  return __half2float(h);
+}
+static void run_s3h(int M, int H, int nl, int kin0, bool bench) {
+  printf("%s s3h M=%d H=%d layers=%d kin0=%d\n", bench ? "bench" : "test", M, H, nl, kin0);
+  const int group = 48, ng = (M + group - 1) / group;
+  std::vector<float> sigma = randn(M, 1.0f);
+  float* dsig = dev(sigma);
+  std::vector<float> full = randn((size_t)M * kin0, 3000.0f), a0h(full.size()), a0l(full.size());
+  for (size_t i = 0; i < full.size(); ++i) { a0h[i] = tf32_rna(full[i]); a0l[i] = tf32_rna(full[i] - a0h[i]); }
+  float *da0h = dev(a0h), *da0l = dev(a0l);
+  std::vector<double> Ain((size_t)M * H, 0.0);
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < kin0; ++k) Ain[(size_t)m * H + k] = (double)a0h[(size_t)m * kin0 + k] + a0l[(size_t)m * kin0 + k];
+  struct LB { std::vector<float> W, bias, gb, colv; std::vector<uint16_t> W16; uint16_t *dW16, *dout; float *dbias, *dgb, *dcolv; int kin, k16; };
+  std::vector<LB> Ls(nl);
+  Chain16Desc d;
+  d.mode = CHAIN_SOFTPLUS3; d.M = M; d.H = H; d.row_scale = dsig;
+  d.A0_32 = da0h; d.lda0_32 = kin0; d.A0lo = da0l; d.lda0lo = kin0;
+  for (int l = 0; l < nl; ++l) {
+    LB& b = Ls[l];
+    b.kin = l == 0 ? kin0 : H;
+    b.k16 = (b.kin + 63) / 64 * 64;
+    b.W = randn((size_t)H * b.kin, l == 0 ? 0.2f : 0.05f);
+    b.W16.assign((size_t)H * 2 * b.k16, 0);
+    for (int o = 0; o < H; ++o)
+      for (int i = 0; i < b.kin; ++i) {
+        const float ws = b.W[(size_t)o * b.kin + i] * 16.0f;
+        const uint16_t hi = f16_bits(ws);
+        b.W16[(size_t)o * 2 * b.k16 + i] = hi;
+        b.W16[(size_t)o * 2 * b.k16 + b.k16 + i] = f16_bits(ws - f16_val(hi));
+      }
+    b.bias = randn(H, 1.0f); b.gb = randn((size_t)ng * H, 1.0f); b.colv = randn(H, 1.0f);
+    b.dW16 = dev(b.W16); b.dbias = dev(b.bias); b.dgb = dev(b.gb); b.dcolv = dev(b.colv);
+    b.dout = dev_fill<uint16_t>((size_t)M * H, 0xFF);
+    Chain16LayerDesc q;
+    q.kin = b.kin; q.W16 = b.dW16; q.ldw16 = 2 * b.k16; q.kin16 = b.k16; q.out = b.dout; q.ldo = H;
+    if (l % 2 == 0) q.bias = b.dbias;
+    else { q.group_bias = b.dgb; q.group = group; q.ldg = H; q.col_vec = b.dcolv; }
+    d.layers.push_back(q);
+  }
+  PreparedChainS3h pr;
+  int rc = prepare_chain_s3h(d, &pr);
+  if (rc) { printf("  prepare failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
+  rc = launch_prepared_chain_s3h(pr, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc || e != cudaSuccess) { printf("  launch failed %d %s\n", rc, cudaGetErrorString(e)); exit(3); }
+  if (bench) {
+    const float ms = time_it([&]() { launch_prepared_chain_s3h(pr, 0); }, 5);
+    const double flops = 2.0 * M * ((double)H * H * (nl - 1) + (double)H * kin0) * 3.0;
+    printf("bench s3h M=%d H=%d layers=%d: %.3f ms (%.1f us/layer) tensor %.0f TFLOP/s executed (fp16 pipe), %.0f algorithmic\n", M, H,
+           nl, ms, ms * 1e3 / nl, flops / ms * 1e-9, flops / 3 / ms * 1e-9);
+  } else {
+    for (int l = 0; l < nl; ++l) {
+      LB& b = Ls[l];
+      auto out = host(b.dout, (size_t)M * H);
+      Cmp c1;
+      std::vector<double> next((size_t)M * H);
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < H; ++n) {
+          double acc = 0, mag = 0;
+          for (int k = 0; k < b.kin; ++k) {
+            const double t = Ain[(size_t)m * H + k] * b.W[(size_t)n * b.kin + k];
+            acc += t; mag += std::fabs(t);
+          }
+          double pre = acc;
+          if (l % 2 == 0) pre += b.bias[n];
+          else pre += b.gb[(size_t)(m / group) * H + n] + (double)sigma[m] * b.colv[n];
+          const double ref = softplus_d(pre);
+          next[(size_t)m * H + n] = ref;
+          // fp32-accurate products (3 x 2^-22 per term, random signs), one bf16 rounding of the stored value
+          c1.add(bf16_f(out[(size_t)m * H + n]), ref, 3e-6 * mag + 4.0e-3 * std::fabs(ref) + 1e-5);
+        }
+      c1.report("s3h out", 3, l);
+      Ain = next;
+    }
+  }
+  for (auto& b : Ls) { cudaFree(b.dW16); cudaFree(b.dbias); cudaFree(b.dgb); cudaFree(b.dcolv); cudaFree(b.dout); }
+  cudaFree(da0h); cudaFree(da0l); cudaFree(dsig);
+}
+
 static void test_tn16(int M, int N, int Ny, int K, int npairs, int ldo, int atomic) {
   printf("tn16 M=%d N=%d Ny=%d K=%d pairs=%d ldo=%d atomic=%d\n", M, N, Ny, K, npairs, ldo, atomic);
   std::vector<std::vector<uint16_t>> X(npairs), Y(npairs);
@@ -387,6 +481,65 @@ static void bench_chain16(int mode, int M, int H, int nl, int kin0, bool narrow)
   cudaFree(const_cast<uint16_t*>(d.A0_16)); cudaFree(const_cast<float*>(d.A0_32)); cudaFree(const_cast<float*>(d.A0lo));
 }
 
+// several same-shape contractions in one launch (gemm_tn16_multi_kernel): each output checked like test_tn16
+static void run_tn16_multi(int M, int N, int K, int nprob, bool bench) {
+  printf("%s tn16_multi M=%d N=%d K=%d problems=%d\n", bench ? "bench" : "test", M, N, K, nprob);
+  std::vector<std::vector<uint16_t>> X(2 * nprob), Y(2 * nprob);
+  std::vector<uint16_t*> dX(2 * nprob), dY(2 * nprob);
+  std::vector<std::vector<float>> out0(nprob);
+  std::vector<float*> dout(nprob);
+  std::vector<GemmTN16Desc> ds(nprob);
+  float* ws = dev_fill<float>(tn16_workspace_bytes(M, N, K) / 4, 0);
+  for (int q = 0; q < nprob; ++q) {
+    GemmTN16Desc& d = ds[q];
+    d.npairs = (!bench && q % 3 == 2) ? 1 : 2;
+    for (int k = 0; k < d.npairs; ++k) {
+      const int i = 2 * q + k;
+      if (bench) { dX[i] = dev_fill<uint16_t>((size_t)K * M, 0x3c); dY[i] = dev_fill<uint16_t>((size_t)K * N, 0x3c); }
+      else {
+        X[i] = to16(randn((size_t)K * M, 1.0f)); Y[i] = to16(randn((size_t)K * N, 1.0f));
+        dX[i] = dev(X[i]); dY[i] = dev(Y[i]);
+      }
+      d.X[k] = dX[i]; d.ldx[k] = M; d.Y[k] = dY[i]; d.ldy[k] = N;
+    }
+    d.M = M; d.N = N; d.Ny = N; d.K = K;
+    out0[q] = randn((size_t)M * N, 1.0f);
+    dout[q] = dev(out0[q]);
+    d.out = dout[q]; d.ldo = N; d.workspace = ws; d.workspace_bytes = tn16_workspace_bytes(M, N, K);
+  }
+  PreparedTN16Multi pr;
+  int rc = prepare_gemm_tn16_multi(ds, &pr);
+  if (rc) { printf("  prepare failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
+  rc = launch_prepared_tn16_multi(pr, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc || e != cudaSuccess) { printf("  launch failed %d %s\n", rc, cudaGetErrorString(e)); exit(3); }
+  if (bench) {
+    const float ms = time_it([&]() { launch_prepared_tn16_multi(pr, 0); }, 5);
+    const double bytes = (double)nprob * 2 * K * (M + N) * 2.0;
+    printf("bench tn16_multi M=%d N=%d K=%d problems=%d grid=%dx%dx%d: %.1f us (%.1f us per problem)  HBM %.0f GB/s\n", M, N, K,
+           nprob, pr.grid.x, pr.grid.y, pr.grid.z, ms * 1e3, ms * 1e3 / nprob, bytes / ms * 1e-6);
+  } else {
+    for (int q = 0; q < nprob; ++q) {
+      auto out = host(dout[q], (size_t)M * N);
+      Cmp c;
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+          double acc = 0, mag = 0;
+          for (int k2 = 0; k2 < ds[q].npairs; ++k2)
+            for (int k = 0; k < K; ++k) {
+              const double t = (double)bf16_f(X[2 * q + k2][(size_t)k * M + m]) * bf16_f(Y[2 * q + k2][(size_t)k * N + n]);
+              acc += t; mag += std::fabs(t);
+            }
+          c.add(out[(size_t)m * N + n], acc + out0[q][(size_t)m * N + n], 2e-6 * mag + 1e-5);
+        }
+      c.report("tn16multi", q, ds[q].npairs);
+    }
+  }
+  for (int i = 0; i < 2 * nprob; ++i) { if (dX[i]) cudaFree(dX[i]); if (dY[i]) cudaFree(dY[i]); }
+  for (int q = 0; q < nprob; ++q) cudaFree(dout[q]);
+  cudaFree(ws);
+}
+
 static void bench_tn16(int M, int N, int K, int npairs) {
   GemmTN16Desc d;
   for (int q = 0; q < npairs; ++q) {
@@ -418,6 +571,8 @@ int main(int argc, char** argv) {
     test_tn16(256, 32, 64, 2048, 4, 32, 1);      // d-wide contraction, four pairs, zero-padded Y
     test_tn16(128, 2, 64, 300, 4, 2, 0);         // toy d = 2 (scalar reductions)
     test_tn16(64, 64, 64, 129, 1, 64, 1);
+    run_tn16_multi(256, 256, 2000, 4, false);
+    run_tn16_multi(128, 128, 700, 3, false);
   }
   if (!*only || !strcmp(only, "chain")) {
     for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
@@ -428,12 +583,20 @@ int main(int argc, char** argv) {
       test_chain16(mode, 520, 256, 3, 256, 0);
     }
   }
+  if (!*only || !strcmp(only, "s3h")) {
+    run_s3h(300, 256, 3, 32, false);
+    run_s3h(1000, 128, 4, 64, false);
+    run_s3h(520, 256, 3, 256, false);
+    run_s3h(200, 256, 4, 96, false);
+  }
   if (bench) {
+    run_s3h(131072, 256, 10, 32, true);
     for (int mode = 0; mode < CHAIN_NUM_MODES; ++mode) {
       const bool fwd = mode == CHAIN_TANGENT || mode == CHAIN_SOFTPLUS3;
       bench_chain16(mode, 131072, 256, fwd ? 10 : 9, fwd ? 32 : 256, mode == CHAIN_MUL_SIG);
     }
     bench_tn16(256, 256, 131072, 2);
+    run_tn16_multi(256, 256, 131072, 8, true);
     bench_tn16(256, 64, 131072, 4);
   }
   printf(g_fail ? "CHAIN16 SELFTEST FAILED (%d)\n" : "CHAIN16 SELFTEST OK\n", g_fail);
