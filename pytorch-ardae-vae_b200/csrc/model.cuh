@@ -113,13 +113,15 @@ struct ModelPlan {
     // fc layer 0: [h, feat+n] = [W_inp | W_noise]
     const int ld0 = feat + n;
     W3 F0i = derive.add(ws, P(iF(0)), h, feat, ld0, true, train);
-    W3 F0n = derive.add(ws, P(iF(0)) ? P(iF(0)) + feat : nullptr, h, n, ld0, true, false);
+    // fused N-row sampling pass (enc_sample_sm100.cuh): MNIST-kind encode plans
+    const bool enc_fused = c.kind == 1 && c.mode == 0 && c.n_fc == 1 && enc_sample_supported(n, h, zd);
+    W3 F0n = derive.add(ws, P(iF(0)) ? P(iF(0)) + feat : nullptr, h, n, ld0, true, false, enc_fused);
     // later fc layers (toy: input is [hid | eps]; mnist has none) and the final fc.fc
     std::vector<W3> Fw(c.n_fc + 1);
     for (int l = 1; l <= c.n_fc; ++l) {
       const int out = l == c.n_fc ? zd : h;
       const int in = toy ? h + n : h;
-      Fw[l] = derive.add(ws, P(iF(l)), out, in, in, true, train);
+      Fw[l] = derive.add(ws, P(iF(l)), out, in, in, true, train, enc_fused && l == c.n_fc);
     }
     for (int l = 0; l < c.n_dec; ++l) {
       const int in = l == 0 ? zd : dwid(l - 1);
@@ -229,8 +231,8 @@ struct ModelPlan {
     });
     // the (HBM-bound, R-row) noise split runs on the plan's side lane underneath the latency-bound B-row input stack;
     // joined right before the first layer that consumes the noise pair
-    if (enc_fc) fwd.fork();
-    if (enc_fc) fwd.add([=](cudaStream_t s) {
+    if (enc_fc && !enc_fused) fwd.fork();
+    if (enc_fc && !enc_fused) fwd.add([=](cudaStream_t s) {
       if (bd->noise != nullptr) {
         split2d_kernel<<<grid_for(static_cast<size_t>(R) * n), 256, 0, s>>>(
             bd->noise, n, epsp.buf.p, epsp.buf.ld, R, n, epsp.kp, 1.0f, 0.0f);
@@ -284,8 +286,31 @@ struct ModelPlan {
       g.bias = P(iF(0) + 1);
       fwd.nt(g);
     }
-    if (enc_fc) fwd.join();
-    if (enc_fc) {
+    if (enc_fc && !enc_fused) fwd.join();
+    if (enc_fused) {
+      EncSampleDesc ed;
+      ed.W1 = F0n.h16.p; ed.ldw1 = F0n.h16.ld; ed.W2 = Fw[c.n_fc].h16.p; ed.ldw2 = Fw[c.n_fc].h16.ld;
+      ed.rowbias = rowbias0.p; ed.ldb = rowbias0.ld; ed.bias2 = P(iF(c.n_fc) + 1); ed.z_out = zbuf.p;
+      ed.R = R; ed.nz = nz; ed.n = n; ed.h = h; ed.zd = zd;
+      if (!dry) {
+        PreparedEncSample pe;
+        int rc2 = prepare_enc_sample(ed, &pe);
+        if (rc2) return rc2;
+        auto sp = std::make_shared<PreparedEncSample>(pe);
+        float* znull = ws.floats(static_cast<size_t>(n) * 128 + 4);  // zero noise rows for encode(std=0) (workspace is zeroed)
+        fwd.add([=](cudaStream_t s) {
+          // noise == NULL (encode(x, std=0)): every row reads the same zero row through a zero row pitch
+          PreparedEncSample q = *sp;
+          if (bd->noise == nullptr) q.params.n = 0;
+          return launch_prepared_enc_sample(q, bd->noise != nullptr ? bd->noise : znull, bd->z_out, s);
+        });
+      } else {
+        ws.floats(static_cast<size_t>(n) * 128 + 4);
+        fwd.add(nullptr);
+      }
+      fwd.tag_last("enc_sample");
+    }
+    if (enc_fc && !enc_fused) {
       Pair out = Fh[0];
       out.w = h;  // write only the hid columns of the (possibly wider) concat buffer
       GemmNTDesc g = nt3_desc(epsp, F0n, out, ACT);
@@ -294,7 +319,7 @@ struct ModelPlan {
       if (h > 256 && h <= 512 && R >= 16384) g.force_block_n = 256;
       fwd.nt(g);
     }
-    if (toy && enc_fc) {
+    if (toy && enc_fc && !enc_fused) {
       // append eps to every concat buffer: columns [h, h+n) of hi and lo halves
       fwd.add([=](cudaStream_t s) {
         for (int l = 0; l < c.n_fc; ++l) {
@@ -310,7 +335,7 @@ struct ModelPlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
-    for (int l = 1; l < c.n_fc && enc_fc; ++l) {
+    for (int l = 1; l < c.n_fc && enc_fc && !enc_fused; ++l) {
       Pair out = Fh[l];
       out.w = h;
       GemmNTDesc g = nt3_desc(Fh[l - 1], Fw[l], out, ACT);
@@ -324,7 +349,7 @@ struct ModelPlan {
         return static_cast<int>(cudaGetLastError());
       });
     }
-    if (enc_fc) {  // z = fc.fc([hid | eps])  (plain fp32 to the user buffer layout, and as a tf32 pair)
+    if (enc_fc && !enc_fused) {  // z = fc.fc([hid | eps])  (plain fp32 to the user buffer layout, and as a tf32 pair)
       GemmNTDesc g = nt3_desc(Fh[c.n_fc - 1], Fw[c.n_fc], zp, EPI_LINEAR);
       g.bias = P(iF(c.n_fc) + 1);
       fwd.nt(g);
