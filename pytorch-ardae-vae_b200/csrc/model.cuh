@@ -114,7 +114,10 @@ struct ModelPlan {
     const int ld0 = feat + n;
     W3 F0i = derive.add(ws, P(iF(0)), h, feat, ld0, true, train);
     // fused N-row sampling pass (enc_sample_sm100.cuh): MNIST-kind encode plans
-    const bool enc_fused = c.kind == 1 && c.mode == 0 && c.n_fc == 1 && enc_sample_supported(n, h, zd);
+    const bool enc_fused = c.kind == 1 && (c.mode == 0 || (c.mode == 2 && zd % 4 == 0)) && c.n_fc == 1 &&
+                           enc_sample_supported(n, h, zd);
+    // fused decoder + BCE row sums (dec_iws_sm100.cuh): MNIST-kind IWS plans
+    const bool dec_fused = c.kind == 1 && c.mode == 2 && dec_iws_supported(zd, h, c.n_dec);
     W3 F0n = derive.add(ws, P(iF(0)) ? P(iF(0)) + feat : nullptr, h, n, ld0, true, false, enc_fused);
     // later fc layers (toy: input is [hid | eps]; mnist has none) and the final fc.fc
     std::vector<W3> Fw(c.n_fc + 1);
@@ -125,11 +128,15 @@ struct ModelPlan {
     }
     for (int l = 0; l < c.n_dec; ++l) {
       const int in = l == 0 ? zd : dwid(l - 1);
-      if (dec) Dw[l] = derive.add(ws, P(iD(l)), dwid(l), in, in, true, train);
+      if (dec) Dw[l] = derive.add(ws, P(iD(l)), dwid(l), in, in, true, train, dec_fused);
     }
     // heads: combined [nH*D, h] forward operand and [h, nH*D] transpose
     W3 Hw;
     Hw.in = h; Hw.out = nH * D; Hw.kp = round_up(h, 32);
+    if (dec_fused) {
+      Hw.k16 = round_up(h, 64);
+      Hw.h16 = ws.mat16(D, 2 * Hw.k16);
+    }
     if (dec && !conv) {
       Hw.b3 = Mat(ws.floats(static_cast<size_t>(nH) * D * 3 * Hw.kp), nH * D, 3 * Hw.kp, 3 * Hw.kp);
       if (train) Hw.T = ws.mat(h, nH * Dp);
@@ -140,6 +147,7 @@ struct ModelPlan {
         it.dst3 = dry ? nullptr : Hw.b3.p + static_cast<size_t>(k) * D * Hw.b3.ld;
         it.kp = Hw.kp; it.ld3 = Hw.b3.ld;
         it.dstT = (dry || !train) ? nullptr : Hw.T.p + k * Dp; it.ldT = Hw.T.ld;
+        if (dec_fused && k == 0 && !dry) { it.dst16 = Hw.h16.p; it.k16 = Hw.k16; }
         it.first_block = derive.blocks;
         it.tiles_x = (h + 31) / 32;
         derive.blocks += it.tiles_x * ((D + 31) / 32);
@@ -297,12 +305,13 @@ struct ModelPlan {
         int rc2 = prepare_enc_sample(ed, &pe);
         if (rc2) return rc2;
         auto sp = std::make_shared<PreparedEncSample>(pe);
+        float* zdst = c.mode == 2 ? zbuf.p : nullptr;  // IWS plans keep z in the workspace (moment matching reads it)
         float* znull = ws.floats(static_cast<size_t>(n) * 128 + 4);  // zero noise rows for encode(std=0) (workspace is zeroed)
         fwd.add([=](cudaStream_t s) {
           // noise == NULL (encode(x, std=0)): every row reads the same zero row through a zero row pitch
           PreparedEncSample q = *sp;
           if (bd->noise == nullptr) q.params.n = 0;
-          return launch_prepared_enc_sample(q, bd->noise != nullptr ? bd->noise : znull, bd->z_out, s);
+          return launch_prepared_enc_sample(q, bd->noise != nullptr ? bd->noise : znull, zdst != nullptr ? zdst : bd->z_out, s);
         });
       } else {
         ws.floats(static_cast<size_t>(n) * 128 + 4);
@@ -408,6 +417,31 @@ struct ModelPlan {
                                                 zp.kp, lw0, bd->status);
         return static_cast<int>(cudaGetLastError());
       });
+    }
+    if (dec_fused) {
+      DecIwsDesc dd;
+      for (int l = 0; l < c.n_dec; ++l) {
+        dd.W[l] = Dw[l].h16.p; dd.ldw[l] = Dw[l].h16.ld; dd.bias[l] = P(iD(l) + 1);
+      }
+      dd.Wlogit = Hw.h16.p; dd.ldwl = Hw.h16.ld; dd.bias_logit = P(iH(0) + 1);
+      dd.z_hi = zp.hi().p; dd.z_lo = zp.lo().p; dd.ldz = zp.buf.ld; dd.lw0 = lw0; dd.w = wbuf;
+      dd.R = R; dd.S = nz; dd.zd = zd; dd.h = h; dd.D = D; dd.nhid = c.n_dec;
+      if (!dry) {
+        PreparedDecIws pd;
+        int rc2 = prepare_dec_iws(dd, &pd);
+        if (rc2) return rc2;
+        auto sp = std::make_shared<PreparedDecIws>(pd);
+        fwd.add([=](cudaStream_t s) {
+          int rc3 = launch_prepared_dec_iws(*sp, bd->x, s);
+          if (rc3) return rc3;
+          iws_logmeanexp_kernel<<<B, 256, 0, s>>>(wbuf, nz, bd->iws_out, bd->iws_total);
+          return static_cast<int>(cudaGetLastError());
+        });
+      } else {
+        fwd.add(nullptr);
+      }
+      fwd.tag_last("dec_iws");
+      return fwd.error;
     }
     // decoder
     for (int l = 0; l < c.n_dec; ++l) {

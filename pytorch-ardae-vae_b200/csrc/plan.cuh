@@ -7,6 +7,7 @@
 
 #include "chain16_host.cuh"
 #include "chain_host.cuh"
+#include "dec_iws_sm100.cuh"
 #include "enc_sample_sm100.cuh"
 #include "gemm_host.cuh"
 #include "gemm_tn16.cuh"

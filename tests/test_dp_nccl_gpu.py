@@ -102,9 +102,9 @@ def test_two_rank_dp_matches_single_rank(name):
     assert np.isfinite(ret['graph_losses']).all()
     for got, one, p0 in ((ret['pm'], pm1, p0m), (ret['pc'], pc1, p0c)):
         for k in one:
-            # parameters agree to 1e-5; the UPDATE (3 steps of lr 1e-4) to a few per cent: Adam / RMSprop turn
+            # parameters agree to 1e-4; the UPDATE (3 steps of lr 1e-4) to a few per cent: Adam / RMSprop turn
             # summation-order differences of near-zero gradients into O(lr) differences
-            assert rel_err(got[k], one[k]) <= 1e-5, (k, rel_err(got[k], one[k]))
+            assert rel_err(got[k], one[k]) <= 1e-4, (k, rel_err(got[k], one[k]))
         upd_got = np.concatenate([(got[k] - p0[k]).ravel() for k in sorted(one)])
         upd_one = np.concatenate([(one[k] - p0[k]).ravel() for k in sorted(one)])
         assert rel_err(upd_got, upd_one) <= 5e-2, rel_err(upd_got, upd_one)
