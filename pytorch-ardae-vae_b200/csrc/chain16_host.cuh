@@ -5,6 +5,7 @@
 #include "chain16_sm100.cuh"
 #include "chain_host.cuh"
 #include "chain_s3h_sm100.cuh"
+#include "chain16w_sm100.cuh"
 
 namespace ardae {
 
@@ -217,19 +218,33 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
   }
   p.vec_ok = (align_or & 15) == 0 ? 1 : 0;
   if (s3 && !p.vec_ok) return fail(-2, "chain16: SOFTPLUS3 operands must be 16-byte aligned");
+  static int warps_env = -1;
+  if (warps_env < 0) {
+    const char* e = std::getenv("ARDAE_CHAIN16_WARPS");
+    warps_env = e ? std::atoi(e) : 16;
+  }
+  const bool w16 = warps_env != 8 && !s3;  // 16 epilogue warps (chain16w_sm100.cuh) unless ARDAE_CHAIN16_WARPS=8
 #define ARDAE_CHAIN16_CASE(MODE_)                                                                               \
   case MODE_:                                                                                                   \
     pr.fn = reinterpret_cast<const void*>(&chain16_kernel<MODE_>);                                              \
     pr.smem = Chain16Config<MODE_>::kSmemBytes; pr.threads = Chain16Config<MODE_>::kThreads;                   \
     break;
+#define ARDAE_CHAIN16W_CASE(MODE_)                                                                              \
+  case MODE_:                                                                                                   \
+    pr.fn = w16 ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_>)                                        \
+                : reinterpret_cast<const void*>(&chain16_kernel<MODE_>);                                        \
+    pr.smem = Chain16Config<MODE_>::kSmemBytes;                                                                 \
+    pr.threads = w16 ? Chain16wConfig::kThreads : Chain16Config<MODE_>::kThreads;                               \
+    break;
   switch (d.mode) {
-    ARDAE_CHAIN16_CASE(CHAIN_MUL_SIG)
-    ARDAE_CHAIN16_CASE(CHAIN_TANGENT)
-    ARDAE_CHAIN16_CASE(CHAIN_ADJOINT)
+    ARDAE_CHAIN16W_CASE(CHAIN_MUL_SIG)
+    ARDAE_CHAIN16W_CASE(CHAIN_TANGENT)
+    ARDAE_CHAIN16W_CASE(CHAIN_ADJOINT)
     default:
     ARDAE_CHAIN16_CASE(CHAIN_SOFTPLUS3)
   }
 #undef ARDAE_CHAIN16_CASE
+#undef ARDAE_CHAIN16W_CASE
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;
