@@ -146,7 +146,20 @@ struct PreparedChain16 {
   const void* fn = nullptr;
   dim3 grid;
   int smem = 0, threads = 0;
+  int cluster = 1;
 };
+
+// CTA pairs (cta_group::2) for the tf32 sweeps: each SM ingests half of the weight stream.  Opt-in (ARDAE_CHAIN16_PAIR=1):
+// measured on B200 it is correct but SLOWER (score / tangent / adjoint sweeps 0.48 / 0.63 / 0.51 ms vs 0.36 / 0.50 / 0.42):
+// the lock-step of the pair costs more than the halved weight stream saves (same finding as round 1 for the fp32 kernel).
+inline bool chain16_pair_default() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("ARDAE_CHAIN16_PAIR");
+    env = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return env != 0;
+}
 
 inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
   const int nl = static_cast<int>(d.layers.size());
@@ -159,6 +172,16 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
   std::memset(&pr.params, 0, sizeof(pr.params));
   Chain16Params& p = pr.params;
   int rc;
+  static int warps_env = -1;
+  if (warps_env < 0) {
+    const char* e = std::getenv("ARDAE_CHAIN16_WARPS");
+    warps_env = e ? std::atoi(e) : 16;
+  }
+  const bool w16 = warps_env != 8 && !s3;  // 16 epilogue warps (chain16w_sm100.cuh) unless ARDAE_CHAIN16_WARPS=8
+  // pairs need 8-row aligned weight halves (H/4 and nout/2 multiples of 8) and at least two row tiles
+  bool cg2 = w16 && chain16_pair_default() && (H / 4) % 8 == 0 && d.M > kBlockM;
+  for (const Chain16LayerDesc& s : d.layers)
+    if (s.nout > 0 && s.nout != H && (s.nout / 2) % 8 != 0) cg2 = false;
   const int kin0 = d.layers[0].kin > 0 ? d.layers[0].kin : H;
   if (kin0 % 32 != 0 || kin0 > H) return fail(-2, "chain16: first-layer input width must be a multiple of 32, <= H");
   uintptr_t align_or = 0;
@@ -191,7 +214,7 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
         (s3 && !s.out))
       return fail(-2, "chain16: missing operand pointer");
     if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * kin : kin, s.w_rows > 0 ? s.w_rows : nout, s.ldw, kBlockK,
-                             narrow ? nout : H / 2)))
+                             (narrow ? nout : H / 2) / (cg2 ? 2 : 1))))
       return rc;
     if (!narrow && !s3) {
       if ((rc = encode_tmap_2d_bf16(&q.tmAux1, s.aux1, H, d.M, s.ld1, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -218,12 +241,6 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
   }
   p.vec_ok = (align_or & 15) == 0 ? 1 : 0;
   if (s3 && !p.vec_ok) return fail(-2, "chain16: SOFTPLUS3 operands must be 16-byte aligned");
-  static int warps_env = -1;
-  if (warps_env < 0) {
-    const char* e = std::getenv("ARDAE_CHAIN16_WARPS");
-    warps_env = e ? std::atoi(e) : 16;
-  }
-  const bool w16 = warps_env != 8 && !s3;  // 16 epilogue warps (chain16w_sm100.cuh) unless ARDAE_CHAIN16_WARPS=8
 #define ARDAE_CHAIN16_CASE(MODE_)                                                                               \
   case MODE_:                                                                                                   \
     pr.fn = reinterpret_cast<const void*>(&chain16_kernel<MODE_>);                                              \
@@ -231,8 +248,9 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
     break;
 #define ARDAE_CHAIN16W_CASE(MODE_)                                                                              \
   case MODE_:                                                                                                   \
-    pr.fn = w16 ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_>)                                        \
-                : reinterpret_cast<const void*>(&chain16_kernel<MODE_>);                                        \
+    pr.fn = cg2 ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_, true>)                                  \
+                : (w16 ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_, false>)                          \
+                       : reinterpret_cast<const void*>(&chain16_kernel<MODE_>));                                \
     pr.smem = Chain16Config<MODE_>::kSmemBytes;                                                                 \
     pr.threads = w16 ? Chain16wConfig::kThreads : Chain16Config<MODE_>::kThreads;                               \
     break;
@@ -246,6 +264,10 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
 #undef ARDAE_CHAIN16_CASE
 #undef ARDAE_CHAIN16W_CASE
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
+  if (cg2) {
+    pr.cluster = 2;
+    pr.grid.x = (pr.grid.x + 1) / 2 * 2;  // an odd tail CTA works on an out-of-range tile (TMA clips)
+  }
   ARDAE_CUDA_OK(cudaFuncSetAttribute(pr.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pr.smem));
   *out = pr;
   return 0;
@@ -253,6 +275,17 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
 
 inline int launch_prepared_chain16(const PreparedChain16& pr, cudaStream_t stream) {
   void* args[1] = {const_cast<Chain16Params*>(&pr.params)};
+  if (pr.cluster > 1) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pr.grid; cfg.blockDim = dim3(pr.threads); cfg.dynamicSmemBytes = pr.smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pr.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ARDAE_CUDA_OK(cudaLaunchKernelExC(&cfg, pr.fn, args));
+    return 0;
+  }
   ARDAE_CUDA_OK(cudaLaunchKernel(pr.fn, pr.grid, dim3(pr.threads), args, pr.smem, stream));
   return 0;
 }

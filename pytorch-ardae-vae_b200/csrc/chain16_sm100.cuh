@@ -53,6 +53,7 @@ struct alignas(64) Chain16Params {
   const float* row_scale;  // [M] (sigma) or null
   int M, H, nlayers;
   int vec_ok;
+  long long* dbg;          // profiling only (chain16w): clock64 stamps of CTA 0, [layer][half][group][8]
   Chain16LayerParams layer[kChainMaxLayers];
 };
 

@@ -38,13 +38,19 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lan
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-template <int MODE>
+// CG2: launched as clusters of two CTAs (adjacent row tiles); the leader issues tcgen05.mma.cta_group::2 for the 256-row
+// pair and every weight k-block is staged HALF in each CTA, so each SM ingests half of the weight stream -- the tf32
+// sweeps move 256 KB of weights per tile and layer through the L2 -> SM path, more than their aux / spill bytes, and
+// are bound by it.
+template <int MODE, bool CG2>
 __global__ void __launch_bounds__(Chain16wConfig::kThreads, 1)
 chain16w_kernel(const __grid_constant__ Chain16Params p) {
   using Cfg = Chain16Config<MODE>;
   static_assert(MODE != CHAIN_SOFTPLUS3, "the primal sweep has its own kernels");
   constexpr bool S3 = false, HAS_AUX2 = Cfg::kAux2, HAS_OUT2 = Cfg::kOut2;
-  constexpr int G = Chain16wConfig::kGroups, NW = Cfg::kNumWStages;
+  constexpr int G = Chain16wConfig::kGroups;
+  constexpr int NW = CG2 ? 12 : Cfg::kNumWStages;          // CG2: twelve half-size stages in the same 96 KB
+  constexpr int kWStage = CG2 ? Cfg::kWStage / 2 : Cfg::kWStage;
   constexpr int NAUX = Cfg::kNumAux > 0 ? Cfg::kNumAux : 1;
 
   extern __shared__ uint8_t smem_raw[];
@@ -92,20 +98,27 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
       }
       for (int h = 0; h < 2; ++h) {
         ptx::mbar_init(&acc_full[h], 1);
-        ptx::mbar_init(&a_ready[h], 4 * G);  // every epilogue warp
+        ptx::mbar_init(&a_ready[h], (CG2 ? 2 : 1) * 4 * G);  // every epilogue warp (of both CTAs of a pair)
       }
       for (int c = 0; c < 4; ++c) ptx::mbar_init(&kfree[c], 1);
       ptx::mbar_init(a0_full, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if (CG2) {
+      ptx::tmem_alloc_2sm(tmem_slot, 512);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG2) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t rank = CG2 ? ptx::cluster_ctarank() : 0;
   const uint32_t acc_t = tmem_base;       // accumulator columns [0, H)
   const uint32_t a_t = tmem_base + 256;   // A operand (SOFTPLUS3: its lo part) columns [256, 256 + H)
   uint8_t* hi_tiles = smem + Cfg::kOffAux;  // SOFTPLUS3 only
@@ -120,90 +133,70 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
         const int NBl = L.kin >> 5;
         const bool narrow = L.nout < H;
         const int nst = S3 ? 2 * NBl : NBl;
-        const uint32_t wbytes = static_cast<uint32_t>(narrow ? L.nout : HH) * kBlockK * 4;
+        const int nrows = narrow ? L.nout : HH;  // B rows of one N-half (per pair when CG2: half lands in each CTA)
+        const uint32_t wbytes = static_cast<uint32_t>(nrows) * kBlockK * 4;
+        const int wrows = CG2 ? nrows / 2 : nrows;
         for (int h = 0; h < (narrow ? 1 : 2); ++h) {
           for (int j = 0; j < nst; ++j, ++it) {
             const int s = it % NW;
             const uint32_t ph = (it / NW) & 1;
             ptx::mbar_wait(&w_empty[s], ph ^ 1);
-            // SOFTPLUS3: k-block kb of Whi (columns [0,kin)) then of Wlo (columns [2kin,3kin)); both serve hi, Whi also lo
-            const int kc = S3 ? (((j & 1) ? 2 * L.kin : 0) + (j >> 1) * kBlockK) : j * kBlockK;
-            ptx::mbar_expect_tx(&w_full[s], wbytes);
-            ptx::tma_load_2d(smem + s * Cfg::kWStage, tw, &w_full[s], kc, h * HH);
+            const int kc = j * kBlockK;
+            if (CG2) {
+              // both CTAs' halves complete on the LEADER's full barrier, armed by the leader for both
+              if (rank == 0) ptx::mbar_expect_tx(&w_full[s], wbytes);
+              ptx::tma_load_2d_2sm(smem + s * kWStage, tw, &w_full[s], kc, h * HH + static_cast<int>(rank) * wrows);
+            } else {
+              ptx::mbar_expect_tx(&w_full[s], wbytes);
+              ptx::tma_load_2d(smem + s * kWStage, tw, &w_full[s], kc, h * HH);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (ptx::elect_one()) {
+    // ------------------------------------------------------------ MMA issuer (CG2: the leader issues for the pair)
+    if ((!CG2 || rank == 0) && ptx::elect_one()) {
+      auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (CG2) ptx::umma_tf32_ts_2sm(d, a, b, idesc, acc); else ptx::umma_tf32_ts(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {  // CG2: the same barrier in both CTAs of the pair
+        if (CG2) ptx::umma_commit_2sm(bar, 0x3); else ptx::umma_commit(bar);
+      };
+      auto wait_a = [&](uint64_t* bar, uint32_t ph) {
+        if (CG2) ptx::mbar_wait_cluster(bar, ph); else ptx::mbar_wait(bar, ph);
+        ptx::tc_fence_after();
+      };
       int it = 0;
       for (int l = 0; l < nl; ++l) {
         const Chain16LayerParams& L = p.layer[l];
         const int NBl = L.kin >> 5;
         const bool narrow = L.nout < H;
-        const uint32_t idesc = ptx::make_idesc_tf32(kBlockM, narrow ? L.nout : HH, 0, 0);
-        if (S3 && l == 0) ptx::mbar_wait(a0_full, 0);  // hi tiles of the initial activation have landed (TMA)
+        const uint32_t idesc = ptx::make_idesc_tf32(CG2 ? 2 * kBlockM : kBlockM, narrow ? L.nout : HH, 0, 0);
         for (int h = 0; h < (narrow ? 1 : 2); ++h) {
           const uint32_t d_t = acc_t + h * HH;
           for (int kb = 0; kb < NBl; ++kb) {
-            if (h == 0 && kb == 0) {
-              ptx::mbar_wait(&a_ready[0], l & 1);  // A chunks [0, NB/2) written, accumulator half 0 drained
-              ptx::tc_fence_after();
-            }
-            if (h == 0 && kb == NB0) {
-              ptx::mbar_wait(&a_ready[1], l & 1);  // A chunks [NB/2, NB) written, accumulator half 1 drained
-              ptx::tc_fence_after();
-            }
-            {
-              const int s = it % NW;
-              const uint32_t ph = (it / NW) & 1;
-              ptx::mbar_wait(&w_full[s], ph);
-              ptx::tc_fence_after();
-              const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
-              if (S3) {
-                const uint32_t h_addr = ptx::smem_u32(hi_tiles + kb * kTileBytes);
-#pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                  const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
-                  const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-                  ptx::umma_tf32(d_t, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-                }
-              }
-#pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-                ptx::umma_tf32_ts(d_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, idesc, (S3 || (kb | k) != 0) ? 1u : 0u);
-              }
-              ptx::umma_commit(&w_empty[s]);
-              ++it;
-            }
-            if (S3) {  // hi . Wlo
-              const int s = it % NW;
-              const uint32_t ph = (it / NW) & 1;
-              ptx::mbar_wait(&w_full[s], ph);
-              ptx::tc_fence_after();
-              const uint32_t b_addr = ptx::smem_u32(smem + s * Cfg::kWStage);
-              const uint32_t h_addr = ptx::smem_u32(hi_tiles + kb * kTileBytes);
-#pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                const uint64_t adesc = ptx::make_smem_desc_sw128(h_addr + k * kUmmaK * 4, 0, 1024);
-                const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
-                ptx::umma_tf32(d_t, adesc, bdesc, idesc, 1u);
-              }
-              ptx::umma_commit(&w_empty[s]);
-              ++it;
-            }
-            // second half: this layer is done with A chunk kb -> the half-0 epilogue may overwrite it
-            if (h == 1 && kb < NB0) ptx::umma_commit(&kfree[kb]);
-          }
-          if (h == 0 && NBl <= NB0 && !narrow) {  // short first layer: consume this layer's a_ready[1] phase as well
-            ptx::mbar_wait(&a_ready[1], l & 1);
+            if (h == 0 && kb == 0) wait_a(&a_ready[0], l & 1);    // A chunks [0, NB/2) written, accumulator half 0 drained
+            if (h == 0 && kb == NB0) wait_a(&a_ready[1], l & 1);  // A chunks [NB/2, NB) written, accumulator half 1 drained
+            const int s = it % NW;
+            const uint32_t ph = (it / NW) & 1;
+            ptx::mbar_wait(&w_full[s], ph);
             ptx::tc_fence_after();
+            const uint32_t b_addr = ptx::smem_u32(smem + s * kWStage);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
+              mma_ts(d_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            commit(&w_empty[s]);
+            ++it;
+            // second half: this layer is done with A chunk kb -> the half-0 epilogue may overwrite it
+            if (h == 1 && kb < NB0) commit(&kfree[kb]);
           }
+          if (h == 0 && NBl <= NB0 && !narrow) wait_a(&a_ready[1], l & 1);  // short first layer: consume this phase too
           if (h == 1)
-            for (int c = NBl; c < NB0; ++c) ptx::umma_commit(&kfree[c]);  // chunks this layer never read
-          ptx::umma_commit(&acc_full[h]);
+            for (int c = NBl; c < NB0; ++c) commit(&kfree[c]);  // chunks this layer never read
+          commit(&acc_full[h]);
         }
       }
     }
@@ -296,8 +289,13 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      ptx::mbar_arrive(&a_ready[0]);
-      ptx::mbar_arrive(&a_ready[1]);
+      if (CG2) {
+        ptx::mbar_arrive_cluster(&a_ready[0], 0);
+        ptx::mbar_arrive_cluster(&a_ready[1], 0);
+      } else {
+        ptx::mbar_arrive(&a_ready[0]);
+        ptx::mbar_arrive(&a_ready[1]);
+      }
     }
 
     int prev_slot = -1;  // slot whose TMA store may still be reading it (released one chunk later)
@@ -329,8 +327,12 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
       const bool want_cs = L.colsum != nullptr || L.colsum_w != nullptr;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
+        long long* dbg = (p.dbg != nullptr && blockIdx.x == 0 && quarter == 1 && lane == 0)
+                             ? p.dbg + ((static_cast<size_t>(l) * 2 + h) * G + g) * 8 : nullptr;
+        if (dbg) dbg[0] = clock64();
         ptx::mbar_wait(&acc_full[h], l & 1);
         ptx::tc_fence_after();
+        if (dbg) dbg[1] = clock64();
 #pragma unroll 1
         for (int c = h * NB0 + g; c < (h + 1) * NB0; c += G) {
           const int nc = c * 32;
@@ -338,9 +340,11 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
             ptx::mbar_wait(&kfree[c], l & 1);
             ptx::tc_fence_after();
           }
+          if (dbg) dbg[2] = clock64();
           const int it = ring_base + NB * l + c;
           const int a = it % NAUX;
           ptx::mbar_wait(&aux_full[a], (it / NAUX) & 1);
+          if (dbg) dbg[3] = clock64();
           uint8_t* slot = smem + Cfg::kOffAux + a * Cfg::kAuxSlot;  // aux tile(s) in, out tile(s) over them in place
           const uint32_t s1 = ptx::smem_u32(slot) + row_off16;      // aux1 / out row of this thread
           const uint32_t s2 = s1 + kTile16Bytes;                    // aux2 / out2
@@ -419,8 +423,10 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
               }
             }
           }
+          if (dbg) dbg[4] = clock64();
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_b, 128);
+          if (dbg) dbg[5] = clock64();
           if (leader) {
             ptx::tma_store_2d(&L.tmOut, slot, nc, m0);
             if (HAS_OUT2) ptx::tma_store_2d(&L.tmOut2, slot + kTile16Bytes, nc, m0);
@@ -453,10 +459,14 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
           }
         }
         // A chunks of this half written (TMEM stores complete, shared-memory writes fenced), accumulator half drained
+        if (dbg) dbg[6] = clock64();
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&a_ready[h]);
+        if (lane == 0) {
+          if (CG2) ptx::mbar_arrive_cluster(&a_ready[h], 0); else ptx::mbar_arrive(&a_ready[h]);
+        }
+        if (dbg) dbg[7] = clock64();
         if (HAS_OUT2 && L.colsum2 != nullptr) ptx::named_bar_sync(bar_a, 128);  // colsum2 re-reads of the slot are done
         if (leader && prev_slot >= 0) {  // do not sit on a slot while waiting for the next accumulator half
           ptx::tma_store_wait_read<0>();
@@ -470,9 +480,10 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG2) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers / read its memory
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (CG2) ptx::tmem_dealloc_2sm(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 

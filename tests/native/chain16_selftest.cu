@@ -470,6 +470,29 @@ static void bench_chain16(int mode, int M, int H, int nl, int kin0, bool narrow)
   PreparedChain16 pr;
   int rc = prepare_chain16(d, &pr);
   if (rc) { printf("bench prepare failed %d: %s\n", rc, last_error_string().c_str()); ++g_fail; return; }
+  if (getenv("CHAIN16_TIMES")) {
+    const int nlay = (int)d.layers.size();
+    long long* dt;
+    const size_t nn = (size_t)nlay * 2 * 4 * 8;
+    CK(cudaMalloc(&dt, nn * sizeof(long long)));
+    CK(cudaMemset(dt, 0, nn * sizeof(long long)));
+    pr.params.dbg = dt;
+    launch_prepared_chain16(pr, 0);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> hdt(nn);
+    CK(cudaMemcpy(hdt.data(), dt, nn * sizeof(long long), cudaMemcpyDeviceToHost));
+    const long long base = hdt[0];
+    printf("  times mode %d (cycles, CTA 0, warp quarter 1): layer half group | start  acc_full  kfree  aux_full  computed  bar_b  pre_arrive  arrived\n", mode);
+    for (int l = 0; l < nlay && l < 4; ++l)
+      for (int h = 0; h < 2; ++h)
+        for (int g = 0; g < 4; ++g) {
+          const long long* t = &hdt[((size_t)(l * 2 + h) * 4 + g) * 8];
+          printf("    %d %d %d | %7lld %7lld %7lld %7lld %7lld %7lld %7lld %7lld\n", l, h, g, t[0] - base, t[1] - base, t[2] - base,
+                 t[3] - base, t[4] - base, t[5] - base, t[6] - base, t[7] - base);
+        }
+    pr.params.dbg = nullptr;
+    cudaFree(dt);
+  }
   const float ms = time_it([&]() { launch_prepared_chain16(pr, 0); }, 5);
   const double arrays = s3 ? 1.0 : (1.0 + (aux2 ? 1 : 0) + 1.0 + (out2 ? 1 : 0));  // per layer: aux reads + out writes
   const double bytes = (arrays * nl + (a0_16 ? 1.0 : 0.0)) * n * 2.0;
