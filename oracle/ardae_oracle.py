@@ -139,7 +139,7 @@ class ModelSpec(object):
     """Architecture of an ImplicitPosteriorVAE as built by ivae_ardae.py:295-314."""
 
     def __init__(self, kind, input_dim, noise_dim, h_dim, z_dim, num_hidden_layers, nonlin):
-        assert kind in ('toy', 'mnist', 'conv')
+        assert kind in ('toy', 'mnist', 'conv', 'auxmnist')
         self.kind, self.input_dim, self.noise_dim = kind, input_dim, noise_dim
         self.h_dim, self.z_dim, self.n_layers, self.nonlin = h_dim, z_dim, num_hidden_layers, nonlin
         if kind == 'toy':
@@ -150,6 +150,12 @@ class ModelSpec(object):
         elif kind == 'conv':
             # models/ivae/conv.py:44-136, models/vae/conv.py:79-136; input_dim = C*H*H, h_dim = 800
             self.dec_keys = mlp_keys('decode.fc', 1)
+        elif kind == 'auxmnist':
+            # hierarchical encoder models/ivae/auxmnist.py:47-131: AuxEncoder (models/vae/auxmnist.py:31-68) +
+            # SimpleEncoder (:147-191); decoder models/vae/mnist.py Decoder (MLP of num_hidden_layers linears + logits)
+            self.aux_keys = mlp_keys('encode.aux_encode.main', num_hidden_layers - 1)
+            self.fc_keys = mlp_keys('encode.encode.fc', num_hidden_layers - 1)
+            self.dec_keys = mlp_keys('decode.main', num_hidden_layers - 1)
         else:
             # models/ivae/mnist.py:148-151,180-181,227 (encoder gets num_hidden_layers+1)
             self.inp_keys = mlp_keys('encode.inp_encode', num_hidden_layers + 1)
@@ -164,6 +170,8 @@ def encoder_forward(spec, P, x, eps, nz):
     B = x.shape[0]
     if spec.kind == 'conv':
         return _conv_encoder_forward(spec, P, x, eps, nz)
+    if spec.kind == 'auxmnist':
+        return _aux_encoder_forward(spec, P, x, eps, nz)
     xin = 2.0 * x - 1.0 if spec.kind == 'mnist' else x
     inp, tape_inp = mlp_forward(P, spec.inp_keys, xin, spec.nonlin, True)
     inp_rep = np.repeat(inp, nz, axis=0)  # row b*nz+k  (unsqueeze(1).expand(-1,nz,-1))
@@ -186,6 +194,8 @@ def encoder_backward(spec, P, tape, dz, nz, G):
     """Backward of encoder_forward for upstream dz [B, nz, d]; accumulates grads into G."""
     if spec.kind == 'conv':
         return _conv_encoder_backward(spec, P, tape, dz, nz, G)
+    if spec.kind == 'auxmnist':
+        return _aux_encoder_backward(spec, P, tape, dz, nz, G)
     tape_inp, tape_fc, xin = tape
     B = xin.shape[0]
     H = spec.h_dim
@@ -204,6 +214,58 @@ def encoder_backward(spec, P, tape, dz, nz, G):
         dinp_rep = dcat[:, :H]
     dinp = dinp_rep.reshape(B, nz, H).sum(1)
     mlp_backward(P, spec.inp_keys, tape_inp, dinp, spec.nonlin, True, G)
+
+
+def _aux_encoder_forward(spec, P, x, eps, nz):
+    """Hierarchical encoder (models/ivae/auxmnist.py:74-105).  eps [B*nz, n + d] packs the two draws of
+    Encoder._forward: eps0 (columns [0, n), the reparametrisation noise of the auxiliary latent z0) and eps (columns
+    [n, n + d), that of z); eps = 0 is `std = 0` (z0 = mu0, z = mu).
+      h0 = MLP(2x - 1) ; mu0, lv0 = heads(h0) ; z0 = mu0 + exp(lv0 / 2) * eps0        (AuxEncoder, vae/auxmnist.py:55-68)
+      h = MLP([2x - 1, z0]) ; mu, lv = heads(h) ; z = mu + exp(lv / 2) * eps          (SimpleEncoder, :185-190)"""
+    B, n, d = x.shape[0], spec.noise_dim, spec.z_dim
+    xin = 2.0 * x - 1.0
+    h0, tape_aux = mlp_forward(P, spec.aux_keys, xin, spec.nonlin, True)
+    mu0 = h0 @ P['encode.aux_encode.reparam.mean_fn.weight'].T + P['encode.aux_encode.reparam.mean_fn.bias']
+    lv0 = h0 @ P['encode.aux_encode.reparam.logvar_fn.weight'].T + P['encode.aux_encode.reparam.logvar_fn.bias']
+    eps0, eps1 = eps[:, :n], eps[:, n:n + d]
+    mu0r, lv0r = np.repeat(mu0, nz, axis=0), np.repeat(lv0, nz, axis=0)
+    z0 = mu0r + np.exp(0.5 * lv0r) * eps0
+    cat = np.concatenate([np.repeat(xin, nz, axis=0), z0], axis=1)
+    h, tape_fc = mlp_forward(P, spec.fc_keys, cat, spec.nonlin, True)
+    mu = h @ P['encode.encode.reparam.mean_fn.weight'].T + P['encode.encode.reparam.mean_fn.bias']
+    lv = h @ P['encode.encode.reparam.logvar_fn.weight'].T + P['encode.encode.reparam.logvar_fn.bias']
+    z = mu + np.exp(0.5 * lv) * eps1
+    return z.reshape(B, nz, d), (tape_aux, tape_fc, xin, h0, lv0r, eps0, h, lv, eps1)
+
+
+def aux_encoder_hidden(spec, P, x):
+    """Encoder.forward_hidden(x, std=0) (models/ivae/auxmnist.py:123-131): cat(h0, h) at eps = 0, [B, 2 h_dim] --
+    the CDAE context of cdae_ctx_type 'hidden1a' (ivae_ardae.py:739-741)."""
+    B = x.shape[0]
+    _, tape = _aux_encoder_forward(spec, P, x, np.zeros((B, spec.noise_dim + spec.z_dim), dtype=x.dtype), 1)
+    return np.concatenate([tape[3], tape[6]], axis=1)
+
+
+def _aux_encoder_backward(spec, P, tape, dz, nz, G):
+    tape_aux, tape_fc, xin, h0, lv0r, eps0, h, lv, eps1 = tape
+    B, D, n = xin.shape[0], xin.shape[1], spec.noise_dim
+    d = dz.reshape(B * nz, spec.z_dim)
+    dmu, dlv = d, d * (0.5 * np.exp(0.5 * lv) * eps1)
+    dh = 0.0
+    for nm, g in (('encode.encode.reparam.mean_fn', dmu), ('encode.encode.reparam.logvar_fn', dlv)):
+        G[nm + '.weight'] = G.get(nm + '.weight', 0.0) + g.T @ h
+        G[nm + '.bias'] = G.get(nm + '.bias', 0.0) + g.sum(0)
+        dh = dh + g @ P[nm + '.weight']
+    dcat = mlp_backward(P, spec.fc_keys, tape_fc, dh, spec.nonlin, True, G)
+    dz0 = dcat[:, D:D + n]
+    dmu0 = dz0.reshape(B, nz, n).sum(1)
+    dlv0 = (dz0 * (0.5 * np.exp(0.5 * lv0r) * eps0)).reshape(B, nz, n).sum(1)
+    dh0 = 0.0
+    for nm, g in (('encode.aux_encode.reparam.mean_fn', dmu0), ('encode.aux_encode.reparam.logvar_fn', dlv0)):
+        G[nm + '.weight'] = G.get(nm + '.weight', 0.0) + g.T @ h0
+        G[nm + '.bias'] = G.get(nm + '.bias', 0.0) + g.sum(0)
+        dh0 = dh0 + g @ P[nm + '.weight']
+    mlp_backward(P, spec.aux_keys, tape_aux, dh0, spec.nonlin, True, G)
 
 
 def _img_h(spec):
@@ -567,14 +629,16 @@ def train_step(spec, cs, Pm, Pc, x_cdae, x_model, noise, hp, opt_state=None):
     S_, delta = hp['std_scale'], hp['delta']
     nz, nstd, nzm, beta = hp['nz_cdae'], hp['nstd'], hp['nz_model'], hp['beta']
     B = x_cdae.shape[0]
-    n = spec.noise_dim
+    n = spec.noise_dim + (spec.z_dim if spec.kind == 'auxmnist' else 0)  # aux: eps0 | eps packed (see _aux_encoder_forward)
     out = {}
     ctx_type = hp.get('ctx_type', 'lt0')  # ivae_ardae.py:729-741: 'lt0' = mean code, 'data' = the input (2x-1 for MNIST)
 
     def context_of(x, zbar_):
         if ctx_type == 'data':
             xx = x.reshape(x.shape[0], 1, -1)
-            return 2.0 * xx - 1.0 if spec.kind in ('mnist', 'conv') else xx
+            return 2.0 * xx - 1.0 if spec.kind in ('mnist', 'conv', 'auxmnist') else xx
+        if ctx_type == 'hidden1a':  # ivae_ardae.py:739-741: model.encode.forward_hidden(x, std=0)
+            return aux_encoder_hidden(spec, Pm, x)[:, None, :]
         return zbar_
     # ---- CDAE update (:713-779)
     zbar, _ = encoder_forward(spec, Pm, x_cdae, np.zeros((B, n), dtype=x_cdae.dtype), 1)  # encode(std=0)
@@ -619,6 +683,8 @@ def iws_logprob(spec, P, x, enc_noise, eta):
         mu = z.mean(0)
         zc = z - mu
         cov = zc.T @ zc / (S - 1)  # get_covmat, utils/stat.py:127-158
+        if spec.kind == 'auxmnist':
+            cov = cov + 1e-5 * np.eye(d)  # models/ivae/auxmnist.py:350
         Lc = np.linalg.cholesky(cov)
         newz = mu + eta[i] @ Lc.T
         logq = -0.5 * (eta[i] ** 2).sum(1) - np.log(np.diag(Lc)).sum() - 0.5 * d * LOG2PI

@@ -55,6 +55,13 @@ CASES = {
                        cdae=dict(input_dim=4, context_dim=4, h_dim=16, num_hidden_layers=3, nonlinearity='softplus'),
                        B=4, hp=dict(std_scale=10000., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
                                     m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
+    # hierarchical encoder family (--model auxmnist, run_vae_dbmnist.sh:40) with --cdae-ctx-type hidden1a: the CDAE
+    # context is cat(h0, h) of the encoder at std = 0 (2 h_dim wide); noise packs eps0 | eps as [R, noise_dim + z_dim]
+    'auxmnist_small': dict(kind='auxmnist', ctx_type='hidden1a',
+                           model=dict(input_dim=20, noise_dim=5, h_dim=12, num_hidden_layers=2, nonlinearity='softplus', z_dim=4),
+                           cdae=dict(input_dim=4, context_dim=24, h_dim=16, num_hidden_layers=3, nonlinearity='softplus'),
+                           B=5, hp=dict(std_scale=10000., delta=0.1, nz_cdae=6, nstd=1, nz_model=1, beta=1.0,
+                                        m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5), wscale=1.0),
     # config 4's model at its real geometry: ConvIPVAE 28x28, z = 32, noise 100 (run_vae_dbmnist.sh:31), two full steps.
     # `sampled`: tensors with more than 16384 elements are stored (gradients, post-step weights) at 8192 fixed random
     # positions ('sample_idx/<name>'); the initial weights are stored in full as float32
@@ -91,6 +98,8 @@ def make_case(name, c):
                     p.copy_(p.float().double())
     mopt, copt = rh.build_optimizers(model, cdae, hp)
     B, n, d = c['B'], c['model']['noise_dim'], c['model']['z_dim']
+    if c['kind'] == 'auxmnist':
+        n = n + d  # eps0 | eps packed
     D = c['model']['input_dim'] if 'input_dim' in c['model'] else c['model']['input_channels'] * c['model']['input_height'] ** 2
     f32 = (lambda a: a.astype(np.float32)) if lite else (lambda a: a)
     nz, nstd, nzm = hp['nz_cdae'], hp['nstd'], hp['nz_model']
@@ -110,7 +119,7 @@ def make_case(name, c):
     for k, v in cdae.state_dict().items():
         arrays['c0/' + k] = f32(v.numpy().copy())
     for step in range(nsteps):
-        if c['kind'] in ('mnist', 'conv'):
+        if c['kind'] in ('mnist', 'conv', 'auxmnist'):
             xc = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
             xm = torch.bernoulli(torch.full((B, D), 0.3, dtype=dt), generator=g)
         else:
@@ -121,7 +130,7 @@ def make_case(name, c):
                      eps_cdae=torch.randn(B, nz * nstd, d, dtype=dt, generator=g),
                      enc_model=torch.randn(B * nzm, n, dtype=dt, generator=g))
         out = rh.ref_train_step(model, cdae, mopt, copt, xc, xm, noise, hp, do_step=True,
-                                ctx_type=c.get('ctx_type', 'lt0'), mnist_like=c['kind'] in ('mnist', 'conv'))
+                                ctx_type=c.get('ctx_type', 'lt0'), mnist_like=c['kind'] in ('mnist', 'conv', 'auxmnist'))
         p = 's%d/' % step
         arrays[p + 'x_cdae'], arrays[p + 'x_model'] = xc.numpy(), xm.numpy()
         for k, v in noise.items():
@@ -166,7 +175,7 @@ def make_case(name, c):
     if lite:  # IWS on the INITIAL weights (the stepped ones are not stored)
         with torch.no_grad():
             model.load_state_dict({k: torch.from_numpy(arrays['m0/' + k]).double() for k in model.state_dict()})
-    if c['kind'] in ('mnist', 'conv'):
+    if c['kind'] in ('mnist', 'conv', 'auxmnist'):
         xe = torch.bernoulli(torch.full((b, D), 0.3, dtype=dt), generator=g)
     else:
         xe = torch.randn(b, D, dtype=dt, generator=g) * 2

@@ -71,6 +71,8 @@ def build_reference(kind, model_kwargs, cdae_kwargs, dtype=None, seed=0, cdae_ki
     torch.manual_seed(seed)
     if kind == 'conv':
         model = net.ConvIPVAE(**model_kwargs)
+    elif kind == 'auxmnist':  # ivae_ardae.py:455-466
+        model = net.MNISTAuxIPVAE(enc_type='simple', clip_z0_logvar='none', clip_z_logvar='none', **model_kwargs)
     else:
         model = (net.ToyIPVAE if kind == 'toy' else net.MNISTIPVAE)(enc_type='concat', **model_kwargs)
     cls = net.MLPGradCARDAE if cdae_kind == 'grad' else net.MLPResCARDAE
@@ -106,8 +108,34 @@ class _NoiseQueue(object):
         return std * eps
 
 
+def _install_aux_noise(model, cmod, q):
+    """Encoder._forward (ivae/auxmnist.py:107-115) draws eps0 [R, n] then eps [R, 1, d] through the module-level
+    sample_noise(sz, device); the injected tensors pack them as [R, n + d].  Calls made with an empty queue are the
+    std = 0 passes (the draws are multiplied by 0 there): they get zeros."""
+    import torch
+    n_, d_ = model.noise_dim, model.z_dim
+    pend = []
+
+    def aux_noise(sz, device):
+        w = next(model.parameters())
+        if len(sz) == 2:
+            if q.q:
+                t = q.q.pop(0)
+                assert t.shape == (sz[0], n_ + d_), (t.shape, sz)
+                pend.append(t[:, n_:])
+                return t[:, :n_].to(w.dtype)
+            pend.append(None)
+            return torch.zeros(*sz, dtype=w.dtype)
+        e = pend.pop(0)
+        return torch.zeros(*sz, dtype=w.dtype) if e is None else e.reshape(sz).to(w.dtype)
+    cmod.sample_noise = aux_noise
+
+
 def _ref_context(model, x, ctx_type, mnist_like):
-    """ivae_ardae.py:729-741 / :807-819: cdae_ctx_type 'lt0' (latent of the mean code) or 'data' (the input itself)."""
+    """ivae_ardae.py:729-741 / :807-819: cdae_ctx_type 'lt0' (latent of the mean code), 'data' (the input itself) or
+    'hidden1a' (hidden features of the hierarchical encoder)."""
+    if ctx_type == 'hidden1a':
+        return model.encode.forward_hidden(x, std=0).detach().unsqueeze(1)
     if ctx_type == 'data':
         context = x.unsqueeze(1)
         if mnist_like:  # "if 'mnist' in opt.dataset"
@@ -124,14 +152,18 @@ def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=
     import torch
     S_, delta = hp['std_scale'], hp['delta']
     nz, nstd, nzm, beta = hp['nz_cdae'], hp['nstd'], hp['nz_model'], hp['beta']
+    aux = model.__class__.__module__.endswith('auxmnist')
     q = _NoiseQueue(model.encode)
-    model.encode.sample_noise = q
+    if not aux:
+        model.encode.sample_noise = q
     # ConvIPVAE.forward / forward_hidden draw through a module-level sample_noise(sz, std, device)
     # (ivae/conv.py:24-27,190,207): route that to the same queue
     cmod = sys.modules.get('_ardae_ref_' + model.__class__.__module__) or sys.modules.get(model.__class__.__module__)
     c_orig = getattr(cmod, 'sample_noise', None) if cmod is not None else None
-    if c_orig is not None:
+    if c_orig is not None and not aux:
         cmod.sample_noise = lambda sz, std=None, device=None: q(sz[0], std=std, device=device)
+    if aux:
+        _install_aux_noise(model, cmod, q)
     out = {}
     model.train(); cdae.train()
     # ---- update cdae (:713-779)
@@ -179,7 +211,8 @@ def ref_train_step(model, cdae, mopt, copt, x_cdae, x_model, noise, hp, do_step=
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             mopt.step()                                                 # :846
-    del model.encode.sample_noise
+    if not aux:
+        del model.encode.sample_noise
     del cdae.add_noise
     if c_orig is not None:
         cmod.sample_noise = c_orig
@@ -193,9 +226,16 @@ def ref_iws(model, x, enc_noise, eta):
     import torch.distributions.multivariate_normal as mvn
     b, S, _ = enc_noise.shape
     q = _NoiseQueue(model.encode)
-    q.q = [enc_noise[i] for i in range(b)]
+    aux = model.__class__.__module__.endswith('auxmnist')
+    cmod = sys.modules.get('_ardae_ref_' + model.__class__.__module__) or sys.modules.get(model.__class__.__module__)
+    c_orig = getattr(cmod, 'sample_noise', None) if cmod is not None else None
     etas = [eta[i].reshape(1, S, -1) for i in range(b)]
-    model.encode.sample_noise = q
+    if aux:  # one Encoder._forward call over all images (ivae/auxmnist.py:346)
+        q.q = [enc_noise.reshape(b * S, -1)]
+        _install_aux_noise(model, cmod, q)
+    else:
+        q.q = [enc_noise[i] for i in range(b)]
+        model.encode.sample_noise = q
     orig = mvn._standard_normal
     mvn._standard_normal = lambda shape, dtype, device: etas.pop(0).reshape(shape).to(dtype)
     try:
@@ -204,6 +244,9 @@ def ref_iws(model, x, enc_noise, eta):
             val = model.logprob(x, sample_size=S)
     finally:
         mvn._standard_normal = orig
-        del model.encode.sample_noise
+        if aux:
+            cmod.sample_noise = c_orig
+        else:
+            del model.encode.sample_noise
         model.train()
     return val

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small', 'mnist_small_res', 'mnist_small_datactx', 'conv28']
+CASES = ['toy_small', 'mnist_small', 'mnist_small_x3', 'conv_small', 'mnist_small_res', 'mnist_small_datactx', 'conv28', 'auxmnist_small']
 
 
 def model_dims(meta):
