@@ -103,6 +103,11 @@ ARDAE_API int ardae_cdae_score(ardae_cdae_t h, const float* x, const float* ctx,
  * kind 2 = conv: `net.ConvIPVAE` (models/ivae/conv.py:44-304 + models/vae/conv.py:79-136): tensors
  *   encode.conv1..3, encode.fc4, encode.fc5, decode.fc.layers.0, decode.fc.fc, decode.deconv1, decode.deconv2,
  *   decode.reparam.logit_fn (n_inp = 3, n_fc = 1, n_dec = 2, h_dim = 800 = fc4 width).
+ * kind 3 = auxmnist: hierarchical `net.MNISTAuxIPVAE` (models/ivae/auxmnist.py:47-300 over models/vae/auxmnist.py:31-68,
+ *   147-191): tensors encode.aux_encode.main (n_inp linears), encode.aux_encode.reparam.{mean_fn,logvar_fn},
+ *   encode.encode.fc (n_fc linears, the first [h, D + noise_dim]), encode.encode.reparam.{mean_fn,logvar_fn},
+ *   decode.main (n_dec linears), decode.reparam.logit_fn.  z0 = mu0(x) + exp(lv0(x)/2) eps0 is noise_dim wide,
+ *   z = mu(x, z0) + exp(lv(x, z0)/2) eps; `noise` is [R, noise_dim + z_dim] = (eps0 | eps).  Modes 0-2.
  */
 typedef struct ardae_model_s* ardae_model_t;
 
@@ -132,6 +137,10 @@ ARDAE_API int ardae_model_encode(ardae_model_t h, const float* x, const float* n
  * the input stack; here the mean code is two or three B-row launches on top of the sampling pass. */
 ARDAE_API int ardae_model_encode_with_mean(ardae_model_t h, const float* x, const float* noise, float* z_out,
                                            float* zbar_out, void* stream);
+/* kind 3 only: the same pass plus Encoder.forward_hidden(x, std=0) (models/ivae/auxmnist.py:123-131), the CDAE context
+ * of cdae_ctx_type 'hidden1a' (ivae_ardae.py:739-741): hidden_out [B, 2*h_dim] = cat(h0, h) at eps0 = eps = 0. */
+ARDAE_API int ardae_model_encode_hidden(ardae_model_t h, const float* x, const float* noise, float* z_out,
+                                        float* zbar_out, float* hidden_out, void* stream);
 /* Replaces ImplicitPosteriorVAE.forward (toy.py:824-858 / mnist.py:267-301, lmbd = 0): encoder,
  * decoder, per-row recon + beta*prior.  sums[3] (device) <- mean loss, recon, prior over
  * 1/inv_rows rows (pass the GLOBAL row count under data parallelism).  heads_out (optional):

@@ -1,6 +1,6 @@
 """ardae -- B200-native AR-DAE hot path behind the reference's model API."""
 from .cdae import ConditionalARDAE, MLPGradCARDAE, MLPResCARDAE, ResidualConditionalARDAE  # noqa: F401
-from .ivae import ConvIPVAE, MNISTIPVAE, ToyIPVAE, normal_energy_func  # noqa: F401
+from .ivae import ConvIPVAE, MNISTAuxIPVAE, MNISTIPVAE, ToyIPVAE, normal_energy_func  # noqa: F401
 from .optim import Adam, RMSprop  # noqa: F401
 from .step import TrainStep  # noqa: F401
 from .data import MinibatchSampler, dynamic_binarize, toy_exp4  # noqa: F401

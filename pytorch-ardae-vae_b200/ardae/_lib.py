@@ -50,6 +50,7 @@ def _declare(lib):
     lib.ardae_model_num_launches.argtypes = [vp, i]
     lib.ardae_model_encode.argtypes = [vp, vp, vp, vp, vp]
     lib.ardae_model_encode_with_mean.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ardae_model_encode_hidden.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.ardae_model_forward.argtypes = [vp, vp, vp, f, f, vp, vp, vp, vp]
     lib.ardae_model_backward.argtypes = [vp, f, vp, f, vp]
     lib.ardae_model_set_beta_device.argtypes = [vp, vp]

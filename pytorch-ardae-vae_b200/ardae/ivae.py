@@ -249,7 +249,7 @@ class ImplicitPosteriorVAE(nn.Module):
         if key not in self._plans:
             L = _lib.lib()
             ar = self._ensure()
-            cfg = _lib.ModelConfig({'toy': 0, 'mnist': 1, 'conv': 2}[self.KIND], self.input_dim, self.noise_dim,
+            cfg = _lib.ModelConfig({'toy': 0, 'mnist': 1, 'conv': 2, 'auxmnist': 3}[self.KIND], self.input_dim, self.noise_dim,
                                    self.h_dim, self.z_dim, self._n_inp, self._n_fc, self._n_dec,
                                    1 if self.nonlinearity == 'softplus' else 0, B, nz, mode,
                                    getattr(self, 'input_height', 0), getattr(self, 'input_channels', 0))
@@ -286,6 +286,24 @@ class ImplicitPosteriorVAE(nn.Module):
         _lib.check(_lib.lib().ardae_model_encode_with_mean(self._plans[key][0], _lib.ptr(xf), _lib.ptr(nf), _lib.ptr(z),
                                                            _lib.ptr(zbar), _lib.stream_ptr()))
         return z.view(B, nz, self.z_dim), zbar.view(B, 1, self.z_dim)
+
+    @property
+    def _noise_width(self):
+        """columns of the `noise` operand of the plans: noise_dim; the hierarchical models pack (eps0 | eps)."""
+        return self.noise_dim + (self.z_dim if self.KIND == 'auxmnist' else 0)
+
+    def _encode_hidden(self, x, noise, nz, slot=0):
+        """auxmnist: (z, zbar, hidden) = (encode(x, noise, nz), encode(x, std=0), encode.forward_hidden(x, std=0))."""
+        B = x.size(0)
+        xf = _lib.require_cuda(x.detach(), 'input').view(B, self.input_dim)
+        nf = None if noise is None else _lib.require_cuda(noise.detach(), 'noise')
+        key = self._plan(B, nz, 0, slot)
+        z = torch.empty(B * nz, self.z_dim, dtype=torch.float32, device=xf.device)
+        zbar = torch.empty(B, self.z_dim, dtype=torch.float32, device=xf.device)
+        hid = torch.empty(B, 2 * self.h_dim, dtype=torch.float32, device=xf.device)
+        _lib.check(_lib.lib().ardae_model_encode_hidden(self._plans[key][0], _lib.ptr(xf), _lib.ptr(nf), _lib.ptr(z),
+                                                        _lib.ptr(zbar), _lib.ptr(hid), _lib.stream_ptr()))
+        return z.view(B, nz, self.z_dim), zbar.view(B, 1, self.z_dim), hid
 
     def _feat_dim(self):
         return self.encode.s_h8 * self.encode.s_h8 * 32 if self.KIND == 'conv' else self.h_dim
@@ -381,7 +399,7 @@ class ImplicitPosteriorVAE(nn.Module):
         S = int(sample_size)
         if noise is None:
             noise = self.encode.sample_noise(batch_size * S, std=std, device=x.device)
-        nf = _lib.require_cuda(noise.detach(), 'noise').reshape(batch_size * S, self.noise_dim)
+        nf = _lib.require_cuda(noise.detach(), 'noise').reshape(batch_size * S, self._noise_width)
         ef = None if eta is None else _lib.require_cuda(eta.detach(), 'eta').reshape(batch_size * S, self.z_dim)
         self._ensure()
         key = self._plan(batch_size, S, 2)
@@ -410,6 +428,98 @@ class MNISTIPVAE(ImplicitPosteriorVAE):
                  nonlinearity='softplus', num_hidden_layers=1, init='gaussian', enc_type='concat'):
         super().__init__(energy_func, input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, init,
                          enc_type)
+
+
+class _AuxStage(nn.Module):
+    """Parameter container of one Gaussian stage of the hierarchical encoder: `AuxEncoder` (models/vae/auxmnist.py:
+    31-53: main + reparam) or `SimpleEncoder` (:147-183: identities + fc + reparam)."""
+
+    def __init__(self, name, in_dim, h_dim, out_dim, nonlinearity, num_hidden_layers, simple):
+        super().__init__()
+        if simple:
+            self.inp_encode, self.nos_encode = Identity(), Identity()
+        self.add_module(name, MLP(in_dim, h_dim, h_dim, nonlinearity, num_hidden_layers - 1, True))
+        self.reparam = NormalDistributionLinear(h_dim, out_dim)
+
+
+class _AuxEncoder(nn.Module):
+    """models/ivae/auxmnist.py:47-131 `Encoder`: z0 ~ q(z0|x) (aux_encode), z ~ q(z|x, z0) (encode)."""
+
+    def __init__(self, input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, enc_type):
+        super().__init__()
+        self.input_dim, self.noise_dim, self.h_dim, self.z_dim = input_dim, noise_dim, h_dim, z_dim
+        self.nonlinearity, self.num_hidden_layers, self.enc_type = nonlinearity, num_hidden_layers, enc_type
+        self.clip_z0_logvar = self.clip_z_logvar = None
+        self.aux_encode = _AuxStage('main', input_dim, h_dim, noise_dim, nonlinearity, num_hidden_layers, False)
+        self.encode = _AuxStage('fc', input_dim + noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, True)
+
+    def sample_noise(self, batch_size, std=None, device=None):
+        """The two draws of Encoder._forward (:107-113) packed as [rows, noise_dim + z_dim] = (eps0 | eps), already
+        scaled by `std` (sample_gaussian multiplies both standard deviations by it, :33-40)."""
+        std = std if std is not None else 1
+        device = device if device is not None else next(self.parameters()).device
+        if std == 0:
+            return torch.zeros(batch_size, self.noise_dim + self.z_dim, device=device)
+        return std * torch.randn(batch_size, self.noise_dim + self.z_dim, device=device)
+
+    def forward(self, x, std=None, nz=1, noise=None):
+        """(:115-120) -> z [B, nz, z_dim].  `noise` (optional [B*nz, noise_dim + z_dim]) injects (eps0 | eps)."""
+        batch_size = x.size(0)
+        if noise is None:
+            zero = std is not None and std == 0
+            noise = None if zero else self.sample_noise(batch_size * nz, std=std, device=x.device)
+        else:
+            assert noise.size(0) == batch_size * nz and noise.size(1) == self.noise_dim + self.z_dim
+        return self._owner()._encode(x, noise, nz)
+
+    def forward_hidden(self, x, std=None, nz=1):
+        """(:122-131) -> cat(h0, h) [B, 2 h_dim].  Only the deterministic call the training step makes
+        (std = 0, ivae_ardae.py:739-741) is planned."""
+        assert nz == 1
+        if std is None or std != 0:
+            raise NotImplementedError('forward_hidden is planned for std=0 (the hidden1a context)')
+        return self._owner()._encode_hidden(x, None, 1)[2]
+
+
+class MNISTAuxIPVAE(ImplicitPosteriorVAE):
+    """net.MNISTAuxIPVAE (models/ivae/auxmnist.py:133-360): hierarchical implicit posterior
+    q(z|x) = int q(z|x, z0) q(z0|x) dz0 with two Gaussian stages, Bernoulli MLP decoder (models/vae/mnist.py)."""
+    KIND = 'auxmnist'
+
+    def __init__(self, energy_func=normal_energy_func, input_dim=784, noise_dim=100, h_dim=300, z_dim=32,
+                 nonlinearity='softplus', num_hidden_layers=2, enc_type='simple', clip_z0_logvar=None,
+                 clip_z_logvar=None, do_xavier=True):
+        nn.Module.__init__(self)
+        if enc_type != 'simple':
+            raise NotImplementedError  # same as the reference (:164)
+        if nonlinearity != 'softplus':
+            raise NotImplementedError("the auxmnist plan is softplus only (what ivae_ardae.py builds)")
+        if energy_func is not normal_energy_func:
+            raise NotImplementedError('only the N(0,I) prior energy is fused')
+        if clip_z0_logvar not in (None, 'none') or clip_z_logvar not in (None, 'none'):
+            raise NotImplementedError('logvar clipping is not planned (ivae_ardae.py default: none)')
+        if num_hidden_layers < 1:
+            raise ValueError('num_hidden_layers must be >= 1')
+        self.energy_func = energy_func
+        self.input_dim, self.noise_dim, self.h_dim, self.z_dim = input_dim, noise_dim, h_dim, z_dim
+        self.latent_dim = z_dim
+        self.nonlinearity, self.num_hidden_layers, self.enc_type = nonlinearity, num_hidden_layers, enc_type
+        self.clip_z0_logvar = self.clip_z_logvar = None
+        self.do_xavier = do_xavier
+        self.encode = _AuxEncoder(input_dim, noise_dim, h_dim, z_dim, nonlinearity, num_hidden_layers, enc_type)
+        self.decode = Decoder('mnist', input_dim, h_dim, z_dim, nonlinearity, num_hidden_layers - 1)
+        if do_xavier:
+            self.apply(_weight_init)
+        self._n_inp = self._n_fc = self._n_dec = num_hidden_layers
+        object.__setattr__(self.encode, '_owner', weakref.ref(self))
+        object.__setattr__(self.decode, '_owner', weakref.ref(self))
+        self._arena = ParamArena(self)
+        self._plans = {}
+        self.inv_rows_override = None
+
+    def forward_hidden(self, input, std=None, nz=1):
+        """(:236-249) -> z [B, nz, z_dim]."""
+        return self.encode(input.view(input.size(0), self.input_dim), std=std, nz=nz)
 
 
 class _ConvEncoder(nn.Module):

@@ -46,8 +46,11 @@ class TrainStep(object):
         self.nz, self.nstd, self.nzm, self.ncu = int(nz_cdae), int(nstd), int(nz_model), int(num_cdae_updates)
         # --cdae-ctx-type (ivae_ardae.py:729-741): 'lt0' = the mean code encode(x, std=0); 'data' = the input itself,
         # mapped to 2x-1 for the MNIST-like models ("if 'mnist' in opt.dataset"), as is for the toy model
-        if ctx_type not in ('lt0', 'data'):
-            raise NotImplementedError("cdae_ctx_type must be 'lt0' or 'data' ('hidden1a' needs the aux encoders)")
+        # 'hidden1a' = model.encode.forward_hidden(x, std=0), the two hidden codes of the hierarchical encoders (:739-741)
+        if ctx_type not in ('lt0', 'data', 'hidden1a'):
+            raise NotImplementedError("cdae_ctx_type must be 'lt0', 'data' or 'hidden1a'")
+        if ctx_type == 'hidden1a' and getattr(model, 'KIND', None) != 'auxmnist':
+            raise ValueError("cdae_ctx_type 'hidden1a' needs a hierarchical model (ivae_ardae.py:572-575)")
         self.ctx_type = ctx_type
         if data_ctx_affine is None:
             data_ctx_affine = (1.0, 0.0) if getattr(model, 'KIND', 'mnist') == 'toy' else (2.0, -1.0)
@@ -148,8 +151,10 @@ class TrainStep(object):
                                           _lib.stream_ptr()))
         return out
 
-    def _context(self, xs, zbar):
+    def _context(self, xs, zbar, hidden=None):
         """CDAE context rows [B, c] for a minibatch (xs: [B, D] view of the inputs)."""
+        if self.ctx_type == 'hidden1a':
+            return hidden
         if self.ctx_type == 'data':
             a, s = self.data_ctx_affine
             return (xs * a + s) if (a != 1.0 or s != 0.0) else xs.contiguous()
@@ -178,12 +183,16 @@ class TrainStep(object):
         L = _lib.lib()
         m, c = self.model, self.cdae
         B = x.size(0)
-        d, n = m.z_dim, m.noise_dim
+        d, n = m.z_dim, m._noise_width
         dev = x.device
         xs = _lib.require_cuda(x, 'x').view(B, -1)
+        hid = None
         with self._seg('encode'):
             enc = noise['enc_cdae'] if noise is not None else self._randn(B * self.nz, n, dev)
-            z, zbar = m._encode_with_mean(xs, enc, self.nz)                              # :735,:748 and :749 in one pass
+            if self.ctx_type == 'hidden1a':
+                z, zbar, hid = m._encode_hidden(xs, enc, self.nz)                        # :740 next to :748,:749
+            else:
+                z, zbar = m._encode_with_mean(xs, enc, self.nz)                          # :735,:748 and :749 in one pass
         N = B * self.nz * self.nstd
         xc = torch.empty(N, d, dtype=torch.float32, device=dev)
         sigma = torch.empty(N, dtype=torch.float32, device=dev)
@@ -205,7 +214,7 @@ class TrainStep(object):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         inv = dp_scales(B, self.nz, self.nstd, d, self.nzm, self.world)['cdae_inv_count']
         with self._seg('cdae_train'):
-            _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(self._context(xs, zbar)), _lib.ptr(sigma), _lib.ptr(eps), gen,
+            _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(self._context(xs, zbar, hid)), _lib.ptr(sigma), _lib.ptr(eps), gen,
                                           self._next_seed(), ctypes.c_float(inv), _lib.ptr(loss), None,
                                           _lib.stream_ptr()))                           # :768-771
         with self._seg('cdae_allreduce'):
@@ -223,7 +232,7 @@ class TrainStep(object):
         L = _lib.lib()
         m = self.model
         B = x.size(0)
-        d, n = m.z_dim, m.noise_dim
+        d, n = m.z_dim, m._noise_width
         dev = x.device
         xs = _lib.require_cuda(x, 'x').view(B, -1)
         R = B * self.nzm
@@ -243,7 +252,11 @@ class TrainStep(object):
             _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),
                                              ctypes.c_float(inv_rows), _lib.ptr(z), _lib.ptr(sums), None,
                                              _lib.stream_ptr()))                        # :801
-            zbar = m._encode(xs, None, 1, slot=1)                                        # :813,:826
+            hid = None
+            if self.ctx_type == 'hidden1a':
+                _, zbar, hid = m._encode_hidden(xs, None, 1, slot=1)                     # :816 next to :826
+            else:
+                zbar = m._encode(xs, None, 1, slot=1)                                    # :813,:826
             if self.keep_noise:
                 self.last_noise.update(zbar_model=zbar)
             xsd = torch.empty(R, d, dtype=torch.float32, device=dev)
@@ -255,7 +268,7 @@ class TrainStep(object):
             ar.stage_flat.zero_()
             _lib.check(L.ardae_model_backward_decoder(hm, ctypes.c_float(1.0), _lib.stream_ptr()))
         return dict(hm=hm, z=z, sums=sums, zbar=zbar, xsd=xsd, inv_rows=inv_rows, B=B, R=R, enc=enc, xs=xs,
-                    ctx=self._context(xs, zbar))
+                    ctx=self._context(xs, zbar, hid))
 
     def model_backward(self, f, beta):
         """Entropy-gradient estimate with the UPDATED cdae (:829), one backward for :804 + :834, Adam (:846)."""

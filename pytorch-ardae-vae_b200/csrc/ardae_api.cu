@@ -181,6 +181,19 @@ ARDAE_API int ardae_model_encode_with_mean(ardae_model_t h, const float* x, cons
   return h->p.fwd_mean.run(static_cast<cudaStream_t>(stream));
 }
 
+ARDAE_API int ardae_model_encode_hidden(ardae_model_t h, const float* x, const float* noise, float* z_out,
+                                        float* zbar_out, float* hidden_out, void* stream) {
+  if (!h || !x || !z_out || !zbar_out || !hidden_out) return fail(-1, "null argument");
+  if (h->p.cfg.mode != 0) return fail(-2, "handle was created with mode = 1 (use ardae_model_forward)");
+  if (h->p.cfg.kind != 3) return fail(-2, "encode_hidden: only the auxmnist kind has a hidden context");
+  ModelBindings& b = h->p.bind;
+  b = ModelBindings();
+  b.x = x; b.noise = noise; b.z_out = z_out; b.zbar_out = zbar_out; b.hidden_out = hidden_out;
+  int rc = h->p.fwd.run(static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  return h->p.fwd_mean.run(static_cast<cudaStream_t>(stream));
+}
+
 ARDAE_API int ardae_model_forward(ardae_model_t h, const float* x, const float* noise, float beta, float inv_rows,
                                   float* z_out, float* sums, float* heads_out, void* stream) {
   if (!h || !x || !z_out || !sums) return fail(-1, "null argument");

@@ -512,6 +512,61 @@ __global__ void dz_total_kernel(const float* __restrict__ dz_dec, int ld_dec, co
   }
 }
 
+// ---------------------------------------------------------------- Gaussian reparametrisation stages of the hierarchical
+// (aux*) encoders: models/ivae/auxmnist.py:33-40,88-101, models/vae/auxmnist.py:24-29
+// out[r, j] = mu[g, j] + exp(0.5 * lv[g, j]) * eps[r, j],  g = r / group  (eps == nullptr: std = 0 -> out = mu).
+// heads [rows/group, ldh] = [mu | lv at +lvoff].  Written as a tf32 pair (hi | lo at +kp), optionally also plain.
+__global__ void aux_reparam_kernel(const float* __restrict__ heads, int ldh, int lvoff, const float* __restrict__ eps,
+                                   int ld_eps, int R, int w, int group, float* __restrict__ pair, int ldp, int kp,
+                                   float* __restrict__ plain, int ld_plain, float* __restrict__ user_out) {
+  const size_t total = static_cast<size_t>(R) * w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / w), j = static_cast<int>(i - static_cast<size_t>(r) * w);
+    const float* hg = heads + static_cast<size_t>(r / group) * ldh;
+    float v = hg[j];
+    if (eps != nullptr) v += __expf(0.5f * hg[lvoff + j]) * eps[static_cast<size_t>(r) * ld_eps + j];
+    const float hi = ptx::round_tf32(v);
+    pair[static_cast<size_t>(r) * ldp + j] = hi;
+    pair[static_cast<size_t>(r) * ldp + kp + j] = ptx::round_tf32(v - hi);
+    if (plain != nullptr) plain[static_cast<size_t>(r) * ld_plain + j] = v;
+    if (user_out != nullptr) user_out[i] = v;
+  }
+}
+// dheads[r, j] = dz[r, j] ; dheads[r, lvoff + j] = dz[r, j] * 0.5 * exp(0.5 lv[r, j]) * eps[r, j]   (tf32-rounded)
+__global__ void aux_reparam_bwd_kernel(const float* __restrict__ dz, int ldz, const float* __restrict__ heads, int ldh,
+                                       int lvoff, const float* __restrict__ eps, int ld_eps, int R, int w,
+                                       float* __restrict__ dheads, int ldd) {
+  const size_t total = static_cast<size_t>(R) * w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / w), j = static_cast<int>(i - static_cast<size_t>(r) * w);
+    const float g = dz[static_cast<size_t>(r) * ldz + j];
+    const float e = eps != nullptr ? eps[static_cast<size_t>(r) * ld_eps + j] : 0.0f;
+    dheads[static_cast<size_t>(r) * ldd + j] = ptx::round_tf32(g);
+    dheads[static_cast<size_t>(r) * ldd + lvoff + j] =
+        ptx::round_tf32(g * 0.5f * __expf(0.5f * heads[static_cast<size_t>(r) * ldh + lvoff + j]) * e);
+  }
+}
+// Same through a per-data-row head: dheads[b, j] = sum_k dz[b*S+k, j] ; dheads[b, lvoff+j] = sum_k dz * 0.5 exp(0.5 lv[b,j]) eps
+__global__ void aux_reparam_bwd_group_kernel(const float* __restrict__ dz, int ldz, const float* __restrict__ heads,
+                                             int ldh, int lvoff, const float* __restrict__ eps, int ld_eps, int B, int S,
+                                             int w, float* __restrict__ dheads, int ldd) {
+  const int b = blockIdx.x;
+  for (int j = threadIdx.x; j < w; j += blockDim.x) {
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int k = 0; k < S; ++k) {
+      const size_t r = static_cast<size_t>(b) * S + k;
+      const float g = dz[r * ldz + j];
+      a0 += g;
+      if (eps != nullptr) a1 += g * eps[r * ld_eps + j];
+    }
+    dheads[static_cast<size_t>(b) * ldd + j] = ptx::round_tf32(a0);
+    dheads[static_cast<size_t>(b) * ldd + lvoff + j] =
+        ptx::round_tf32(a1 * 0.5f * __expf(0.5f * heads[static_cast<size_t>(b) * ldh + lvoff + j]));
+  }
+}
+
 // ---------------------------------------------------------------- sigma schedule (ivae_ardae.py:753-767)
 // One block per data row b.  lsm = S*(z - zbar); s_b = delta * mean_d std_k(lsm) (unbiased over nz);
 // outputs: x_out[(b*nz + k)*nstd + t, :] = lsm[b,k,:] ; sigma_out[same] = s_b * xi[same] ;
@@ -619,7 +674,7 @@ __global__ void scaled_diff_kernel(const float* __restrict__ z, const float* __r
 __global__ void iws_moments_kernel(const float* __restrict__ z, int ldz, int S, int d,
                                    const float* __restrict__ eta, uint64_t seed,
                                    float* __restrict__ newz_pair, int ldp, int kp,
-                                   float* __restrict__ lw0, int* __restrict__ status) {
+                                   float* __restrict__ lw0, int* __restrict__ status, float diag_eps = 0.0f) {
   extern __shared__ float sm[];
   float* cov = sm;               // [d*d]
   float* mu = cov + d * d;       // [d]
@@ -655,7 +710,8 @@ __global__ void iws_moments_kernel(const float* __restrict__ z, int ldz, int S, 
     }
     __syncthreads();
   }
-  for (int e = tid; e < d * d; e += nt) cov[e] *= 1.0f / (S - 1);
+  // (diag_eps: the hierarchical models add 1e-5 I to the covariance, models/ivae/auxmnist.py:350)
+  for (int e = tid; e < d * d; e += nt) cov[e] = cov[e] * (1.0f / (S - 1)) + ((e / d == e % d) ? diag_eps : 0.0f);
   __syncthreads();
   // ---- Cholesky (in place, lower), warp 0; column j at a time
   if (tid < 32) {

@@ -31,6 +31,7 @@ struct ModelBindings {
   const float* noise = nullptr;  // [R, n] or null (= zeros: encode(std=0))
   float* z_out = nullptr;        // [R, zd]
   float* zbar_out = nullptr;     // [B, zd] mean code encode(x, std=0) from the same pass (fwd_mean plan), or null
+  float* hidden_out = nullptr;   // kind 3: [B, 2h] cat(h0, h) at std = 0 (Encoder.forward_hidden, the 'hidden1a' context), or null
   float* heads_out = nullptr;    // [R, D] logits | [R, 2D] mu,logvar  (optional)
   float* sums = nullptr;         // [3] loss, recon, prior (device; overwritten)
   float beta = 1.0f;
@@ -62,14 +63,385 @@ struct ModelPlan {
   size_t tn_need = 0;
 
   int n_heads() const { return cfg.kind == 0 ? 2 : (cfg.kind == 2 ? 3 : 1); }  // kind 2: deconv1, deconv2, logit_fn
-  int ntensors() const { return 2 * (cfg.n_inp + cfg.n_fc + 1 + cfg.n_dec + n_heads()); }
+  int ntensors() const {
+    if (cfg.kind == 3) return 2 * (cfg.n_inp + 2 + cfg.n_fc + 2 + cfg.n_dec + 1);  // aux main + 2 heads, fc + 2 heads, decoder + logits
+    return 2 * (cfg.n_inp + cfg.n_fc + 1 + cfg.n_dec + n_heads());
+  }
+
+  // ------------------------------------------------------------------------------------------------------------------
+  // kind 3: hierarchical implicit-posterior VAE `net.MNISTAuxIPVAE` (models/ivae/auxmnist.py:47-300, encoders
+  // models/vae/auxmnist.py:31-68,147-191, decoder models/vae/mnist.py): z0 = mu0(x) + exp(lv0(x)/2) eps0 on the noise
+  // width, z = mu(x, z0) + exp(lv(x, z0)/2) eps.  `noise` packs the two draws as [R, n + zd] (eps0 | eps); a null noise
+  // pointer is `std = 0`.  Tensor order = state_dict order: aux_encode.main (n_inp linears), aux_encode.reparam
+  // (mean_fn, logvar_fn), encode.fc (n_fc linears, first one [h, D + n]), encode.reparam (mean_fn, logvar_fn),
+  // decode.main (n_dec linears), decode.reparam.logit_fn.  The x-half of encode.fc layer 0 enters once per data row
+  // (rowbias0), as in the concat models.
+  int build_aux(float* const* params, float* const* grads) {
+    const ModelConfig& c = cfg;
+    const int D = c.D, n = c.n, h = c.h, zd = c.zd, B = c.B, nz = c.nz, R = B * nz;
+    if (c.mode < 0 || c.mode > 3) return fail(-2, "model: the auxmnist kind supports modes 0 (encode), 1 (train), 2 (IWS), 3 (decode)");
+    if (c.mode == 3 && nz != 1) return fail(-2, "model: sub-module plans (modes 3-5) take nz = 1");
+    if (c.act != 1) return fail(-2, "model: the auxmnist kind is softplus only");
+    if (c.mode == 2 && (zd > 64 || nz < 2 * zd)) return fail(-2, "iws: need z_dim <= 64 and sample_size >= 2*z_dim");
+    const bool dry = ws.dry, train = c.mode == 1, dec = c.mode >= 1;
+    fwd.dry = bwd_dec.dry = bwd_enc.dry = fwd_mean.dry = dry;
+    const int ACT = EPI_SOFTPLUS, DACT = EPI_MUL_SIG;
+    auto P = [&](int i) -> float* { return dry ? nullptr : params[i]; };
+    auto G = [&](int i) -> float* { return (dry || !train) ? nullptr : grads[i]; };
+    auto iA = [&](int l) { return 2 * l; };
+    auto iAH = [&](int k) { return 2 * (c.n_inp + k); };
+    auto iF = [&](int l) { return 2 * (c.n_inp + 2 + l); };
+    auto iFH = [&](int k) { return 2 * (c.n_inp + 2 + c.n_fc + k); };
+    auto iD = [&](int l) { return 2 * (c.n_inp + 2 + c.n_fc + 2 + l); };
+    const int iH = 2 * (c.n_inp + 2 + c.n_fc + 2 + c.n_dec);
+    const int np = round_up(n, 4), zdp = round_up(zd, 4), Dp = round_up(D, 4), ne = n + zd;
+
+    // ---- derived weights
+    derive = DeriveList();
+    std::vector<W3> Aw(c.n_inp), Fw(c.n_fc), Dw(c.n_dec);
+    for (int l = 0; l < c.n_inp; ++l) Aw[l] = derive.add(ws, P(iA(l)), h, l == 0 ? D : h, l == 0 ? D : h, true, train && l > 0);
+    const int ld0 = D + n;
+    W3 F0i = derive.add(ws, P(iF(0)), h, D, ld0, true, false);
+    W3 F0n = derive.add(ws, P(iF(0)) ? P(iF(0)) + D : nullptr, h, n, ld0, true, train);
+    for (int l = 1; l < c.n_fc; ++l) Fw[l] = derive.add(ws, P(iF(l)), h, h, h, true, train);
+    for (int l = 0; l < c.n_dec && dec; ++l) Dw[l] = derive.add(ws, P(iD(l)), h, l == 0 ? zd : h, l == 0 ? zd : h, true, train);
+    // two-head operands: forward [2*out, 3*kp] (heads stacked), transposed [h, 2*outp] for the backward
+    auto heads_w = [&](int i0, int out, int outp, bool want) {
+      W3 w;
+      w.in = h; w.out = 2 * out; w.kp = round_up(h, 32);
+      if (!want) return w;
+      w.b3 = Mat(ws.floats(static_cast<size_t>(2) * out * 3 * w.kp), 2 * out, 3 * w.kp, 3 * w.kp);
+      if (train) w.T = ws.mat(h, 2 * outp);
+      for (int k = 0; k < 2; ++k) {
+        DeriveItem it;
+        std::memset(&it, 0, sizeof(it));
+        it.src = P(i0 + 2 * k); it.rows = out; it.cols = h; it.src_ld = h;
+        it.dst3 = dry ? nullptr : w.b3.p + static_cast<size_t>(k) * out * w.b3.ld;
+        it.kp = w.kp; it.ld3 = w.b3.ld;
+        it.dstT = (dry || !train) ? nullptr : w.T.p + k * outp; it.ldT = train ? w.T.ld : 0;
+        it.first_block = derive.blocks;
+        it.tiles_x = (h + 31) / 32;
+        derive.blocks += it.tiles_x * ((out + 31) / 32);
+        derive.host.push_back(it);
+      }
+      return w;
+    };
+    W3 AH = heads_w(iAH(0), n, np, true), FH = heads_w(iFH(0), zd, zdp, true);
+    W3 Hw;  // decoder logits
+    Hw.in = h; Hw.out = D; Hw.kp = round_up(h, 32);
+    if (dec) {
+      Hw.b3 = Mat(ws.floats(static_cast<size_t>(D) * 3 * Hw.kp), D, 3 * Hw.kp, 3 * Hw.kp);
+      if (train) Hw.T = ws.mat(h, Dp);
+      DeriveItem it;
+      std::memset(&it, 0, sizeof(it));
+      it.src = P(iH); it.rows = D; it.cols = h; it.src_ld = h;
+      it.dst3 = dry ? nullptr : Hw.b3.p; it.kp = Hw.kp; it.ld3 = Hw.b3.ld;
+      it.dstT = (dry || !train) ? nullptr : Hw.T.p; it.ldT = train ? Hw.T.ld : 0;
+      it.first_block = derive.blocks;
+      it.tiles_x = (h + 31) / 32;
+      derive.blocks += it.tiles_x * ((D + 31) / 32);
+      derive.host.push_back(it);
+    }
+    int rc = derive.emit(ws, fwd);
+    if (rc) return rc;
+
+    // ---- buffers
+    Pair xin = make_pair(ws, B, D);
+    std::vector<Pair> A(c.n_inp), Fh(c.n_fc), Dh(c.n_dec);
+    for (int l = 0; l < c.n_inp; ++l) A[l] = make_pair(ws, B, h);
+    Mat M0 = ws.mat(B, 2 * np);  // [mu0 | lv0]
+    Pair z0p = make_pair(ws, R, n);
+    Mat rowbias0 = ws.mat(B, h);
+    for (int l = 0; l < c.n_fc; ++l) Fh[l] = make_pair(ws, R, h);
+    Mat M = ws.mat(R, 2 * zdp);  // [mu | lv]
+    Pair zp = make_pair(ws, R, zd);
+    Mat zbuf = ws.mat(R, zd);
+    Mat heads, dheads, dzdec, dzt, dM, dz0, dM0, gsum0;
+    std::vector<Mat> dD(c.n_dec), dF(c.n_fc), dA(c.n_inp);
+    float *lw0 = nullptr, *wbuf = nullptr, *tn_ws = nullptr;
+    size_t tn_bytes = 0;
+    if (dec) {
+      for (int l = 0; l < c.n_dec; ++l) Dh[l] = make_pair(ws, R, h);
+      heads = ws.mat(R, Dp);
+    }
+    if (c.mode == 2) {
+      lw0 = ws.floats(R);
+      wbuf = ws.floats(R);
+    }
+    if (train) {
+      dheads = ws.mat(R, Dp);
+      dzdec = ws.mat(R, zd);
+      dzt = ws.mat(R, zd);
+      dM = ws.mat(R, 2 * zdp);
+      dz0 = ws.mat(R, n);
+      dM0 = ws.mat(B, 2 * np);
+      gsum0 = ws.mat(B, h);
+      for (int l = 0; l < c.n_dec; ++l) dD[l] = ws.mat(R, h);
+      for (int l = 0; l < c.n_fc; ++l) dF[l] = ws.mat(R, h);
+      for (int l = 0; l < c.n_inp; ++l) dA[l] = ws.mat(B, h);
+      if (dry) {
+        const int shapes[8][3] = {{h, h, R}, {h, n, R}, {2 * zd, h, R}, {D, h, R}, {h, zd, R}, {h, D, B}, {h, h, B}, {2 * n, h, B}};
+        tn_need = 0;
+        for (auto& sh : shapes) {
+          const size_t b = tn_workspace_bytes(sh[0], sh[1], sh[2]);
+          if (b > tn_need) tn_need = b;
+        }
+      }
+      tn_bytes = tn_need;
+      tn_ws = ws.floats(tn_bytes / 4);
+    }
+    ModelBindings* bd = &bind;
+
+    // ---- decoder (models/vae/mnist.py Decoder: n_dec softplus layers + logits)
+    auto decoder_fwd = [&]() {
+      for (int l = 0; l < c.n_dec; ++l) {
+        GemmNTDesc g = nt3_desc(l == 0 ? zp : Dh[l - 1], Dw[l], Dh[l], ACT);
+        g.bias = P(iD(l) + 1);
+        fwd.nt(g);
+      }
+      GemmNTDesc g = nt3_desc_plain(Dh[c.n_dec - 1], Hw, heads.cols_from(0, D), EPI_LINEAR);
+      g.bias = P(iH + 1);
+      fwd.nt(g);
+    };
+    if (c.mode == 3) {  // Decoder.forward(z) minus the sampler
+      fwd.add([=](cudaStream_t s) {
+        split2d_kernel<<<grid_for(static_cast<size_t>(R) * zd), 256, 0, s>>>(bd->z_in, zd, zp.buf.p, zp.buf.ld, R, zd, zp.kp, 1.0f, 0.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+      decoder_fwd();
+      fwd.add([=](cudaStream_t s) {
+        unpad_kernel<<<grid_for(static_cast<size_t>(R) * D), 256, 0, s>>>(heads.p, heads.ld, bd->heads_out, R, D, 1.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return fwd.error;
+    }
+
+    // ================================================================= forward
+    fwd.add([=](cudaStream_t s) {
+      split2d_kernel<<<grid_for(static_cast<size_t>(B) * D), 256, 0, s>>>(bd->x, D, xin.buf.p, xin.buf.ld, B, D, xin.kp, 2.0f, -1.0f);
+      if (bd->sums) ARDAE_CUDA_OK(cudaMemsetAsync(bd->sums, 0, 3 * sizeof(float), s));
+      return static_cast<int>(cudaGetLastError());
+    });
+    for (int l = 0; l < c.n_inp; ++l) {  // aux_encode.main on the data rows
+      GemmNTDesc g = nt3_desc(l == 0 ? xin : A[l - 1], Aw[l], A[l], ACT);
+      g.bias = P(iA(l) + 1);
+      fwd.nt(g);
+    }
+    auto two_heads = [&](Plan& pl, const Pair& in, const W3& w, int out, int outp, const Mat& dst, int ib0) {
+      for (int k = 0; k < 2; ++k) {
+        W3 hk = w;
+        hk.out = out;
+        hk.b3 = w.b3.rows_from(k * out, out);
+        GemmNTDesc g = nt3_desc_plain(in, hk, dst.cols_from(k * outp, out), EPI_LINEAR);
+        g.bias = P(ib0 + 2 * k + 1);
+        pl.nt(g);
+      }
+    };
+    two_heads(fwd, A[c.n_inp - 1], AH, n, np, M0, iAH(0));
+    fwd.add([=](cudaStream_t s) {  // z0 = mu0[b] + exp(lv0[b] / 2) eps0[r]
+      aux_reparam_kernel<<<grid_for(static_cast<size_t>(R) * n), 256, 0, s>>>(
+          M0.p, M0.ld, np, bd->noise, ne, R, n, nz, z0p.buf.p, z0p.buf.ld, z0p.kp, nullptr, 0, nullptr);
+      return static_cast<int>(cudaGetLastError());
+    });
+    {
+      GemmNTDesc g = nt3_desc_plain(xin, F0i, rowbias0, EPI_LINEAR);
+      g.bias = P(iF(0) + 1);
+      fwd.nt(g);
+    }
+    {
+      GemmNTDesc g = nt3_desc(z0p, F0n, Fh[0], ACT);
+      g.group_bias = rowbias0.p; g.group = nz; g.ldg = rowbias0.ld;
+      fwd.nt(g);
+    }
+    for (int l = 1; l < c.n_fc; ++l) {
+      GemmNTDesc g = nt3_desc(Fh[l - 1], Fw[l], Fh[l], ACT);
+      g.bias = P(iF(l) + 1);
+      fwd.nt(g);
+    }
+    two_heads(fwd, Fh[c.n_fc - 1], FH, zd, zdp, M, iFH(0));
+    fwd.add([=](cudaStream_t s) {  // z = mu + exp(lv / 2) eps
+      aux_reparam_kernel<<<grid_for(static_cast<size_t>(R) * zd), 256, 0, s>>>(
+          M.p, M.ld, zdp, bd->noise != nullptr ? bd->noise + n : nullptr, ne, R, zd, 1, zp.buf.p, zp.buf.ld, zp.kp, zbuf.p,
+          zbuf.ld, bd->z_out);
+      return static_cast<int>(cudaGetLastError());
+    });
+    if (c.mode == 0) {
+      // ---- std = 0 pass on the data rows: z-bar = mu(x, mu0(x)) and the 'hidden1a' context cat(h0, h)
+      std::vector<Pair> Fb(c.n_fc);
+      for (int l = 0; l < c.n_fc; ++l) Fb[l] = make_pair(ws, B, h);
+      Pair z0b = make_pair(ws, B, n), zbp = make_pair(ws, B, zd);
+      Mat Mb = ws.mat(B, 2 * zdp), hbuf = ws.mat(B, 2 * h);
+      fwd_mean.add([=](cudaStream_t s) {
+        aux_reparam_kernel<<<grid_for(static_cast<size_t>(B) * n), 256, 0, s>>>(M0.p, M0.ld, np, nullptr, 0, B, n, 1, z0b.buf.p,
+                                                                              z0b.buf.ld, z0b.kp, nullptr, 0, nullptr);
+        return static_cast<int>(cudaGetLastError());
+      });
+      {
+        GemmNTDesc g = nt3_desc(z0b, F0n, Fb[0], ACT);
+        g.group_bias = rowbias0.p; g.group = 1; g.ldg = rowbias0.ld;
+        fwd_mean.nt(g);
+      }
+      for (int l = 1; l < c.n_fc; ++l) {
+        GemmNTDesc g = nt3_desc(Fb[l - 1], Fw[l], Fb[l], ACT);
+        g.bias = P(iF(l) + 1);
+        fwd_mean.nt(g);
+      }
+      two_heads(fwd_mean, Fb[c.n_fc - 1], FH, zd, zdp, Mb, iFH(0));
+      {
+        const Pair a_last = A[c.n_inp - 1], f_last = Fb[c.n_fc - 1];
+        fwd_mean.add([=](cudaStream_t s) {
+          aux_reparam_kernel<<<grid_for(static_cast<size_t>(B) * zd), 256, 0, s>>>(Mb.p, Mb.ld, zdp, nullptr, 0, B, zd, 1, zbp.buf.p,
+                                                                                 zbp.buf.ld, zbp.kp, nullptr, 0, bd->zbar_out);
+          if (bd->hidden_out != nullptr) {  // [B, 2h] = [h0 | h], contiguous rows
+            pair_sum_kernel<<<grid_for(static_cast<size_t>(B) * h), 256, 0, s>>>(a_last.hi().p, a_last.lo().p, a_last.buf.ld,
+                                                                               hbuf.p, hbuf.ld, nullptr, B, h);
+            pair_sum_kernel<<<grid_for(static_cast<size_t>(B) * h), 256, 0, s>>>(f_last.hi().p, f_last.lo().p, f_last.buf.ld,
+                                                                               hbuf.p + h, hbuf.ld, nullptr, B, h);
+            unpad_kernel<<<grid_for(static_cast<size_t>(B) * 2 * h), 256, 0, s>>>(hbuf.p, hbuf.ld, bd->hidden_out, B, 2 * h, 1.0f);
+          }
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      return fwd.error ? fwd.error : fwd_mean.error;
+    }
+    if (c.mode == 2) {
+      const size_t smem = sizeof(float) * (static_cast<size_t>(zd) * zd + 2 * zd + 64 * zd);
+      fwd.add([=](cudaStream_t s) {
+        iws_moments_kernel<<<B, 256, smem, s>>>(zbuf.p, zbuf.ld, nz, zd, bd->eta, bd->seed, zp.buf.p, zp.buf.ld, zp.kp, lw0,
+                                                bd->status, 1e-5f);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    decoder_fwd();
+    if (c.mode == 2) {
+      fwd.add([=](cudaStream_t s) {
+        iws_loglik_kernel<<<R, 128, 0, s>>>(heads.p, heads.ld, Dp, bd->x, D, nz, 1, lw0, wbuf);
+        iws_logmeanexp_kernel<<<B, 256, 0, s>>>(wbuf, nz, bd->iws_out, bd->iws_total);
+        return static_cast<int>(cudaGetLastError());
+      });
+      return fwd.error;
+    }
+    fwd.add([=](cudaStream_t s) {
+      bern_elbo_kernel<<<R, 256, 0, s>>>(heads.p, heads.ld, bd->x, D, zbuf.p, zbuf.ld, zd, nz, bd->beta, bd->inv_rows, bd->sums,
+                                         dheads.p, dheads.ld, bd->beta_dev);
+      if (bd->heads_out)
+        unpad_kernel<<<grid_for(static_cast<size_t>(R) * D), 256, 0, s>>>(heads.p, heads.ld, bd->heads_out, R, D, 1.0f);
+      return static_cast<int>(cudaGetLastError());
+    });
+
+    // ================================================================= backward
+    auto tn1 = [&](Plan& pl, const Mat& X, const Mat& Y, float* dst, int ldo) {
+      GemmTNDesc t;
+      t.X0 = X.p; t.ldx0 = X.ld; t.Y0 = Y.p; t.ldy0 = Y.ld;
+      t.M = X.cols; t.N = Y.cols; t.K = X.rows; t.out = dst; t.ldo = ldo;
+      t.scale = 1.0f; t.beta = 1.0f; t.workspace = tn_ws; t.workspace_bytes = tn_bytes;
+      pl.tn(t);
+    };
+    auto colsum_op = [&](Plan& pl, const Mat& X, float* dst) {
+      pl.add([=](cudaStream_t s) {
+        dim3 grid((X.cols + 31) / 32, X.rows >= 2048 ? 32 : (X.rows + 63) / 64);
+        colsum_kernel<<<grid, 256, 0, s>>>(X.p, X.ld, X.rows, X.cols, dst, 1.0f);
+        return static_cast<int>(cudaGetLastError());
+      });
+    };
+    // ---- decoder part
+    {
+      const Mat dh = dheads.cols_from(0, D);
+      tn1(bwd_dec, dh, Dh[c.n_dec - 1].hi(), G(iH), h);
+      colsum_op(bwd_dec, dh, G(iH + 1));
+      GemmNTDesc g = nt_desc(dheads, Hw.T, dD[c.n_dec - 1], DACT);
+      set_aux1(g, Dh[c.n_dec - 1].hi());
+      g.colsum = G(iD(c.n_dec - 1) + 1);
+      bwd_dec.nt(g);
+    }
+    for (int l = c.n_dec - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(dD[l], Dw[l].T, dD[l - 1], DACT);
+      set_aux1(g, Dh[l - 1].hi());
+      g.colsum = G(iD(l - 1) + 1);
+      bwd_dec.nt(g);
+    }
+    for (int l = c.n_dec - 1; l >= 1; --l) tn1(bwd_dec, dD[l], Dh[l - 1].hi(), G(iD(l)), h);
+    tn1(bwd_dec, dD[0], zp.hi(), G(iD(0)), zd);
+    {
+      GemmNTDesc g = nt_desc(dD[0], Dw[0].T, dzdec, EPI_LINEAR);
+      g.round_out = 0;
+      bwd_dec.nt(g);
+    }
+    // ---- encoder part: z = mu + exp(lv/2) eps  ->  d mu = dz, d lv = dz * (z - mu) / 2
+    bwd_enc.add([=](cudaStream_t s) {
+      dz_total_kernel<<<grid_for(static_cast<size_t>(R) * zd), 256, 0, s>>>(
+          dzdec.p, dzdec.ld, zbuf.p, zbuf.ld, bd->gz, bd->gz_scale, bd->loss_scale, bd->beta * bd->inv_rows, dzt.p, dzt.ld, R, zd,
+          bd->beta_dev, bd->inv_rows);
+      aux_reparam_bwd_kernel<<<grid_for(static_cast<size_t>(R) * zd), 256, 0, s>>>(
+          dzt.p, dzt.ld, M.p, M.ld, zdp, bd->noise != nullptr ? bd->noise + n : nullptr, ne, R, zd, dM.p, dM.ld);
+      return static_cast<int>(cudaGetLastError());
+    });
+    for (int k = 0; k < 2; ++k) {
+      const Mat dk = dM.cols_from(k * zdp, zd);
+      tn1(bwd_enc, dk, Fh[c.n_fc - 1].hi(), G(iFH(k)), h);
+      colsum_op(bwd_enc, dk, G(iFH(k) + 1));
+    }
+    {
+      GemmNTDesc g = nt_desc(dM, FH.T, dF[c.n_fc - 1], DACT);
+      set_aux1(g, Fh[c.n_fc - 1].hi());
+      g.colsum = G(iF(c.n_fc - 1) + 1);
+      bwd_enc.nt(g);
+    }
+    for (int l = c.n_fc - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(dF[l], Fw[l].T, dF[l - 1], DACT);
+      set_aux1(g, Fh[l - 1].hi());
+      g.colsum = G(iF(l - 1) + 1);
+      bwd_enc.nt(g);
+    }
+    for (int l = c.n_fc - 1; l >= 1; --l) tn1(bwd_enc, dF[l], Fh[l - 1].hi(), G(iF(l)), h);
+    // fc layer 0: z0 half over the R rows, x half through the per-data-row sum
+    tn1(bwd_enc, dF[0], z0p.hi(), G(iF(0)) ? G(iF(0)) + D : nullptr, ld0);
+    {
+      const Mat d0 = dF[0];
+      bwd_enc.add([=](cudaStream_t s) {
+        group_sum_kernel<<<B, 256, 0, s>>>(d0.p, d0.ld, gsum0.p, gsum0.ld, B, nz, h, 1);
+        return static_cast<int>(cudaGetLastError());
+      });
+    }
+    tn1(bwd_enc, gsum0, xin.hi(), G(iF(0)), ld0);
+    {  // d z0 = d hid_0 . W_z0
+      GemmNTDesc g = nt_desc(dF[0], F0n.T, dz0, EPI_LINEAR);
+      g.round_out = 0;
+      bwd_enc.nt(g);
+    }
+    bwd_enc.add([=](cudaStream_t s) {  // through z0 = mu0[b] + exp(lv0[b]/2) eps0[r]
+      aux_reparam_bwd_group_kernel<<<B, 128, 0, s>>>(dz0.p, dz0.ld, M0.p, M0.ld, np, bd->noise, ne, B, nz, n, dM0.p, dM0.ld);
+      return static_cast<int>(cudaGetLastError());
+    });
+    for (int k = 0; k < 2; ++k) {
+      const Mat dk = dM0.cols_from(k * np, n);
+      tn1(bwd_enc, dk, A[c.n_inp - 1].hi(), G(iAH(k)), h);
+      colsum_op(bwd_enc, dk, G(iAH(k) + 1));
+    }
+    {
+      GemmNTDesc g = nt_desc(dM0, AH.T, dA[c.n_inp - 1], DACT);
+      set_aux1(g, A[c.n_inp - 1].hi());
+      g.colsum = G(iA(c.n_inp - 1) + 1);
+      bwd_enc.nt(g);
+    }
+    for (int l = c.n_inp - 1; l >= 1; --l) {
+      GemmNTDesc g = nt_desc(dA[l], Aw[l].T, dA[l - 1], DACT);
+      set_aux1(g, A[l - 1].hi());
+      g.colsum = G(iA(l - 1) + 1);
+      bwd_enc.nt(g);
+    }
+    for (int l = c.n_inp - 1; l >= 1; --l) tn1(bwd_enc, dA[l], A[l - 1].hi(), G(iA(l)), h);
+    tn1(bwd_enc, dA[0], xin.hi(), G(iA(0)), D);
+    return fwd.error ? fwd.error : (bwd_dec.error ? bwd_dec.error : bwd_enc.error);
+  }
 
   int build(float* const* params, float* const* grads) {
     const ModelConfig& c = cfg;
     const int D = c.D, n = c.n, h = c.h, zd = c.zd, B = c.B, nz = c.nz, R = B * nz;
     if (D <= 0 || n <= 0 || h <= 0 || zd <= 0 || B <= 0 || nz <= 0 || c.n_inp < 1 || c.n_fc < 1 || c.n_dec < 1)
       return fail(-2, "model: bad config");
-    if (c.kind < 0 || c.kind > 2) return fail(-2, "model: kind must be 0 (toy), 1 (mnist) or 2 (conv)");
+    if (c.kind < 0 || c.kind > 3) return fail(-2, "model: kind must be 0 (toy), 1 (mnist), 2 (conv) or 3 (auxmnist)");
+    if (c.kind == 3) return build_aux(params, grads);
     const bool conv = c.kind == 2;
     // conv geometry (models/ivae/conv.py:64-67): three 5x5 stride-2 pad-2 convs
     auto cos_ = [](int hin) { return (hin + 4 - 5) / 2 + 1; };

@@ -23,6 +23,10 @@ def build_model(meta):
     if meta['kind'] == 'conv':
         return ardae.ConvIPVAE(input_height=m['input_height'], input_channels=m['input_channels'], z_dim=m['z_dim'],
                                noise_dim=m['noise_dim'], nonlinearity=m['nonlinearity'])
+    if meta['kind'] == 'auxmnist':
+        return ardae.MNISTAuxIPVAE(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
+                                   num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'],
+                                   enc_type='simple', z_dim=m['z_dim'])
     cls = ardae.ToyIPVAE if meta['kind'] == 'toy' else ardae.MNISTIPVAE
     return cls(input_dim=m['input_dim'], noise_dim=m['noise_dim'], h_dim=m['h_dim'],
                num_hidden_layers=m['num_hidden_layers'], nonlinearity=m['nonlinearity'], enc_type='concat',

@@ -6,7 +6,7 @@ Tolerances (tf32 backward sweeps, 3xTF32 forward):
   z, zbar                               rel <= 1e-5      (fp32-accurate forward)
   sigma scale std_b                     rel <= 1e-4
   CDAE score / entropy gradient         rel-L2 <= 1e-2
-  every parameter gradient tensor       rel-L2 <= 2e-2
+  every parameter gradient tensor       rel-L2 <= 2e-2   (auxmnist_small, second step: 6e-2, see below)
   parameter UPDATE (after - before)     rel-L2 <= 5e-2 (RMSprop) / 0.15 (Adam): at t = 1 Adam's update is
                                         lr*g/(|g|+eps) ~ lr*sign(g), so the few elements whose |g| is below
                                         the 1e-3 gradient error flip sign; the optimizer arithmetic itself is
@@ -97,7 +97,10 @@ def test_fused_step_matches_reference_fixture(name):
                                                     out['model_loss'].item(), float(z[p + 'model_loss']), eg, ue_c, ue_m))
         assert ue_c <= (0.3 if loose else 5e-2) and ue_m <= (0.3 if loose else 0.15)
         # the gradients the optimizers consumed are still in the stage arenas
-        gtol = 0.2 if loose else 2e-2
+        # step >= 1 of the hierarchical case starts from parameters carrying step 0's update error (4-5 % of an
+        # RMSprop / Adam update); with the fp64 oracle alone, that perturbation moves the step-1 CDAE gradients by
+        # 1.5e-2 .. 3.6e-2 (scripts/step1_sensitivity.py).  Step 0 (same kernels, exact start) holds 2e-2.
+        gtol = 0.2 if loose else (6e-2 if (meta['kind'] == 'auxmnist' and s >= 1) else 2e-2)
         for mod, pref in ((cdae, 'cdae_grads/'), (model, 'model_grads/')):
             ar, ref = mod._arena, sub(z, p + pref)
             for k, nme in enumerate(ar.names):
@@ -309,3 +312,34 @@ def test_two_cdae_updates_per_iteration():
     for a, b in ((pm_a, pm_b), (pc_a, pc_b)):
         for k in a:
             assert rel_err(a[k], b[k]) <= 1e-5, k
+
+
+def test_aux_encoder_full_width_vs_oracle():
+    """Hierarchical encoder at the reference's MNIST widths (784/300/100/32, 2 hidden layers, ivae_ardae.py:455-467):
+    z, the mean code, the 'hidden1a' context cat(h0, h) and the decoder logits against the fp64 oracle."""
+    import ardae
+    import ardae_oracle as orc
+    torch.manual_seed(5)
+    model = ardae.MNISTAuxIPVAE(input_dim=784, noise_dim=100, h_dim=300, z_dim=32, num_hidden_layers=2).cuda()
+    spec = orc.ModelSpec('auxmnist', 784, 100, 300, 32, 2, 'softplus')
+    P = params_np(model)
+    rng = np.random.RandomState(2)
+    B, nz = 6, 8
+    x = (rng.rand(B, 784) > 0.6).astype(np.float64)
+    eps = rng.randn(B * nz, 132)
+    z_ref, _ = orc.encoder_forward(spec, P, x, eps, nz)
+    zbar_ref, _ = orc.encoder_forward(spec, P, x, np.zeros((B, 132)), 1)
+    z, zbar, hid = model._encode_hidden(t(x), t(eps), nz)
+    assert rel_err(z.cpu().numpy(), z_ref) <= 1e-5
+    assert rel_err(zbar.cpu().numpy(), zbar_ref) <= 1e-5
+    assert rel_err(hid.cpu().numpy(), orc.aux_encoder_hidden(spec, P, x)) <= 1e-5
+    assert rel_err(model.encode(t(x), nz=nz, noise=t(eps)).cpu().numpy(), z_ref) <= 1e-5
+    assert rel_err(model.encode.forward_hidden(t(x), std=0).cpu().numpy(), orc.aux_encoder_hidden(spec, P, x)) <= 1e-5
+    assert rel_err(model.forward_hidden(t(x), std=0).cpu().numpy(), zbar_ref) <= 1e-5
+    zz = rng.randn(10, 32)
+    heads, _ = orc.decoder_forward(spec, P, zz)
+    xs, logit = model.decode(t(zz))
+    assert xs.shape == logit.shape == (10, 784)
+    assert rel_err(logit.cpu().numpy(), heads[0] if isinstance(heads, (tuple, list)) else heads) <= 1e-5
+    out, mean, zg = model.generate(4)
+    assert out.shape == mean.shape == (4, 784) and zg.shape == (4, 32)
