@@ -75,7 +75,13 @@ def test_cdae_matches_reference_fixture(name):
     std = z['s0/std'] * z['s0/noise/xi']
     eps = z['s0/noise/eps_cdae']
     # context rows: the mean code ('lt0') or the input mapped to 2x-1 ('data'), ivae_ardae.py:729-741
-    ctx = z['s0/zbar'] if meta.get('ctx_type', 'lt0') == 'lt0' else (2.0 * z['s0/x_cdae'] - 1.0)[:, None, :]
+    ct = meta.get('ctx_type', 'lt0')
+    if ct == 'hidden1a':  # cat(h0, h) of the hierarchical encoder at std = 0 (:739-741), from the oracle (not stored)
+        from test_oracle_golden import specs
+        Pm = {k: np.asarray(v, dtype=np.float64) for k, v in sub(z, 'm0/').items()}
+        ctx = orc.aux_encoder_hidden(specs(meta)[0], Pm, np.asarray(z['s0/x_cdae'], dtype=np.float64))[:, None, :]
+    else:
+        ctx = z['s0/zbar'] if ct == 'lt0' else (2.0 * z['s0/x_cdae'] - 1.0)[:, None, :]
     # the fixture's own numbers (reference, fp64) agree with the oracle by test_oracle_golden
     check_against(m, cs, P64, lsm, ctx, std, eps, name)
     ref_loss = float(z['s0/cdae_loss'])
