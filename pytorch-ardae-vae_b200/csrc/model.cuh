@@ -10,8 +10,9 @@
 //   toy  : inp_encode (n_inp linears), fc.layers (n_fc), fc.fc, decode.main (n_dec), mean_fn, logvar_fn
 //   mnist: inp_encode (n_inp linears), fc.layers (n_fc), fc.fc, decode.main (n_dec), logit_fn
 #pragma once
+#include <array>
 #include "cdae.cuh"
-#include "conv_kernels.cuh"
+#include "conv_gemm.cuh"
 
 namespace ardae {
 
@@ -526,8 +527,37 @@ struct ModelPlan {
         derive.host.push_back(it);
       }
     }
+    // conv layers as GEMMs (conv_gemm.cuh): encoder convs in the standard layouts ([Co, Ci*25] forward operand and
+    // its transpose); the deconvs need the transposed 3xTF32 operand, derived by derive_t3_kernel below
+    const bool cg = conv && conv_gemm_enabled();
+    const int IC_ = c.img_c;
+    std::vector<W3> Cw(3);
+    Mat dT3[3], dWr[3];                       // deconv1, deconv2, logit deconv: [Co*25, 3*kp] and [Ci, Co*25]
+    const int dci[3] = {32, 32, 16};          // deconv input channels
+    const int dck[3] = {32 * 25, 16 * 25, IC_ * 25};
+    if (cg) {
+      const int cci[3] = {IC_, 16, 32}, cco[3] = {16, 32, 32};
+      for (int l = 0; l < 3 && enc_inp; ++l)
+        Cw[l] = derive.add(ws, P(iI(l)), cco[l], cci[l] * 25, cci[l] * 25, true, train && l > 0);
+      for (int k = 0; k < 3 && dec; ++k) {
+        dT3[k] = Mat(ws.floats(static_cast<size_t>(dck[k]) * 96), dck[k], 96, 96);  // kp = 32 >= Ci
+        if (train) dWr[k] = ws.mat(dci[k], dck[k]);
+      }
+    }
     int rc = derive.emit(ws, fwd);
     if (rc) return rc;
+    if (cg && dec) {
+      const float* wsrc[3] = {P(iH(0)), P(iH(1)), P(iH(2))};
+      for (int k = 0; k < 3; ++k) {
+        const float* w = wsrc[k];
+        const Mat t3 = dT3[k], wr = dWr[k];
+        const int rows = dci[k], cols = dck[k];
+        fwd.add([=](cudaStream_t s) {
+          derive_t3_kernel<<<grid_for(static_cast<size_t>(rows) * cols), 256, 0, s>>>(w, rows, cols, t3.p, 32, wr.p, wr.ld);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+    }
 
     // ---- buffers
     Pair xin;
@@ -536,12 +566,22 @@ struct ModelPlan {
     for (int l = 0; l < c.n_inp && !conv; ++l) I[l] = make_pair(ws, B, h);
     // conv front end: NCHW fp32 feature maps on the B data rows, then the flattened conv3 output as a pair
     float *c1 = nullptr, *c2 = nullptr, *c3 = nullptr;
-    if (conv) {
+    // GEMM form: im2col pairs col_l [B*Ho^2, Ci*25] and pixel-major activated outputs a_l [B*Ho^2, Co]
+    Pair colp[3];
+    Mat act_[3];
+    const int eho[3] = {s2, s4, s8}, eci[3] = {c.img_c, 16, 32}, eco[3] = {16, 32, 32};
+    if (conv && !cg) {
       c1 = ws.floats(static_cast<size_t>(B) * 16 * s2 * s2);
       c2 = ws.floats(static_cast<size_t>(B) * 32 * s4 * s4);
       c3 = ws.floats(static_cast<size_t>(B) * feat);
-      I[c.n_inp - 1] = make_pair(ws, B, feat);
     }
+    if (cg && enc_inp) {
+      for (int l = 0; l < 3; ++l) {
+        colp[l] = make_pair(ws, B * eho[l] * eho[l], eci[l] * 25);
+        act_[l] = ws.mat(B * eho[l] * eho[l], eco[l]);
+      }
+    }
+    if (conv) I[c.n_inp - 1] = make_pair(ws, B, feat);
     const Pair inp_pair = I[c.n_inp - 1];
     Pair epsp = make_pair(ws, R, n);
     Mat rowbias0 = ws.mat(B, h);
@@ -557,13 +597,29 @@ struct ModelPlan {
     float *lw0 = nullptr, *wbuf = nullptr;
     // conv back end (vae/conv.py:126-131): h1 [R,32,s8,s8] -> deconv1 -> pad -> deconv2 -> logit deconv -> crop
     float *h1 = nullptr, *h2p = nullptr, *h3 = nullptr, *dh3 = nullptr, *dh2 = nullptr, *dh1 = nullptr;
+    Pair dp_[3];
+    float* dcols_fwd = nullptr;
+    Mat dcolb[3], ddp[3];   // backward: im2col'd upstream gradients [rows, Co*25] and d pre-activations (pixel-major)
+    Mat ecol[3], eda[3];    // encoder backward: dcol_l [B*Ho^2, Ci*25] (l = 1, 2) and dA_l [B*Ho^2, Co]
     if (dec) {
       for (int l = 0; l < c.n_dec; ++l) Dh[l] = make_pair(ws, R, dwid(l));
       if (conv) {
         heads = Mat(ws.floats(static_cast<size_t>(R) * D), R, D, D);
-        h1 = ws.floats(static_cast<size_t>(R) * feat);
-        h2p = ws.floats(static_cast<size_t>(R) * 32 * d8 * d8);   // zero-padded (pad row/col never written)
-        h3 = ws.floats(static_cast<size_t>(R) * 16 * d15 * d15);
+        if (!cg) {
+          h1 = ws.floats(static_cast<size_t>(R) * feat);
+          h2p = ws.floats(static_cast<size_t>(R) * 32 * d8 * d8);   // zero-padded (pad row/col never written)
+          h3 = ws.floats(static_cast<size_t>(R) * 16 * d15 * d15);
+        } else {
+          // pixel-major pairs: p1 = decode.fc output [R*s8^2, 32], p2 = padded deconv1 output [R*d8^2, 32] (pad row /
+          // column stay zero), p3 = deconv2 output [R*d15^2, 16]; one scratch for the three column matrices
+          dp_[0] = make_pair(ws, R * s8 * s8, 32);
+          dp_[1] = make_pair(ws, R * d8 * d8, 32);
+          dp_[2] = make_pair(ws, R * d15 * d15, 16);
+          size_t need = static_cast<size_t>(R) * s8 * s8 * dck[0];
+          need = std::max(need, static_cast<size_t>(R) * d8 * d8 * dck[1]);
+          need = std::max(need, static_cast<size_t>(R) * d15 * d15 * round_up(dck[2], 4));
+          dcols_fwd = ws.floats(need);
+        }
       } else {
         heads = ws.mat(R, nH * Dp);
       }
@@ -580,14 +636,31 @@ struct ModelPlan {
       for (int l = 0; l < c.n_fc; ++l) dF[l] = ws.mat(R, h);
       for (int l = 0; l < c.n_inp; ++l) dI[l] = ws.mat(B, (conv && l == c.n_inp - 1) ? feat : (conv ? 4 : h));
       gsum0 = ws.mat(B, h);
-      if (conv) {
+      if (conv && !cg) {
         dh3 = ws.floats(static_cast<size_t>(R) * 16 * d15 * d15);
         dh2 = ws.floats(static_cast<size_t>(R) * 32 * d8 * d8);
         dh1 = ws.floats(static_cast<size_t>(R) * feat);
       }
+      if (cg) {
+        const int drows[3] = {R * s8 * s8, R * d8 * d8, R * d15 * d15};
+        for (int k = 0; k < 3; ++k) {
+          dcolb[k] = ws.mat(drows[k], dck[k]);
+          ddp[k] = ws.mat(drows[k], dci[k]);
+        }
+        for (int l = 0; l < 3; ++l) {
+          eda[l] = ws.mat(B * eho[l] * eho[l], eco[l]);
+          if (l > 0) ecol[l] = ws.mat(B * eho[l] * eho[l], eci[l] * 25);
+        }
+      }
       if (dry) {
-        const int shapes[10][3] = {{h, h + n, R}, {h, h, R}, {zd, h + n, R}, {nH * D, h, R}, {h, zd, R},
-                                   {h, D, B}, {h, h, B}, {h, n, R}, {h, feat, B}, {feat, 300, R}};
+        std::vector<std::array<int, 3>> shapes = {{h, h + n, R}, {h, h, R}, {zd, h + n, R}, {nH * D, h, R}, {h, zd, R},
+                                                  {h, D, B}, {h, h, B}, {h, n, R}, {h, feat, B}, {feat, 300, R}};
+        if (cg) {
+          for (int l = 0; l < 3; ++l) shapes.push_back({eco[l], eci[l] * 25, B * eho[l] * eho[l]});
+          shapes.push_back({dci[0], dck[0], R * s8 * s8});
+          shapes.push_back({dci[1], dck[1], R * d8 * d8});
+          shapes.push_back({dci[2], dck[2], R * d15 * d15});
+        }
         tn_need = 0;
         for (auto& sh : shapes) {
           const size_t b = tn_workspace_bytes(sh[0], sh[1], sh[2]);
@@ -635,7 +708,34 @@ struct ModelPlan {
       g.bias = P(iI(l) + 1);
       fwd.nt(g);
     }
-    if (conv && enc_inp) {
+    if (cg && enc_inp) {
+      // x <- 2x-1, conv(1->16) -> conv(16->32) -> conv(32->32), 5x5 s2 p2 + activation (ivae/conv.py:84-96):
+      // im2col (pair) -> 3xTF32 GEMM with the bias + activation epilogue, pixel-major outputs
+      const int hin[3] = {c.img_h, s2, s4};
+      for (int l = 0; l < 3; ++l) {
+        const Pair cp = colp[l];
+        const Mat prev = l > 0 ? act_[l - 1] : Mat();
+        const int Ho = eho[l], Hi = hin[l], Ci = eci[l];
+        fwd.add([=](cudaStream_t s) {
+          const ImgView in = l == 0 ? img_nchw(const_cast<float*>(bd->x), Ci, Hi) : img_pix(prev.p, prev.ld, Ci, Hi, Hi);
+          im2col5s2_kernel<<<grid_for(static_cast<size_t>(B) * Ho * Ho * Ci * 25), 256, 0, s>>>(
+              in, Ho, l == 0 ? 2.0f : 1.0f, l == 0 ? -1.0f : 0.0f, cp.buf.p, cp.buf.ld, cp.kp, B);
+          return static_cast<int>(cudaGetLastError());
+        });
+        GemmNTDesc g = nt3_desc_plain(colp[l], Cw[l], act_[l], ACT);
+        g.bias = P(iI(l) + 1);
+        fwd.nt(g);
+      }
+      {
+        const Mat a3 = act_[2];
+        fwd.add([=](cudaStream_t s) {  // flatten in the reference's NCHW order (feature c*P + p), as a pair
+          chw_pix_permute_kernel<false><<<grid_for(static_cast<size_t>(B) * feat), 256, 0, s>>>(
+              a3.p, a3.ld, 0, inp_pair.buf.p, inp_pair.buf.ld, inp_pair.kp, B, 32, s8 * s8, 0);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+    }
+    if (conv && !cg && enc_inp) {
       // x <- 2x-1, conv(1->16) -> conv(16->32) -> conv(32->32), all 5x5 s2 p2 + activation (ivae/conv.py:84-96)
       const float *w1 = P(iI(0)), *b1 = P(iI(0) + 1), *w2 = P(iI(1)), *b2 = P(iI(1) + 1), *w3 = P(iI(2)), *b3 = P(iI(2) + 1);
       fwd.add([=](cudaStream_t s) {
@@ -829,7 +929,40 @@ struct ModelPlan {
       g.bias = P(iH(k) + 1);
       fwd.nt(g);
     }
-    if (conv) {
+    if (cg) {
+      // deconv = (in . W) scattered by col2im (+ bias, activation); the reference pads deconv1's activated output to
+      // d8 x d8 and crops the last row / column of the logits (vae/conv.py:128-131)
+      const Pair hl = Dh[c.n_dec - 1];
+      {
+        const Pair p1 = dp_[0];
+        fwd.add([=](cudaStream_t s) {
+          chw_pix_permute_kernel<true><<<grid_for(static_cast<size_t>(R) * feat), 256, 0, s>>>(
+              hl.buf.p, hl.buf.ld, hl.kp, p1.buf.p, p1.buf.ld, p1.kp, R, 32, s8 * s8, 0);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      const int gin[3] = {s8, d8, d15};            // grid of the GEMM rows (input pixels)
+      const int gout[3] = {d7, d15, c.img_h};      // logical output size (the logit deconv's 29th row / column is cropped)
+      const int gpitch[3] = {d8, d15, c.img_h};
+      const int gco[3] = {32, 16, c.img_c};
+      for (int k = 0; k < 3; ++k) {
+        const Mat cols = Mat(dcols_fwd, R * gin[k] * gin[k], dck[k], round_up(dck[k], 4));
+        W3 wk;
+        wk.in = dci[k]; wk.out = dck[k]; wk.kp = 32; wk.b3 = dT3[k];
+        GemmNTDesc g = nt3_desc_plain(dp_[k], wk, cols, EPI_LINEAR);
+        fwd.nt(g);
+        const float* bias = P(iH(k) + 1);
+        const Pair nxt = k < 2 ? dp_[k + 1] : Pair();
+        const int Ho = gin[k], Hout = gout[k], pitch = gpitch[k], Co = gco[k];
+        fwd.add([=](cudaStream_t s) {
+          const ImgView out = k < 2 ? img_pix(nxt.buf.p, nxt.buf.ld, Co, Hout, pitch) : img_nchw(heads.p, Co, Hout);
+          col2im5s2_kernel<<<grid_for(static_cast<size_t>(R) * Hout * Hout * Co), 256, 0, s>>>(
+              cols.p, cols.ld, Ho, out, bias, CACT, k < 2 ? C2I_ACT_PAIR : C2I_PLAIN, k < 2 ? nxt.kp : 0, nullptr, R);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+    }
+    if (conv && !cg) {
       // deconvs as the adjoint (backward-data) form of the 5x5 s2 p2 conv; the reference pads deconv1's
       // activated output to d8 x d8 and crops the last row/column of the logits (vae/conv.py:128-131)
       const Pair hl = Dh[c.n_dec - 1];
@@ -903,6 +1036,46 @@ struct ModelPlan {
       set_aux1(g, Dh[c.n_dec - 1].hi());
       g.colsum = G(iD(c.n_dec - 1) + 1);
       bwd_dec.nt(g);
+    } else if (cg) {
+      // logit deconv <- deconv2 <- deconv1: dcols = im2col(d out) ; dW += in^T . dcols ; d in_pre = (dcols . W^T) * act'(in)
+      // (act'(0) = 0 on the pad row / column of p2); the bias gradients are the column sums of the d pre-activations
+      const int gin[3] = {s8, d8, d15}, gout[3] = {d7, d15, c.img_h}, gpitch[3] = {d8, d15, c.img_h};
+      const int gco[3] = {32, 16, c.img_c};
+      const Mat dlast = dD[c.n_dec - 1];
+      float* gb_last = G(iD(c.n_dec - 1) + 1);
+      {
+        float* gbl = G(iH(2) + 1);
+        const int P2 = c.img_h * c.img_h, ICc = c.img_c;
+        bwd_dec.add([=](cudaStream_t s) {
+          chan_sum_nchw_kernel<<<dim3(ICc, 128), 256, 0, s>>>(dheads.p, dheads.ld, R, ICc, P2, gbl);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      for (int k = 2; k >= 0; --k) {
+        const Mat dc = dcolb[k], din = ddp[k];
+        const Mat up = k < 2 ? ddp[k + 1] : Mat();
+        const int Ho = gin[k], Hout = gout[k], pitch = gpitch[k], Co = gco[k];
+        bwd_dec.add([=](cudaStream_t s) {
+          const ImgView src = k < 2 ? img_pix(up.p, up.ld, Co, Hout, pitch) : img_nchw(dheads.p, Co, Hout);
+          im2col5s2_kernel<<<grid_for(static_cast<size_t>(R) * Ho * Ho * Co * 25), 256, 0, s>>>(src, Ho, 1.0f, 0.0f, dc.p, dc.ld, 0, R);
+          return static_cast<int>(cudaGetLastError());
+        });
+        tn1(bwd_dec, dp_[k].hi(), dc, G(iH(k)), dck[k]);
+        GemmNTDesc g = nt_desc(dc, dWr[k], din, DACT);
+        set_aux1(g, dp_[k].hi());
+        if (k > 0) g.colsum = G(iH(k - 1) + 1);  // bias of the deconv below = sum of this d pre-activation
+        bwd_dec.nt(g);
+      }
+      {
+        const Mat d1 = ddp[0];
+        bwd_dec.add([=](cudaStream_t s) {  // back to the NCHW-flattened rows of decode.fc's output
+          chw_pix_permute_kernel<false><<<grid_for(static_cast<size_t>(R) * feat), 256, 0, s>>>(
+              d1.p, d1.ld, 0, dlast.p, dlast.ld, 0, R, 32, s8 * s8, 1);
+          dim3 grid((feat + 31) / 32, R >= 2048 ? 32 : (R + 63) / 64);
+          colsum_kernel<<<grid, 256, 0, s>>>(dlast.p, dlast.ld, R, feat, gb_last, 1.0f);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
     } else {
       float *gwd1 = G(iH(0)), *gbd1 = G(iH(0) + 1), *gwd2 = G(iH(1)), *gbd2 = G(iH(1) + 1), *gwl = G(iH(2)), *gbl = G(iH(2) + 1);
       const float *wd1 = P(iH(0)), *wd2 = P(iH(1)), *wl = P(iH(2));
@@ -989,6 +1162,33 @@ struct ModelPlan {
       if (!conv) g.colsum = G(iI(c.n_inp - 1) + 1);  // conv: the bias is per channel, summed below
       if (conv) g.round_out = 0;
       bwd_enc.nt(g);
+    }
+    if (cg) {
+      // back through conv3, conv2, conv1 (dI[last] = d pre-activation of conv3's output in NCHW order):
+      // dW_l += dA_l^T . col_l ; db_l = column sums ; dA_{l-1} = col2im(dA_l . W_l) * act'(a_{l-1})
+      {
+        const Mat dl = dI[c.n_inp - 1], d3 = eda[2];
+        bwd_enc.add([=](cudaStream_t s) {
+          chw_pix_permute_kernel<true><<<grid_for(static_cast<size_t>(B) * feat), 256, 0, s>>>(
+              dl.p, dl.ld, 0, d3.p, d3.ld, 0, B, 32, s8 * s8, 1);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      for (int l = 2; l >= 0; --l) {
+        tn1(bwd_enc, eda[l], colp[l].hi(), G(iI(l)), eci[l] * 25);
+        colsum_op(bwd_enc, eda[l], G(iI(l) + 1));
+        if (l == 0) break;
+        GemmNTDesc g = nt_desc(eda[l], Cw[l].T, ecol[l], EPI_LINEAR);
+        bwd_enc.nt(g);
+        const Mat dc = ecol[l], dprev = eda[l - 1], uprev = act_[l - 1];
+        const int Ho = eho[l], Hi = eho[l - 1], Ci = eci[l];
+        bwd_enc.add([=](cudaStream_t s) {
+          col2im5s2_kernel<<<grid_for(static_cast<size_t>(B) * Hi * Hi * Ci), 256, 0, s>>>(
+              dc.p, dc.ld, Ho, img_pix(dprev.p, dprev.ld, Ci, Hi, Hi), nullptr, CACT, C2I_MUL_DACT, 0, uprev.p, B);
+          return static_cast<int>(cudaGetLastError());
+        });
+      }
+      return fwd.error ? fwd.error : (bwd_dec.error ? bwd_dec.error : bwd_enc.error);
     }
     if (conv) {
       // back through conv3, conv2, conv1 (dI[last] = d pre-activation of conv3's output, [B, 32*s8*s8])
