@@ -36,23 +36,38 @@ inline ImgView img_nchw(float* p, int C, int H) {
 
 // col[(b*Ho + oh)*Ho + ow, c*25 + kh*5 + kw] = a * in(b, c, 2oh-2+kh, 2ow-2+kw) + s   (0 outside the image)
 // kp > 0: written as a tf32 pair (hi at k, lo at kp + k); kp == 0: one tf32-rounded value.
-__global__ void im2col5s2_kernel(ImgView in, int Ho, float a, float s, float* __restrict__ col, int ldc, int kp, int B) {
+// A block walks rows; KT threads cover the K columns of one row (256 / KT rows per pass), so the row decode is
+// per pass and the column decode (constant divisors) is hoisted out of the row loop.
+__global__ void im2col5s2_kernel(ImgView in, int Ho, float a, float s, float* __restrict__ col, int ldc, int kp, int B,
+                                 int KT) {
   const int K = in.C * 25;
-  const size_t total = static_cast<size_t>(B) * Ho * Ho * K;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t row = i / K;
-    const int k = static_cast<int>(i - row * K);
-    const int c = k / 25, t = k - c * 25, kh = t / 5, kw = t - kh * 5;
+  const int rpb = blockDim.x / KT;                       // rows per pass
+  const int kt = threadIdx.x % KT, rl = threadIdx.x / KT;
+  const size_t rows = static_cast<size_t>(B) * Ho * Ho;
+  for (size_t row = static_cast<size_t>(blockIdx.x) * rpb + rl; row < rows; row += static_cast<size_t>(gridDim.x) * rpb) {
     const int ow = static_cast<int>(row % Ho), oh = static_cast<int>((row / Ho) % Ho);
     const size_t b = row / (static_cast<size_t>(Ho) * Ho);
-    const int y = 2 * oh - 2 + kh, x = 2 * ow - 2 + kw;
-    float v = 0.0f;
-    if (y >= 0 && y < in.H && x >= 0 && x < in.H) v = fmaf(a, in.p[b * in.sb + c * in.sc + y * in.sy + x * in.sx], s);
-    const float hi = ptx::round_tf32(v);
-    col[row * ldc + k] = hi;
-    if (kp > 0) col[row * ldc + kp + k] = ptx::round_tf32(v - hi);
+    const float* ib = in.p + b * in.sb;
+    float* cr = col + row * ldc;
+    for (int k = kt; k < K; k += KT) {
+      const int c = k / 25, t = k - c * 25, kh = t / 5, kw = t - kh * 5;
+      const int y = 2 * oh - 2 + kh, x = 2 * ow - 2 + kw;
+      float v = 0.0f;
+      if (y >= 0 && y < in.H && x >= 0 && x < in.H) v = fmaf(a, ib[c * in.sc + y * in.sy + x * in.sx], s);
+      const float hi = ptx::round_tf32(v);
+      cr[k] = hi;
+      if (kp > 0) cr[kp + k] = ptx::round_tf32(v - hi);
+    }
   }
+}
+inline void launch_im2col5s2(const ImgView& in, int Ho, float a, float s, float* col, int ldc, int kp, int B, cudaStream_t st) {
+  const int K = in.C * 25;
+  int KT = 32;
+  while (KT < K && KT < 256) KT *= 2;
+  const size_t rows = static_cast<size_t>(B) * Ho * Ho;
+  const size_t passes = (rows + (256 / KT) - 1) / (256 / KT);
+  const int grid = static_cast<int>(std::min<size_t>(passes, 148 * 16));
+  im2col5s2_kernel<<<grid, 256, 0, st>>>(in, Ho, a, s, col, ldc, kp, B, KT);
 }
 
 enum Col2ImPost : int { C2I_ACT_PAIR = 0, C2I_PLAIN = 1, C2I_MUL_DACT = 2 };

@@ -340,7 +340,11 @@ struct ModelPlan {
     };
     auto colsum_op = [&](Plan& pl, const Mat& X, float* dst) {
       pl.add([=](cudaStream_t s) {
-        dim3 grid((X.cols + 31) / 32, X.rows >= 2048 ? 32 : (X.rows + 63) / 64);
+        // tall-skinny operands (pixel-major conv gradients: 1e5 rows x 16..32 columns) need many row slabs
+        const int col_blocks = (X.cols + 31) / 32;
+        int slabs = X.rows >= 2048 ? 32 : (X.rows + 63) / 64;
+        if (X.rows >= 16384 && col_blocks * slabs < 592) slabs = std::min(X.rows / 256, 592 / col_blocks);
+        dim3 grid(col_blocks, slabs);
         colsum_kernel<<<grid, 256, 0, s>>>(X.p, X.ld, X.rows, X.cols, dst, 1.0f);
         return static_cast<int>(cudaGetLastError());
       });
@@ -718,8 +722,7 @@ struct ModelPlan {
         const int Ho = eho[l], Hi = hin[l], Ci = eci[l];
         fwd.add([=](cudaStream_t s) {
           const ImgView in = l == 0 ? img_nchw(const_cast<float*>(bd->x), Ci, Hi) : img_pix(prev.p, prev.ld, Ci, Hi, Hi);
-          im2col5s2_kernel<<<grid_for(static_cast<size_t>(B) * Ho * Ho * Ci * 25), 256, 0, s>>>(
-              in, Ho, l == 0 ? 2.0f : 1.0f, l == 0 ? -1.0f : 0.0f, cp.buf.p, cp.buf.ld, cp.kp, B);
+          launch_im2col5s2(in, Ho, l == 0 ? 2.0f : 1.0f, l == 0 ? -1.0f : 0.0f, cp.buf.p, cp.buf.ld, cp.kp, B, s);
           return static_cast<int>(cudaGetLastError());
         });
         GemmNTDesc g = nt3_desc_plain(colp[l], Cw[l], act_[l], ACT);
@@ -1020,7 +1023,11 @@ struct ModelPlan {
     };
     auto colsum_op = [&](Plan& pl, const Mat& X, float* dst) {
       pl.add([=](cudaStream_t s) {
-        dim3 grid((X.cols + 31) / 32, X.rows >= 2048 ? 32 : (X.rows + 63) / 64);
+        // tall-skinny operands (pixel-major conv gradients: 1e5 rows x 16..32 columns) need many row slabs
+        const int col_blocks = (X.cols + 31) / 32;
+        int slabs = X.rows >= 2048 ? 32 : (X.rows + 63) / 64;
+        if (X.rows >= 16384 && col_blocks * slabs < 592) slabs = std::min(X.rows / 256, 592 / col_blocks);
+        dim3 grid(col_blocks, slabs);
         colsum_kernel<<<grid, 256, 0, s>>>(X.p, X.ld, X.rows, X.cols, dst, 1.0f);
         return static_cast<int>(cudaGetLastError());
       });
@@ -1057,7 +1064,7 @@ struct ModelPlan {
         const int Ho = gin[k], Hout = gout[k], pitch = gpitch[k], Co = gco[k];
         bwd_dec.add([=](cudaStream_t s) {
           const ImgView src = k < 2 ? img_pix(up.p, up.ld, Co, Hout, pitch) : img_nchw(dheads.p, Co, Hout);
-          im2col5s2_kernel<<<grid_for(static_cast<size_t>(R) * Ho * Ho * Co * 25), 256, 0, s>>>(src, Ho, 1.0f, 0.0f, dc.p, dc.ld, 0, R);
+          launch_im2col5s2(src, Ho, 1.0f, 0.0f, dc.p, dc.ld, 0, R, s);
           return static_cast<int>(cudaGetLastError());
         });
         tn1(bwd_dec, dp_[k].hi(), dc, G(iH(k)), dck[k]);
