@@ -21,11 +21,16 @@ class _TrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, loss_dev, *params):
         ctx.module = module
+        ctx.gen = module._stage_gen
         return loss_dev.clone().reshape(())
 
     @staticmethod
     def backward(ctx, gloss):
         m = ctx.module
+        if ctx.gen != m._stage_gen:
+            # the gradients of this forward lived in the staging arena and a later forward() overwrote them
+            raise RuntimeError('ConditionalARDAE: forward() was called again before this loss.backward(); the fused '
+                               'plan keeps one set of staged gradients -- call backward() before the next forward()')
         m._arena.accumulate_staged(gloss, skip=m.no_grad_params)
         return (None, None) + (None,) * len(m._arena.params)
 
@@ -59,6 +64,7 @@ class ConditionalARDAE(nn.Module):
         self._plans = {}
         self.inv_count_override = None  # data parallel: 1 / (global N * d)
         self.last_score = None
+        self._stage_gen = 0  # bumped by every training forward (see _TrainFn.backward)
 
     @property
     def no_grad_params(self):
@@ -138,6 +144,7 @@ class ConditionalARDAE(nn.Module):
             epsb = _lib.require_cuda(eps.detach(), 'eps').reshape(B * S, d).clone()
             seed = 0
         ar.stage_flat.zero_()
+        self._stage_gen += 1
         loss_dev = torch.empty(1, dtype=torch.float32, device=x.device)
         score = torch.empty(B * S, d, dtype=torch.float32, device=x.device)
         inv = self.inv_count_override if self.inv_count_override is not None else 1.0 / float(B * S * d)

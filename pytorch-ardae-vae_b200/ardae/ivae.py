@@ -169,12 +169,17 @@ class _ForwardFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, key, z, sums, *params):
         ctx.model, ctx.key = model, key
+        ctx.gen = model._plan_gen.get(key, 0)
         ctx.set_materialize_grads(False)
         return z, sums[0].clone()
 
     @staticmethod
     def backward(ctx, gz, gloss):
         m = ctx.model
+        if ctx.key not in m._plans or m._plan_gen.get(ctx.key, 0) != ctx.gen:
+            # the activations of this forward lived in the plan workspace and a later forward() overwrote them
+            raise RuntimeError('ImplicitPosteriorVAE: forward() was called again with the same (batch, nz) before this '
+                               'backward(); the plan keeps one set of activations -- call backward() first')
         h = m._plans[ctx.key][0]
         ar = m._arena
         L = _lib.lib()
@@ -232,6 +237,15 @@ class ImplicitPosteriorVAE(nn.Module):
             self._arena.ensure()
             self._drop_plans()
         return self._arena
+
+    @property
+    def _plan_gen(self):
+        """forward() generation per training plan: backward() of a stale forward raises instead of using the
+        activations of a newer one."""
+        g = self.__dict__.get('_plan_gen_')
+        if g is None:
+            g = self.__dict__['_plan_gen_'] = {}
+        return g
 
     def _drop_plans(self):
         for _, (h, _ws) in self._plans.items():
@@ -375,6 +389,7 @@ class ImplicitPosteriorVAE(nn.Module):
         nH = 2 if self.KIND == 'toy' else 1
         heads = torch.empty(nH, R, self.input_dim, dtype=torch.float32, device=x.device)
         inv_rows = self.inv_rows_override if self.inv_rows_override is not None else 1.0 / R
+        self._plan_gen[key] = self._plan_gen.get(key, 0) + 1
         _lib.check(_lib.lib().ardae_model_forward(self._plans[key][0], _lib.ptr(x), _lib.ptr(nf),
                                                   ctypes.c_float(beta), ctypes.c_float(inv_rows), _lib.ptr(z),
                                                   _lib.ptr(sums), _lib.ptr(heads), _lib.stream_ptr()))

@@ -205,6 +205,7 @@ class TrainStep(object):
         ar = c._ensure()
         h = c._plan(B, self.nz * self.nstd, True)
         ar.stage_flat.zero_()
+        c._stage_gen += 1  # a pending drop-in loss.backward() of this module is stale from here on
         if noise is not None:
             eps = _lib.require_cuda(noise['eps_cdae'], 'eps').reshape(N, d).clone()
             gen = 0
@@ -247,6 +248,7 @@ class TrainStep(object):
             self.last_noise.update(enc_model=enc)
         if self.graph and self._beta_dev is None:  # sub-step driven by hand before the first __call__
             self._set_beta(beta, dev)
+        m._plan_gen[key] = m._plan_gen.get(key, 0) + 1
         _lib.check(L.ardae_model_set_beta_device(hm, _lib.ptr(self._beta_dev) if self.graph else None))
         with self._seg('model_fwd'):
             _lib.check(L.ardae_model_forward(hm, _lib.ptr(xs), _lib.ptr(enc), ctypes.c_float(beta),

@@ -343,3 +343,25 @@ def test_aux_encoder_full_width_vs_oracle():
     assert rel_err(logit.cpu().numpy(), heads[0] if isinstance(heads, (tuple, list)) else heads) <= 1e-5
     out, mean, zg = model.generate(4)
     assert out.shape == mean.shape == (4, 784) and zg.shape == (4, 32)
+
+
+def test_stale_forward_raises_in_backward():
+    """The plans keep ONE set of activations / staged gradients per shape: backward() of a forward that was
+    superseded by a newer forward() of the same shape must raise instead of returning the newer input's gradients."""
+    z, meta = load_case('mnist_small')
+    model, cdae, _, _ = build(meta, z)
+    x = t(z['s0/x_model'])
+    loss_a = model(x, beta=1.0, nz=1)[3]
+    loss_b = model(x * 0.5, beta=1.0, nz=1)[3]
+    with pytest.raises(RuntimeError, match='forward\\(\\) was called again'):
+        loss_a.backward()
+    loss_b.backward()
+    assert model.decode.reparam.logit_fn.weight.grad is not None
+    B = x.size(0)
+    xs, ctx = torch.randn(B, 4, meta['cdae']['input_dim'], device='cuda'), torch.randn(B, 1, meta['cdae']['context_dim'], device='cuda')
+    std = torch.rand(B, 4, 1, device='cuda')
+    _, l1 = cdae(xs, ctx, std=std)
+    _, l2 = cdae(xs * 2, ctx, std=std)
+    with pytest.raises(RuntimeError, match='forward\\(\\) was called again'):
+        l1.backward()
+    l2.backward()
