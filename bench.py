@@ -39,6 +39,12 @@ CFG4 = dict(  # BASELINE.json configs[3]: dbMNIST conv implicit encoder / decode
     m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5)
 
 
+CFG_AUX = dict(  # run_vae_dbmnist.sh:28,34,40: hierarchical MNISTAuxIPVAE + the 'hidden1a' CDAE context
+    kind='auxmnist', D=784, n=100, h=300, z=32, model_layers=2, nonlin='softplus', ctx_type='hidden1a', ctx_dim=600,
+    cdae_h=256, cdae_L=5, B=512, nz=256, nstd=1, nz_model=1, std_scale=10000., delta=0.1, beta=1.0,
+    m_lr=1e-4, m_beta1=0.5, d_lr=1e-4, d_momentum=0.5)
+
+
 def cdae_alg_flops(B, nz, d, c, H, L):
     """6 sweeps x 2 x N x G + context branch on the B distinct rows."""
     N = B * nz
@@ -200,11 +206,14 @@ def build_models(c, dev, cdae_kind='grad'):
     elif c['kind'] == 'conv':
         model = ardae.ConvIPVAE(input_height=28, input_channels=1, z_dim=c['z'], noise_dim=c['n'],
                                 nonlinearity=c['nonlin']).to(dev)
+    elif c['kind'] == 'auxmnist':
+        model = ardae.MNISTAuxIPVAE(input_dim=c['D'], noise_dim=c['n'], h_dim=c['h'], num_hidden_layers=c['model_layers'],
+                                    nonlinearity=c['nonlin'], enc_type='simple', z_dim=c['z']).to(dev)
     else:
         model = ardae.MNISTIPVAE(input_dim=c['D'], noise_dim=c['n'], h_dim=c['h'], num_hidden_layers=c['model_layers'],
                                  nonlinearity=c['nonlin'], enc_type='concat', z_dim=c['z']).to(dev)
     cdae_cls = ardae.MLPGradCARDAE if cdae_kind == 'grad' else ardae.MLPResCARDAE
-    cdae = cdae_cls(input_dim=c['z'], context_dim=c['z'], std=1., h_dim=c['cdae_h'],
+    cdae = cdae_cls(input_dim=c['z'], context_dim=c.get('ctx_dim', c['z']), std=1., h_dim=c['cdae_h'],
                     num_hidden_layers=c['cdae_L'], nonlinearity='softplus').to(dev)
     mopt = ardae.Adam(model.parameters(), lr=c['m_lr'], betas=(c['m_beta1'], 0.999))
     copt = ardae.RMSprop(cdae.parameters(), lr=c['d_lr'], momentum=c['d_momentum'])
@@ -223,7 +232,8 @@ class Harness(object):
         self.model, self.cdae, self.mopt, self.copt = build_models(c, dev, cdae_kind)
         self.step = ardae.TrainStep(self.model, self.cdae, self.mopt, self.copt, std_scale=c['std_scale'],
                                     delta=c['delta'], nz_cdae=c['nz'], nstd=c['nstd'], nz_model=c['nz_model'],
-                                    process_group=dist.group.WORLD if world > 1 else None, seed=1234, graph=graph)
+                                    process_group=dist.group.WORLD if world > 1 else None, seed=1234, graph=graph,
+                                    ctx_type=c.get('ctx_type', 'lt0'))
         gen = torch.Generator().manual_seed(999 + rank)
         if c['kind'] == 'toy':   # 25-Gaussians mixture, generated on the device (ardae.toy_exp4)
             data, _ = ardae.toy_exp4(num_data=50000, seed=1 + rank, device=dev)
@@ -505,6 +515,9 @@ def main():
                                                   'configs[0] 25gaussians ToyIPVAE z=2 h=256 relu + mlp-grad CDAE h=256 L=3, batch 512 per GPU, nz 256')
         extra['config4_conv'] = sub_record(CFG4, CFG4['B'], dev, world, rank, Ws, Ks,
                                            'configs[3] dbMNIST ConvIPVAE 28x28 z=32 + mlp-grad CDAE h=256 L=5, 1024 rows per GPU (8192 over 8), nz 256')
+        extra['aux_hidden1a'] = sub_record(CFG_AUX, CFG_AUX['B'], dev, world, rank, Ws, Ks,
+                                           'run_vae_dbmnist.sh:28 family: MNISTAuxIPVAE 784/300/100/32 + mlp-grad CDAE h=256 L=5 on the hidden1a context (600 wide), batch 512 per GPU, nz 256',
+                                           with_e2e=False)
         extra['config5_iws'] = iws_record(dev, world, rank)
 
     if rank != 0:

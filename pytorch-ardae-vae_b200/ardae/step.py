@@ -107,6 +107,8 @@ class TrainStep(object):
         n = 0
         n += L.ardae_model_num_launches(m._plans[m._plan(B, self.nz, 0)][0], 2)      # zbar (cdae minibatch): mean-code branch
         n += L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0, 1)][0], 0)         # zbar (model minibatch)
+        if self.ctx_type == 'hidden1a':                                              # + its std=0 branch (hidden context)
+            n += L.ardae_model_num_launches(m._plans[m._plan(B, 1, 0, 1)][0], 2)
         n += L.ardae_model_num_launches(m._plans[m._plan(B, self.nz, 0)][0], 0)      # z samples
         n += L.ardae_cdae_num_launches(c._plan(B, self.nz * self.nstd, True))
         n += L.ardae_cdae_num_launches(c._plan(B, self.nzm, False))
