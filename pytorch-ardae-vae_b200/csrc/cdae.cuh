@@ -210,6 +210,7 @@ struct CdaePlan {
       cd.mode = mode; cd.M = N; cd.H = H; cd.row_scale = sig;
       return cd;
     };
+    bool delta_fused = false;
     // ---- sweep 1: primal forward (3xTF32), all 2L layers
     {
       Chain16Desc cd = base(CHAIN_SOFTPLUS3);
@@ -228,10 +229,16 @@ struct CdaePlan {
         cd.layers.push_back(q);
       }
       for (int l = 1; l < L; ++l) cd.layers.push_back(s3(Ww[l], P(iW(l) + 1), V[l], H));
+      // the fp16-pipe kernel also emits delta_L from its last epilogue (wo 16-byte aligned: arena tensors are)
+      const bool fuse_delta = s3h && (reinterpret_cast<uintptr_t>(wo) & 15) == 0;
+      if (fuse_delta) {
+        cd.wo = wo; cd.delta16 = DP[L - 1].p; cd.ld_delta16 = DP[L - 1].ld;
+      }
+      delta_fused = fuse_delta;
       if (s3h) plan.chain_s3h(cd); else plan.chain16(cd);
     }
     // ---- sweep 2: score backward, ending in g = delta a_1 . A_1 (fp32 [N, kp])
-    {
+    if (!delta_fused) {
       const Mat16 vl = V[L - 1], dpl = DP[L - 1];
       plan.add([=](cudaStream_t s) {
         cdae_init_delta16_kernel<<<grid_for(static_cast<size_t>(N) * H / 8), 256, 0, s>>>(vl.p, vl.ld, wo, dpl.p, dpl.ld, N, H);

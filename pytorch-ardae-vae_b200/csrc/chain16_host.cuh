@@ -70,6 +70,9 @@ struct Chain16Desc {
   const float* A0_32 = nullptr; int lda0_32 = 0;
   const float* A0lo = nullptr; int lda0lo = 0;
   const float* row_scale = nullptr;
+  // chain_s3h only: the last layer also writes delta_L = -w_o * sig(v_L) (bf16), the start of the score sweep
+  const float* wo = nullptr;
+  uint16_t* delta16 = nullptr; int ld_delta16 = 0;
   std::vector<Chain16LayerDesc> layers;
 };
 
@@ -124,6 +127,12 @@ inline int prepare_chain_s3h(const Chain16Desc& d, PreparedChainS3h* out) {
     align_or |= reinterpret_cast<uintptr_t>(s.bias) | reinterpret_cast<uintptr_t>(s.group_bias) |
                 reinterpret_cast<uintptr_t>(s.col_vec) | (static_cast<uintptr_t>(s.ldg) * 4) |
                 reinterpret_cast<uintptr_t>(s.out) | (static_cast<uintptr_t>(s.ldo) * 2);
+  }
+  if (d.delta16 != nullptr) {
+    if (!d.wo) return fail(-2, "chain_s3h: delta output needs w_o");
+    p.wo = d.wo; p.delta16 = d.delta16; p.ld_delta16 = d.ld_delta16;
+    align_or |= reinterpret_cast<uintptr_t>(d.wo) | reinterpret_cast<uintptr_t>(d.delta16) |
+                (static_cast<uintptr_t>(d.ld_delta16) * 2);
   }
   if ((align_or & 15) != 0) return fail(-2, "chain_s3h: operands must be 16-byte aligned");
   p.vec_ok = 1;

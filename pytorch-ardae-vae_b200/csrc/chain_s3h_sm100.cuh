@@ -47,6 +47,11 @@ struct alignas(64) ChainS3hParams {
   const float* row_scale;   // [M] (sigma) or null
   int M, H, nlayers;
   int vec_ok;
+  // optional second output of the LAST layer: delta_L[m, n] = -w_o[n] * (1 - exp(-v_L[m, n])) as bf16 -- the start of
+  // the score sweep (graddae/mlp.py:426-441: d E / d pre-activation of the last hidden layer), from the bf16-rounded v_L
+  const float* wo;
+  uint16_t* delta16;
+  int ld_delta16;
   ChainS3hLayerParams layer[kChainMaxLayers];
 };
 
@@ -359,6 +364,28 @@ chain_s3h_kernel(const __grid_constant__ ChainS3hParams p) {
               uint16_t* dst = L.out16 + static_cast<size_t>(m) * L.ld_out16 + ns;
               asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(ow[0]), "r"(ow[1]),
                            "r"(ow[2]), "r"(ow[3]), "r"(ow[4]), "r"(ow[5]), "r"(ow[6]), "r"(ow[7])
+                           : "memory");
+            }
+            if (last && p.delta16 != nullptr && row_ok) {  // delta_L from the rounded v_L (what the later sweeps re-read)
+              uint32_t dw[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.wo + ns) + q);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t pk = ow[q * 2 + (e >> 1)];
+                  const float u = __uint_as_float((e & 1) ? (pk & 0xFFFF0000u) : (pk << 16));
+                  const float sg = (u < 0.01f) ? u * (1.0f - u * (0.5f - u * (1.0f / 6.0f))) : 1.0f - __expf(-u);
+                  o[e] = -wv[e] * sg;
+                }
+                dw[q * 2] = pack_bf16x2(o[0], o[1]);
+                dw[q * 2 + 1] = pack_bf16x2(o[2], o[3]);
+              }
+              uint16_t* dd = p.delta16 + static_cast<size_t>(m) * p.ld_delta16 + ns;
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dd), "r"(dw[0]), "r"(dw[1]),
+                           "r"(dw[2]), "r"(dw[3]), "r"(dw[4]), "r"(dw[5]), "r"(dw[6]), "r"(dw[7])
                            : "memory");
             }
           }

@@ -180,3 +180,37 @@ for fmt in ('bf16', 'fp16rs', 'p24'):
         for t in (SPILL if cls == 'ALL' else [cls]):
             on[t] = fmt
         report('PROD + %s -> %s' % (cls, fmt), Q(on))
+
+# == would the backward sweeps survive fp16 MMA operands (same 10-bit mantissa as tf32, 5-bit exponent)?
+# chain operands (delta, tangents, adjoints, r) and backward weights rounded to fp16 after a STATIC power-of-two
+# scale per class; prints the magnitude range of each class so the scale can be judged.
+if os.environ.get('FP16_SWEEPS'):
+    STATS = {}
+    def make_f16(k):
+        def f(a):
+            a = np.asarray(a, dtype=np.float64)
+            with np.errstate(over='ignore'):
+                return (a * 2.0 ** k).astype(np.float16).astype(np.float64) / 2.0 ** k
+        return f
+    class QS(Q):
+        def __call__(self, tag, a):
+            base = tag.split('@')[0]
+            if base in ('delta', 'tan', 'adj', 'r', 'w_bwd'):
+                m = np.abs(np.asarray(a))
+                st = STATS.setdefault(base, [0.0, np.inf, []])
+                st[0] = max(st[0], m.max()); nz = m[m > 0]
+                if nz.size:
+                    st[1] = min(st[1], nz.min()); st[2].append(np.median(np.abs(a).max(axis=1)) if a.ndim == 2 else m.max())
+            return Q.__call__(self, tag, a)
+    print('== fp16 chain operands with static scales, on top of PROD + bf16 spill')
+    base = {t: 'tf32' for t in PROD}
+    for t in SPILL:
+        base[t] = 'bf16'
+    report('PROD + bf16 spill (today)', QS(base))
+    for t, (mx, mn, med) in STATS.items():
+        print('   class %-6s max %.3e  min nonzero %.3e  median row-max %.3e' % (t, mx, mn, float(np.median(med))))
+    for kd, kt, ka, kr, kw in ((0, 0, 0, 0, 0), (8, 8, 8, 8, 4), (12, 12, 12, 12, 4), (4, 4, 4, 4, 4)):
+        ROUND.update(f16d=make_f16(kd), f16t=make_f16(kt), f16a=make_f16(ka), f16r=make_f16(kr), f16w=make_f16(kw))
+        on = dict(base)
+        on.update(delta='f16d', tan='f16t', adj='f16a', r='f16r', w_bwd='f16w')
+        report('fp16 sweeps, scales 2^(%d,%d,%d,%d;w %d)' % (kd, kt, ka, kr, kw), Q(on))
