@@ -280,22 +280,23 @@ class Harness(object):
         return ms, {k: float(out[k].item()) for k in ('cdae_loss', 'model_loss')}
 
     def time_e2e(self, K):
-        """The same iterations fed from pinned host memory: H2D of both minibatches and a D2H read of the losses every
-        step, synchronised every step (the caller reads the losses)."""
+        """The same iterations fed from pinned host memory through the public call: every step copies both minibatches
+        host -> device (TrainStep.stage: a copy stream, double-buffered, so the copy of step i+1 runs underneath step i)
+        and reads the four losses device -> host, synchronised every step (the caller reads the losses)."""
         import torch
         c = self.c
-        xbuf = [torch.empty_like(self.resident[0][0]) for _ in range(2)]
         hloss = torch.empty(4, pin_memory=True)
         for i in range(2):
             self.step(*self.resident[i % self.nb], beta=c['beta'])
         self.barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
+        self.step.stage(*self.host[0])
         for i in range(K):
-            xbuf[0].copy_(self.host[i % self.nb][0], non_blocking=True)
-            xbuf[1].copy_(self.host[i % self.nb][1], non_blocking=True)
-            o = self.step(xbuf[0], xbuf[1], beta=c['beta'])
-            hloss.copy_(torch.cat([o['cdae_loss'], o['model_loss'], o['recon'], o['prior']]), non_blocking=True)
+            o = self.step(beta=c['beta'])
+            if i + 1 < K:
+                self.step.stage(*self.host[(i + 1) % self.nb])
+            hloss.copy_(o['losses'], non_blocking=True)
             torch.cuda.current_stream().synchronize()
         f1.record()
         self.barrier()

@@ -81,6 +81,7 @@ class TrainStep(object):
         self._g = None          # (CUDAGraph, static x_cdae list, static x_model, outputs, beta, shapes)
         self._g_eager_calls = 0
         self._g_ctr = None
+        self._stg = None        # input staging (stage() / __call__() without inputs)
 
     class _Seg(object):
         def __init__(self, owner, name):
@@ -302,9 +303,57 @@ class TrainStep(object):
     def model_update(self, x, beta, noise=None):
         return self.model_backward(self.model_forward(x, beta, noise), beta)
 
-    def __call__(self, x_cdae, x_model, beta=1.0, noise=None):
+    def stage(self, x_cdae_host, x_model_host):
+        """Start copying the NEXT iteration's minibatches from pinned host memory on a copy stream (double-buffered
+        device staging).  The following `__call__()` without inputs consumes them, so the transfer runs underneath
+        the current iteration instead of in front of the next one -- what the reference gets from its DataLoader
+        workers + `.to(device)` (ivae_ardae.py:707-712).  x_cdae_host: one tensor (shared by all CDAE updates)."""
+        dev = next(self.model.parameters()).device
+        if self._stg is None:
+            self._stg = dict(stream=torch.cuda.Stream(device=dev), k=0, bufs=[None, None], ready=[None, None],
+                             consumed=[None, None], pending=None)
+        st = self._stg
+        k = st['k']
+        st['k'] = 1 - k
+        shapes = (tuple(x_cdae_host.shape), tuple(x_model_host.shape))
+        if st['bufs'][k] is None or st['bufs'][k][2] != shapes:
+            st['bufs'][k] = (torch.empty(shapes[0], dtype=torch.float32, device=dev),
+                             torch.empty(shapes[1], dtype=torch.float32, device=dev), shapes)
+        if st['consumed'][k] is not None:      # the iteration that read this pair last must have copied it out
+            st['stream'].wait_event(st['consumed'][k])
+        with torch.cuda.stream(st['stream']):
+            st['bufs'][k][0].copy_(x_cdae_host, non_blocking=True)
+            st['bufs'][k][1].copy_(x_model_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st['stream'])
+        st['ready'][k] = ev
+        st['pending'] = k
+
+    def _take_staged(self):
+        st = self._stg
+        if st is None or st['pending'] is None:
+            raise RuntimeError('TrainStep(): no inputs given and nothing staged (call stage(x_cdae_host, x_model_host) first)')
+        k = st['pending']
+        st['pending'] = None
+        torch.cuda.current_stream().wait_event(st['ready'][k])
+        return k, st['bufs'][k][0], st['bufs'][k][1]
+
+    def __call__(self, x_cdae=None, x_model=None, beta=1.0, noise=None):
         """One iteration.  x_cdae: the minibatch (or list of num_cdae_updates minibatches) for the CDAE
-        update(s); x_model: the minibatch of the model update.  Returns device tensors (no sync)."""
+        update(s); x_model: the minibatch of the model update; both None: the pair handed to `stage()`.
+        Returns device tensors (no sync)."""
+        staged = None
+        if x_cdae is None and x_model is None:
+            staged, x_cdae, x_model = self._take_staged()
+        out = self._iterate(x_cdae, x_model, beta, noise)
+        if staged is not None:
+            # graph mode copied the pair into the static buffers before the replay; eager mode read it in place
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._stg['consumed'][staged] = ev
+        return out
+
+    def _iterate(self, x_cdae, x_model, beta, noise):
         self.iter += 1
         self.draw = 0
         if self.graph:
@@ -452,5 +501,6 @@ class TrainStep(object):
         else:
             fwd = self.model_forward(x_model, beta, noise)
         sums, g, z = self.model_backward(fwd, beta)
+        # `losses` = (cdae_loss, model_loss, recon, prior) in one tensor: one device->host read per logged iteration
         return dict(cdae_loss=closs, model_loss=sums[0:1], recon=sums[1:2], prior=sums[2:3], std=self.last_std,
-                    entropy_grad=g, z_model=z)
+                    entropy_grad=g, z_model=z, losses=torch.cat([closs.reshape(1), sums[0:3]]))

@@ -365,3 +365,42 @@ def test_stale_forward_raises_in_backward():
     with pytest.raises(RuntimeError, match='forward\\(\\) was called again'):
         l1.backward()
     l2.backward()
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_staged_inputs_match_direct_inputs(graph):
+    """TrainStep.stage(pinned host pair) + step() must give what step(device pair) gives (same Philox seeds),
+    eagerly and through the CUDA-graph replay, and `losses` packs the four scalars."""
+    import ardae
+    z, meta = load_case('mnist_small')
+    hp = meta['hp']
+    xs = [(torch.from_numpy(np.ascontiguousarray(z['s%d/x_cdae' % (i % 2)])).float().pin_memory(),
+           torch.from_numpy(np.ascontiguousarray(z['s%d/x_model' % (i % 2)])).float().pin_memory()) for i in range(5)]
+    outs = []
+    for staged in (False, True):
+        model, cdae, mopt, copt = build(meta, z)
+        step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=hp['std_scale'], delta=hp['delta'], nz_cdae=hp['nz_cdae'],
+                               nstd=hp['nstd'], nz_model=hp['nz_model'], seed=7, graph=graph)
+        rec = []
+        if staged:
+            step.stage(*xs[0])
+        for i in range(5):
+            if staged:
+                o = step(beta=hp['beta'])
+                if i + 1 < 5:
+                    step.stage(*xs[i + 1])
+            else:
+                o = step(xs[i][0].cuda(), xs[i][1].cuda(), beta=hp['beta'])
+            l = o['losses'].cpu().numpy().copy()
+            assert l.shape == (4,)
+            assert l[0] == o['cdae_loss'].item() and l[1] == o['model_loss'].item()
+            rec.append(l)
+        torch.cuda.synchronize()
+        outs.append((np.stack(rec), params_np(model)))
+        if staged:
+            with pytest.raises(RuntimeError, match='nothing staged'):
+                step(beta=hp['beta'])
+    # same seeds, same kernels; the scalar reductions use float atomics, so two runs agree to an ulp, not bitwise
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=0)
+    for k in outs[0][1]:
+        assert rel_err(outs[0][1][k], outs[1][1][k]) <= 1e-5, k
