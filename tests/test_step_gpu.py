@@ -12,11 +12,13 @@ Tolerances (tf32 backward sweeps, 3xTF32 forward):
                                         the 1e-3 gradient error flip sign; the optimizer arithmetic itself is
                                         pinned to 1e-6 in test_optimizers_match_oracle.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from golden_util import CASES, build_cdae, build_model, is_lite, load_case, num_steps, pick, rel_err, sub
+from golden_util import CASES, GOLDEN_DIR, build_cdae, build_model, is_lite, load_case, num_steps, pick, rel_err, sub
 
 pytestmark = pytest.mark.gpu
 
@@ -404,3 +406,51 @@ def test_staged_inputs_match_direct_inputs(graph):
     assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=0)
     for k in outs[0][1]:
         assert rel_err(outs[0][1][k], outs[1][1][k]) <= 1e-5, k
+
+
+def test_training_trajectory_tracks_reference():
+    """400 consecutive iterations on the 25-Gaussians problem, same initial weights, data and injected noise as the
+    reference's own fp64 run (oracle/make_curve.py -> tests/golden/toy_curve.npz).  With std_scale = 1e4 the problem
+    amplifies rounding along a trajectory: the reference's own fp32 run -- what a user of the reference executes --
+    drifts from its fp64 run by up to 14 % (CDAE loss, first 25 iterations) and 12 % (25-iteration means).  That drift
+    is the yardstick: the GPU trajectory (itself not bit-reproducible: float atomics) must stay within 3x of it (+2 %)
+    of the fp64 trajectory, per quantity, both per iteration over the first 25 iterations and in 25-iteration means over
+    the whole run; the final importance-weighted log-likelihood of 64 held-out points within 0.25 nat."""
+    import ardae
+    import curve_util as cu
+    import json
+    z = np.load(os.path.join(GOLDEN_DIR, 'toy_curve.npz'), allow_pickle=True)
+    C = json.loads(str(z['meta']))
+    hp, B, T, seed = C['hp'], C['B'], C['T'], C['seed']
+    meta = dict(kind='toy', model=C['model'], cdae=C['cdae'], hp=hp)
+    model, cdae, mopt, copt = build(meta, z)
+    step = ardae.TrainStep(model, cdae, mopt, copt, std_scale=hp['std_scale'], delta=hp['delta'], nz_cdae=hp['nz_cdae'],
+                           nstd=hp['nstd'], nz_model=hp['nz_model'])
+    n, d = C['model']['noise_dim'], C['model']['z_dim']
+    got = torch.zeros(T, 5, device='cuda')
+    for it in range(T):
+        nz = {k: t(v) for k, v in cu.noise(seed, it, B, n, d, hp).items()}
+        o = step(t(cu.batch(seed, it, B, 0)), t(cu.batch(seed, it, B, 1)), beta=hp['beta'], noise=nz)
+        got[it, :4] = o['losses']
+        got[it, 4] = o['std'].mean()
+    got = got.cpu().numpy().astype(np.float64)
+    ref, ref32 = z['curve'], z['curve_ref_fp32']
+    if os.environ.get('ARDAE_CURVE_DUMP'):
+        np.save(os.environ['ARDAE_CURVE_DUMP'], got)
+    assert np.isfinite(got).all()
+    win = lambda a: a.reshape(T // 25, 25, 5).mean(axis=1)
+    early = lambda a: np.abs(a[:25] / ref[:25] - 1.0).max(axis=0)
+    smooth = lambda a: np.abs(win(a) / win(ref) - 1.0).max(axis=0)
+    x, en, eta = cu.iws_inputs(seed, 64, 64, n, d)
+    lp = model.logprob(t(x), sample_size=64, noise=t(en), eta=t(eta)).item()
+    print('quantities: cdae_loss, model_loss, recon, prior, sigma scale')
+    print('first 25 iterations, max rel deviation from the fp64 reference: GPU', early(got), ' reference fp32', early(ref32))
+    print('25-iteration means,  max rel deviation from the fp64 reference: GPU', smooth(got), ' reference fp32', smooth(ref32))
+    print('last 25 iterations: model_loss %.4f (fp64 ref %.4f, fp32 ref %.4f); iws %.4f (fp64 ref %.4f, fp32 ref %.4f)' % (
+        got[-25:, 1].mean(), ref[-25:, 1].mean(), ref32[-25:, 1].mean(), lp, float(z['iws_logprob']),
+        float(z['iws_logprob_ref_fp32'])))
+    assert (early(got) <= 3.0 * early(ref32) + 0.02).all(), (early(got), early(ref32))
+    assert (smooth(got) <= 3.0 * smooth(ref32) + 0.02).all(), (smooth(got), smooth(ref32))
+    assert abs(lp - float(z['iws_logprob'])) <= 0.25
+    # the run must actually have trained: the ELBO loss falls from 32.8 to ~5.5
+    assert got[0, 1] > 30.0 and got[-25:, 1].mean() < 6.5
