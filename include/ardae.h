@@ -226,6 +226,23 @@ ARDAE_API int ardae_bernoulli(const float* probs, float* out, size_t n, uint64_t
 ARDAE_API int ardae_set_replay_counter(const unsigned long long* device_counter);
 ARDAE_API int ardae_bump_replay_counter(unsigned long long* device_counter, void* stream);
 
+/* ---- data parallel over NVLink peer memory (no reference counterpart: the reference is single-device) ----
+ * One process per GPU.  Every rank allocates an exchange buffer of ardae_dp_xchg_bytes(n, world) ZEROED bytes (n = floats
+ * of the largest arena), exports it with ardae_ipc_export (CUDA IPC handle of the underlying allocation + byte offset),
+ * exchanges the 64-byte handles out of band (torch.distributed) and opens the peers' buffers with ardae_ipc_import.
+ * ardae_dp_fused_step then replaces `allreduce(g); optimizer.step()` (ivae_ardae.py:779,846 under batch sharding) by
+ * ONE kernel: gradient slices are pushed to their owner ranks, each rank reduces and updates its 1/world slice of the
+ * arena (kind 0: utils.Adam, utils/optim.py:49-108; kind 1: torch RMSprop) and pushes the updated parameters back;
+ * parameters stay replicated bit for bit, optimizer state is advanced on the owner rank only.  All ranks must call it
+ * in the same order.  epoch_barrier_status: 4 zero-initialised uint64 of local device memory kept for the lifetime of
+ * the communicator ([2] becomes non-zero if a peer never answered).  Safe to capture in a CUDA graph. */
+ARDAE_API int ardae_ipc_export(const void* ptr, unsigned char* handle64, size_t* offset);
+ARDAE_API int ardae_ipc_import(const unsigned char* handle64, size_t offset, void** out);
+ARDAE_API int ardae_dp_xchg_bytes(size_t n, int world, size_t* bytes);
+ARDAE_API int ardae_dp_fused_step(int kind, int rank, int world, float* p, const float* g, float* s1, float* s2, size_t n,
+                                  void* const* peer_xchg, unsigned long long* epoch_barrier_status, float lr, float beta1,
+                                  float beta2_or_alpha, float eps, float momentum, int step, float gscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,10 @@ def _declare(lib):
     lib.ardae_set_replay_counter.argtypes = [vp]
     lib.ardae_bump_replay_counter.argtypes = [vp, vp]
     lib.ardae_rmsprop_step.argtypes = [vp, vp, vp, vp, sz, f, f, f, f, f, vp]
+    lib.ardae_ipc_export.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(sz)]
+    lib.ardae_ipc_import.argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(vp)]
+    lib.ardae_dp_xchg_bytes.argtypes = [sz, i, ctypes.POINTER(sz)]
+    lib.ardae_dp_fused_step.argtypes = [i, i, i, vp, vp, vp, vp, sz, ctypes.POINTER(vp), vp, f, f, f, f, f, i, f, vp]
     return lib
 
 

@@ -129,6 +129,23 @@ class Adam(_FlatOptimizer):
                                               int(t), ctypes.c_float(self.grad_scale), _lib.stream_ptr()))
 
 
+    @torch.no_grad()
+    def step_flat_dp(self, grad_flat, comm, skip=()):
+        """Data-parallel fused-driver entry: gradient exchange over peer memory + update in ONE kernel (ardae/dp.py)."""
+        ar = self._setup()
+        group = self.param_groups[0]
+        t = None
+        for k, p in enumerate(ar.params):
+            if k in skip:
+                continue
+            self.state[p]['step'] += 1
+            t = self.state[p]['step']
+        b1, b2 = group['betas']
+        m, v = self._bufs
+        comm.fused_step(0, ar.flat, grad_flat, m, v, ar.total, group['lr'], b1, b2, group['eps'], 0.0, int(t),
+                        self.grad_scale)
+
+
 class RMSprop(_FlatOptimizer):
     STATE_NAMES = ('square_avg', 'momentum_buffer')
 
@@ -168,3 +185,14 @@ class RMSprop(_FlatOptimizer):
                                                  ctypes.c_float(group['alpha']), ctypes.c_float(group['eps']),
                                                  ctypes.c_float(group['momentum']), ctypes.c_float(self.grad_scale),
                                                  _lib.stream_ptr()))
+
+    @torch.no_grad()
+    def step_flat_dp(self, grad_flat, comm, skip=()):
+        ar = self._setup()
+        group = self.param_groups[0]
+        for k, p in enumerate(ar.params):
+            if k not in skip:
+                self.state[p]['step'] += 1
+        sq, buf = self._bufs
+        comm.fused_step(1, ar.flat, grad_flat, sq, buf, ar.total, group['lr'], 0.0, group['alpha'], group['eps'],
+                        group['momentum'], 1, self.grad_scale)

@@ -82,6 +82,12 @@ class TrainStep(object):
         self._g_eager_calls = 0
         self._g_ctr = None
         self._stg = None        # input staging (stage() / __call__() without inputs)
+        import os
+        self.dp_one_graph = os.environ.get('ARDAE_DP_ONE_GRAPH', '0') == '1'  # capture the collectives too (opt-in)
+        # data parallel: gradient exchange + optimizer as one peer-memory kernel per arena (ardae/dp.py) instead of
+        # NCCL allreduce + optimizer launch; the iteration then holds no collective call and is ONE graph per rank
+        self.dp_fused = self.world > 1 and os.environ.get('ARDAE_DP_FUSED', '0') == '1'
+        self._comm = None
 
     class _Seg(object):
         def __init__(self, owner, name):
@@ -163,6 +169,20 @@ class TrainStep(object):
             return (xs * a + s) if (a != 1.0 or s != 0.0) else xs.contiguous()
         return zbar
 
+    def _peer_comm(self):
+        if self._comm is None:
+            from .dp import PeerComm
+            mar, car = self.model._ensure(), self.cdae._ensure()
+            self._comm = PeerComm(self.pg, mar.flat.device, max(mar.total, car.total))
+        return self._comm
+
+    def gather_optimizer_state(self):
+        """With the fused data-parallel update every rank advances only its slice of the optimizer state: call this
+        before saving / inspecting optimizer state (no-op otherwise)."""
+        if self._comm is not None:
+            self._comm.gather_state(self.copt)
+            self._comm.gather_state(self.mopt)
+
     def _allreduce(self, flat):
         if self.world <= 1:
             return
@@ -221,10 +241,14 @@ class TrainStep(object):
             _lib.check(L.ardae_cdae_train(h, _lib.ptr(xc), _lib.ptr(self._context(xs, zbar, hid)), _lib.ptr(sigma), _lib.ptr(eps), gen,
                                           self._next_seed(), ctypes.c_float(inv), _lib.ptr(loss), None,
                                           _lib.stream_ptr()))                           # :768-771
-        with self._seg('cdae_allreduce'):
-            self._allreduce(ar.stage_flat)
-        with self._seg('cdae_opt'):
-            self.copt.step_flat(ar.stage_flat, skip=c.no_grad_params)               # :779
+        if self.dp_fused:
+            with self._seg('cdae_opt'):
+                self.copt.step_flat_dp(ar.stage_flat, self._peer_comm(), skip=c.no_grad_params)   # :779, all ranks
+        else:
+            with self._seg('cdae_allreduce'):
+                self._allreduce(ar.stage_flat)
+            with self._seg('cdae_opt'):
+                self.copt.step_flat(ar.stage_flat, skip=c.no_grad_params)           # :779
         self.last_std = std
         if self.keep_noise:
             self.last_noise.update(enc_cdae=enc, sigma=sigma, std=std, eps_cdae=eps, z_cdae=z, zbar_cdae=zbar)
@@ -294,10 +318,14 @@ class TrainStep(object):
         with self._seg('model_bwd'):
             _lib.check(L.ardae_model_backward_encoder(f['hm'], ctypes.c_float(1.0), _lib.ptr(g),
                                                       ctypes.c_float(gz_scale), _lib.stream_ptr()))  # :804 + :834 (encoder half)
-        with self._seg('model_allreduce'):
-            self._allreduce(ar.stage_flat)
-        with self._seg('model_opt'):
-            self.mopt.step_flat(ar.stage_flat)                                           # :846
+        if self.dp_fused:
+            with self._seg('model_opt'):
+                self.mopt.step_flat_dp(ar.stage_flat, self._peer_comm())                 # :846, all ranks
+        else:
+            with self._seg('model_allreduce'):
+                self._allreduce(ar.stage_flat)
+            with self._seg('model_opt'):
+                self.mopt.step_flat(ar.stage_flat)                                       # :846
         return f['sums'], g, f['z']
 
     def model_update(self, x, beta, noise=None):
@@ -434,11 +462,15 @@ class TrainStep(object):
             _lib.check(L.ardae_set_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr())))
             steps_before = [[opt.state[p]['step'] for p in opt._setup().params] for opt in (self.copt, self.mopt)]
             try:
-                if self.world > 1:
+                if self.world > 1 and not (self.dp_one_graph or self.dp_fused):
                     g = self._capture_segments(gxs, gxm, beta)
                     out = g.out
                 else:
-                  with torch.cuda.graph(g):
+                  # world > 1 here: the two NCCL allreduces are captured with the rest (thread-local capture mode: the
+                  # process group's watchdog thread keeps making CUDA calls)
+                  if self.dp_fused:
+                      self._peer_comm()  # IPC setup is a collective: not inside the capture
+                  with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
                     out = self._call_eager(gxs, gxm, beta, None)
                     _lib.check(L.ardae_bump_replay_counter(ctypes.c_void_p(self._g_ctr.data_ptr()), _lib.stream_ptr()))
             except Exception as e:  # e.g. a collective that cannot be captured: stay eager, loudly

@@ -4,6 +4,7 @@
 #include <cmath>
 
 #include "model.cuh"
+#include "dp_fused.cuh"
 
 using namespace ardae;
 
@@ -358,3 +359,69 @@ ARDAE_API int ardae_bump_replay_counter(unsigned long long* device_counter, void
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- data parallel: peer memory + fused exchange / update
+ARDAE_API int ardae_ipc_export(const void* ptr, unsigned char* handle64, size_t* offset) {
+  if (!ptr || !handle64 || !offset) return fail(-1, "null argument");
+  typedef CUresult (*PFN_range)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static PFN_range fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_range>(p);
+  }
+  if (fn == nullptr) return fail(-10, "cuMemGetAddressRange entry point unavailable");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return fail(-2, "ipc_export: not a device allocation");
+  cudaIpcMemHandle_t h;
+  ARDAE_CUDA_OK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle64, &h, 64);
+  *offset = reinterpret_cast<uintptr_t>(ptr) - static_cast<uintptr_t>(base);
+  return 0;
+}
+
+ARDAE_API int ardae_ipc_import(const unsigned char* handle64, size_t offset, void** out) {
+  if (!handle64 || !out) return fail(-1, "null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  ARDAE_CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *out = static_cast<unsigned char*>(base) + offset;
+  return 0;
+}
+
+ARDAE_API int ardae_dp_xchg_bytes(size_t n, int world, size_t* bytes) {
+  if (!bytes || world < 1 || world > kDpMaxWorld || n % 4 != 0) return fail(-2, "dp_xchg_bytes: bad arguments");
+  *bytes = dp_xchg_bytes(n, world);
+  return 0;
+}
+
+ARDAE_API int ardae_dp_fused_step(int kind, int rank, int world, float* p, const float* g, float* s1, float* s2, size_t n,
+                                  void* const* peer_xchg, unsigned long long* epoch_barrier_status, float lr, float beta1,
+                                  float beta2_or_alpha, float eps, float momentum, int step, float gscale, void* stream) {
+  if (!p || !g || !s1 || !s2 || !peer_xchg || !epoch_barrier_status) return fail(-1, "null argument");
+  if (world < 2 || world > kDpMaxWorld || rank < 0 || rank >= world) return fail(-2, "dp_fused_step: bad rank / world");
+  if (kind != 0 && kind != 1) return fail(-2, "dp_fused_step: kind must be 0 (Adam) or 1 (RMSprop)");
+  if (n % 4 != 0 || ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s1) |
+                      reinterpret_cast<uintptr_t>(s2)) & 15))
+    return fail(-11, "optimizer arenas must be 16-byte aligned with n % 4 == 0");
+  if (kind == 0 && step < 1) return fail(-2, "adam: step must be >= 1");
+  DpFusedParams a;
+  std::memset(&a, 0, sizeof(a));
+  a.p = p; a.g = g; a.s1 = s1; a.s2 = s2; a.n = n; a.rank = rank; a.world = world; a.kind = kind;
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2_or_alpha; a.alpha = beta2_or_alpha; a.eps = eps; a.mu = momentum; a.gscale = gscale;
+  a.step0 = step; a.ctr = replay_counter();
+  a.epoch = epoch_barrier_status; a.barrier = epoch_barrier_status + 1;
+  a.status = reinterpret_cast<int*>(epoch_barrier_status + 2);
+  for (int r = 0; r < world; ++r) {
+    if (!peer_xchg[r]) return fail(-1, "dp_fused_step: null exchange buffer");
+    a.xchg[r] = static_cast<unsigned char*>(peer_xchg[r]);
+  }
+  dp_fused_step_kernel<<<kDpGrid, kDpBlock, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  ARDAE_CUDA_OK(cudaGetLastError());
+  return 0;
+}
