@@ -429,6 +429,12 @@ def main():
     W, K = max(3, args.warmup), max(1, args.steps)
     B = c['B']
 
+    # roofline denominator first, on the idle GPU (a burst figure, like MEASURED_PEAKS.json's bf16_tflops): measured
+    # after minutes of load the same probe reads 4-5 % lower (power cap), which would flatter the fraction
+    tf32_peak, tf32_clocks = measure_tf32_peak(dev, local) if rank == 0 else (0.0, {})
+    if world > 1:
+        dist.barrier()
+
     # ================= headline: configs[1], 512 rows per GPU (weak scaling across --gpus)
     h = Harness(c, B, dev, world, rank, graph=not args.no_graph, cdae_kind=args.cdae)
     step, model, cdae = h.step, h.model, h.cdae
@@ -534,9 +540,8 @@ def main():
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     hbm_src = 'MEASURED_PEAKS.json (hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
-    tf32_peak, tf32_clocks = measure_tf32_peak(dev, local)
     bf16_peak = float(peaks.get('bf16_tflops', 2 * tf32_peak))
-    tf32_src = ('torch.matmul tf32 8192^3, best of 10, measured in this run with its own clock record '
+    tf32_src = ('torch.matmul tf32 8192^3, best of 10, measured at the start of this run (idle GPU) with its own clock record '
                 '(MEASURED_PEAKS.json holds bf16 only: %s burst; half of it = %.0f)' % (peaks.get('bf16_tflops'), bf16_peak / 2))
 
     flops = cdae_alg_flops(B, c['nz'] * c['nstd'], c['z'], c['z'], c['cdae_h'], c['cdae_L'])

@@ -74,6 +74,47 @@ def test_model_workspace_query(lib):
     assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(7, 2, 10, 256, 2, 2, 2, 2, 0, 512, 256, 0)), ctypes.byref(n)) < 0
 
 
+def test_hierarchical_and_conv_kinds_plan_on_the_host(lib):
+    """kind 2 (ConvIPVAE) and kind 3 (MNISTAuxIPVAE): the dry build of every supported mode sizes a workspace; bad modes
+    are refused with a message (no GPU needed)."""
+    class MCfg(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_int) for k in ('kind', 'input_dim', 'noise_dim', 'h_dim', 'z_dim', 'n_inp', 'n_fc',
+                                                'n_dec', 'act', 'batch', 'nz', 'mode', 'img_h', 'img_c')]
+    lib.ardae_last_error.restype = ctypes.c_char_p
+    n = ctypes.c_size_t(0)
+    sizes = {}
+    for mode, nz in ((0, 256), (1, 1), (2, 64), (3, 1)):
+        cfg = MCfg(3, 784, 100, 300, 32, 2, 2, 2, 1, 64, nz, mode, 0, 0)
+        assert lib.ardae_model_workspace_bytes(ctypes.byref(cfg), ctypes.byref(n)) == 0, (mode, lib.ardae_last_error())
+        sizes[mode] = n.value
+    assert sizes[0] > sizes[3] > 0 and sizes[1] > sizes[3]
+    assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(3, 784, 100, 300, 32, 2, 2, 2, 1, 64, 1, 4, 0, 0)), ctypes.byref(n)) < 0
+    assert b'auxmnist' in lib.ardae_last_error()
+    assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(3, 784, 100, 300, 32, 2, 2, 2, 0, 64, 1, 1, 0, 0)), ctypes.byref(n)) < 0
+    assert b'softplus' in lib.ardae_last_error()
+    for mode, nz in ((0, 256), (1, 1), (2, 64), (3, 1), (4, 1), (5, 1)):
+        cfg = MCfg(2, 784, 100, 800, 32, 3, 1, 2, 1, 32, nz, mode, 28, 1)
+        assert lib.ardae_model_workspace_bytes(ctypes.byref(cfg), ctypes.byref(n)) == 0, (mode, lib.ardae_last_error())
+    assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(2, 784, 100, 800, 32, 3, 1, 2, 1, 32, 1, 1, 27, 1)), ctypes.byref(n)) < 0
+
+
+def test_data_parallel_entry_points_validate_arguments(lib):
+    lib.ardae_last_error.restype = ctypes.c_char_p
+    n = ctypes.c_size_t(0)
+    assert lib.ardae_dp_xchg_bytes(ctypes.c_size_t(1 << 20), 8, ctypes.byref(n)) == 0
+    # header + 8 slots of one slice + the parameter area = 2 x the arena + change
+    assert 2 * 4 * (1 << 20) <= n.value <= 2 * 4 * (1 << 20) + 8192
+    assert lib.ardae_dp_xchg_bytes(ctypes.c_size_t(1 << 20), 17, ctypes.byref(n)) < 0
+    assert lib.ardae_dp_xchg_bytes(ctypes.c_size_t(1001), 2, ctypes.byref(n)) < 0
+    lib.ardae_dp_fused_step.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p,
+                                                                                     ctypes.c_void_p] + [ctypes.c_float] * 5 + [
+        ctypes.c_int, ctypes.c_float, ctypes.c_void_p]
+    assert lib.ardae_dp_fused_step(0, 0, 2, None, None, None, None, 16, None, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) < 0
+    assert b'null' in lib.ardae_last_error()
+    lib.ardae_ipc_export.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]
+    assert lib.ardae_ipc_export(None, ctypes.create_string_buffer(64), ctypes.byref(n)) < 0
+
+
 def test_no_gpu_means_loud_failure(lib):
     import torch
     if torch.cuda.is_available():
