@@ -72,6 +72,9 @@ def test_model_workspace_query(lib):
     assert n.value > 0
     assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(0, 2, 10, 256, 2, 2, 2, 2, 0, 512, 256, 0)), ctypes.byref(n)) == 0
     assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(7, 2, 10, 256, 2, 2, 2, 2, 0, 512, 256, 0)), ctypes.byref(n)) < 0
+    # empty batches are refused (the reference would fail inside torch.std over an empty dimension)
+    assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(0, 2, 10, 256, 2, 2, 2, 2, 0, 0, 256, 0)), ctypes.byref(n)) < 0
+    assert lib.ardae_model_workspace_bytes(ctypes.byref(MCfg(0, 2, 10, 256, 2, 2, 2, 2, 0, 512, 0, 0)), ctypes.byref(n)) < 0
 
 
 def test_hierarchical_and_conv_kinds_plan_on_the_host(lib):
