@@ -303,6 +303,12 @@ class Harness(object):
         h2d = 2 * self.resident[0][0].numel() * 4
         return self.max_over_ranks(f0.elapsed_time(f1)), h2d
 
+    def check_comm(self):
+        """Raises if a fused data-parallel step ever timed out waiting for a peer (the numbers would be void)."""
+        comm = getattr(self.step, '_comm', None)
+        if comm is not None and getattr(self.step, 'dp_fused', False):
+            comm.check()
+
     def close(self):
         import gc
         import torch
@@ -323,6 +329,7 @@ def sub_record(c, B, dev, world, rank, W, K, label, with_e2e=True):
         e2e_ms, h2d = h.time_e2e(K)
         rec['e2e'] = dict(value=B * world * K / (e2e_ms * 1e-3), unit='samples/s', ms_per_step=e2e_ms / K,
                           h2d_bytes_per_step=h2d, d2h_bytes_per_step=16)
+    h.check_comm()
     h.close()
     return rec
 
@@ -438,6 +445,7 @@ def main():
     # ================= headline: configs[1], 512 rows per GPU (weak scaling across --gpus)
     h = Harness(c, B, dev, world, rank, graph=not args.no_graph, cdae_kind=args.cdae)
     step, model, cdae = h.step, h.model, h.cdae
+    dp_fused = bool(getattr(step, 'dp_fused', False))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -470,6 +478,7 @@ def main():
 
     # ---------------- end-to-end: pinned host inputs -> H2D every step, losses D2H every step
     e2e_ms, h2d_bytes = h.time_e2e(K)
+    h.check_comm()
     sampler.stop_flag = True  # clocks / throttle reasons sampled across both timed regions (value and e2e)
     launches_per_step = step.count_launches(B)
     n_cdae = sum(p.numel() for p in cdae.parameters())
@@ -611,9 +620,13 @@ def main():
                     arithmetic='tf32 tensor-core operands, fp32 accumulate; primal forward 3xTF32; [N,H] activation spill stored bf16; weight gradients bf16 x bf16 -> fp32',
                     l2='no flush needed: per-step working set (activation spill) ~3 GB >> 126 MB L2',
                     launch=(('one CUDA-graph replay per step (%d kernels on 3 streams captured)' % launches_per_step
-                             if world == 1 else
+                             if (world == 1 or dp_fused) else
                              '3 CUDA-graph replays + 2 eager NCCL allreduces per step (%d kernels captured)' % launches_per_step)
                             if graph_used else 'eager launches'),
+                    dp_exchange=('none (1 GPU)' if world == 1 else
+                                 ('fused peer-memory kernel: gradient slices pushed over NVLink, reduce + optimizer update '
+                                  '+ parameter push in one launch per arena (csrc/dp_fused.cuh)' if dp_fused else
+                                  'NCCL SUM allreduce of the two flat gradient arenas + optimizer launch')),
                     ms_per_step_eager_profiled=eager_ms,
                     noise='in-kernel Philox', final_losses=final_losses),
         clocks=sampler.summary(),

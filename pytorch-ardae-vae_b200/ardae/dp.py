@@ -14,7 +14,26 @@ import torch
 from . import _lib
 
 
+_COMMS = {}      # (process-group id, device index) -> PeerComm: one exchange buffer per process, shared by all TrainSteps
+_IMPORTED = {}   # IPC handle bytes -> base pointer in this process (an allocation is opened once)
+
+
+class PeerCommUnavailable(RuntimeError):
+    """Raised on EVERY rank when some rank could not map its peers (the caller then uses the NCCL path)."""
+
+
 class PeerComm(object):
+    @staticmethod
+    def get(process_group, device, max_floats):
+        """The communicator of (process_group, device), created on first use or when a larger arena shows up.
+        Collective: every rank calls it with the same sizes in the same order."""
+        key = (id(process_group), torch.device(device).index)
+        c = _COMMS.get(key)
+        if c is None or c.max_floats < max_floats:
+            c = PeerComm(process_group, device, max_floats)
+            _COMMS[key] = c          # (a replaced communicator stays mapped: peers may still hold its handle)
+        return c
+
     def __init__(self, process_group, device, max_floats):
         dist = torch.distributed
         self.pg = process_group
@@ -22,13 +41,14 @@ class PeerComm(object):
         self.rank = dist.get_rank(process_group)
         self.device = device
         if self.world > 16:
-            raise RuntimeError('PeerComm: at most 16 ranks (one NVSwitch domain)')
+            raise PeerCommUnavailable('PeerComm: at most 16 ranks (one NVSwitch domain)')
         L = _lib.lib()
         if max_floats % 4 != 0:
-            raise RuntimeError('PeerComm: arena sizes must be multiples of 4 floats')
+            raise PeerCommUnavailable('PeerComm: arena sizes must be multiples of 4 floats')
         self.max_floats = int(max_floats)
         nbytes = ctypes.c_size_t(0)
         _lib.check(L.ardae_dp_xchg_bytes(ctypes.c_size_t(self.max_floats), self.world, ctypes.byref(nbytes)))
+        err = None
         with torch.cuda.device(device):
             self.xchg = torch.zeros(nbytes.value + 256, dtype=torch.uint8, device=device)
             self.ebs = torch.zeros(4, dtype=torch.int64, device=device)  # epoch, grid barrier, status, pad
@@ -36,20 +56,35 @@ class PeerComm(object):
             torch.cuda.synchronize(device)
             handle = ctypes.create_string_buffer(64)
             off = ctypes.c_size_t(0)
-            _lib.check(L.ardae_ipc_export(ctypes.c_void_p(base), handle, ctypes.byref(off)))
-            mine = (bytes(handle.raw), int(off.value))
+            try:
+                _lib.check(L.ardae_ipc_export(ctypes.c_void_p(base), handle, ctypes.byref(off)))
+                mine = (bytes(handle.raw), int(off.value))
+            except RuntimeError as e:
+                err, mine = e, None
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine, group=process_group)
             self.ptrs = (ctypes.c_void_p * self.world)()
-            for r, (hb, o) in enumerate(everyone):
+            for r, item in enumerate(everyone):
                 if r == self.rank:
                     self.ptrs[r] = base
-                else:
-                    out = ctypes.c_void_p(0)
-                    _lib.check(L.ardae_ipc_import(hb, ctypes.c_size_t(o), ctypes.byref(out)))
-                    self.ptrs[r] = out.value
+                    continue
+                try:
+                    if item is None:
+                        raise RuntimeError('rank %d could not export its exchange buffer' % r)
+                    hb, o = item
+                    if hb not in _IMPORTED:
+                        out = ctypes.c_void_p(0)
+                        _lib.check(L.ardae_ipc_import(hb, ctypes.c_size_t(0), ctypes.byref(out)))
+                        _IMPORTED[hb] = out.value
+                    self.ptrs[r] = _IMPORTED[hb] + o
+                except RuntimeError as e:
+                    err = err or e
             torch.cuda.synchronize(device)
-        dist.barrier(group=process_group)  # every rank has zeroed and mapped everything before the first step
+            # collective verdict (doubles as the barrier: every rank has zeroed and mapped everything before step one)
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+        if int(ok.item()) == 0:
+            raise PeerCommUnavailable('peer memory could not be mapped on every rank (%s)' % (err,))
 
     def fused_step(self, kind, p, g, s1, s2, n, lr, b1, b2_or_alpha, eps, momentum, step, gscale):
         if n > self.max_floats:
@@ -76,3 +111,4 @@ class PeerComm(object):
             own[lo:hi] = buf[lo:hi]
             dist.all_reduce(own, op=dist.ReduceOp.SUM, group=self.pg)
             buf.copy_(own)
+        opt._state_sharded = False

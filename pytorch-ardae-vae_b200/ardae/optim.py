@@ -77,6 +77,14 @@ class _FlatOptimizer(Optimizer):
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._ar = None  # re-alias the loaded state tensors into flat buffers on the next step
+        self._state_sharded = False
+
+    def state_dict(self):
+        # fused data-parallel updates advance each slice of the state on its owner rank only (ardae/dp.py)
+        if getattr(self, '_state_sharded', False):
+            raise RuntimeError('optimizer state is sharded over the data-parallel ranks: call '
+                               'TrainStep.gather_optimizer_state() on every rank before state_dict()')
+        return super().state_dict()
 
 
 class Adam(_FlatOptimizer):
@@ -144,6 +152,7 @@ class Adam(_FlatOptimizer):
         m, v = self._bufs
         comm.fused_step(0, ar.flat, grad_flat, m, v, ar.total, group['lr'], b1, b2, group['eps'], 0.0, int(t),
                         self.grad_scale)
+        self._state_sharded = True
 
 
 class RMSprop(_FlatOptimizer):
@@ -196,3 +205,4 @@ class RMSprop(_FlatOptimizer):
         sq, buf = self._bufs
         comm.fused_step(1, ar.flat, grad_flat, sq, buf, ar.total, group['lr'], 0.0, group['alpha'], group['eps'],
                         group['momentum'], 1, self.grad_scale)
+        self._state_sharded = True

@@ -86,8 +86,11 @@ class TrainStep(object):
         self.dp_one_graph = os.environ.get('ARDAE_DP_ONE_GRAPH', '0') == '1'  # capture the collectives too (opt-in)
         # data parallel: gradient exchange + optimizer as one peer-memory kernel per arena (ardae/dp.py) instead of
         # NCCL allreduce + optimizer launch; the iteration then holds no collective call and is ONE graph per rank
-        self.dp_fused = self.world > 1 and os.environ.get('ARDAE_DP_FUSED', '0') == '1'
+        self.dp_fused = self.world > 1 and os.environ.get('ARDAE_DP_FUSED', '1') == '1' and \
+            torch.distributed.get_backend(process_group) == 'nccl'
         self._comm = None
+        if self.dp_fused:
+            self._init_dp_fused()
 
     class _Seg(object):
         def __init__(self, owner, name):
@@ -173,13 +176,23 @@ class TrainStep(object):
         if self._comm is None:
             from .dp import PeerComm
             mar, car = self.model._ensure(), self.cdae._ensure()
-            self._comm = PeerComm(self.pg, mar.flat.device, max(mar.total, car.total))
+            self._comm = PeerComm.get(self.pg, mar.flat.device, max(mar.total, car.total))
         return self._comm
+
+    def _init_dp_fused(self):
+        """Decide, collectively, whether the peer-memory exchange is available (else: NCCL allreduce)."""
+        from .dp import PeerCommUnavailable
+        try:
+            self._peer_comm()
+        except PeerCommUnavailable as e:
+            import warnings
+            warnings.warn('ardae.TrainStep: %s; using NCCL allreduce' % (e,))
+            self.dp_fused = False
 
     def gather_optimizer_state(self):
         """With the fused data-parallel update every rank advances only its slice of the optimizer state: call this
         before saving / inspecting optimizer state (no-op otherwise)."""
-        if self._comm is not None:
+        if self._comm is not None and self.dp_fused:
             self._comm.gather_state(self.copt)
             self._comm.gather_state(self.mopt)
 
