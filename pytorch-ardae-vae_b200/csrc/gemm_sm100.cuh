@@ -586,6 +586,7 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
   using Cfg = GemmNTPersistConfig<MODE, SPLIT>;
   constexpr int NSTAGE = Cfg::kNumStages;
   constexpr int NAUX = Cfg::kNumAux;
+  constexpr int NAUXD = NAUX > 0 ? NAUX : 1;  // divisor in code that only runs when NAUX > 0
   constexpr bool kHasAux1 = Cfg::kHasAux1, kHasAux2 = Cfg::kHasAux2, kHasOut2 = Cfg::kHasOut2;
   constexpr int NCHUNK = 8;
 
@@ -694,8 +695,8 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
         const int m0 = tile * kBlockM;
         for (int c = 0; c < NCHUNK; ++c) {
           if (c * 32 >= p.N) break;
-          const int a = cc % NAUX;
-          const uint32_t ph = (cc / NAUX) & 1;
+          const int a = cc % NAUXD;
+          const uint32_t ph = (cc / NAUXD) & 1;
           ptx::mbar_wait(&aux_empty[a], ph ^ 1);
           ptx::mbar_expect_tx(&aux_full[a], Cfg::kAuxSlotBytes);
           uint8_t* slot = smem + Cfg::kOffAux + a * Cfg::kAuxSlotBytes;
@@ -732,8 +733,8 @@ gemm_nt_persist_kernel(const __grid_constant__ GemmNTParams p) {
         if (nc >= p.N) break;
         uint32_t accu[32];
         ptx::tmem_ld_32x32(tmem_base + buf * 256 + (static_cast<uint32_t>(quarter * 32) << 16) + nc, accu);
-        const int a = kHasAux1 ? cc % NAUX : 0;
-        if (kHasAux1) ptx::mbar_wait(&aux_full[a], (cc / NAUX) & 1);
+        const int a = kHasAux1 ? cc % NAUXD : 0;
+        if (kHasAux1) ptx::mbar_wait(&aux_full[a], (cc / NAUXD) & 1);
         ptx::tmem_ld_wait();
         const uint8_t* slot = smem + Cfg::kOffAux + a * Cfg::kAuxSlotBytes;
         uint8_t* ob = out_base + (cc % Cfg::kNumOut) * kTileBytes;
