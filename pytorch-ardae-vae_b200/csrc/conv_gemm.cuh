@@ -190,13 +190,10 @@ __global__ void chan_sum_nchw_kernel(const float* __restrict__ x, int ld, int R,
   if (threadIdx.x == 0) atomicAdd(out + c, acc);
 }
 
+// read at plan-build time (not cached: tests build both variants in one process)
 inline bool conv_gemm_enabled() {
-  static int env = -1;
-  if (env < 0) {
-    const char* e = std::getenv("ARDAE_CONV_GEMM");
-    env = (e && std::atoi(e) == 0) ? 0 : 1;
-  }
-  return env == 1;
+  const char* e = std::getenv("ARDAE_CONV_GEMM");
+  return !(e && std::atoi(e) == 0);
 }
 
 }  // namespace ardae

@@ -323,3 +323,32 @@ def test_submodule_calls(name):
     ztol = 2e-5 if spec.kind == 'conv' else 1e-5  # conv: 612- and 800-long fp32 contractions
     assert rel_err(z_parts.cpu().numpy(), z_ref) <= ztol
     assert rel_err(z_full.cpu().numpy(), z_ref) <= ztol
+
+
+def test_conv_gemm_path_equals_direct_kernels(monkeypatch):
+    """ConvIPVAE 28x28: the im2col + tcgen05-GEMM conv layers (default) against the direct fp32 CUDA-core kernels
+    (ARDAE_CONV_GEMM=0) on the same weights, inputs and noise: logits / z to 1e-5 (both forwards are fp32-accurate),
+    every gradient tensor to 5e-3 (tf32 backward GEMMs vs exact fp32 accumulation)."""
+    import ardae
+    torch.manual_seed(3)
+    ref = ardae.ConvIPVAE(input_height=28, input_channels=1, z_dim=32, noise_dim=100, nonlinearity='softplus')
+    state = {k: v.clone() for k, v in ref.state_dict().items()}
+    x = (torch.rand(12, 784, device='cuda') < 0.2).float()
+    noise = torch.randn(12 * 2, 100, device='cuda')
+    res = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('ARDAE_CONV_GEMM', flag)
+        m = ardae.ConvIPVAE(input_height=28, input_channels=1, z_dim=32, noise_dim=100, nonlinearity='softplus')
+        m.load_state_dict(state)
+        m = m.cuda()
+        xhat, mean, z, loss, recon, prior = m(x, beta=0.7, nz=2, noise=noise)
+        loss.backward()
+        torch.cuda.synchronize()
+        res[flag] = dict(mean=mean.detach().cpu().numpy().astype(np.float64), z=z.detach().cpu().numpy().astype(np.float64),
+                         loss=loss.item(), grads={k: p.grad.detach().cpu().numpy().astype(np.float64)
+                                                  for k, p in m.named_parameters()})
+    a, b = res['0'], res['1']
+    assert abs(a['loss'] - b['loss']) <= 1e-6 * abs(a['loss'])
+    assert rel_err(b['z'], a['z']) <= 1e-5 and rel_err(b['mean'], a['mean']) <= 1e-5
+    for k in a['grads']:
+        assert rel_err(b['grads'][k], a['grads'][k]) <= 5e-3, (k, rel_err(b['grads'][k], a['grads'][k]))
