@@ -8,6 +8,7 @@ inside the iteration, so the whole iteration is one CUDA graph on every rank.
 Parameters stay replicated bit for bit; optimizer state is advanced only on the rank that owns a slice, so
 `gather_state` must run before the optimizer state is saved or inspected."""
 import ctypes
+import os
 
 import torch
 
@@ -57,6 +58,8 @@ class PeerComm(object):
             handle = ctypes.create_string_buffer(64)
             off = ctypes.c_size_t(0)
             try:
+                if os.environ.get('ARDAE_DP_FUSED_FAIL_RANK') == str(self.rank):  # test hook: one rank cannot export
+                    raise RuntimeError('simulated export failure (ARDAE_DP_FUSED_FAIL_RANK)')
                 _lib.check(L.ardae_ipc_export(ctypes.c_void_p(base), handle, ctypes.byref(off)))
                 mine = (bytes(handle.raw), int(off.value))
             except RuntimeError as e:

@@ -142,3 +142,24 @@ def test_two_rank_dp_matches_single_rank(name):
             assert e_all <= 5e-2, (key, e_all)
         else:
             assert e_hi <= 0.3, (key, e_hi)
+
+
+@pytest.mark.parametrize('fail_rank', [None, 1])
+def test_peer_mapping_decision_is_collective(fail_rank):
+    """scripts/dp_fallback_check.py: two ranks that each see only their own GPU.  Without a fault the peer mapping is
+    used; with a simulated export failure on one rank EVERY rank falls back to the NCCL exchange (no hang, no split
+    decision) and the replicas stay bit-identical."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs (gpurun --gpus 2)')
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.pop('ARDAE_DP_FUSED', None)
+    if fail_rank is not None:
+        env['ARDAE_DP_FUSED_FAIL_RANK'] = str(fail_rank)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'dp_fallback_check.py')], env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    want = 'dp_fused=%s replicas identical=True' % (fail_rank is None)
+    assert r.stdout.count(want) == 2, r.stdout + r.stderr
