@@ -170,6 +170,18 @@ inline bool chain16_pair_default() {
   return env != 0;
 }
 
+// Weight multicast across CTA pairs (chain16w_kernel<MODE, false, true>): opt-in, ARDAE_CHAIN16_MC=1.  Measured on B200:
+// halving the L2 -> SM weight traffic this way changes nothing (0.365 / 0.501 / 0.410 ms vs 0.367 / 0.496 / 0.416), i.e.
+// the sweeps are not bound by the weight stream.
+inline bool chain16_mc_default() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = std::getenv("ARDAE_CHAIN16_MC");
+    env = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return env != 0;
+}
+
 inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
   const int nl = static_cast<int>(d.layers.size());
   if (d.M <= 0 || !chain_supported(d.H, nl)) return fail(-2, "chain16: unsupported shape");
@@ -189,8 +201,9 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
   const bool w16 = warps_env != 8 && !s3;  // 16 epilogue warps (chain16w_sm100.cuh) unless ARDAE_CHAIN16_WARPS=8
   // pairs need 8-row aligned weight halves (H/4 and nout/2 multiples of 8) and at least two row tiles
   bool cg2 = w16 && chain16_pair_default() && (H / 4) % 8 == 0 && d.M > kBlockM;
+  bool mc = w16 && !cg2 && chain16_mc_default() && (H / 4) % 8 == 0 && d.M > kBlockM;
   for (const Chain16LayerDesc& s : d.layers)
-    if (s.nout > 0 && s.nout != H && (s.nout / 2) % 8 != 0) cg2 = false;
+    if (s.nout > 0 && s.nout != H && (s.nout / 2) % 8 != 0) cg2 = mc = false;
   const int kin0 = d.layers[0].kin > 0 ? d.layers[0].kin : H;
   if (kin0 % 32 != 0 || kin0 > H) return fail(-2, "chain16: first-layer input width must be a multiple of 32, <= H");
   uintptr_t align_or = 0;
@@ -223,7 +236,7 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
         (s3 && !s.out))
       return fail(-2, "chain16: missing operand pointer");
     if ((rc = encode_tmap_2d(&q.tmW, s.W, s3 ? 3 * kin : kin, s.w_rows > 0 ? s.w_rows : nout, s.ldw, kBlockK,
-                             (narrow ? nout : H / 2) / (cg2 ? 2 : 1))))
+                             (narrow ? nout : H / 2) / ((cg2 || mc) ? 2 : 1))))
       return rc;
     if (!narrow && !s3) {
       if ((rc = encode_tmap_2d_bf16(&q.tmAux1, s.aux1, H, d.M, s.ld1, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -258,8 +271,9 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
 #define ARDAE_CHAIN16W_CASE(MODE_)                                                                              \
   case MODE_:                                                                                                   \
     pr.fn = cg2 ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_, true>)                                  \
-                : (w16 ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_, false>)                          \
-                       : reinterpret_cast<const void*>(&chain16_kernel<MODE_>));                                \
+                : (mc ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_, false, true>)                     \
+                      : (w16 ? reinterpret_cast<const void*>(&chain16w_kernel<MODE_, false>)                    \
+                             : reinterpret_cast<const void*>(&chain16_kernel<MODE_>)));                         \
     pr.smem = Chain16Config<MODE_>::kSmemBytes;                                                                 \
     pr.threads = w16 ? Chain16wConfig::kThreads : Chain16Config<MODE_>::kThreads;                               \
     break;
@@ -273,7 +287,7 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
 #undef ARDAE_CHAIN16_CASE
 #undef ARDAE_CHAIN16W_CASE
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
-  if (cg2) {
+  if (cg2 || mc) {
     pr.cluster = 2;
     pr.grid.x = (pr.grid.x + 1) / 2 * 2;  // an odd tail CTA works on an out-of-range tile (TMA clips)
   }

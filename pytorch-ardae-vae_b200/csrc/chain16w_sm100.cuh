@@ -42,9 +42,14 @@ __device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lan
 // pair and every weight k-block is staged HALF in each CTA, so each SM ingests half of the weight stream -- the tf32
 // sweeps move 256 KB of weights per tile and layer through the L2 -> SM path, more than their aux / spill bytes, and
 // are bound by it.
-template <int MODE, bool CG2>
+// MC: clusters of two CTAs on adjacent row tiles that stay independent (own MMAs, own accumulators) but SHARE the weight
+// stream: each CTA fetches half of every weight k-block and TMA-multicasts it into both shared memories, so the
+// L2 -> SM weight traffic per SM halves without the pair's MMA lock-step (a stage is recycled when both CTAs' MMAs
+// have consumed it: the multicast commit arrives on both empty barriers).
+template <int MODE, bool CG2, bool MC = false>
 __global__ void __launch_bounds__(Chain16wConfig::kThreads, 1)
 chain16w_kernel(const __grid_constant__ Chain16Params p) {
+  static_assert(!(CG2 && MC), "CG2 and MC are exclusive");
   using Cfg = Chain16Config<MODE>;
   static_assert(MODE != CHAIN_SOFTPLUS3, "the primal sweep has its own kernels");
   constexpr bool S3 = false, HAS_AUX2 = Cfg::kAux2, HAS_OUT2 = Cfg::kOut2;
@@ -90,7 +95,7 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
     if (lane == 0) {
       for (int s = 0; s < NW; ++s) {
         ptx::mbar_init(&w_full[s], 1);
-        ptx::mbar_init(&w_empty[s], 1);
+        ptx::mbar_init(&w_empty[s], MC ? 2 : 1);  // MC: both CTAs' MMAs release a stage
       }
       for (int a = 0; a < 16; ++a) {
         ptx::mbar_init(&aux_full[a], 1);
@@ -115,10 +120,10 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG2) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
+  if (CG2 || MC) ptx::cluster_sync_all();  // the peer's barriers exist before anything remote touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t rank = CG2 ? ptx::cluster_ctarank() : 0;
+  const uint32_t rank = (CG2 || MC) ? ptx::cluster_ctarank() : 0;
   const uint32_t acc_t = tmem_base;       // accumulator columns [0, H)
   const uint32_t a_t = tmem_base + 256;   // A operand (SOFTPLUS3: its lo part) columns [256, 256 + H)
   uint8_t* hi_tiles = smem + Cfg::kOffAux;  // SOFTPLUS3 only
@@ -135,7 +140,7 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
         const int nst = S3 ? 2 * NBl : NBl;
         const int nrows = narrow ? L.nout : HH;  // B rows of one N-half (per pair when CG2: half lands in each CTA)
         const uint32_t wbytes = static_cast<uint32_t>(nrows) * kBlockK * 4;
-        const int wrows = CG2 ? nrows / 2 : nrows;
+        const int wrows = (CG2 || MC) ? nrows / 2 : nrows;
         for (int h = 0; h < (narrow ? 1 : 2); ++h) {
           for (int j = 0; j < nst; ++j, ++it) {
             const int s = it % NW;
@@ -146,6 +151,11 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
               // both CTAs' halves complete on the LEADER's full barrier, armed by the leader for both
               if (rank == 0) ptx::mbar_expect_tx(&w_full[s], wbytes);
               ptx::tma_load_2d_2sm(smem + s * kWStage, tw, &w_full[s], kc, h * HH + static_cast<int>(rank) * wrows);
+            } else if (MC) {
+              // the whole k-block lands here (this CTA's half + the peer's half); this CTA issues its half for both
+              ptx::mbar_expect_tx(&w_full[s], wbytes);
+              ptx::tma_load_2d_mc(smem + s * kWStage + rank * (static_cast<uint32_t>(wrows) * kBlockK * 4), tw, &w_full[s],
+                                  kc, h * HH + static_cast<int>(rank) * wrows, 0x3);
             } else {
               ptx::mbar_expect_tx(&w_full[s], wbytes);
               ptx::tma_load_2d(smem + s * kWStage, tw, &w_full[s], kc, h * HH);
@@ -162,6 +172,9 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
       };
       auto commit = [&](uint64_t* bar) {  // CG2: the same barrier in both CTAs of the pair
         if (CG2) ptx::umma_commit_2sm(bar, 0x3); else ptx::umma_commit(bar);
+      };
+      auto commit_w = [&](uint64_t* bar) {  // weight stage consumed (MC: tell both CTAs' producers)
+        if (MC) ptx::umma_commit_mc(bar, 0x3); else commit(bar);
       };
       auto wait_a = [&](uint64_t* bar, uint32_t ph) {
         if (CG2) ptx::mbar_wait_cluster(bar, ph); else ptx::mbar_wait(bar, ph);
@@ -188,7 +201,7 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
               const uint64_t bdesc = ptx::make_smem_desc_sw128(b_addr + k * kUmmaK * 4, 0, 1024);
               mma_ts(d_t, a_t + kb * kBlockK + k * kUmmaK, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            commit(&w_empty[s]);
+            commit_w(&w_empty[s]);
             ++it;
             // second half: this layer is done with A chunk kb -> the half-0 epilogue may overwrite it
             if (h == 1 && kb < NB0) commit(&kfree[kb]);
@@ -480,7 +493,7 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG2) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers / read its memory
+  if (CG2 || MC) ptx::cluster_sync_all();  // no CTA exits while its peer may still signal its barriers / read its memory
   if (warp == 1) {
     ptx::tc_fence_after();
     if (CG2) ptx::tmem_dealloc_2sm(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
