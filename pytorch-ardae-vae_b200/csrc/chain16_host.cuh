@@ -1,5 +1,6 @@
 // Host-side preparation (TMA tensor maps) and launch of the 16-bit-spill layer-chain kernel (chain16_sm100.cuh).
 #pragma once
+#include <cstdio>
 #include <vector>
 
 #include "chain16_sm100.cuh"
@@ -287,6 +288,8 @@ inline int prepare_chain16(const Chain16Desc& d, PreparedChain16* out) {
 #undef ARDAE_CHAIN16_CASE
 #undef ARDAE_CHAIN16W_CASE
   pr.grid = dim3((d.M + kBlockM - 1) / kBlockM, 1, 1);
+  if ((cg2 || mc) && std::getenv("ARDAE_VERBOSE") != nullptr)
+    std::fprintf(stderr, "chain16: mode %d M=%d runs as CTA pairs (%s)\n", d.mode, d.M, cg2 ? "cta_group::2" : "weight multicast");
   if (cg2 || mc) {
     pr.cluster = 2;
     pr.grid.x = (pr.grid.x + 1) / 2 * 2;  // an odd tail CTA works on an out-of-range tile (TMA clips)
