@@ -64,13 +64,27 @@ struct Chain16Config {
   static constexpr bool kOut2 = MODE == CHAIN_TANGENT;
   static constexpr int kGroups = 2;
   static constexpr int kWStage = 128 * kBlockK * 4;
-  static constexpr int kNumWStages = 6;
+  // The weight ring is what feeds the MMAs: a 16 KB k-block is consumed every ~500 cycles with 6 stages in flight --
+  // stages x 16 KB / (L2 -> SM latency), Little's law, not L2 bandwidth (halving the bytes by multicast changes
+  // nothing).  The 224 KB of shared memory are therefore split in favour of the weight ring: 8 stages (128 KB) + 96 KB
+  // of aux / out slots (score sweep: 12 slots of 8 KB; tangent / adjoint: 6 slots of two tiles -- every epilogue group
+  // holds one slot per N-half and hands it back at the end of the half, so NB/2 slots are in use and the rest is
+  // prefetch).  Measured at config 2 (score / tangent / adjoint, ms): 6 stages 0.365 / 0.500 / 0.413, 7 stages
+  // 0.350 / 0.466 / 0.389, 8 stages 0.335 / 0.430 / 0.375, 10 stages (4 slots, no prefetch) 0.337 / 0.621 / 0.434.
+#ifndef ARDAE_CHAIN16_WSTAGES_1
+#define ARDAE_CHAIN16_WSTAGES_1 8
+#endif
+#ifndef ARDAE_CHAIN16_WSTAGES_2
+#define ARDAE_CHAIN16_WSTAGES_2 8
+#endif
+  static constexpr int kNumWStages = kS3 ? 6 : (kAux2 ? ARDAE_CHAIN16_WSTAGES_2 : ARDAE_CHAIN16_WSTAGES_1);
   static constexpr int kAuxSlot = kS3 ? 0 : (kAux2 ? 2 : 1) * kTile16Bytes;
-  static constexpr int kNumAux = kS3 ? 0 : (kAux2 ? 8 : 16);
+  static constexpr int kAuxBytes = (14 - kNumWStages) * kTileBytes;   // 14 x 16 KB = 224 KB in all
+  static constexpr int kNumAux = kS3 ? 0 : kAuxBytes / kAuxSlot;
   static constexpr int kOffAux = kNumWStages * kWStage;
-  static constexpr int kDataBytes = kOffAux + 8 * kTileBytes;
+  static constexpr int kDataBytes = kOffAux + kAuxBytes;
   static constexpr int kSmemBytes = kDataBytes + 1024 + 768;
-  static_assert(kSmemBytes <= 232448 && kNumAux <= 16 && kNumAux * kAuxSlot <= 8 * kTileBytes, "shared memory budget");
+  static_assert(kSmemBytes <= 232448 && kNumAux <= 16 && (kS3 ? kAuxBytes == 8 * kTileBytes : kNumAux >= 4), "shared memory budget");
   static constexpr int kThreads = 128 + kGroups * 128;
 };
 

@@ -54,7 +54,7 @@ chain16w_kernel(const __grid_constant__ Chain16Params p) {
   static_assert(MODE != CHAIN_SOFTPLUS3, "the primal sweep has its own kernels");
   constexpr bool S3 = false, HAS_AUX2 = Cfg::kAux2, HAS_OUT2 = Cfg::kOut2;
   constexpr int G = Chain16wConfig::kGroups;
-  constexpr int NW = CG2 ? 12 : Cfg::kNumWStages;          // CG2: twelve half-size stages in the same 96 KB
+  constexpr int NW = CG2 ? 2 * Cfg::kNumWStages : Cfg::kNumWStages;  // CG2: twice as many half-size stages
   constexpr int kWStage = CG2 ? Cfg::kWStage / 2 : Cfg::kWStage;
   constexpr int NAUX = Cfg::kNumAux > 0 ? Cfg::kNumAux : 1;
 
