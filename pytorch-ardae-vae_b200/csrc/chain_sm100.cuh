@@ -75,14 +75,21 @@ struct ChainConfig {
   static constexpr int kGroups = 2;
   // one k-block of one N-half ([<=128, 32] weight rows); a CTA pair (CG2) stages half of it in each CTA
   static constexpr int kWStage = (CG2 ? 64 : 128) * kBlockK * 4;
-  static constexpr int kNumWStages = CG2 ? 12 : 6;
+  // score-type sweep of the residual CDAE (one aux tile per slot): 8 weight stages + 6 slots, as in chain16_sm100.cuh
+  // (the weight ring is bound by stages in flight x L2 -> SM latency); the other modes keep the 6 + 8-tile split
+#ifndef ARDAE_CHAIN_WSTAGES_1
+#define ARDAE_CHAIN_WSTAGES_1 8
+#endif
+  static constexpr bool kDeepW = !kS3 && !kAux2 && !CG2 && MC == 1;
+  static constexpr int kNumWStages = CG2 ? 12 : (kDeepW ? ARDAE_CHAIN_WSTAGES_1 : 6);
   // One ring serves aux loads AND out stores: a slot receives the aux tile(s) of a chunk by TMA, the epilogue
   // overwrites them IN PLACE with the out tile(s), the TMA store leaves from the same bytes, and the slot is
   // recycled once that store has read it.  128 KB of HBM traffic in flight per SM instead of 64.
   static constexpr int kAuxSlot = kS3 ? 0 : (kAux2 ? 2 : 1) * kTileBytes;
-  static constexpr int kNumAux = kS3 ? 0 : (kAux2 ? 4 : 8);
+  static constexpr int kAuxTiles = kDeepW ? 14 - kNumWStages : 8;
+  static constexpr int kNumAux = kS3 ? 0 : (kAux2 ? 4 : kAuxTiles);
   static constexpr int kOffAux = kNumWStages * kWStage;        // SOFTPLUS3: the 8 hi tiles start here
-  static constexpr int kDataBytes = kOffAux + 8 * kTileBytes;
+  static constexpr int kDataBytes = kOffAux + kAuxTiles * kTileBytes;
   static constexpr int kSmemBytes = kDataBytes + 1024 + 512;
   static_assert(kSmemBytes <= 232448 && kNumAux <= 8, "shared memory budget");
   static constexpr int kThreads = 128 + kGroups * 128;
