@@ -11,9 +11,9 @@
 //   C. after the second flag: copies the other ranks' updated slices from its exchange buffer into its parameter arena.
 // Flags are 64-bit epochs written with release / read with acquire semantics at system scope; the epoch lives in device
 // memory and is advanced by the kernel, so CUDA-graph replays need no host involvement.  Pushes (posted stores) keep
-// NVLink read latency off the path.  Optimizer state of slices a rank does not own is never read again by that rank,
-// so it simply goes stale there (checkpoints gather it with ardae_dp_fused_gather_state... not needed for parameters,
-// which stay replicated bit-for-bit: every rank receives the same updated values).
+// NVLink read latency off the path.  Optimizer state of slices a rank does not own is never read again by that rank, so
+// it goes stale there: the host side gathers it before it is saved or inspected (ardae/dp.py: PeerComm.gather_state).
+// Parameters stay replicated bit for bit: every rank receives the same updated values.
 //
 // Exchange buffer of one rank (device memory, opened by every peer through CUDA IPC):
 //   [0, 1024)            flags A: world x uint64   (slot r written by rank r)
