@@ -84,9 +84,11 @@ class TrainStep(object):
         self._stg = None        # input staging (stage() / __call__() without inputs)
         import os
         self.dp_one_graph = os.environ.get('ARDAE_DP_ONE_GRAPH', '0') == '1'  # capture the collectives too (opt-in)
-        # data parallel: gradient exchange + optimizer as one peer-memory kernel per arena (ardae/dp.py) instead of
-        # NCCL allreduce + optimizer launch; the iteration then holds no collective call and is ONE graph per rank
-        self.dp_fused = self.world > 1 and os.environ.get('ARDAE_DP_FUSED', '1') == '1' and \
+        # data parallel, opt-in (ARDAE_DP_FUSED=1): gradient exchange + optimizer as one peer-memory kernel per arena
+        # (ardae/dp.py) instead of NCCL allreduce + optimizer launch; the iteration then holds no collective call and is
+        # ONE graph per rank.  Measured +2-3 % at 8 GPUs; the NCCL path is the default because one of four 8-GPU runs
+        # of the fused path did not finish within its time limit and could not be diagnosed
+        self.dp_fused = self.world > 1 and os.environ.get('ARDAE_DP_FUSED', '0') == '1' and \
             torch.distributed.get_backend(process_group) == 'nccl'
         self._comm = None
         if self.dp_fused:

@@ -154,7 +154,7 @@ def test_peer_mapping_decision_is_collective(fail_rank):
     import subprocess
     import sys
     env = dict(os.environ)
-    env.pop('ARDAE_DP_FUSED', None)
+    env['ARDAE_DP_FUSED'] = '1'  # the peer-memory exchange is opt-in
     if fail_rank is not None:
         env['ARDAE_DP_FUSED_FAIL_RANK'] = str(fail_rank)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
